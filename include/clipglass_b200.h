@@ -1,0 +1,130 @@
+/*
+ * clipglass_b200.h — C ABI of the B200-native CLIP-GLaSS fitness-evaluation path.
+ *
+ * Drop-in boundary.  The reference has no FFI: the path is the
+ * Python call chain
+ *
+ *     problem.py:14-29    GenerationProblem._evaluate(x, out)
+ *       latent.py:37-38   StyleGAN2LatentSpace.set_from_population   (f64 -> f32, H2D)
+ *       generator.py:29-34  Generator.generate(ls, minibatch)        (models.py:108-118 loop over G)
+ *       generator.py:43-51  Generator.clip_similarity(generated)     (kornia.resize -> CLIP.encode_image -> cosine)
+ *       generator.py:36-38  Generator.discriminate(generated, minibatch) (models.py:120-130 loop over D)
+ *
+ * Each entry point below replaces one of those calls and is what a ctypes stub
+ * in the reference's generator.py / problem.py binds.
+ * Plain pointers and sizes only; no torch types.  All functions return 0 on
+ * success or a negative glass_status; glass_last_error() gives the message.
+ * There is no CPU fallback: every compute entry point fails with
+ * GLASS_ERR_CUDA when no sm_100 device is usable.
+ */
+#ifndef CLIPGLASS_B200_H_
+#define CLIPGLASS_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct glass_engine glass_engine;   /* opaque; owns device weights + workspace */
+
+typedef enum glass_status {
+  GLASS_OK = 0,
+  GLASS_ERR_ARG = -1,       /* bad argument (mirrors the reference's AssertionError, models.py:112,124) */
+  GLASS_ERR_CUDA = -2,      /* CUDA runtime / driver failure, or no sm_100 device */
+  GLASS_ERR_STATE = -3,     /* call order (weights missing, not finalized, ...) */
+  GLASS_ERR_NOMEM = -4
+} glass_status;
+
+#define GLASS_MAX_BLOCKS 12
+
+/* Architecture + run shape.  Mirrors what the reference spreads over
+ * config.py:74-94 (StyleGAN2_ffhq_d), the G/D pickles and clip/model.py:363-392. */
+typedef struct glass_config {
+  int32_t num_blocks;                     /* resolutions 4 .. 4*2^(num_blocks-1) */
+  int32_t channels[GLASS_MAX_BLOCKS];     /* per block, 4x4 first (G order)      */
+  int32_t latent_size;                    /* config.dim_z = 512                  */
+  int32_t mapping_layers;                 /* 8                                   */
+  int32_t batch_size;                     /* config.batch_size: noise scope (modules.py:426-452)
+                                             and MinibatchStd scope (modules.py:726) */
+  int32_t mbstd_group_size;               /* 4 (models.py:1047)                  */
+  int32_t use_discriminator;              /* config.use_discriminator            */
+  int32_t clip_width, clip_layers, clip_patch, clip_resolution, clip_embed_dim;
+  int32_t max_population;                 /* workspace is sized for this many candidates per call */
+  int32_t device;                         /* CUDA ordinal                        */
+  int32_t conv_impl;                      /* 0 = tcgen05 tensor-core path (product);
+                                             1 = SIMT bring-up kernels (same epilogues; tests only) */
+} glass_config;
+
+/* -- lifetime ------------------------------------------------------------- */
+/* Replaces Generator.__init__ (generator.py:12-27): allocate the engine. */
+int glass_create(const glass_config* cfg, glass_engine** out);
+/* Upload one packed weight tensor from HOST memory (names and layouts are
+ * documented in clip_glass_b200/packing.py; produced from the reference's
+ * G.pth / D.pth / ViT-B-32.pt state_dict layouts). */
+int glass_set_tensor(glass_engine* e, const char* name, const void* host_data, size_t nbytes);
+/* After all tensors are set: build TMA descriptors and the launch plan. */
+int glass_finalize(glass_engine* e);
+/* generator.py:23-24 caches text_features [1,E]; fp32 here. */
+int glass_set_text_features(glass_engine* e, const float* host_text, int32_t n);
+int glass_destroy(glass_engine* e);
+
+/* -- the hot path ---------------------------------------------------------- */
+/* Noise for NoiseInjectionWrapper (modules.py:414-453).  Either explicit
+ * tensors — `noise` points to HOST or DEVICE fp32 laid out as
+ * [n_groups][sum over noise layers of H*W] (groups = population/batch_size,
+ * layers in forward order) — or, when `noise` is NULL, drawn on the device
+ * from `seed` (Philox4x32-10 + Box-Muller), one independent draw per group,
+ * which is what "fresh normal_() per minibatch forward" means. */
+typedef struct glass_noise {
+  const float* noise;       /* NULL => use seed */
+  int32_t noise_on_device;  /* 1 if `noise` is a device pointer */
+  uint64_t seed;
+} glass_noise;
+
+/* problem.py:14-29.  x: HOST float64 [pop, latent_size] exactly as pymoo
+ * passes it.  Outputs (HOST): neg_sim[pop] (= -sim, fp32; the reference's
+ * value is fp16-rounded), hinge[pop] (relu(1-D), only if the engine was
+ * created with use_discriminator; may be NULL otherwise).  pop must be a
+ * multiple of batch_size (models.py:112,124).  `stream` is a cudaStream_t
+ * (0 = default stream).  Synchronous: returns when outputs are on the host. */
+int glass_evaluate_host(glass_engine* e, const double* x, int32_t pop,
+                        const glass_noise* noise, float* neg_sim, float* hinge,
+                        void* stream);
+
+/* Same, inputs/outputs resident in device memory (z fp32 [pop, latent]);
+ * asynchronous on `stream`. */
+int glass_evaluate_device(glass_engine* e, const float* z_dev, int32_t pop,
+                          const glass_noise* noise, float* neg_sim_dev, float* hinge_dev,
+                          void* stream);
+
+/* Generator.generate (generator.py:29-34): latents -> images in [0,1],
+ * fp32 NCHW [pop,3,R,R] written to DEVICE memory `images_dev`. */
+int glass_generate(glass_engine* e, const float* z_dev, int32_t pop,
+                   const glass_noise* noise, float* images_dev, void* stream);
+/* Generator.clip_similarity (generator.py:43-51), txt2img branch:
+ * images fp32 NCHW in [0,1] (device) -> sim[pop] fp32 (device). */
+int glass_clip_similarity(glass_engine* e, const float* images_dev, int32_t pop,
+                          float* sim_dev, void* stream);
+/* Generator.discriminate (generator.py:36-38): images in [0,1] (device) ->
+ * D logits [pop] fp32 (device); denorm x*2-1 is applied inside. */
+int glass_discriminate(glass_engine* e, const float* images_dev, int32_t pop,
+                       float* logits_dev, void* stream);
+
+/* -- introspection ---------------------------------------------------------- */
+const char* glass_last_error(void);
+/* Number of kernels launched by this engine since creation (bench.py's gpu_launches). */
+int64_t glass_launch_count(const glass_engine* e);
+/* Copy a named intermediate of the last call to HOST as fp32 (tests only;
+ * names documented in engine.cu: "w", "styles", "act:<layer>", "rgb:<block>",
+ * "tokens", "features", ...).  Returns element count or a negative status. */
+int64_t glass_debug_read(glass_engine* e, const char* name, float* host_out, int64_t capacity);
+/* Time (ms, CUDA events on `stream`) spent in the tensor-core conv/GEMM
+ * kernels during the last evaluate call, and their launch count. */
+int glass_last_conv_time(const glass_engine* e, float* ms, int32_t* launches);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CLIPGLASS_B200_H_ */
