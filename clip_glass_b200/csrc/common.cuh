@@ -1,0 +1,156 @@
+// Shared declarations for the clip-glass-b200 CUDA library (sm_100a only).
+#pragma once
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace glass {
+
+constexpr float kSqrt2 = 1.4142135623730951f;
+constexpr float kInvSqrt2 = 0.7071067811865476f;
+
+// ---------------------------------------------------------------------------
+// Implicit-GEMM convolution / GEMM description.
+//
+// Accumulator space: M = Nimg*H*W "pixels" (NHWC activations, fp16), N = Ntot
+// output columns, K = taps*Cin.  Tap t = ky*3+kx reads the input at offset
+// (ky-1, kx-1) with zero fill outside the image (taps==1: plain GEMM / 1x1).
+// A tile of 128 accumulator rows is a box TN x TH x TW of pixels.
+// ---------------------------------------------------------------------------
+enum StoreMode : int {
+  kStoreRegular = 0,       // out[pix][Ntot]
+  kStoreDepthToSpace = 1,  // Ntot = 4*Cout, column (py*2+px)*Cout+o -> out[2y+py][2x+px][o]   (G up-conv)
+  kStoreSpaceToDepth = 2   // out[y/2][x/2][(y&1)*2+(x&1)][Ntot]                               (D conv0 -> conv1 input)
+};
+enum Act : int { kActNone = 0, kActLrelu = 1, kActQuickGelu = 2 };
+
+struct EpiParams {
+  const float* dmod;        // [Nimg][Cout] demodulation coefficients, or null
+  const float* bias;        // [Cout] or null
+  const float* noise;       // [groups][Hout*Wout] or null
+  const float* noise_strength;  // device scalar
+  int noise_group_div;      // images per noise group (config.batch_size)
+  size_t noise_group_stride;  // floats between consecutive groups (all noise layers of one group)
+  int act;
+  int round_fp16_before_act;  // mimic the reference's fp16 op boundaries (CLIP)
+  const float* rgb_w;       // [Nimg][3][Cout] per-sample toRGB weights (W*s) or null
+  float4* rgb_out;          // [n_tiles][Nimg*H*W] partial toRGB sums
+  const float* out_scale;   // next layer's style s[img*out_scale_stride + o], or null
+  int out_scale_stride;
+  const __half* residual;   // [pix][Ntot] (regular layout) or null
+  float post_scale;         // applied after the residual add
+  __half* out;              // null => nothing stored (G's last conv only feeds toRGB)
+  int store_mode;
+  int Cout;                 // per-phase channel count (== Ntot unless depth-to-space)
+};
+
+struct ConvParams {
+  int Nimg, H, W;           // accumulator grid
+  int TN, TH, TW;           // tile box, TN*TH*TW == 128
+  int tiles_n, tiles_y, tiles_x;
+  int Cin;                  // K per tap (multiple of BK)
+  int taps;                 // 9 or 1
+  int Ntot;                 // multiple of BN
+  int BN, BK;
+  const __half* in;         // [Nimg][H][W][Cin]   (SIMT bring-up path; the TC path reads through TMA)
+  const __half* wgt;        // [taps][Ntot][Cin]
+  EpiParams epi;
+};
+
+__device__ __forceinline__ float act_apply(float v, int act) {
+  if (act == kActLrelu) {
+    v = (v > 0.f ? v : 0.2f * v) * kSqrt2;
+  } else if (act == kActQuickGelu) {
+    v = v / (1.f + __expf(-1.702f * v));
+  }
+  return v;
+}
+
+// Epilogue for one accumulator row (pixel) and 16 consecutive columns
+// [n0, n0+16).  Shared verbatim by the tcgen05 kernel and the SIMT bring-up
+// kernel so that everything after the accumulator is tested once.
+__device__ __forceinline__ void epilogue_row16(const ConvParams& p, int img, int y, int x, int n0,
+                                               float (&v)[16], float (&rgb)[3]) {
+  const EpiParams& e = p.epi;
+  const int Cout = e.Cout;
+  const int phase = n0 / Cout;
+  const int o0 = n0 - phase * Cout;
+  int yo = y, xo = x, Ho = p.H, Wo = p.W;
+  if (e.store_mode == kStoreDepthToSpace) {
+    yo = 2 * y + (phase >> 1);
+    xo = 2 * x + (phase & 1);
+    Ho = 2 * p.H;
+    Wo = 2 * p.W;
+  }
+  float nz = 0.f;
+  if (e.noise != nullptr) {
+    nz = __ldg(e.noise_strength) *
+         __ldg(e.noise + (size_t)(img / e.noise_group_div) * e.noise_group_stride + (size_t)yo * Wo + xo);
+  }
+  size_t out_idx;
+  if (e.store_mode == kStoreRegular) {
+    out_idx = ((size_t)(img * p.H + y) * p.W + x) * p.Ntot + n0;
+  } else if (e.store_mode == kStoreDepthToSpace) {
+    out_idx = ((size_t)(img * Ho + yo) * Wo + xo) * Cout + o0;
+  } else {
+    out_idx = (((size_t)(img * (p.H >> 1) + (y >> 1)) * (p.W >> 1) + (x >> 1)) * 4 + ((y & 1) * 2 + (x & 1))) *
+                  p.Ntot + n0;
+  }
+  float res[16];
+  if (e.residual != nullptr) {
+    const uint4* rp = reinterpret_cast<const uint4*>(e.residual + ((size_t)(img * p.H + y) * p.W + x) * p.Ntot + n0);
+    uint4 r0 = __ldg(rp), r1 = __ldg(rp + 1);
+    const __half2* h0 = reinterpret_cast<const __half2*>(&r0);
+    const __half2* h1 = reinterpret_cast<const __half2*>(&r1);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float2 a = __half22float2(h0[j]), b = __half22float2(h1[j]);
+      res[2 * j] = a.x; res[2 * j + 1] = a.y; res[8 + 2 * j] = b.x; res[8 + 2 * j + 1] = b.y;
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    const int o = o0 + j;
+    float t = v[j];
+    if (e.dmod != nullptr) t *= __ldg(e.dmod + (size_t)img * Cout + o);
+    t += nz;
+    if (e.bias != nullptr) t += __ldg(e.bias + o);
+    if (e.round_fp16_before_act) t = __half2float(__float2half_rn(t));
+    t = act_apply(t, e.act);
+    if (e.rgb_w != nullptr) {
+      const float* rw = e.rgb_w + (size_t)img * 3 * Cout + o;
+      rgb[0] = fmaf(t, __ldg(rw), rgb[0]);
+      rgb[1] = fmaf(t, __ldg(rw + Cout), rgb[1]);
+      rgb[2] = fmaf(t, __ldg(rw + 2 * Cout), rgb[2]);
+    }
+    if (e.residual != nullptr) t += res[j];
+    t *= e.post_scale;
+    if (e.out_scale != nullptr) t *= __ldg(e.out_scale + (size_t)img * e.out_scale_stride + o);
+    v[j] = t;
+  }
+  if (e.out != nullptr) {
+    uint4 w0, w1;
+    __half2* h0 = reinterpret_cast<__half2*>(&w0);
+    __half2* h1 = reinterpret_cast<__half2*>(&w1);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      h0[j] = __floats2half2_rn(v[2 * j], v[2 * j + 1]);
+      h1[j] = __floats2half2_rn(v[8 + 2 * j], v[8 + 2 * j + 1]);
+    }
+    uint4* op = reinterpret_cast<uint4*>(e.out + out_idx);
+    op[0] = w0;
+    op[1] = w1;
+  }
+}
+
+// launchers (conv_tc.cu)
+struct TmaMaps {
+  CUtensorMap a;   // activations [C, W, H, N]
+  CUtensorMap b;   // weights     [Cin, Ntot, taps]
+};
+cudaError_t launch_conv_tc(const ConvParams& p, const TmaMaps& maps, int num_sms, cudaStream_t s);
+cudaError_t launch_conv_simt(const ConvParams& p, cudaStream_t s);
+size_t conv_tc_smem_bytes(int BN, int BK);
+
+}  // namespace glass

@@ -1,0 +1,917 @@
+// C ABI + host-side engine: owns packed weights, workspace, TMA descriptors and
+// the per-generation launch sequence of the fitness path
+//   latents -> mapping -> styles/demod -> 2*nb-1 modulated convs (+fused toRGB)
+//   -> skip-sum/upsample -> image -> resize+im2col -> ViT -> cosine
+//   [-> fromRGB -> resnet down blocks -> mbstd -> dense -> hinge]
+// See include/clipglass_b200.h for the contract and DESIGN.md for the layout.
+#include <cudaTypedefs.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/clipglass_b200.h"
+#include "common.cuh"
+#include "kernels.cuh"
+
+using namespace glass;
+
+namespace {
+
+thread_local std::string g_last_error;
+
+int fail(int code, const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_last_error = buf;
+  return code;
+}
+
+#define CUDA_OK(expr)                                                                            \
+  do {                                                                                           \
+    cudaError_t err__ = (expr);                                                                  \
+    if (err__ != cudaSuccess)                                                                    \
+      return fail(GLASS_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(err__), __FILE__, __LINE__); \
+  } while (0)
+
+struct DevTensor {
+  void* ptr = nullptr;
+  size_t bytes = 0;
+};
+
+struct GLayer {
+  int block, l, cin, cout, up, res;   // res = output resolution
+};
+
+struct ConvLaunch {
+  ConvParams p;
+  TmaMaps maps;
+  double flops = 0;   // algorithmic (as written by the reference) — for reporting
+};
+
+struct Arena {
+  uint8_t* base = nullptr;
+  size_t cap = 0, off = 0;
+  void* take(size_t bytes) {
+    off = (off + 1023) & ~size_t(1023);
+    void* p = base ? base + off : nullptr;
+    off += bytes;
+    return p;
+  }
+};
+
+}  // namespace
+
+struct glass_engine {
+  glass_config cfg{};
+  int num_sms = 148;
+  std::map<std::string, DevTensor> tensors;
+  bool finalized = false;
+  PFN_cuTensorMapEncodeTiled_v12000 encode = nullptr;
+
+  // derived architecture
+  std::vector<GLayer> glayers;
+  std::vector<int> conv_off, rgb_off;
+  int S = 0;                 // total style width
+  std::vector<int> gch;      // channels, 4x4 first
+  int R = 0;                 // output resolution
+  size_t noise_per_group = 0;
+  std::vector<size_t> noise_layer_off;
+
+  // workspace (sized for cfg.max_population)
+  Arena arena;
+  float *z32 = nullptr, *wA = nullptr, *wB = nullptr, *styles = nullptr, *noise = nullptr;
+  std::vector<float*> dmod;
+  std::vector<float*> rgbw;
+  __half *actA = nullptr, *actB = nullptr;
+  float4 *slabs = nullptr, *yA = nullptr, *yB = nullptr;
+  float* images = nullptr;
+  __half *patches = nullptr, *patch_emb = nullptr, *tokens = nullptr, *hbuf = nullptr, *qkv = nullptr, *att = nullptr,
+         *fc = nullptr;
+  float *features = nullptr, *sim = nullptr, *neg_sim = nullptr, *text = nullptr;
+  __half *dXd = nullptr, *dR = nullptr, *dOut = nullptr, *dFin = nullptr, *dFinOut = nullptr, *dDense = nullptr;
+  float *dlogits = nullptr, *hinge = nullptr;
+  double* x_host_stage = nullptr;   // device staging for f64 latents
+  bool have_text = false;
+
+  // plan (rebuilt when pop changes)
+  int plan_pop = -1;
+  std::vector<ConvLaunch> g_convs, c_convs, d_convs;
+
+  int64_t launches = 0;
+  // timing of tensor-core launches
+  bool timing = false;
+  std::vector<cudaEvent_t> ev;
+  size_t ev_used = 0;
+  float last_conv_ms = 0.f;
+  int last_conv_launches = 0;
+  // debug capture
+  bool capture = false;
+  std::map<std::string, std::vector<float>> captured;
+};
+
+namespace {
+
+DevTensor* find_tensor(glass_engine* e, const std::string& name) {
+  auto it = e->tensors.find(name);
+  return it == e->tensors.end() ? nullptr : &it->second;
+}
+template <class T>
+T* tptr(glass_engine* e, const std::string& name) {
+  DevTensor* t = find_tensor(e, name);
+  return t ? reinterpret_cast<T*>(t->ptr) : nullptr;
+}
+
+int check_tensor(glass_engine* e, const std::string& name, size_t bytes) {
+  DevTensor* t = find_tensor(e, name);
+  if (!t) return fail(GLASS_ERR_STATE, "weight tensor '%s' was not set", name.c_str());
+  if (t->bytes != bytes)
+    return fail(GLASS_ERR_ARG, "weight tensor '%s' has %zu bytes, expected %zu", name.c_str(), t->bytes, bytes);
+  return GLASS_OK;
+}
+
+int encode_map(glass_engine* e, CUtensorMap* map, const void* ptr, int rank, const uint64_t* dims,
+               const uint64_t* strides_bytes, const uint32_t* box, int inner_bytes) {
+  cuuint64_t gdim[5];
+  cuuint64_t gstr[4];
+  cuuint32_t bdim[5], estr[5];
+  for (int i = 0; i < rank; ++i) {
+    gdim[i] = dims[i];
+    bdim[i] = box[i];
+    estr[i] = 1;
+    if (i > 0) gstr[i - 1] = strides_bytes[i - 1];
+  }
+  CUtensorMapSwizzle sw = inner_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                        : inner_bytes == 64  ? CU_TENSOR_MAP_SWIZZLE_64B
+                                             : CU_TENSOR_MAP_SWIZZLE_NONE;
+  if (sw == CU_TENSOR_MAP_SWIZZLE_NONE) return fail(GLASS_ERR_ARG, "unsupported TMA inner box of %d bytes", inner_bytes);
+  CUresult r = e->encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, rank, const_cast<void*>(ptr), gdim, gstr, bdim, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    return fail(GLASS_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d): rank %d dims %llu,%llu,%llu,%llu box %u,%u,%u,%u",
+                (int)r, rank, (unsigned long long)dims[0], (unsigned long long)dims[1],
+                (unsigned long long)(rank > 2 ? dims[2] : 0), (unsigned long long)(rank > 3 ? dims[3] : 0), box[0],
+                box[1], rank > 2 ? box[2] : 0, rank > 3 ? box[3] : 0);
+  }
+  return GLASS_OK;
+}
+
+int pick_bn(int ntot) {
+  for (int bn : {256, 128, 64, 32})
+    if (ntot % bn == 0) return bn;
+  return 0;
+}
+
+// Build one implicit-GEMM launch.  gemm=true: plain [M x K] @ [Ntot x K]^T with M = W.
+int make_conv(glass_engine* e, ConvLaunch* out, const __half* in, int Nimg, int H, int W, int Cin, const __half* wgt,
+              int taps, int Ntot, const EpiParams& epi, bool gemm) {
+  ConvParams& p = out->p;
+  memset(&p, 0, sizeof(p));
+  p.Nimg = Nimg; p.H = H; p.W = W; p.Cin = Cin; p.taps = taps; p.Ntot = Ntot;
+  p.in = in; p.wgt = wgt; p.epi = epi;
+  if (gemm) {
+    p.TW = 128; p.TH = 1; p.TN = 1;
+  } else {
+    p.TW = std::min(W, 16);
+    p.TH = std::min(H, 128 / p.TW);
+    p.TN = 128 / (p.TW * p.TH);
+  }
+  p.tiles_x = (W + p.TW - 1) / p.TW;
+  p.tiles_y = (H + p.TH - 1) / p.TH;
+  p.tiles_n = (Nimg + p.TN - 1) / p.TN;
+  p.BN = pick_bn(Ntot);
+  p.BK = (Cin % 64 == 0) ? 64 : 32;
+  if (p.BN == 0 || Cin % 32 != 0 || Ntot % 16 != 0)
+    return fail(GLASS_ERR_ARG, "unsupported conv shape Cin=%d Ntot=%d", Cin, Ntot);
+  if (e->cfg.conv_impl != 0) return GLASS_OK;   // SIMT bring-up path needs no descriptors
+  // activations: [C, W, H, N]; outermost extent rounded up to the box (buffers carry the slack)
+  const uint64_t wdecl = gemm ? (uint64_t)p.tiles_x * 128 : (uint64_t)W;
+  const uint64_t ndecl = (uint64_t)p.tiles_n * p.TN;
+  uint64_t dims[4] = {(uint64_t)Cin, wdecl, (uint64_t)H, ndecl};
+  uint64_t strides[3] = {(uint64_t)Cin * 2, (uint64_t)Cin * 2 * wdecl, (uint64_t)Cin * 2 * wdecl * H};
+  uint32_t box[4] = {(uint32_t)p.BK, (uint32_t)p.TW, (uint32_t)p.TH, (uint32_t)p.TN};
+  int rc = encode_map(e, &out->maps.a, in, 4, dims, strides, box, p.BK * 2);
+  if (rc != GLASS_OK) return rc;
+  uint64_t wd[3] = {(uint64_t)Cin, (uint64_t)Ntot, (uint64_t)taps};
+  uint64_t ws[2] = {(uint64_t)Cin * 2, (uint64_t)Cin * 2 * Ntot};
+  uint32_t wb[3] = {(uint32_t)p.BK, (uint32_t)p.BN, 1};
+  return encode_map(e, &out->maps.b, wgt, 3, wd, ws, wb, p.BK * 2);
+}
+
+int run_conv(glass_engine* e, const ConvLaunch& c, cudaStream_t s) {
+  cudaError_t err;
+  if (e->cfg.conv_impl == 0) {
+    if (e->timing && e->ev_used + 2 <= e->ev.size()) {
+      cudaEventRecord(e->ev[e->ev_used], s);
+      err = launch_conv_tc(c.p, c.maps, e->num_sms, s);
+      cudaEventRecord(e->ev[e->ev_used + 1], s);
+      e->ev_used += 2;
+    } else {
+      err = launch_conv_tc(c.p, c.maps, e->num_sms, s);
+    }
+  } else {
+    err = launch_conv_simt(c.p, s);
+  }
+  e->launches++;
+  if (err != cudaSuccess) return fail(GLASS_ERR_CUDA, "conv launch failed: %s", cudaGetErrorString(err));
+  return GLASS_OK;
+}
+
+#define LAUNCH(expr)                                                                       \
+  do {                                                                                     \
+    cudaError_t err__ = (expr);                                                            \
+    e->launches++;                                                                         \
+    if (err__ != cudaSuccess)                                                              \
+      return fail(GLASS_ERR_CUDA, "%s failed: %s", #expr, cudaGetErrorString(err__));      \
+  } while (0)
+#define RC(expr)                 \
+  do {                           \
+    int rc__ = (expr);           \
+    if (rc__ != GLASS_OK) return rc__; \
+  } while (0)
+
+int capture_f32(glass_engine* e, const std::string& name, const float* dev, size_t n, cudaStream_t s) {
+  if (!e->capture) return GLASS_OK;
+  std::vector<float>& v = e->captured[name];
+  v.resize(n);
+  CUDA_OK(cudaStreamSynchronize(s));
+  CUDA_OK(cudaMemcpy(v.data(), dev, n * sizeof(float), cudaMemcpyDeviceToHost));
+  return GLASS_OK;
+}
+int capture_f16(glass_engine* e, const std::string& name, const __half* dev, size_t n, cudaStream_t s) {
+  if (!e->capture) return GLASS_OK;
+  std::vector<__half> tmp(n);
+  CUDA_OK(cudaStreamSynchronize(s));
+  CUDA_OK(cudaMemcpy(tmp.data(), dev, n * sizeof(__half), cudaMemcpyDeviceToHost));
+  std::vector<float>& v = e->captured[name];
+  v.resize(n);
+  for (size_t i = 0; i < n; ++i) v[i] = __half2float(tmp[i]);
+  return GLASS_OK;
+}
+
+// ---------------------------------------------------------------------------
+// architecture bookkeeping
+// ---------------------------------------------------------------------------
+void derive_arch(glass_engine* e) {
+  const glass_config& c = e->cfg;
+  e->gch.assign(c.channels, c.channels + c.num_blocks);
+  e->glayers.clear();
+  for (int b = 0; b < c.num_blocks; ++b) {
+    const int res = 4 << b;
+    if (b == 0) {
+      e->glayers.push_back({0, 0, e->gch[0], e->gch[0], 0, res});
+    } else {
+      e->glayers.push_back({b, 0, e->gch[b - 1], e->gch[b], 1, res});
+      e->glayers.push_back({b, 1, e->gch[b], e->gch[b], 0, res});
+    }
+  }
+  e->conv_off.clear();
+  e->rgb_off.clear();
+  int off = 0;
+  for (const GLayer& l : e->glayers) { e->conv_off.push_back(off); off += l.cin; }
+  for (int b = 0; b < c.num_blocks; ++b) { e->rgb_off.push_back(off); off += e->gch[b]; }
+  e->S = off;
+  e->R = 4 << (c.num_blocks - 1);
+  e->noise_layer_off.clear();
+  size_t noff = 0;
+  for (const GLayer& l : e->glayers) { e->noise_layer_off.push_back(noff); noff += (size_t)l.res * l.res; }
+  e->noise_per_group = noff;
+}
+
+int validate_weights(glass_engine* e) {
+  const glass_config& c = e->cfg;
+  const int L = c.latent_size;
+  char nm[64];
+  for (int i = 0; i < c.mapping_layers; ++i) {
+    snprintf(nm, sizeof nm, "g.map.w%d", i); RC(check_tensor(e, nm, (size_t)L * L * 4));
+    snprintf(nm, sizeof nm, "g.map.b%d", i); RC(check_tensor(e, nm, (size_t)L * 4));
+  }
+  RC(check_tensor(e, "g.style.w", (size_t)L * e->S * 4));
+  RC(check_tensor(e, "g.style.b", (size_t)e->S * 4));
+  RC(check_tensor(e, "g.const", (size_t)16 * e->gch[0] * 4));
+  for (size_t li = 0; li < e->glayers.size(); ++li) {
+    const GLayer& l = e->glayers[li];
+    const int ntot = l.up ? 4 * l.cout : l.cout;
+    snprintf(nm, sizeof nm, "g.conv%zu.w", li); RC(check_tensor(e, nm, (size_t)9 * ntot * l.cin * 2));
+    snprintf(nm, sizeof nm, "g.conv%zu.wsq", li); RC(check_tensor(e, nm, (size_t)l.cin * l.cout * 4));
+    snprintf(nm, sizeof nm, "g.conv%zu.bias", li); RC(check_tensor(e, nm, (size_t)l.cout * 4));
+    snprintf(nm, sizeof nm, "g.conv%zu.nstr", li); RC(check_tensor(e, nm, 4));
+  }
+  for (int b = 0; b < c.num_blocks; ++b) {
+    snprintf(nm, sizeof nm, "g.rgb%d.w", b); RC(check_tensor(e, nm, (size_t)3 * e->gch[b] * 4));
+    snprintf(nm, sizeof nm, "g.rgb%d.bias", b); RC(check_tensor(e, nm, 12));
+  }
+  const int Wd = c.clip_width, T = (c.clip_resolution / c.clip_patch) * (c.clip_resolution / c.clip_patch) + 1;
+  RC(check_tensor(e, "c.patch.w", (size_t)Wd * 3 * c.clip_patch * c.clip_patch * 2));
+  RC(check_tensor(e, "c.cls", (size_t)Wd * 4));
+  RC(check_tensor(e, "c.pos", (size_t)T * Wd * 4));
+  for (const char* n : {"c.lnpre.w", "c.lnpre.b", "c.lnpost.w", "c.lnpost.b"}) RC(check_tensor(e, n, (size_t)Wd * 4));
+  RC(check_tensor(e, "c.proj", (size_t)Wd * c.clip_embed_dim * 4));
+  for (int l = 0; l < c.clip_layers; ++l) {
+    auto nmf = [&](const char* suffix) { snprintf(nm, sizeof nm, "c.l%d.%s", l, suffix); return std::string(nm); };
+    for (const char* n : {"ln1.w", "ln1.b", "ln2.w", "ln2.b", "out.b", "proj.b"}) RC(check_tensor(e, nmf(n), (size_t)Wd * 4));
+    RC(check_tensor(e, nmf("qkv.w"), (size_t)3 * Wd * Wd * 2));
+    RC(check_tensor(e, nmf("qkv.b"), (size_t)3 * Wd * 4));
+    RC(check_tensor(e, nmf("out.w"), (size_t)Wd * Wd * 2));
+    RC(check_tensor(e, nmf("fc.w"), (size_t)4 * Wd * Wd * 2));
+    RC(check_tensor(e, nmf("fc.b"), (size_t)4 * Wd * 4));
+    RC(check_tensor(e, nmf("proj.w"), (size_t)4 * Wd * Wd * 2));
+  }
+  if (c.use_discriminator) {
+    // D channel order is last-G-layer first
+    const int nb = c.num_blocks;
+    auto dch = [&](int i) { return e->gch[nb - 1 - i]; };
+    RC(check_tensor(e, "d.frgb.w", (size_t)3 * dch(0) * 4));
+    RC(check_tensor(e, "d.frgb.b", (size_t)dch(0) * 4));
+    for (int b = 0; b < nb - 1; ++b) {
+      auto nmf = [&](const char* suffix) { snprintf(nm, sizeof nm, "d.b%d.%s", b, suffix); return std::string(nm); };
+      RC(check_tensor(e, nmf("c0.w"), (size_t)9 * dch(b) * dch(b) * 2));
+      RC(check_tensor(e, nmf("c0.b"), (size_t)dch(b) * 4));
+      RC(check_tensor(e, nmf("c1.w"), (size_t)9 * dch(b + 1) * 4 * dch(b) * 2));
+      RC(check_tensor(e, nmf("c1.b"), (size_t)dch(b + 1) * 4));
+      RC(check_tensor(e, nmf("proj.w"), (size_t)dch(b + 1) * dch(b) * 2));
+    }
+    const int C = dch(nb - 1);
+    const int cpad = ((C + 1 + 63) / 64) * 64;
+    RC(check_tensor(e, "d.fin.w", (size_t)9 * C * cpad * 2));
+    RC(check_tensor(e, "d.fin.b", (size_t)C * 4));
+    RC(check_tensor(e, "d.dense0.w", (size_t)C * 16 * C * 2));
+    RC(check_tensor(e, "d.dense0.b", (size_t)C * 4));
+    RC(check_tensor(e, "d.dense1.w", (size_t)C * 4));
+    RC(check_tensor(e, "d.dense1.b", 4));
+  }
+  return GLASS_OK;
+}
+
+constexpr size_t kSlackRows = 256;   // rows of slack behind every TMA-read buffer (boxes may overhang)
+
+void layout_workspace(glass_engine* e, Arena& a) {
+  const glass_config& c = e->cfg;
+  const size_t P = c.max_population;
+  const int L = c.latent_size;
+  const int nb = c.num_blocks;
+  e->x_host_stage = (double*)a.take(P * L * 8);
+  e->z32 = (float*)a.take(P * L * 4);
+  e->wA = (float*)a.take(P * L * 4);
+  e->wB = (float*)a.take(P * L * 4);
+  e->styles = (float*)a.take(P * e->S * 4);
+  e->noise = (float*)a.take((P / c.batch_size) * e->noise_per_group * 4);
+  e->dmod.clear();
+  for (const GLayer& l : e->glayers) e->dmod.push_back((float*)a.take(P * l.cout * 4));
+  e->rgbw.clear();
+  for (int b = 0; b < nb; ++b) e->rgbw.push_back((float*)a.take(P * 3 * e->gch[b] * 4));
+  size_t act_elems = P * 16 * e->gch[0];
+  size_t slab_elems = 0;
+  for (const GLayer& l : e->glayers) {
+    act_elems = std::max(act_elems, P * (size_t)l.res * l.res * l.cout);
+    const int bn = pick_bn(l.cout);
+    if (bn) slab_elems = std::max(slab_elems, (size_t)(l.cout / bn) * P * l.res * l.res);
+  }
+  // every activation row is at least 32 channels wide; slack covers box overhang in the outermost dim
+  const size_t slack = kSlackRows * 512;
+  e->actA = (__half*)a.take((act_elems + slack) * 2);
+  e->actB = (__half*)a.take((act_elems + slack) * 2);
+  e->slabs = (float4*)a.take(slab_elems * 16);
+  e->yA = (float4*)a.take(P * (size_t)e->R * e->R * 16);
+  e->yB = (float4*)a.take(P * (size_t)e->R * e->R * 16);
+  e->images = (float*)a.take(P * 3 * (size_t)e->R * e->R * 4);
+  // CLIP
+  const int g = c.clip_resolution / c.clip_patch, T = g * g + 1, Wd = c.clip_width;
+  const size_t kdim = (size_t)3 * c.clip_patch * c.clip_patch;
+  e->patches = (__half*)a.take((P * g * g + kSlackRows) * kdim * 2);
+  e->patch_emb = (__half*)a.take((P * g * g + kSlackRows) * Wd * 2);
+  e->tokens = (__half*)a.take((P * T + kSlackRows) * Wd * 2);
+  e->hbuf = (__half*)a.take((P * T + kSlackRows) * Wd * 2);
+  e->qkv = (__half*)a.take((P * T + kSlackRows) * 3 * Wd * 2);
+  e->att = (__half*)a.take((P * T + kSlackRows) * Wd * 2);
+  e->fc = (__half*)a.take((P * T + kSlackRows) * 4 * Wd * 2);
+  e->features = (float*)a.take(P * c.clip_embed_dim * 4);
+  e->sim = (float*)a.take(P * 4);
+  e->neg_sim = (float*)a.take(P * 4);
+  e->text = (float*)a.take((size_t)c.clip_embed_dim * 4);
+  if (c.use_discriminator) {
+    const int C0 = e->gch[nb - 1], C1 = nb > 1 ? e->gch[nb - 2] : C0;
+    const size_t half_pix = P * (size_t)(e->R / 2) * (e->R / 2);
+    e->dXd = (__half*)a.take((half_pix * C0 + slack) * 2);
+    // channels at most double per block while pixels quarter, so block 0 bounds these
+    e->dR = (__half*)a.take((half_pix * std::max(C1, 2 * C0) + slack) * 2);
+    e->dOut = (__half*)a.take((half_pix * std::max(C1, 2 * C0) + slack) * 2);
+    const int C = e->gch[0];
+    const int cpad = ((C + 1 + 63) / 64) * 64;
+    e->dFin = (__half*)a.take((P * 16 * cpad + slack) * 2);
+    e->dFinOut = (__half*)a.take((P + kSlackRows) * 16 * C * 2);   // read as a [P x 16C] GEMM operand
+    e->dDense = (__half*)a.take((P * C + slack) * 2);
+    e->dlogits = (float*)a.take(P * 4);
+    e->hinge = (float*)a.take(P * 4);
+  }
+}
+
+EpiParams epi_default() {
+  EpiParams ep;
+  memset(&ep, 0, sizeof(ep));
+  ep.post_scale = 1.f;
+  ep.noise_group_div = 1;
+  return ep;
+}
+
+// ---------------------------------------------------------------------------
+// plan: all conv/GEMM launches for a population of P candidates
+// ---------------------------------------------------------------------------
+int build_plan(glass_engine* e, int P) {
+  const glass_config& c = e->cfg;
+  e->g_convs.clear();
+  e->c_convs.clear();
+  e->d_convs.clear();
+  char nm[64];
+  // ---- G ----
+  __half* bufs[2] = {e->actA, e->actB};
+  int cur = 0;   // x0 lives in actA
+  const size_t nl = e->glayers.size();
+  for (size_t li = 0; li < nl; ++li) {
+    const GLayer& l = e->glayers[li];
+    const bool last_in_block = (li + 1 == nl) || (e->glayers[li + 1].block != l.block);
+    const int in_res = l.up ? l.res / 2 : l.res;
+    EpiParams ep = epi_default();
+    ep.dmod = e->dmod[li];
+    snprintf(nm, sizeof nm, "g.conv%zu.bias", li); ep.bias = tptr<float>(e, nm);
+    snprintf(nm, sizeof nm, "g.conv%zu.nstr", li); ep.noise_strength = tptr<float>(e, nm);
+    ep.noise = e->noise + e->noise_layer_off[li];
+    ep.noise_group_div = c.batch_size;
+    ep.noise_group_stride = e->noise_per_group;
+    ep.act = kActLrelu;
+    ep.Cout = l.cout;
+    ep.store_mode = l.up ? kStoreDepthToSpace : kStoreRegular;
+    if (last_in_block) {
+      ep.rgb_w = e->rgbw[l.block];
+      ep.rgb_out = e->slabs;
+    }
+    if (li + 1 < nl) {
+      ep.out_scale = e->styles + e->conv_off[li + 1];
+      ep.out_scale_stride = e->S;
+      ep.out = bufs[cur ^ 1];
+    } else {
+      ep.out = nullptr;
+    }
+    snprintf(nm, sizeof nm, "g.conv%zu.w", li);
+    ConvLaunch cl;
+    RC(make_conv(e, &cl, bufs[cur], P, in_res, in_res, l.cin, tptr<__half>(e, nm), 9, l.up ? 4 * l.cout : l.cout, ep,
+                 false));
+    // the noise tensor index inside a group is per-layer; stride between groups is noise_per_group
+    cl.flops = 2.0 * 9.0 * (double)P * in_res * in_res * l.cin * l.cout;   // as written by the reference
+    e->g_convs.push_back(cl);
+    cur ^= 1;
+  }
+  // ---- CLIP ----
+  {
+    const int g = c.clip_resolution / c.clip_patch, T = g * g + 1, Wd = c.clip_width;
+    const int kdim = 3 * c.clip_patch * c.clip_patch;
+    const int Mp = P * g * g, M = P * T;
+    EpiParams ep = epi_default();
+    ep.Cout = Wd; ep.out = e->patch_emb;
+    ConvLaunch cl;
+    RC(make_conv(e, &cl, e->patches, 1, 1, Mp, kdim, tptr<__half>(e, "c.patch.w"), 1, Wd, ep, true));
+    cl.flops = 2.0 * Mp * (double)kdim * Wd;
+    e->c_convs.push_back(cl);
+    for (int l = 0; l < c.clip_layers; ++l) {
+      auto nmf = [&](const char* suffix) { snprintf(nm, sizeof nm, "c.l%d.%s", l, suffix); return std::string(nm); };
+      // qkv
+      ep = epi_default(); ep.Cout = 3 * Wd; ep.bias = tptr<float>(e, nmf("qkv.b")); ep.out = e->qkv;
+      RC(make_conv(e, &cl, e->hbuf, 1, 1, M, Wd, tptr<__half>(e, nmf("qkv.w")), 1, 3 * Wd, ep, true));
+      cl.flops = 2.0 * M * (double)Wd * 3 * Wd; e->c_convs.push_back(cl);
+      // out proj + residual (in place on tokens: each element read then written by the same thread)
+      ep = epi_default(); ep.Cout = Wd; ep.bias = tptr<float>(e, nmf("out.b")); ep.round_fp16_before_act = 1;
+      ep.residual = e->tokens; ep.out = e->tokens;
+      RC(make_conv(e, &cl, e->att, 1, 1, M, Wd, tptr<__half>(e, nmf("out.w")), 1, Wd, ep, true));
+      cl.flops = 2.0 * M * (double)Wd * Wd; e->c_convs.push_back(cl);
+      // fc + QuickGELU
+      ep = epi_default(); ep.Cout = 4 * Wd; ep.bias = tptr<float>(e, nmf("fc.b")); ep.round_fp16_before_act = 1;
+      ep.act = kActQuickGelu; ep.out = e->fc;
+      RC(make_conv(e, &cl, e->hbuf, 1, 1, M, Wd, tptr<__half>(e, nmf("fc.w")), 1, 4 * Wd, ep, true));
+      cl.flops = 2.0 * M * (double)Wd * 4 * Wd; e->c_convs.push_back(cl);
+      // proj + residual
+      ep = epi_default(); ep.Cout = Wd; ep.bias = tptr<float>(e, nmf("proj.b")); ep.round_fp16_before_act = 1;
+      ep.residual = e->tokens; ep.out = e->tokens;
+      RC(make_conv(e, &cl, e->fc, 1, 1, M, 4 * Wd, tptr<__half>(e, nmf("proj.w")), 1, Wd, ep, true));
+      cl.flops = 2.0 * M * (double)Wd * 4 * Wd; e->c_convs.push_back(cl);
+    }
+  }
+  // ---- D ----
+  if (c.use_discriminator) {
+    const int nb = c.num_blocks;
+    auto dch = [&](int i) { return e->gch[nb - 1 - i]; };
+    __half* x = e->actA;          // fromRGB output
+    __half* outs[2] = {e->dOut, e->actA};
+    int res = e->R;
+    for (int b = 0; b < nb - 1; ++b) {
+      const int Ci = dch(b), Co = dch(b + 1);
+      auto nmf = [&](const char* suffix) { snprintf(nm, sizeof nm, "d.b%d.%s", b, suffix); return std::string(nm); };
+      ConvLaunch cl;
+      // conv0: 3x3 Ci->Ci, bias, lrelu; stored space-to-depth for conv1
+      EpiParams ep = epi_default();
+      ep.Cout = Ci; ep.bias = tptr<float>(e, nmf("c0.b")); ep.act = kActLrelu; ep.out = e->actB;
+      ep.store_mode = kStoreSpaceToDepth;
+      RC(make_conv(e, &cl, x, P, res, res, Ci, tptr<__half>(e, nmf("c0.w")), 9, Ci, ep, false));
+      cl.flops = 2.0 * 9.0 * (double)P * res * res * Ci * Ci; e->d_convs.push_back(cl);
+      // projection: 1x1 on the FIR-downsampled input
+      ep = epi_default(); ep.Cout = Co; ep.out = e->dR;
+      RC(make_conv(e, &cl, e->dXd, P, res / 2, res / 2, Ci, tptr<__half>(e, nmf("proj.w")), 1, Co, ep, false));
+      cl.flops = 2.0 * (double)P * (res / 2) * (res / 2) * Ci * Co; e->d_convs.push_back(cl);
+      // conv1: folded FIR + 3x3 stride 2 == 3x3 over the space-to-depth tensor (4*Ci channels)
+      ep = epi_default();
+      ep.Cout = Co; ep.bias = tptr<float>(e, nmf("c1.b")); ep.act = kActLrelu; ep.residual = e->dR;
+      ep.post_scale = kInvSqrt2; ep.out = outs[b & 1];
+      RC(make_conv(e, &cl, e->actB, P, res / 2, res / 2, 4 * Ci, tptr<__half>(e, nmf("c1.w")), 9, Co, ep, false));
+      cl.flops = 2.0 * 9.0 * (double)P * (res / 2) * (res / 2) * Ci * Co; e->d_convs.push_back(cl);
+      x = outs[b & 1];
+      res /= 2;
+    }
+    const int C = dch(nb - 1);
+    const int cpad = ((C + 1 + 63) / 64) * 64;
+    ConvLaunch cl;
+    EpiParams ep = epi_default();
+    ep.Cout = C; ep.bias = tptr<float>(e, "d.fin.b"); ep.act = kActLrelu; ep.out = e->dFinOut;
+    RC(make_conv(e, &cl, e->dFin, P, 4, 4, cpad, tptr<__half>(e, "d.fin.w"), 9, C, ep, false));
+    cl.flops = 2.0 * 9.0 * (double)P * 16 * (C + 1) * C; e->d_convs.push_back(cl);
+    ep = epi_default();
+    ep.Cout = C; ep.bias = tptr<float>(e, "d.dense0.b"); ep.act = kActLrelu; ep.out = e->dDense;
+    RC(make_conv(e, &cl, e->dFinOut, 1, 1, P, 16 * C, tptr<__half>(e, "d.dense0.w"), 1, C, ep, true));
+    cl.flops = 2.0 * (double)P * 16 * C * C; e->d_convs.push_back(cl);
+  }
+  e->plan_pop = P;
+  return GLASS_OK;
+}
+
+// ---------------------------------------------------------------------------
+// stages
+// ---------------------------------------------------------------------------
+int fill_noise(glass_engine* e, int P, const glass_noise* nz, cudaStream_t s) {
+  const size_t groups = (size_t)P / e->cfg.batch_size;
+  const size_t n = groups * e->noise_per_group;
+  if (nz != nullptr && nz->noise != nullptr) {
+    CUDA_OK(cudaMemcpyAsync(e->noise, nz->noise, n * 4,
+                            nz->noise_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, s));
+  } else {
+    LAUNCH(k_noise(e->noise, n, nz ? nz->seed : 0ull, 0ull, s));
+  }
+  return GLASS_OK;
+}
+
+int run_generator(glass_engine* e, const float* z, int P, const glass_noise* nz, float* images_out, cudaStream_t s) {
+  const glass_config& c = e->cfg;
+  const int L = c.latent_size;
+  char nm[64];
+  RC(fill_noise(e, P, nz, s));
+  // mapping (stylegan2/models.py:590-627)
+  LAUNCH(k_pixelnorm(z, e->wA, P, L, s));
+  float* cur = e->wA;
+  float* nxt = e->wB;
+  for (int i = 0; i < c.mapping_layers; ++i) {
+    snprintf(nm, sizeof nm, "g.map.w%d", i);
+    const float* w = tptr<float>(e, nm);
+    snprintf(nm, sizeof nm, "g.map.b%d", i);
+    LAUNCH(k_vecmat(cur, L, w, tptr<float>(e, nm), nxt, L, P, L, L, 1, s));
+    std::swap(cur, nxt);
+  }
+  RC(capture_f32(e, "w", cur, (size_t)P * L, s));
+  // all style affines in one pass (same dlatent for every layer, models.py:427-430)
+  LAUNCH(k_vecmat(cur, L, tptr<float>(e, "g.style.w"), tptr<float>(e, "g.style.b"), e->styles, e->S, P, L, e->S, 0, s));
+  RC(capture_f32(e, "styles", e->styles, (size_t)P * e->S, s));
+  for (size_t li = 0; li < e->glayers.size(); ++li) {
+    const GLayer& l = e->glayers[li];
+    snprintf(nm, sizeof nm, "g.conv%zu.wsq", li);
+    LAUNCH(k_vecmat(e->styles + e->conv_off[li], e->S, tptr<float>(e, nm), nullptr, e->dmod[li], l.cout, P, l.cin,
+                    l.cout, 2, s));
+  }
+  for (int b = 0; b < c.num_blocks; ++b) {
+    snprintf(nm, sizeof nm, "g.rgb%d.w", b);
+    LAUNCH(k_rgb_weights(tptr<float>(e, nm), e->styles + e->rgb_off[b], e->S, e->rgbw[b], P, e->gch[b], s));
+  }
+  LAUNCH(k_const_input(tptr<float>(e, "g.const"), e->styles + e->conv_off[0], e->S, e->actA, P, e->gch[0], s));
+  RC(capture_f16(e, "x0", e->actA, (size_t)P * 16 * e->gch[0], s));
+  float4* ybuf[2] = {e->yA, e->yB};
+  int ycur = 0;
+  bool have_y = false;
+  const size_t nl = e->glayers.size();
+  for (size_t li = 0; li < nl; ++li) {
+    const GLayer& l = e->glayers[li];
+    const ConvLaunch& cl = e->g_convs[li];
+    RC(run_conv(e, cl, s));
+    if (cl.p.epi.out != nullptr) {
+      snprintf(nm, sizeof nm, "xs%zu", li);
+      RC(capture_f16(e, nm, cl.p.epi.out, (size_t)P * l.res * l.res * l.cout, s));
+    }
+    const bool last_in_block = (li + 1 == nl) || (e->glayers[li + 1].block != l.block);
+    if (last_in_block) {
+      const bool final_block = (li + 1 == nl);
+      snprintf(nm, sizeof nm, "g.rgb%d.bias", l.block);
+      const int n_slabs = cl.p.Ntot / cl.p.BN;
+      LAUNCH(k_rgb_combine(have_y ? ybuf[ycur] : nullptr, e->slabs, n_slabs, tptr<float>(e, nm), ybuf[ycur ^ 1],
+                           final_block ? images_out : nullptr, P, l.res, l.res, s));
+      ycur ^= 1;
+      have_y = true;
+      snprintf(nm, sizeof nm, "rgb%d", l.block);
+      RC(capture_f32(e, nm, reinterpret_cast<float*>(ybuf[ycur]), (size_t)P * l.res * l.res * 4, s));
+    }
+  }
+  return GLASS_OK;
+}
+
+int run_clip(glass_engine* e, const float* images, int P, float* sim_out, float* neg_sim_out, cudaStream_t s) {
+  const glass_config& c = e->cfg;
+  if (!e->have_text) return fail(GLASS_ERR_STATE, "glass_set_text_features was not called");
+  const int g = c.clip_resolution / c.clip_patch, T = g * g + 1, Wd = c.clip_width;
+  char nm[64];
+  LAUNCH(k_resize_patches(images, e->patches, P, e->R, c.clip_resolution, c.clip_patch, s));
+  size_t ci = 0;
+  RC(run_conv(e, e->c_convs[ci++], s));
+  LAUNCH(k_embed_lnpre(e->patch_emb, tptr<float>(e, "c.cls"), tptr<float>(e, "c.pos"), tptr<float>(e, "c.lnpre.w"),
+                       tptr<float>(e, "c.lnpre.b"), e->tokens, P, T, Wd, s));
+  RC(capture_f16(e, "ln_pre", e->tokens, (size_t)P * T * Wd, s));
+  for (int l = 0; l < c.clip_layers; ++l) {
+    auto nmf = [&](const char* suffix) { snprintf(nm, sizeof nm, "c.l%d.%s", l, suffix); return std::string(nm); };
+    LAUNCH(k_layernorm(e->tokens, tptr<float>(e, nmf("ln1.w")), tptr<float>(e, nmf("ln1.b")), e->hbuf, P * T, Wd, s));
+    RC(run_conv(e, e->c_convs[ci++], s));   // qkv
+    LAUNCH(k_attention(e->qkv, e->att, P, T, Wd, s));
+    RC(run_conv(e, e->c_convs[ci++], s));   // out + residual
+    LAUNCH(k_layernorm(e->tokens, tptr<float>(e, nmf("ln2.w")), tptr<float>(e, nmf("ln2.b")), e->hbuf, P * T, Wd, s));
+    RC(run_conv(e, e->c_convs[ci++], s));   // fc
+    RC(run_conv(e, e->c_convs[ci++], s));   // proj + residual
+    snprintf(nm, sizeof nm, "block%d", l);
+    RC(capture_f16(e, nm, e->tokens, (size_t)P * T * Wd, s));
+  }
+  LAUNCH(k_final_cosine(e->tokens, tptr<float>(e, "c.lnpost.w"), tptr<float>(e, "c.lnpost.b"), tptr<float>(e, "c.proj"),
+                        e->text, e->features, sim_out, neg_sim_out, P, T, Wd, c.clip_embed_dim, s));
+  RC(capture_f32(e, "features", e->features, (size_t)P * c.clip_embed_dim, s));
+  return GLASS_OK;
+}
+
+int run_discriminator(glass_engine* e, const float* images, int P, float* logits_out, float* hinge_out,
+                      cudaStream_t s) {
+  const glass_config& c = e->cfg;
+  if (!c.use_discriminator) return fail(GLASS_ERR_STATE, "engine was created without a discriminator");
+  const int nb = c.num_blocks;
+  auto dch = [&](int i) { return e->gch[nb - 1 - i]; };
+  char nm[64];
+  LAUNCH(k_from_rgb(images, tptr<float>(e, "d.frgb.w"), tptr<float>(e, "d.frgb.b"), e->actA, P, e->R, dch(0), s));
+  const __half* x = e->actA;
+  int res = e->R;
+  size_t ci = 0;
+  for (int b = 0; b < nb - 1; ++b) {
+    LAUNCH(k_fir_down(x, e->dXd, P, res, res, dch(b), s));
+    RC(run_conv(e, e->d_convs[ci++], s));   // conv0 -> actB (space-to-depth)
+    RC(run_conv(e, e->d_convs[ci++], s));   // projection -> dR
+    const ConvLaunch& c1 = e->d_convs[ci++];
+    RC(run_conv(e, c1, s));                 // conv1 + residual
+    x = c1.p.epi.out;
+    res /= 2;
+    snprintf(nm, sizeof nm, "d%d", b);
+    RC(capture_f16(e, nm, x, (size_t)P * res * res * dch(b + 1), s));
+  }
+  const int C = dch(nb - 1);
+  const int cpad = ((C + 1 + 63) / 64) * 64;
+  int group = c.mbstd_group_size > 0 ? c.mbstd_group_size : c.batch_size;
+  LAUNCH(k_mbstd(x, e->dFin, P, c.batch_size, group, C, cpad, s));
+  RC(run_conv(e, e->d_convs[ci++], s));     // final 3x3
+  RC(run_conv(e, e->d_convs[ci++], s));     // dense0
+  LAUNCH(k_dense1_hinge(e->dDense, tptr<float>(e, "d.dense1.w"), tptr<float>(e, "d.dense1.b"), logits_out, hinge_out, P,
+                        C, s));
+  return GLASS_OK;
+}
+
+int check_pop(glass_engine* e, int pop) {
+  if (!e || !e->finalized) return fail(GLASS_ERR_STATE, "engine is not finalized");
+  if (pop <= 0 || pop % e->cfg.batch_size != 0)
+    return fail(GLASS_ERR_ARG, "population %d is not a positive multiple of batch_size %d (models.py:112,124)", pop,
+                e->cfg.batch_size);
+  if (pop > e->cfg.max_population)
+    return fail(GLASS_ERR_ARG, "population %d exceeds max_population %d", pop, e->cfg.max_population);
+  if (e->plan_pop != pop) RC(build_plan(e, pop));
+  return GLASS_OK;
+}
+
+void timing_begin(glass_engine* e) { e->ev_used = 0; }
+int timing_end(glass_engine* e, cudaStream_t s) {
+  if (!e->timing) return GLASS_OK;
+  CUDA_OK(cudaStreamSynchronize(s));
+  float total = 0.f;
+  for (size_t i = 0; i + 1 < e->ev_used; i += 2) {
+    float ms = 0.f;
+    CUDA_OK(cudaEventElapsedTime(&ms, e->ev[i], e->ev[i + 1]));
+    total += ms;
+  }
+  e->last_conv_ms = total;
+  e->last_conv_launches = (int)(e->ev_used / 2);
+  return GLASS_OK;
+}
+
+}  // namespace
+
+// ===========================================================================
+// C ABI
+// ===========================================================================
+extern "C" {
+
+const char* glass_last_error(void) { return g_last_error.c_str(); }
+
+int glass_create(const glass_config* cfg, glass_engine** out) {
+  if (!cfg || !out) return fail(GLASS_ERR_ARG, "null argument");
+  if (cfg->num_blocks < 2 || cfg->num_blocks > GLASS_MAX_BLOCKS) return fail(GLASS_ERR_ARG, "num_blocks out of range");
+  if (cfg->batch_size <= 0 || cfg->max_population <= 0 || cfg->max_population % cfg->batch_size != 0)
+    return fail(GLASS_ERR_ARG, "max_population must be a positive multiple of batch_size");
+  for (int i = 0; i < cfg->num_blocks; ++i)
+    if (cfg->channels[i] % 32 != 0 || cfg->channels[i] <= 0 || cfg->channels[i] > 512)
+      return fail(GLASS_ERR_ARG, "channels must be multiples of 32 in [32,512]");
+  if (cfg->latent_size <= 0 || cfg->latent_size > 1024 || cfg->clip_width % 64 != 0)
+    return fail(GLASS_ERR_ARG, "unsupported latent_size / clip_width");
+  int ndev = 0;
+  cudaError_t err = cudaGetDeviceCount(&ndev);
+  if (err != cudaSuccess || ndev == 0 || cfg->device >= ndev)
+    return fail(GLASS_ERR_CUDA, "no usable CUDA device (%s); this library has no CPU fallback",
+                err == cudaSuccess ? "device ordinal out of range" : cudaGetErrorString(err));
+  CUDA_OK(cudaSetDevice(cfg->device));
+  cudaDeviceProp prop;
+  CUDA_OK(cudaGetDeviceProperties(&prop, cfg->device));
+  if (prop.major != 10)
+    return fail(GLASS_ERR_CUDA, "device %d is sm_%d%d; this library is built for sm_100a only", cfg->device, prop.major,
+                prop.minor);
+  glass_engine* e = new glass_engine();
+  e->cfg = *cfg;
+  e->num_sms = prop.multiProcessorCount;
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  err = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+  if (err != cudaSuccess || fn == nullptr || qres != cudaDriverEntryPointSuccess) {
+    delete e;
+    return fail(GLASS_ERR_CUDA, "cuTensorMapEncodeTiled is unavailable");
+  }
+  e->encode = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(fn);
+  derive_arch(e);
+  *out = e;
+  return GLASS_OK;
+}
+
+int glass_set_tensor(glass_engine* e, const char* name, const void* host_data, size_t nbytes) {
+  if (!e || !name || !host_data || nbytes == 0) return fail(GLASS_ERR_ARG, "null argument");
+  CUDA_OK(cudaSetDevice(e->cfg.device));
+  DevTensor& t = e->tensors[name];
+  if (t.ptr && t.bytes != nbytes) {
+    cudaFree(t.ptr);
+    t.ptr = nullptr;
+  }
+  if (!t.ptr) CUDA_OK(cudaMalloc(&t.ptr, nbytes));
+  t.bytes = nbytes;
+  CUDA_OK(cudaMemcpy(t.ptr, host_data, nbytes, cudaMemcpyHostToDevice));
+  e->plan_pop = -1;
+  return GLASS_OK;
+}
+
+int glass_finalize(glass_engine* e) {
+  if (!e) return fail(GLASS_ERR_ARG, "null engine");
+  CUDA_OK(cudaSetDevice(e->cfg.device));
+  RC(validate_weights(e));
+  Arena probe;
+  layout_workspace(e, probe);
+  const size_t need = probe.off + 4096;
+  void* base = nullptr;
+  cudaError_t err = cudaMalloc(&base, need);
+  if (err != cudaSuccess)
+    return fail(GLASS_ERR_NOMEM, "workspace of %.2f GB for max_population=%d: %s", need / 1e9, e->cfg.max_population,
+                cudaGetErrorString(err));
+  CUDA_OK(cudaMemset(base, 0, need));
+  e->arena.base = (uint8_t*)base;
+  e->arena.cap = need;
+  e->arena.off = 0;
+  layout_workspace(e, e->arena);
+  e->ev.resize(512);
+  for (auto& ev : e->ev) CUDA_OK(cudaEventCreate(&ev));
+  e->finalized = true;
+  return GLASS_OK;
+}
+
+int glass_set_text_features(glass_engine* e, const float* host_text, int32_t n) {
+  if (!e || !e->finalized) return fail(GLASS_ERR_STATE, "engine is not finalized");
+  if (n != e->cfg.clip_embed_dim) return fail(GLASS_ERR_ARG, "text feature length %d != embed dim %d", n, e->cfg.clip_embed_dim);
+  CUDA_OK(cudaMemcpy(e->text, host_text, (size_t)n * 4, cudaMemcpyHostToDevice));
+  e->have_text = true;
+  return GLASS_OK;
+}
+
+int glass_destroy(glass_engine* e) {
+  if (!e) return GLASS_OK;
+  cudaSetDevice(e->cfg.device);
+  for (auto& kv : e->tensors) cudaFree(kv.second.ptr);
+  if (e->arena.base) cudaFree(e->arena.base);
+  for (auto& ev : e->ev) cudaEventDestroy(ev);
+  delete e;
+  return GLASS_OK;
+}
+
+int glass_generate(glass_engine* e, const float* z_dev, int32_t pop, const glass_noise* noise, float* images_dev,
+                   void* stream) {
+  RC(check_pop(e, pop));
+  cudaStream_t s = (cudaStream_t)stream;
+  timing_begin(e);
+  RC(run_generator(e, z_dev, pop, noise, images_dev ? images_dev : e->images, s));
+  return timing_end(e, s);
+}
+
+int glass_clip_similarity(glass_engine* e, const float* images_dev, int32_t pop, float* sim_dev, void* stream) {
+  RC(check_pop(e, pop));
+  cudaStream_t s = (cudaStream_t)stream;
+  timing_begin(e);
+  RC(run_clip(e, images_dev, pop, sim_dev, nullptr, s));
+  return timing_end(e, s);
+}
+
+int glass_discriminate(glass_engine* e, const float* images_dev, int32_t pop, float* logits_dev, void* stream) {
+  RC(check_pop(e, pop));
+  cudaStream_t s = (cudaStream_t)stream;
+  timing_begin(e);
+  RC(run_discriminator(e, images_dev, pop, logits_dev, nullptr, s));
+  return timing_end(e, s);
+}
+
+int glass_evaluate_device(glass_engine* e, const float* z_dev, int32_t pop, const glass_noise* noise,
+                          float* neg_sim_dev, float* hinge_dev, void* stream) {
+  RC(check_pop(e, pop));
+  if (e->cfg.use_discriminator && hinge_dev == nullptr) return fail(GLASS_ERR_ARG, "hinge output is required");
+  cudaStream_t s = (cudaStream_t)stream;
+  timing_begin(e);
+  RC(run_generator(e, z_dev, pop, noise, e->images, s));
+  RC(run_clip(e, e->images, pop, e->sim, neg_sim_dev, s));
+  if (e->cfg.use_discriminator) RC(run_discriminator(e, e->images, pop, e->dlogits, hinge_dev, s));
+  return timing_end(e, s);
+}
+
+int glass_evaluate_host(glass_engine* e, const double* x, int32_t pop, const glass_noise* noise, float* neg_sim,
+                        float* hinge, void* stream) {
+  RC(check_pop(e, pop));
+  if (!x || !neg_sim) return fail(GLASS_ERR_ARG, "null argument");
+  if (e->cfg.use_discriminator && hinge == nullptr) return fail(GLASS_ERR_ARG, "hinge output is required");
+  cudaStream_t s = (cudaStream_t)stream;
+  const size_t n = (size_t)pop * e->cfg.latent_size;
+  CUDA_OK(cudaMemcpyAsync(e->x_host_stage, x, n * 8, cudaMemcpyHostToDevice, s));
+  LAUNCH(k_latents_to_f32(e->x_host_stage, e->z32, n, s));
+  RC(glass_evaluate_device(e, e->z32, pop, noise, e->neg_sim, e->cfg.use_discriminator ? e->hinge : nullptr, stream));
+  CUDA_OK(cudaMemcpyAsync(neg_sim, e->neg_sim, (size_t)pop * 4, cudaMemcpyDeviceToHost, s));
+  if (e->cfg.use_discriminator)
+    CUDA_OK(cudaMemcpyAsync(hinge, e->hinge, (size_t)pop * 4, cudaMemcpyDeviceToHost, s));
+  CUDA_OK(cudaStreamSynchronize(s));
+  return GLASS_OK;
+}
+
+int64_t glass_launch_count(const glass_engine* e) { return e ? e->launches : 0; }
+
+int glass_set_debug(glass_engine* e, int32_t capture, int32_t timing) {
+  if (!e) return fail(GLASS_ERR_ARG, "null engine");
+  e->capture = capture != 0;
+  e->timing = timing != 0;
+  if (!e->capture) e->captured.clear();
+  return GLASS_OK;
+}
+
+int64_t glass_debug_read(glass_engine* e, const char* name, float* host_out, int64_t capacity) {
+  if (!e || !name) return fail(GLASS_ERR_ARG, "null argument");
+  auto it = e->captured.find(name);
+  if (it == e->captured.end()) return fail(GLASS_ERR_ARG, "no captured tensor named '%s'", name);
+  const int64_t n = (int64_t)it->second.size();
+  if (host_out != nullptr) {
+    if (capacity < n) return fail(GLASS_ERR_ARG, "capacity %lld < %lld", (long long)capacity, (long long)n);
+    memcpy(host_out, it->second.data(), (size_t)n * 4);
+  }
+  return n;
+}
+
+int glass_last_conv_time(const glass_engine* e, float* ms, int32_t* launches) {
+  if (!e) return fail(GLASS_ERR_ARG, "null engine");
+  if (ms) *ms = e->last_conv_ms;
+  if (launches) *launches = e->last_conv_launches;
+  return GLASS_OK;
+}
+
+// Per-launch breakdown of the last timed call: fills up to `cap` entries of (ms, algorithmic flops).
+int glass_conv_breakdown(glass_engine* e, float* ms, double* flops, int32_t cap) {
+  if (!e) return fail(GLASS_ERR_ARG, "null engine");
+  std::vector<const ConvLaunch*> all;
+  for (auto& c : e->g_convs) all.push_back(&c);
+  for (auto& c : e->c_convs) all.push_back(&c);
+  for (auto& c : e->d_convs) all.push_back(&c);
+  int n = 0;
+  for (size_t i = 0; i + 1 < e->ev_used && n < cap && (size_t)n < all.size(); i += 2, ++n) {
+    float t = 0.f;
+    cudaEventElapsedTime(&t, e->ev[i], e->ev[i + 1]);
+    ms[n] = t;
+    flops[n] = all[n]->flops;
+  }
+  return n;
+}
+
+}  // extern "C"

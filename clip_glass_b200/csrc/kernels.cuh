@@ -1,0 +1,54 @@
+// HBM-bound helper kernels of the fitness path (declarations; kernels.cu).
+#pragma once
+#include "common.cuh"
+
+namespace glass {
+
+// latent.py:38  f64 -> f32
+cudaError_t k_latents_to_f32(const double* x, float* z, size_t n, cudaStream_t s);
+// stylegan2/models.py:625-626 pixel norm
+cudaError_t k_pixelnorm(const float* z, float* out, int P, int L, cudaStream_t s);
+// out[b,n] = f( sum_k g(in[b*in_stride + k]) * Wt[k*N + n] + bias[n] )
+//   mode 0: linear; 1: lrelu(0.2)*sqrt2; 2: g = square, f = rsqrt(. + 1e-8) (demodulation, modules.py:945-954)
+cudaError_t k_vecmat(const float* in, int in_stride, const float* Wt, const float* bias, float* out, int out_stride,
+                     int P, int K, int N, int mode, cudaStream_t s);
+// x0[b][pix][c] = fp16(const[pix][c] * s[b*stride + c])   (models.py:987 + pre-scale by the first style)
+cudaError_t k_const_input(const float* cst, const float* styles, int stride, __half* out, int P, int C, cudaStream_t s);
+// wr[b][c][o] = W[c][o] * styles[b*stride + off + o]   (toRGB modulated 1x1 weights, no demod; models.py:848-871)
+cudaError_t k_rgb_weights(const float* W, const float* styles, int stride, float* out, int P, int C, cudaStream_t s);
+// y[b][Y][X] = up2(yprev)[Y][X] + sum_slabs t + bias   (modules.py:580-602 polyphase; models.py:1004-1013)
+// final: also writes image NCHW fp32 = clip((y+1)/2, 0, 1)  (utils.py:14-17)
+cudaError_t k_rgb_combine(const float4* yprev, const float4* slabs, int n_slabs, const float* bias, float4* yout,
+                          float* image, int P, int H, int W, cudaStream_t s);
+// noise: Philox4x32-10 + Box-Muller, n floats
+cudaError_t k_noise(float* out, size_t n, uint64_t seed, uint64_t offset, cudaStream_t s);
+
+// ---- CLIP tower ----
+// generator.py:45 (bilinear 1024->224, align_corners=False) fused with the im2col of
+// clip/model.py:219 conv1 (k=32,s=32): patches[b*g*g + gy*g+gx][c*p*p + py*p + px] fp16
+cudaError_t k_resize_patches(const float* images, __half* patches, int P, int Rin, int Rout, int patch, cudaStream_t s);
+// clip/model.py:222-224: cat cls, + pos (fp16 adds), ln_pre -> tokens fp16 [P*T][W]
+cudaError_t k_embed_lnpre(const __half* patch_emb, const float* cls, const float* pos, const float* lw, const float* lb,
+                          __half* tokens, int P, int T, int W, cudaStream_t s);
+// clip/model.py:152-158
+cudaError_t k_layernorm(const __half* x, const float* w, const float* b, __half* out, int M, int W, cudaStream_t s);
+// nn.MultiheadAttention core (clip/model.py:180-182): qkv [P*T][3W] -> out [P*T][W]; heads of 64
+cudaError_t k_attention(const __half* qkv, __half* out, int P, int T, int W, cudaStream_t s);
+// clip/model.py:230-233 + generator.py:51: ln_post(cls) @ proj -> features; cosine vs text
+cudaError_t k_final_cosine(const __half* tokens, const float* lw, const float* lb, const float* proj,
+                           const float* text, float* features, float* sim, float* neg_sim, int P, int T, int W, int E,
+                           cudaStream_t s);
+
+// ---- discriminator ----
+// utils.py:19-21 denorm + models.py:1121-1144 fromRGB 1x1 + bias + lrelu*sqrt2 -> NHWC fp16
+cudaError_t k_from_rgb(const float* images, const float* Wt, const float* bias, __half* out, int P, int R, int C,
+                       cudaStream_t s);
+// projection path FIR (pad 1) sampled at stride 2 (modules.py:1204-1220, 1243-1246): [N,H,W,C] -> [N,H/2,W/2,C]
+cudaError_t k_fir_down(const __half* x, __half* out, int N, int H, int W, int C, cudaStream_t s);
+// modules.py:701-747 incl. the in-place centring; x [P,16,C] -> out [P,16,Cpad] (channel C = std feature)
+cudaError_t k_mbstd(const __half* x, __half* out, int P, int batch, int group, int C, int Cpad, cudaStream_t s);
+// models.py:1224-1225 last dense + problem.py:23 hinge
+cudaError_t k_dense1_hinge(const __half* x, const float* w, const float* b, float* logits, float* hinge, int P, int C,
+                           cudaStream_t s);
+
+}  // namespace glass

@@ -120,6 +120,13 @@ int64_t glass_launch_count(const glass_engine* e);
  * names documented in engine.cu: "w", "styles", "act:<layer>", "rgb:<block>",
  * "tokens", "features", ...).  Returns element count or a negative status. */
 int64_t glass_debug_read(glass_engine* e, const char* name, float* host_out, int64_t capacity);
+/* capture != 0: keep host copies of intermediates for glass_debug_read (slow;
+ * tests only).  timing != 0: bracket every tensor-core launch with CUDA events. */
+int glass_set_debug(glass_engine* e, int32_t capture, int32_t timing);
+/* Per-launch device time (ms) and algorithmic FLOPs (as the reference writes
+ * the op) of the tensor-core launches of the last timed call, in launch order
+ * (G convs, CLIP GEMMs, D convs).  Returns the number of entries written. */
+int glass_conv_breakdown(glass_engine* e, float* ms, double* flops, int32_t cap);
 /* Time (ms, CUDA events on `stream`) spent in the tensor-core conv/GEMM
  * kernels during the last evaluate call, and their launch count. */
 int glass_last_conv_time(const glass_engine* e, float* ms, int32_t* launches);
