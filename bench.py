@@ -1,0 +1,335 @@
+#!/usr/bin/env python
+"""bench.py — candidates evaluated per second through the fitness path.
+
+One "step" = one generation's ``GenerationProblem._evaluate`` over a synthetic
+population (problem.py:14-29): latents -> StyleGAN2 ffhq-config-f G -> CLIP
+ViT-B/32 -> cosine -> StyleGAN2 D hinge.  Workload = BASELINE.json configs[1]
+(StyleGAN2_ffhq_d, pop 64 per GPU, batch_size 4); at N GPUs the population is
+N*64 sharded by whole minibatches with one all-gather of F (configs[3] at N=8):
+weak scaling.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Prints ONE JSON line (rank 0).  See the module-level contract in the task
+statement; keys: metric value unit n_gpus steps warmup ms_per_step
+higher_is_better scaling vs_baseline dtype data config clocks e2e gpu_launches
+roofline cpu_baseline.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, REPO)
+
+METRIC = "candidate latents evaluated/sec StyleGAN2_ffhq+CLIP (problem._evaluate path)"
+UNIT = "candidates/s"
+# algorithmic work per candidate as the reference writes the ops (BASELINE.md §2 / SURVEY.md §8d)
+GFLOP_PER_CAND = {"_d": 317.1, "_nod": 159.6}
+
+
+def measured_peaks():
+    path = os.path.join(REPO, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            d = json.load(f)
+        return dict(tflops_burst=d.get("bf16_tflops"), tflops_sustained=d.get("bf16_tflops_sustained"),
+                    hbm_gbs=d.get("hbm_gbs"), source="measured (MEASURED_PEAKS.json)")
+    return dict(tflops_burst=1590.0, tflops_sustained=1400.0, hbm_gbs=6650.0, source="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons every 200 ms while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index, self.rows, self._stop_evt, self.proc = index, [], threading.Event(), None
+
+    def run(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                 "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                if self._stop_evt.is_set():
+                    break
+                self.rows.append([c.strip() for c in line.split(",")])
+        except Exception:
+            pass
+
+    def stop(self):
+        self._stop_evt.set()
+        if self.proc is not None:
+            self.proc.terminate()
+
+    def summary(self):
+        sm, mx, reasons = [], 0, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx = max(mx, float(r[1]))
+                for n, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                continue
+        return dict(sm_mhz=statistics.median(sm) if sm else None, sm_max_mhz=mx or None,
+                    reasons=sorted(reasons), samples=len(sm))
+
+
+def cpu_oracle_step(pop, batch, use_d, seed, threads):
+    """One bounded sample of the SAME workload on the host cores: the oracle port of
+    problem.py:14-29 (full ffhq-config-f G + ViT-B/32 + D, fp32 G/D, CLIP fp16 as built)."""
+    import torch
+    from clip_glass_b200 import weights as W
+    from oracle import evaluate_oracle
+    torch.set_num_threads(threads)
+    st = cpu_oracle_step.__dict__.setdefault("state", {})
+    if not st:
+        st["g"] = W.make_generator_weights(W.FFHQ, 1000)
+        st["d"] = W.make_discriminator_weights(W.FFHQ, 1001)
+        st["c"] = W.clip_as_built(W.make_clip_visual_weights(W.VIT_B32, 1002))
+        st["t"] = torch.randn(1, 512, generator=torch.Generator().manual_seed(5)).half()
+    x = W.make_latents(pop, 512, seed)
+    noise = W.make_noise(W.FFHQ, pop // batch, seed + 1)
+    t0 = time.perf_counter()
+    evaluate_oracle.evaluate(x, st["g"], st["d"], st["c"], st["t"], W.FFHQ, W.VIT_B32, batch, use_d, noise=noise)
+    return time.perf_counter() - t0
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's CPU path (oracle port; /root/reference cannot travel to the GPU box),
+    timed on the host cores with every thread it can use.  Rank 0 only."""
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    use_d = args.variant == "_d"
+    sample = args.cpu_sample
+    budget_s = 270.0
+    t_begin = time.perf_counter()
+    times = []
+    done_w = 0
+    for i in range(args.warmup):
+        if time.perf_counter() - t_begin > budget_s * 0.4 and done_w >= 1:
+            break
+        cpu_oracle_step(sample, args.batch, use_d, 10 + i, threads)
+        done_w += 1
+    for i in range(args.steps):
+        if times and time.perf_counter() - t_begin + times[-1] > budget_s:
+            break
+        times.append(cpu_oracle_step(sample, args.batch, use_d, 100 + i, threads))
+    ms = 1e3 * sum(times) / len(times)
+    value = sample / (ms / 1e3)
+    line = dict(
+        impl="reference", metric=METRIC, value=value, unit=UNIT, n_gpus=args.gpus, steps=len(times),
+        warmup=done_w, ms_per_step=ms, higher_is_better=True, scaling="weak", vs_baseline=None,
+        dtype="fp32 (G/D), fp16-as-built (CLIP)", data="synthetic",
+        config=dict(workload=f"StyleGAN2_ffhq{args.variant} ffhq-config-f 1024^2 + CLIP ViT-B/32, batch_size {args.batch}",
+                    population_per_step=sample, note="bounded sample of the same workload on host cores"),
+        cpu_baseline=dict(value=value, unit=UNIT, cores=threads, kind="port",
+                          sample=f"{sample} candidates per step x {len(times)} steps (oracle port of problem.py:14-29; "
+                                 "steps stop early once ~4.5 min of wall time is used)"),
+        e2e=dict(value=value, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0),
+    )
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--pop-per-gpu", type=int, default=64)
+    ap.add_argument("--batch", type=int, default=4)
+    ap.add_argument("--variant", default="_d", choices=["_d", "_nod"])
+    ap.add_argument("--cpu-sample", type=int, default=4)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as tdist
+    from clip_glass_b200 import weights as W
+    from clip_glass_b200.config import make_namespace
+    from clip_glass_b200.problem import GenerationProblem
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the fitness path has no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        tdist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    W_ = max(args.warmup, 3)
+    use_d = args.variant == "_d"
+    P_local = args.pop_per_gpu
+    P = P_local * world
+    cfg_name = "StyleGAN2_ffhq_d" if use_d else "StyleGAN2_ffhq_nod"
+    text = torch.randn(1, 512, generator=torch.Generator().manual_seed(5))
+    config = make_namespace(cfg_name, device=f"cuda:{local_rank}", target="synthetic", pop_size=P,
+                            batch_size=args.batch, max_population=P_local, synthetic_seed=1000,
+                            text_features=text, noise_seed=7)
+    problem = GenerationProblem(config)
+    eng = problem.generator.engine
+    stream = torch.cuda.current_stream()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")     # > 126 MB L2
+
+    def barrier():
+        if world > 1:
+            tdist.barrier()
+        torch.cuda.synchronize()
+
+    from clip_glass_b200 import dist as gdist
+    bounds = gdist.shard_bounds(P, args.batch, world)
+    s0, e0 = bounds[rank]
+
+    # ---------------- device-resident step: inputs already in HBM -----------------
+    z_all = [torch.from_numpy(W.make_latents(P, 512, 50 + i)[s0:e0]).float().cuda() for i in range(4)]
+
+    def step_device(i):
+        neg_sim, hinge = eng.evaluate_device(z_all[i % 4], seed=1 + i, first_group=s0 // args.batch)
+        local = torch.stack([neg_sim, hinge], 1) if hinge is not None else neg_sim[:, None]
+        if world > 1:
+            out = torch.empty(world * local.shape[0], local.shape[1], device="cuda")
+            tdist.all_gather_into_tensor(out, local)      # the one collective on the path
+            return out
+        return local
+
+    def timed(step_fn, n_steps, first):
+        """EXACTLY n_steps, each bracketed by CUDA events on the launching stream; L2 flushed between steps
+        (outside the events).  Returns per-step ms (max over ranks)."""
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n_steps)]
+        barrier()
+        for i in range(n_steps):
+            flush.zero_()
+            ev[i][0].record(stream)
+            step_fn(first + i)
+            ev[i][1].record(stream)
+        barrier()
+        ms = torch.tensor([a.elapsed_time(b) for a, b in ev], dtype=torch.float64, device="cuda")
+        if world > 1:
+            tdist.all_reduce(ms, op=tdist.ReduceOp.MAX)
+        return ms.cpu().numpy()
+
+    for i in range(W_):
+        step_device(i)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    launches0 = eng.launch_count
+    ms_dev = timed(step_device, args.steps, W_)
+    launches = eng.launch_count - launches0
+
+    # ---------------- e2e: host f64 population -> host F through the plugin API ----------------
+    xs = [W.make_latents(P, 512, 80 + i) for i in range(4)]
+    pinned = [torch.from_numpy(x).pin_memory().numpy() for x in xs]
+
+    def step_e2e(i):
+        out = {}
+        problem._evaluate(pinned[i % 4], out)
+        return out
+
+    for i in range(2):
+        step_e2e(i)
+    e2e_wall = []
+    barrier()
+    for i in range(args.steps):
+        flush.zero_()
+        torch.cuda.synchronize()
+        if world > 1:
+            tdist.barrier()
+        t0 = time.perf_counter()
+        out = step_e2e(i)
+        torch.cuda.synchronize()
+        e2e_wall.append((time.perf_counter() - t0) * 1e3)
+    e2e_ms = torch.tensor(e2e_wall, dtype=torch.float64, device="cuda")
+    if world > 1:
+        tdist.all_reduce(e2e_ms, op=tdist.ReduceOp.MAX)
+    e2e_ms = e2e_ms.cpu().numpy()
+    if rank == 0:
+        sampler.stop()
+
+    # ---------------- roofline of the dominant kernel (conv_tc), measured live ----------------
+    roofline = None
+    eng.set_debug(capture=False, timing=True)
+    for i in range(2):
+        eng.evaluate_device(z_all[i % 4], seed=100 + i)
+    torch.cuda.synchronize()
+    bd = eng.conv_breakdown()
+    eng.set_debug(capture=False, timing=False)
+    peaks = measured_peaks()
+    if bd:
+        conv_ms = sum(m for m, _ in bd)
+        conv_flops = sum(f for _, f in bd)
+        achieved = conv_flops / (conv_ms * 1e-3) / 1e12
+        peak = peaks["tflops_sustained"] or peaks["tflops_burst"]
+        traffic = None
+        tpath = os.path.join(REPO, "profiles", "conv_tc_traffic.json")
+        if os.path.exists(tpath):
+            with open(tpath) as f:
+                traffic = json.load(f).get("bytes_per_launch")
+        roofline = dict(bound="tensor", kernel="conv_tc_kernel (all tcgen05 conv/GEMM launches of one step)",
+                        achieved=achieved, peak=peak, unit="TFLOP/s", frac=achieved / peak, traffic=traffic,
+                        peak_source=peaks["source"] + ", sustained bf16 figure (kernel timed inside a long step)",
+                        launches_per_step=len(bd), kernel_ms_per_step=conv_ms,
+                        share_of_step=conv_ms / float(ms_dev.mean()),
+                        algorithmic_gflop_per_step=conv_flops / 1e9)
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        cpu_oracle_step(args.cpu_sample, args.batch, use_d, 3, threads)            # warm
+        ts = [cpu_oracle_step(args.cpu_sample, args.batch, use_d, 4 + i, threads) for i in range(2)]
+        v = args.cpu_sample / statistics.median(ts)
+        cpu_baseline = dict(value=v, unit=UNIT, cores=threads, kind="port",
+                            sample=f"{args.cpu_sample} candidates (one minibatch) x 2 timed repetitions, median; "
+                                   "oracle port of problem.py:14-29 on torch CPU")
+
+    if rank == 0:
+        ms = float(ms_dev.mean())
+        e2e = float(e2e_ms.mean())
+        line = dict(
+            metric=METRIC, value=P / (ms / 1e3), unit=UNIT, n_gpus=world, steps=args.steps, warmup=W_,
+            ms_per_step=ms, higher_is_better=True, scaling="weak", vs_baseline=None,
+            dtype="fp16 operands, fp32 accumulate (tcgen05 kind::f16)", data="synthetic",
+            config=dict(workload=f"{cfg_name} ffhq-config-f 1024^2 + CLIP ViT-B/32", population=P,
+                        population_per_gpu=P_local, batch_size=args.batch, parallelism=f"population-sharded dp{world}",
+                        weights="seeded random (no checkpoints offline)", noise="device Philox, fresh per minibatch group",
+                        l2="per-step working set (>8 GB activations) >> 126 MB L2, plus a 256 MB flush between timed steps"),
+            clocks=sampler.summary() if rank == 0 else None,
+            e2e=dict(value=P / (e2e / 1e3), unit=UNIT, ms_per_step=e2e,
+                     h2d_bytes_per_step=int(P_local * 512 * 8), d2h_bytes_per_step=int(P_local * (2 if use_d else 1) * 4),
+                     api="GenerationProblem._evaluate(x: float64 ndarray) -> out['F'] (glass_evaluate_host)"),
+            gpu_launches=int(launches),
+            gflop_per_candidate=GFLOP_PER_CAND[args.variant],
+            roofline=roofline, cpu_baseline=cpu_baseline,
+        )
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        tdist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -18,7 +18,7 @@ SYMBOLS = [
     "glass_create", "glass_set_tensor", "glass_finalize", "glass_set_text_features", "glass_destroy",
     "glass_evaluate_host", "glass_evaluate_device", "glass_generate", "glass_clip_similarity",
     "glass_discriminate", "glass_last_error", "glass_launch_count", "glass_debug_read",
-    "glass_set_debug", "glass_conv_breakdown", "glass_last_conv_time",
+    "glass_set_debug", "glass_conv_breakdown", "glass_last_conv_time", "glass_set_batch_size",
 ]
 
 
@@ -47,6 +47,7 @@ class GlassNoise(ctypes.Structure):
         ("noise", ctypes.c_void_p),
         ("noise_on_device", ctypes.c_int32),
         ("seed", ctypes.c_uint64),
+        ("first_group", ctypes.c_uint64),
     ]
 
 
@@ -88,6 +89,7 @@ def load_library() -> ctypes.CDLL:
     lib.glass_debug_read.argtypes = [vp, ctypes.c_char_p, vp, i64]
     lib.glass_debug_read.restype = i64
     lib.glass_set_debug.argtypes = [vp, i32, i32]
+    lib.glass_set_batch_size.argtypes = [vp, i32]
     lib.glass_conv_breakdown.argtypes = [vp, vp, vp, i32]
     lib.glass_last_conv_time.argtypes = [vp, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(i32)]
     for name in SYMBOLS:

@@ -105,6 +105,7 @@ struct glass_engine {
   int plan_pop = -1;
   std::vector<ConvLaunch> g_convs, c_convs, d_convs;
 
+  int max_groups = 0;        // noise buffer capacity in minibatch groups
   int64_t launches = 0;
   // timing of tensor-core launches
   bool timing = false;
@@ -363,7 +364,8 @@ void layout_workspace(glass_engine* e, Arena& a) {
   e->wA = (float*)a.take(P * L * 4);
   e->wB = (float*)a.take(P * L * 4);
   e->styles = (float*)a.take(P * e->S * 4);
-  e->noise = (float*)a.take((P / c.batch_size) * e->noise_per_group * 4);
+  e->max_groups = (int)(P / c.batch_size);
+  e->noise = (float*)a.take((size_t)e->max_groups * e->noise_per_group * 4);
   e->dmod.clear();
   for (const GLayer& l : e->glayers) e->dmod.push_back((float*)a.take(P * l.cout * 4));
   e->rgbw.clear();
@@ -559,7 +561,8 @@ int fill_noise(glass_engine* e, int P, const glass_noise* nz, cudaStream_t s) {
     CUDA_OK(cudaMemcpyAsync(e->noise, nz->noise, n * 4,
                             nz->noise_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, s));
   } else {
-    LAUNCH(k_noise(e->noise, n, nz ? nz->seed : 0ull, 0ull, s));
+    const uint64_t first = nz ? nz->first_group : 0ull;
+    LAUNCH(k_noise(e->noise, n, nz ? nz->seed : 0ull, first * (e->noise_per_group / 4), s));
   }
   return GLASS_OK;
 }
@@ -693,6 +696,9 @@ int check_pop(glass_engine* e, int pop) {
                 e->cfg.batch_size);
   if (pop > e->cfg.max_population)
     return fail(GLASS_ERR_ARG, "population %d exceeds max_population %d", pop, e->cfg.max_population);
+  if (pop / e->cfg.batch_size > e->max_groups)
+    return fail(GLASS_ERR_ARG, "population %d / batch_size %d needs more noise groups than the %d allocated", pop,
+                e->cfg.batch_size, e->max_groups);
   if (e->plan_pop != pop) RC(build_plan(e, pop));
   return GLASS_OK;
 }
@@ -865,6 +871,16 @@ int glass_evaluate_host(glass_engine* e, const double* x, int32_t pop, const gla
   if (e->cfg.use_discriminator)
     CUDA_OK(cudaMemcpyAsync(hinge, e->hinge, (size_t)pop * 4, cudaMemcpyDeviceToHost, s));
   CUDA_OK(cudaStreamSynchronize(s));
+  return GLASS_OK;
+}
+
+int glass_set_batch_size(glass_engine* e, int32_t batch_size) {
+  if (!e || !e->finalized) return fail(GLASS_ERR_STATE, "engine is not finalized");
+  if (batch_size <= 0) return fail(GLASS_ERR_ARG, "batch_size must be positive");
+  if (batch_size != e->cfg.batch_size) {
+    e->cfg.batch_size = batch_size;
+    e->plan_pop = -1;
+  }
   return GLASS_OK;
 }
 

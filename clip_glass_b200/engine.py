@@ -79,10 +79,17 @@ class GlassEngine:
         t = np.ascontiguousarray(np.asarray(torch.as_tensor(text_features).float().cpu()).reshape(-1), dtype=np.float32)
         check(self.lib.glass_set_text_features(self._h, t.ctypes.data, t.size))
 
+    def set_batch_size(self, batch_size: int) -> None:
+        """Noise / MinibatchStd scope of later calls (the reference's ``minibatch`` argument)."""
+        if batch_size != self.batch_size:
+            check(self.lib.glass_set_batch_size(self._h, int(batch_size)))
+            self.batch_size = int(batch_size)
+
     # -- helpers -----------------------------------------------------------
-    def _noise_arg(self, noise, seed, pop, keep):
+    def _noise_arg(self, noise, seed, pop, keep, first_group=0):
         nz = GlassNoise()
         nz.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
+        nz.first_group = int(first_group)
         nz.noise = None
         nz.noise_on_device = 0
         if noise is not None:
@@ -104,12 +111,12 @@ class GlassEngine:
         return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
     # -- the hot path ------------------------------------------------------
-    def evaluate(self, x: np.ndarray, noise=None, seed: int = 0):
+    def evaluate(self, x: np.ndarray, noise=None, seed: int = 0, first_group: int = 0):
         """problem.py:14-29 through ``glass_evaluate_host``: host f64 in, host fp32 out."""
         x = np.ascontiguousarray(x, dtype=np.float64)
         pop = x.shape[0]
         keep: list = []
-        nz = self._noise_arg(noise, seed, pop, keep)
+        nz = self._noise_arg(noise, seed, pop, keep, first_group)
         neg_sim = np.empty(pop, dtype=np.float32)
         hinge = np.empty(pop, dtype=np.float32) if self.use_discriminator else None
         check(self.lib.glass_evaluate_host(
@@ -117,12 +124,12 @@ class GlassEngine:
             hinge.ctypes.data if hinge is not None else None, self._stream()))
         return neg_sim, hinge
 
-    def evaluate_device(self, z: torch.Tensor, noise=None, seed: int = 0):
+    def evaluate_device(self, z: torch.Tensor, noise=None, seed: int = 0, first_group: int = 0):
         """Device-resident variant (z fp32 cuda [P,L]); returns cuda tensors, asynchronous."""
         assert z.is_cuda and z.dtype == torch.float32 and z.is_contiguous()
         pop = z.shape[0]
         keep: list = []
-        nz = self._noise_arg(noise, seed, pop, keep)
+        nz = self._noise_arg(noise, seed, pop, keep, first_group)
         neg_sim = torch.empty(pop, dtype=torch.float32, device=z.device)
         hinge = torch.empty(pop, dtype=torch.float32, device=z.device) if self.use_discriminator else None
         check(self.lib.glass_evaluate_device(

@@ -1,0 +1,86 @@
+"""Mirror of the reference's problem.py: the pymoo ``Problem`` plugin.
+
+``GenerationProblem._evaluate(x, out)`` has the reference's contract
+(problem.py:14-29): ``x`` float64 [P, n_var] from pymoo; sets ``out["F"]``
+([P] = -sim for n_obj 1, [P,2] = (-sim, hinge) for NSGA-II) and
+``out["G"]`` = zeros[P].  Two equivalent routes:
+
+  fused=True  (default)  one ``glass_evaluate_host`` call per generation
+                         (H2D of x, all kernels, D2H of F);
+  fused=False            the reference's three façade calls
+                         (generate -> clip_similarity -> discriminate).
+
+With ``torch.distributed`` initialised the population is sharded over ranks
+(clip_glass_b200/dist.py) and F is all-gathered, so every rank returns the
+full F exactly as a single-GPU run would.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from .generator import Generator
+
+try:                                    # pymoo==0.4.2.1 is not installable offline
+    from pymoo.model.problem import Problem as _Base
+    HAVE_PYMOO = True
+except Exception:                       # pragma: no cover - depends on the box
+    HAVE_PYMOO = False
+
+    class _Base:                        # the attributes pymoo's Problem.__init__ sets and run.py reads
+        def __init__(self, n_var=-1, n_obj=-1, n_constr=0, xl=None, xu=None, **kwargs):
+            self.n_var, self.n_obj, self.n_constr = n_var, n_obj, n_constr
+            self.xl = np.full(n_var, xl, dtype=float) if np.isscalar(xl) else xl
+            self.xu = np.full(n_var, xu, dtype=float) if np.isscalar(xu) else xu
+
+        def evaluate(self, x, *args, **kwargs):
+            out = {}
+            self._evaluate(np.atleast_2d(x), out, *args, **kwargs)
+            return out
+
+
+class GenerationProblem(_Base):
+    def __init__(self, config, generator=None):
+        self.generator = generator if generator is not None else Generator(config)
+        self.config = config
+        self.generation = 0
+        super().__init__(**self.config.problem_args)
+
+    def _two_objective(self):
+        return self.config.problem_args["n_obj"] == 2 and self.config.use_discriminator
+
+    def _evaluate(self, x, out, *args, **kwargs):
+        self.generation += 1
+        if getattr(self.config, "fused", True):
+            from . import dist
+            seed = int(getattr(self.config, "noise_seed", 0)) + self.generation
+            self.generator.engine.set_batch_size(self.config.batch_size)
+            noise = kwargs.get("noise")     # explicit noise: [groups][layers] tensors (tests / parity runs)
+
+            def local(xs, first_group):
+                nz = None
+                if noise is not None:
+                    nz = noise[first_group:first_group + xs.shape[0] // self.config.batch_size]
+                return self.generator.engine.evaluate(xs, noise=nz, seed=seed, first_group=first_group)
+
+            neg_sim, hinge = dist.sharded_evaluate(x, self.config.batch_size, local)
+            if self._two_objective():
+                out["F"] = np.column_stack((neg_sim, hinge))
+            else:
+                out["F"] = neg_sim
+            out["G"] = np.zeros((x.shape[0]))
+            return
+        # the reference's own call sequence (problem.py:15-29)
+        ls = self.config.latent(self.config)
+        ls.set_from_population(x)
+        with torch.no_grad():
+            generated = self.generator.generate(ls, minibatch=self.config.batch_size)
+            sim = self.generator.clip_similarity(generated).cpu().numpy()
+            if self._two_objective():
+                dis = self.generator.discriminate(generated, minibatch=self.config.batch_size)
+                hinge = torch.relu(1 - dis)
+                hinge = hinge.squeeze(1).cpu().numpy()
+                out["F"] = np.column_stack((-sim, hinge))
+            else:
+                out["F"] = -sim
+            out["G"] = np.zeros((x.shape[0]))

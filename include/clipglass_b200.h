@@ -69,6 +69,11 @@ int glass_finalize(glass_engine* e);
 /* generator.py:23-24 caches text_features [1,E]; fp32 here. */
 int glass_set_text_features(glass_engine* e, const float* host_text, int32_t n);
 int glass_destroy(glass_engine* e);
+/* Change the minibatch size used for the noise / MinibatchStd scope of later
+ * calls (`minibatch` argument of Generator.generate / discriminate,
+ * generator.py:29-38; minibatch=None in the reference == batch_size = pop).
+ * pop / batch_size may not exceed max_population / creation batch_size. */
+int glass_set_batch_size(glass_engine* e, int32_t batch_size);
 
 /* -- the hot path ---------------------------------------------------------- */
 /* Noise for NoiseInjectionWrapper (modules.py:414-453).  Either explicit
@@ -81,6 +86,9 @@ typedef struct glass_noise {
   const float* noise;       /* NULL => use seed */
   int32_t noise_on_device;  /* 1 if `noise` is a device pointer */
   uint64_t seed;
+  uint64_t first_group;     /* global index of this call's first minibatch group: the seeded stream is
+                               indexed by (seed, global group, element), so a population shard evaluated
+                               on another rank draws exactly the noise the single-GPU run would */
 } glass_noise;
 
 /* problem.py:14-29.  x: HOST float64 [pop, latent_size] exactly as pymoo
