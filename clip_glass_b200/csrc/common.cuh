@@ -53,6 +53,7 @@ struct ConvParams {
   int taps;                 // 9 or 1
   int Ntot;                 // multiple of BN
   int BN, BK;
+  int mode;                 // 0 = streamed taps, 1 = resident taps + halo copies (conv_tc.cu)
   const __half* in;         // [Nimg][H][W][Cin]   (SIMT bring-up path; the TC path reads through TMA)
   const __half* wgt;        // [taps][Ntot][Cin]
   EpiParams epi;
@@ -151,6 +152,5 @@ struct TmaMaps {
 };
 cudaError_t launch_conv_tc(const ConvParams& p, const TmaMaps& maps, int num_sms, cudaStream_t s);
 cudaError_t launch_conv_simt(const ConvParams& p, cudaStream_t s);
-size_t conv_tc_smem_bytes(int BN, int BK);
 
 }  // namespace glass

@@ -22,7 +22,7 @@ namespace glass {
 namespace {
 
 constexpr int kBlockM = 128;
-constexpr int kNumThreads = 192;
+constexpr int kNumThreads = 64 + 8 * 32;   // TMA warp, MMA warp, 8 epilogue warps
 constexpr long long kWaitLimitCycles = 4000000000ll;   // ~2 s at 1.9 GHz
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -112,33 +112,137 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
   return (uint64_t)((saddr & 0x3FFFF) >> 4) | (1ull << 16) | (kSbo << 32) | (1ull << 46) | (kLayout << 61);
 }
 
-template <int BN, int BK>
+constexpr int kEpiWarps = 8;
+constexpr int kEpiThreads = kEpiWarps * 32;
+constexpr int kNumParams = 6;   // scale, shift, oscale, rgb0, rgb1, rgb2
+
+// MODE 0 ("stream"): one pipeline stage per (filter tap, 64-channel chunk): A box + B box per stage.
+// MODE 1 ("halo"):   for layers whose whole K per tap is one chunk (Cin == BK in {32,64}): the filter taps of the
+//                    n-tile stay resident in shared memory for the whole kernel, and a stage holds the input
+//                    tile ONCE per horizontal shift: 3 copies of (TH+2) x TW pixels (dx = -1,0,+1).  The nine
+//                    taps are nine descriptor offsets into those copies (a vertical shift is a whole number of
+//                    1024-byte swizzle atoms), so L2->SM traffic drops from 9x to 3.75x the tile and the
+//                    producer issues 3 TMA ops per tile instead of 18.
+constexpr int kHaloTH = 8, kHaloTW = 16;
+
+template <int BN, int BK, int MODE>
 struct Cfg {
   static constexpr int kABytes = kBlockM * BK * 2;
   static constexpr int kBBytes = BN * BK * 2;
-  static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kBudget = 196 * 1024;
+  static constexpr int kCopyBytes = (kHaloTH + 2) * kHaloTW * BK * 2;          // one dx-copy of the halo tile
+  static constexpr int kStageBytes = MODE == 0 ? kABytes + kBBytes : 3 * kCopyBytes;
+  static constexpr int kWBytes = MODE == 0 ? 0 : 9 * kBBytes;                  // resident taps (MODE 1)
+  static constexpr int kParamBytes = 2 * kNumParams * BN * 4;      // double-buffered per-tile epilogue parameters
+  static constexpr int kBudget = 200 * 1024 - kParamBytes - kWBytes;
   static constexpr int kStagesRaw = kBudget / kStageBytes;
   static constexpr int kStages = kStagesRaw > 12 ? 12 : kStagesRaw;
+  static_assert(kStages >= 2, "not enough shared memory for a double-buffered pipeline");
   static constexpr int kTmemCols = (2 * BN < 32) ? 32 : 2 * BN;   // power of two for BN in {32,64,128,256}
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int kSmemBytes = kWBytes + kStages * kStageBytes + kParamBytes + 1024 /*align*/ + 256 /*barriers*/;
   // instruction descriptor: D=f32 [4,6)=1, A=B=f16 (0), K-major both, N>>3 [17,23), M>>4 [24,29)
   static constexpr uint32_t kIdesc = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(kBlockM >> 4) << 24);
 };
 
-template <int BN, int BK>
+__device__ __forceinline__ void tc_ld16_issue(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tc_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory"); }
+
+// Fast epilogue for one row and 16 columns with the per-tile parameters staged in shared memory.
+//   t = act(acc*scale + shift + nz) ; rgb += t*rgbw ; t = (t + residual) * oscale ; store fp16
+// (the sqrt(2) gain of lrelu is folded into scale/shift/nz: lrelu(a)*g == lrelu(a*g) for g > 0)
+template <bool kRgb>
+__device__ __forceinline__ void epilogue_fast16(const EpiParams& e, const float* __restrict__ par, int BN, int j0,
+                                                const uint32_t (&acc)[16], float nz, const __half* res_ptr,
+                                                __half* out_ptr, float (&rgb)[3]) {
+  const float4* sc = reinterpret_cast<const float4*>(par + 0 * BN + j0);
+  const float4* sh = reinterpret_cast<const float4*>(par + 1 * BN + j0);
+  const float4* os = reinterpret_cast<const float4*>(par + 2 * BN + j0);
+  float t[16];
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    const float4 a = sc[g], b = sh[g];
+    t[4 * g + 0] = fmaf(__uint_as_float(acc[4 * g + 0]), a.x, b.x + nz);
+    t[4 * g + 1] = fmaf(__uint_as_float(acc[4 * g + 1]), a.y, b.y + nz);
+    t[4 * g + 2] = fmaf(__uint_as_float(acc[4 * g + 2]), a.z, b.z + nz);
+    t[4 * g + 3] = fmaf(__uint_as_float(acc[4 * g + 3]), a.w, b.w + nz);
+  }
+  if (e.round_fp16_before_act) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) t[j] = __half2float(__float2half_rn(t[j]));
+  }
+  if (e.act == kActLrelu) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) t[j] = fmaxf(t[j], 0.2f * t[j]);
+  } else if (e.act == kActQuickGelu) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) t[j] = t[j] / (1.f + __expf(-1.702f * t[j]));
+  }
+  if (kRgb) {
+    const float4* r0 = reinterpret_cast<const float4*>(par + 3 * BN + j0);
+    const float4* r1 = reinterpret_cast<const float4*>(par + 4 * BN + j0);
+    const float4* r2 = reinterpret_cast<const float4*>(par + 5 * BN + j0);
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      const float4 a = r0[g], b = r1[g], c = r2[g];
+      rgb[0] = fmaf(t[4 * g + 0], a.x, rgb[0]); rgb[0] = fmaf(t[4 * g + 1], a.y, rgb[0]);
+      rgb[0] = fmaf(t[4 * g + 2], a.z, rgb[0]); rgb[0] = fmaf(t[4 * g + 3], a.w, rgb[0]);
+      rgb[1] = fmaf(t[4 * g + 0], b.x, rgb[1]); rgb[1] = fmaf(t[4 * g + 1], b.y, rgb[1]);
+      rgb[1] = fmaf(t[4 * g + 2], b.z, rgb[1]); rgb[1] = fmaf(t[4 * g + 3], b.w, rgb[1]);
+      rgb[2] = fmaf(t[4 * g + 0], c.x, rgb[2]); rgb[2] = fmaf(t[4 * g + 1], c.y, rgb[2]);
+      rgb[2] = fmaf(t[4 * g + 2], c.z, rgb[2]); rgb[2] = fmaf(t[4 * g + 3], c.w, rgb[2]);
+    }
+  }
+  if (res_ptr != nullptr) {
+    const uint4* rp = reinterpret_cast<const uint4*>(res_ptr);
+    const uint4 q0 = __ldg(rp), q1 = __ldg(rp + 1);
+    const __half2* h0 = reinterpret_cast<const __half2*>(&q0);
+    const __half2* h1 = reinterpret_cast<const __half2*>(&q1);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 a = __half22float2(h0[j]), b = __half22float2(h1[j]);
+      t[2 * j] += a.x; t[2 * j + 1] += a.y; t[8 + 2 * j] += b.x; t[8 + 2 * j + 1] += b.y;
+    }
+  }
+  if (out_ptr != nullptr) {
+    uint4 w0, w1;
+    __half2* h0 = reinterpret_cast<__half2*>(&w0);
+    __half2* h1 = reinterpret_cast<__half2*>(&w1);
+#pragma unroll
+    for (int g = 0; g < 2; ++g) {
+      const float4 a = os[g], b = os[g + 2];
+      h0[2 * g] = __floats2half2_rn(t[4 * g] * a.x, t[4 * g + 1] * a.y);
+      h0[2 * g + 1] = __floats2half2_rn(t[4 * g + 2] * a.z, t[4 * g + 3] * a.w);
+      h1[2 * g] = __floats2half2_rn(t[8 + 4 * g] * b.x, t[8 + 4 * g + 1] * b.y);
+      h1[2 * g + 1] = __floats2half2_rn(t[8 + 4 * g + 2] * b.z, t[8 + 4 * g + 3] * b.w);
+    }
+    uint4* op = reinterpret_cast<uint4*>(out_ptr);
+    op[0] = w0;
+    op[1] = w1;
+  }
+}
+
+template <int BN, int BK, int MODE>
 __global__ void __launch_bounds__(kNumThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                const ConvParams p) {
-  using C = Cfg<BN, BK>;
+  using C = Cfg<BN, BK, MODE>;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::kStages * C::kStageBytes);
+  uint8_t* smem_w = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_w + C::kWBytes;       // pipeline stages
+  float* params = reinterpret_cast<float*>(smem + C::kStages * C::kStageBytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::kStages * C::kStageBytes + C::kParamBytes);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + C::kStages;
   uint64_t* tmem_full = bars + 2 * C::kStages;
   uint64_t* tmem_empty = tmem_full + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  uint64_t* w_bar = tmem_empty + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_bar + 1);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -157,8 +261,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full[s], 1);
-      mbar_init(&tmem_empty[s], 4);
+      mbar_init(&tmem_empty[s], kEpiWarps);
     }
+    mbar_init(w_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -176,6 +281,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
+      if (MODE == 1) {
+        // resident filter taps of this CTA's n-tile (grid is a multiple of n_tiles, so n_tile is fixed)
+        const int n_tile = blockIdx.x % n_tiles;
+        mbar_expect_tx(w_bar, p.taps * C::kBBytes);
+        for (int tap = 0; tap < p.taps; ++tap)
+          tma_load_3d(&map_b, smem_w + tap * C::kBBytes, w_bar, 0, n_tile * BN, tap);
+      }
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const int n_tile = tile % n_tiles;
         int m = tile / n_tiles;
@@ -183,6 +295,21 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         const int ty = m % p.tiles_y;
         const int tn = m / p.tiles_y;
         const int x0 = tx * p.TW, y0 = ty * p.TH, i0 = tn * p.TN;
+        if (MODE == 1) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * C::kStageBytes;
+          if (p.taps == 9) {
+            mbar_expect_tx(&full_bar[stage], 3 * C::kCopyBytes);
+#pragma unroll
+            for (int c = 0; c < 3; ++c)
+              tma_load_4d(&map_a, sa + c * C::kCopyBytes, &full_bar[stage], 0, x0 + c - 1, y0 - 1, i0);
+          } else {
+            mbar_expect_tx(&full_bar[stage], C::kABytes);
+            tma_load_4d(&map_a, sa, &full_bar[stage], 0, x0, y0, i0);
+          }
+          if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+          continue;
+        }
         for (int kit = 0; kit < kiters; ++kit) {
           const int tap = kit / kchunks;
           const int kc = kit - tap * kchunks;
@@ -204,12 +331,36 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
+      if (MODE == 1) {
+        mbar_wait(w_bar, 0);
+        tc_fence_after();
+      }
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
         const int as = it & 1;
         const uint32_t aphase = (it >> 1) & 1;
         mbar_wait(&tmem_empty[as], aphase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + as * BN;
+        if (MODE == 1) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * C::kStageBytes);
+          const uint32_t sw = smem_u32(smem_w);
+          for (int tap = 0; tap < p.taps; ++tap) {
+            // tap (ky,kx): copy kx holds the tile shifted by dx = kx-1; row offset ky*TW pixels shifts by dy = ky-1
+            const int ky = tap / 3, kx = tap - ky * 3;
+            const uint32_t a_addr = (p.taps == 9) ? sa + kx * C::kCopyBytes + ky * (kHaloTW * BK * 2) : sa;
+            const uint64_t da = make_smem_desc<BK>(a_addr);
+            const uint64_t db = make_smem_desc<BK>(sw + tap * C::kBBytes);
+#pragma unroll
+            for (int k = 0; k < BK / 16; ++k)
+              tc_mma_f16(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), C::kIdesc, (tap | k) != 0);
+          }
+          tc_commit(&empty_bar[stage]);
+          if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+          tc_commit(&tmem_full[as]);
+          continue;
+        }
         for (int kit = 0; kit < kiters; ++kit) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
@@ -228,15 +379,26 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       }
     }
   } else {
-    // ===================== epilogue (warps 2..5) =====================
+    // ===================== epilogue (warps 2..9) =====================
+    // Two warps per TMEM lane quarter; each owns half of the tile's columns.
+    const EpiParams& e = p.epi;
+    const int ew = warp - 2;
     const int q = warp & 3;                 // TMEM lane quarter this warp may access
+    const int half = ew >> 2;               // column half
+    const int et = threadIdx.x - 64;        // 0..255
     const int row = q * 32 + lane;          // accumulator row == pixel within the tile
     const int thw = p.TH * p.TW;
     const int ri = row / thw;
     const int rr = row - ri * thw;
     const int ry = rr / p.TW;
     const int rx = rr - ry * p.TW;
+    const bool fast = (p.TN == 1);          // every row of a tile belongs to one image
+    const float gain = (e.act == kActLrelu) ? kSqrt2 : 1.f;
+    constexpr int kHalf = BN / 2;
+    constexpr int kChunks = kHalf / 16;
     int it = 0;
+    int staged_img = -1, staged_ntile = -1;
+    int pbuf = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
       const int n_tile = tile % n_tiles;
       int m = tile / n_tiles;
@@ -247,19 +409,100 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       const bool valid = img < p.Nimg && y < p.H && x < p.W;
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
-      mbar_wait(&tmem_full[as], aphase);
-      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + as * BN + half * kHalf;
       float rgb[3] = {0.f, 0.f, 0.f};
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + as * BN;
+
+      if (fast) {
+        // ---- stage the per-(image, n_tile) parameters once; reuse while they do not change ----
+        const int timg = tn;                 // TN == 1
+        if (timg != staged_img || n_tile != staged_ntile) {
+          pbuf ^= 1;
+          float* par = params + pbuf * (kNumParams * BN);
+          if (et < BN) {
+            const int n = n_tile * BN + et;
+            const int o = n % e.Cout;
+            const float d = e.dmod != nullptr ? __ldg(e.dmod + (size_t)timg * e.Cout + o) : 1.f;
+            const float b = e.bias != nullptr ? __ldg(e.bias + o) : 0.f;
+            const float osn = e.out_scale != nullptr ? __ldg(e.out_scale + (size_t)timg * e.out_scale_stride + o) : 1.f;
+            par[0 * BN + et] = d * gain;
+            par[1 * BN + et] = b * gain;
+            par[2 * BN + et] = osn * e.post_scale;
+            if (e.rgb_w != nullptr) {
+              const float* rw = e.rgb_w + (size_t)timg * 3 * e.Cout + o;
+              par[3 * BN + et] = __ldg(rw);
+              par[4 * BN + et] = __ldg(rw + e.Cout);
+              par[5 * BN + et] = __ldg(rw + 2 * e.Cout);
+            }
+          }
+          staged_img = timg;
+          staged_ntile = n_tile;
+          epi_bar_sync();                    // all 8 epilogue warps take the same branch (uniform condition)
+        }
+        const float* par = params + pbuf * (kNumParams * BN);
+        // ---- per-row constants (issued before waiting for the accumulator) ----
+        const int n_first = n_tile * BN + half * kHalf;
+        float nz = 0.f;
+        size_t out_base = 0, res_base = 0;
+        int chunk_stride = 16;               // elements between consecutive 16-column chunks in the output
+        if (valid) {
+          res_base = ((size_t)(img * p.H + y) * p.W + x) * p.Ntot + n_first;
+          if (e.store_mode == kStoreRegular) {
+            out_base = res_base;
+          } else if (e.store_mode == kStoreSpaceToDepth) {
+            out_base = (((size_t)(img * (p.H >> 1) + (y >> 1)) * (p.W >> 1) + (x >> 1)) * 4 + ((y & 1) * 2 + (x & 1))) *
+                           p.Ntot + n_first;
+          }
+          if (e.noise != nullptr && e.store_mode != kStoreDepthToSpace) {
+            nz = gain * __ldg(e.noise_strength) *
+                 __ldg(e.noise + (size_t)(img / e.noise_group_div) * e.noise_group_stride + (size_t)y * p.W + x);
+          }
+        }
+        (void)chunk_stride;
+        mbar_wait(&tmem_full[as], aphase);
+        tc_fence_after();
+        uint32_t acc[2][16];
+        tc_ld16_issue(taddr, acc[0]);
+#pragma unroll
+        for (int c = 0; c < kChunks; ++c) {
+          tc_ld_wait();
+          if (c + 1 < kChunks) tc_ld16_issue(taddr + (c + 1) * 16, acc[(c + 1) & 1]);
+          if (valid) {
+            const int j0 = half * kHalf + c * 16;
+            float nzc = nz;
+            __half* optr = nullptr;
+            if (e.store_mode == kStoreDepthToSpace) {
+              // column n -> phase (py,px) and channel o; output pixel (2y+py, 2x+px)
+              const int n0 = n_tile * BN + j0;
+              const int ph = n0 / e.Cout, o0 = n0 - ph * e.Cout;
+              const int yo = 2 * y + (ph >> 1), xo = 2 * x + (ph & 1);
+              if (e.noise != nullptr) {
+                nzc = gain * __ldg(e.noise_strength) *
+                      __ldg(e.noise + (size_t)(img / e.noise_group_div) * e.noise_group_stride +
+                            (size_t)yo * (2 * p.W) + xo);
+              }
+              if (e.out != nullptr) optr = e.out + ((size_t)(img * 2 * p.H + yo) * (2 * p.W) + xo) * e.Cout + o0;
+            } else if (e.out != nullptr) {
+              optr = e.out + out_base + c * 16;
+            }
+            const __half* rptr = e.residual != nullptr ? e.residual + res_base + c * 16 : nullptr;
+            if (e.rgb_w != nullptr) epilogue_fast16<true>(e, par, BN, j0, acc[c & 1], nzc, rptr, optr, rgb);
+            else epilogue_fast16<false>(e, par, BN, j0, acc[c & 1], nzc, rptr, optr, rgb);
+          }
+        }
+      } else {
+        // ---- generic path (tiles that span several images: 4x4 / 8x8 layers) ----
+        mbar_wait(&tmem_full[as], aphase);
+        tc_fence_after();
 #pragma unroll 1
-      for (int c = 0; c < BN / 16; ++c) {
-        float v[16];
-        tc_ld16(taddr + c * 16, v);
-        if (valid) epilogue_row16(p, img, y, x, n_tile * BN + c * 16, v, rgb);
+        for (int c = 0; c < kChunks; ++c) {
+          float v[16];
+          tc_ld16(taddr + c * 16, v);
+          if (valid) epilogue_row16(p, img, y, x, n_tile * BN + half * kHalf + c * 16, v, rgb);
+        }
       }
-      if (valid && p.epi.rgb_w != nullptr) {
+      if (valid && e.rgb_w != nullptr) {
         const size_t pix = ((size_t)img * p.H + y) * p.W + x;
-        p.epi.rgb_out[(size_t)n_tile * p.Nimg * p.H * p.W + pix] = make_float4(rgb[0], rgb[1], rgb[2], 0.f);
+        e.rgb_out[(size_t)(n_tile * 2 + half) * p.Nimg * p.H * p.W + pix] = make_float4(rgb[0], rgb[1], rgb[2], 0.f);
       }
       tc_fence_before();
       __syncwarp();
@@ -276,19 +519,22 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   }
 }
 
-template <int BN, int BK>
+template <int BN, int BK, int MODE>
 cudaError_t launch_one(const ConvParams& p, const TmaMaps& maps, int num_sms, cudaStream_t s) {
-  using C = Cfg<BN, BK>;
+  using C = Cfg<BN, BK, MODE>;
   static bool configured = false;
   if (!configured) {
-    cudaError_t err =
-        cudaFuncSetAttribute(conv_tc_kernel<BN, BK>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes);
+    cudaError_t err = cudaFuncSetAttribute(conv_tc_kernel<BN, BK, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           C::kSmemBytes);
     if (err != cudaSuccess) return err;
     configured = true;
   }
-  const int total = p.tiles_n * p.tiles_y * p.tiles_x * (p.Ntot / BN);
-  const int grid = total < num_sms ? total : num_sms;
-  conv_tc_kernel<BN, BK><<<grid, kNumThreads, C::kSmemBytes, s>>>(maps.a, maps.b, p);
+  const int n_tiles = p.Ntot / BN;
+  const int total = p.tiles_n * p.tiles_y * p.tiles_x * n_tiles;
+  int grid = total < num_sms ? total : num_sms;
+  if (MODE == 1) grid = (grid / n_tiles) * n_tiles;   // keeps tile % n_tiles constant per CTA (resident taps)
+  if (grid <= 0) return cudaErrorInvalidValue;
+  conv_tc_kernel<BN, BK, MODE><<<grid, kNumThreads, C::kSmemBytes, s>>>(maps.a, maps.b, p);
   return cudaGetLastError();
 }
 
@@ -330,7 +576,7 @@ __global__ void conv_simt_kernel(const ConvParams p) {
     epilogue_row16(p, img, y, x, g * 16, acc, rgb);
     if (p.epi.rgb_w != nullptr) {
       const size_t opix = ((size_t)img * p.H + y) * p.W + x;
-      const int slab = (g * 16) / p.BN;
+      const int slab = (g * 16) / (p.BN / 2);   // same half-tile slabs as the tensor-core path
       float* dst = reinterpret_cast<float*>(p.epi.rgb_out + (size_t)slab * p.Nimg * p.H * p.W + opix);
       atomicAdd(dst + 0, rgb[0]);
       atomicAdd(dst + 1, rgb[1]);
@@ -341,24 +587,22 @@ __global__ void conv_simt_kernel(const ConvParams p) {
 
 }  // namespace
 
-size_t conv_tc_smem_bytes(int BN, int BK) {
-  const size_t stage = (size_t)kBlockM * BK * 2 + (size_t)BN * BK * 2;
-  size_t stages = (196 * 1024) / stage;
-  if (stages > 12) stages = 12;
-  return stages * stage + 1024 + 256;
-}
-
 cudaError_t launch_conv_tc(const ConvParams& p, const TmaMaps& maps, int num_sms, cudaStream_t s) {
-#define GLASS_CASE(bn, bk) \
-  if (p.BN == bn && p.BK == bk) return launch_one<bn, bk>(p, maps, num_sms, s);
-  GLASS_CASE(32, 32)
-  GLASS_CASE(32, 64)
-  GLASS_CASE(64, 64)
-  GLASS_CASE(128, 64)
-  GLASS_CASE(256, 64)
-  GLASS_CASE(64, 32)
-  GLASS_CASE(128, 32)
-  GLASS_CASE(256, 32)
+#define GLASS_CASE(bn, bk, md) \
+  if (p.BN == bn && p.BK == bk && p.mode == md) return launch_one<bn, bk, md>(p, maps, num_sms, s);
+  GLASS_CASE(32, 32, 0)
+  GLASS_CASE(32, 64, 0)
+  GLASS_CASE(64, 64, 0)
+  GLASS_CASE(128, 64, 0)
+  GLASS_CASE(256, 64, 0)
+  GLASS_CASE(64, 32, 0)
+  GLASS_CASE(128, 32, 0)
+  GLASS_CASE(256, 32, 0)
+  GLASS_CASE(32, 32, 1)
+  GLASS_CASE(64, 32, 1)
+  GLASS_CASE(128, 32, 1)
+  GLASS_CASE(32, 64, 1)
+  GLASS_CASE(64, 64, 1)
 #undef GLASS_CASE
   return cudaErrorInvalidValue;
 }
@@ -370,7 +614,7 @@ cudaError_t launch_conv_simt(const ConvParams& p, cudaStream_t s) {
   if (p.epi.rgb_w != nullptr) {
     // bring-up path accumulates toRGB partials with atomics: clear the slabs first
     cudaError_t err = cudaMemsetAsync(p.epi.rgb_out, 0,
-                                      sizeof(float4) * (size_t)(p.Ntot / p.BN) * p.Nimg * p.H * p.W, s);
+                                      sizeof(float4) * (size_t)(2 * p.Ntot / p.BN) * p.Nimg * p.H * p.W, s);
     if (err != cudaSuccess) return err;
   }
   conv_simt_kernel<<<blocks, 128, 0, s>>>(p);

@@ -192,13 +192,22 @@ int make_conv(glass_engine* e, ConvLaunch* out, const __half* in, int Nimg, int 
   p.BK = (Cin % 64 == 0) ? 64 : 32;
   if (p.BN == 0 || Cin % 32 != 0 || Ntot % 16 != 0)
     return fail(GLASS_ERR_ARG, "unsupported conv shape Cin=%d Ntot=%d", Cin, Ntot);
+  // Small-channel layers (the whole K of a tap is one chunk) on full 16x8 tiles: resident taps + halo copies.
+  p.mode = 0;
+  if (!gemm && (Cin == 32 || Cin == 64) && p.TW == 16 && p.TH == 8 && p.TN == 1 && (taps == 9 || taps == 1)) {
+    p.mode = 1;
+    const int bn_cap = (Cin == 64) ? 64 : 128;         // 9 resident taps must leave room for >= 2 stages
+    while (p.BN > bn_cap) p.BN /= 2;
+  }
   if (e->cfg.conv_impl != 0) return GLASS_OK;   // SIMT bring-up path needs no descriptors
   // activations: [C, W, H, N]; outermost extent rounded up to the box (buffers carry the slack)
   const uint64_t wdecl = gemm ? (uint64_t)p.tiles_x * 128 : (uint64_t)W;
   const uint64_t ndecl = (uint64_t)p.tiles_n * p.TN;
   uint64_t dims[4] = {(uint64_t)Cin, wdecl, (uint64_t)H, ndecl};
   uint64_t strides[3] = {(uint64_t)Cin * 2, (uint64_t)Cin * 2 * wdecl, (uint64_t)Cin * 2 * wdecl * H};
-  uint32_t box[4] = {(uint32_t)p.BK, (uint32_t)p.TW, (uint32_t)p.TH, (uint32_t)p.TN};
+  // mode 1 with 3x3 taps loads the tile plus one halo row above and below per horizontal shift
+  const uint32_t box_h = (p.mode == 1 && taps == 9) ? (uint32_t)p.TH + 2 : (uint32_t)p.TH;
+  uint32_t box[4] = {(uint32_t)p.BK, (uint32_t)p.TW, box_h, (uint32_t)p.TN};
   int rc = encode_map(e, &out->maps.a, in, 4, dims, strides, box, p.BK * 2);
   if (rc != GLASS_OK) return rc;
   uint64_t wd[3] = {(uint64_t)Cin, (uint64_t)Ntot, (uint64_t)taps};
@@ -375,7 +384,7 @@ void layout_workspace(glass_engine* e, Arena& a) {
   for (const GLayer& l : e->glayers) {
     act_elems = std::max(act_elems, P * (size_t)l.res * l.res * l.cout);
     const int bn = pick_bn(l.cout);
-    if (bn) slab_elems = std::max(slab_elems, (size_t)(l.cout / bn) * P * l.res * l.res);
+    if (bn) slab_elems = std::max(slab_elems, (size_t)(2 * l.cout / bn) * P * l.res * l.res);   // half-tile slabs
   }
   // every activation row is at least 32 channels wide; slack covers box overhang in the outermost dim
   const size_t slack = kSlackRows * 512;
@@ -615,7 +624,7 @@ int run_generator(glass_engine* e, const float* z, int P, const glass_noise* nz,
     if (last_in_block) {
       const bool final_block = (li + 1 == nl);
       snprintf(nm, sizeof nm, "g.rgb%d.bias", l.block);
-      const int n_slabs = cl.p.Ntot / cl.p.BN;
+      const int n_slabs = 2 * cl.p.Ntot / cl.p.BN;   // each epilogue warp pair writes its own half-tile partial
       LAUNCH(k_rgb_combine(have_y ? ybuf[ycur] : nullptr, e->slabs, n_slabs, tptr<float>(e, nm), ybuf[ycur ^ 1],
                            final_block ? images_out : nullptr, P, l.res, l.res, s));
       ycur ^= 1;

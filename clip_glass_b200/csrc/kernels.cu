@@ -377,16 +377,20 @@ __global__ void from_rgb_kernel(const float* __restrict__ images, const float* _
   }
 }
 
+// 8 channels (one 16-byte vector) per thread; the 4x4 taps of neighbouring outputs overlap by half, so the
+// re-reads are L1/L2 hits and DRAM sees each input byte about once.
 __global__ void fir_down_kernel(const __half* __restrict__ x, __half* __restrict__ out, int N, int H, int W, int C) {
-  const int Ho = H >> 1, Wo = W >> 1, C2 = C >> 1;
-  const size_t n = (size_t)N * Ho * Wo * C2;
+  const int Ho = H >> 1, Wo = W >> 1, C8 = C >> 3;
+  const size_t n = (size_t)N * Ho * Wo * C8;
   const float f[4] = {0.125f, 0.375f, 0.375f, 0.125f};
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-    const int c2 = (int)(i % C2);
-    const int zx = (int)((i / C2) % Wo);
-    const int zy = (int)((i / ((size_t)C2 * Wo)) % Ho);
-    const int b = (int)(i / ((size_t)C2 * Wo * Ho));
-    float a0 = 0.f, a1 = 0.f;
+    const int c8 = (int)(i % C8);
+    const int zx = (int)((i / C8) % Wo);
+    const int zy = (int)((i / ((size_t)C8 * Wo)) % Ho);
+    const int b = (int)(i / ((size_t)C8 * Wo * Ho));
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
 #pragma unroll
     for (int jy = 0; jy < 4; ++jy) {
       const int yy = 2 * zy + jy - 1;
@@ -395,14 +399,22 @@ __global__ void fir_down_kernel(const __half* __restrict__ x, __half* __restrict
       for (int jx = 0; jx < 4; ++jx) {
         const int xx = 2 * zx + jx - 1;
         if (xx < 0 || xx >= W) continue;
-        const float2 v = __half22float2(
-            *reinterpret_cast<const __half2*>(x + (((size_t)b * H + yy) * W + xx) * C + 2 * c2));
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(x + (((size_t)b * H + yy) * W + xx) * C + 8 * c8));
+        const __half2* h2 = reinterpret_cast<const __half2*>(&v);
         const float wgt = f[jy] * f[jx];
-        a0 = fmaf(wgt, v.x, a0);
-        a1 = fmaf(wgt, v.y, a1);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 t = __half22float2(h2[j]);
+          acc[2 * j] = fmaf(wgt, t.x, acc[2 * j]);
+          acc[2 * j + 1] = fmaf(wgt, t.y, acc[2 * j + 1]);
+        }
       }
     }
-    *reinterpret_cast<__half2*>(out + (((size_t)b * Ho + zy) * Wo + zx) * C + 2 * c2) = __floats2half2_rn(a0, a1);
+    uint4 o;
+    __half2* oh = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) oh[j] = __floats2half2_rn(acc[2 * j], acc[2 * j + 1]);
+    *reinterpret_cast<uint4*>(out + (((size_t)b * Ho + zy) * Wo + zx) * C + 8 * c8) = o;
   }
 }
 
@@ -541,7 +553,7 @@ cudaError_t k_from_rgb(const float* images, const float* Wt, const float* bias, 
   GLASS_RET();
 }
 cudaError_t k_fir_down(const __half* x, __half* out, int N, int H, int W, int C, cudaStream_t s) {
-  fir_down_kernel<<<blocks_for((size_t)N * (H / 2) * (W / 2) * (C / 2)), kThreads, 0, s>>>(x, out, N, H, W, C);
+  fir_down_kernel<<<blocks_for((size_t)N * (H / 2) * (W / 2) * (C / 8), kThreads, 148 * 32), kThreads, 0, s>>>(x, out, N, H, W, C);
   GLASS_RET();
 }
 cudaError_t k_mbstd(const __half* x, __half* out, int P, int batch, int group, int C, int Cpad, cudaStream_t s) {
