@@ -133,7 +133,7 @@ struct Cfg {
   static constexpr int kStageBytes = MODE == 0 ? kABytes + kBBytes : 3 * kCopyBytes;
   static constexpr int kWBytes = MODE == 0 ? 0 : 9 * kBBytes;                  // resident taps (MODE 1)
   static constexpr int kParamBytes = 2 * kNumParams * BN * 4;      // double-buffered per-tile epilogue parameters
-  static constexpr int kBudget = 200 * 1024 - kParamBytes - kWBytes;
+  static constexpr int kBudget = 222 * 1024 - kParamBytes - kWBytes;   // 227 KB/CTA minus alignment + barriers
   static constexpr int kStagesRaw = kBudget / kStageBytes;
   static constexpr int kStages = kStagesRaw > 12 ? 12 : kStagesRaw;
   static_assert(kStages >= 2, "not enough shared memory for a double-buffered pipeline");
