@@ -53,6 +53,7 @@ struct ConvParams {
   int taps;                 // 9 or 1
   int Ntot;                 // multiple of BN
   int BN, BK;
+  int pow2, sh_n, sh_x, sh_y;  // tile grid is a power of two in every dimension: decode with shifts
   int mode;                 // 0 = streamed taps, 1 = resident taps + halo copies (conv_tc.cu)
   const __half* in;         // [Nimg][H][W][Cin]   (SIMT bring-up path; the TC path reads through TMA)
   const __half* wgt;        // [taps][Ntot][Cin]

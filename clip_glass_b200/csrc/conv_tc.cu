@@ -39,12 +39,14 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 }
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
+  // the suspend-time hint lets the hardware park the thread instead of burning issue slots that the
+  // epilogue warps on the same scheduler need
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
       "selp.b32 %0, 1, 0, p;\n\t}"
       : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(20000u)
       : "memory");
   return ok != 0;
 }
@@ -52,8 +54,9 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
   const long long t0 = clock64();
+  uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > kWaitLimitCycles) {
+    if ((++spins & 63u) == 0 && clock64() - t0 > kWaitLimitCycles) {
       printf("glass conv_tc: mbarrier timeout (block %d thread %d)\n", blockIdx.x, threadIdx.x);
       __trap();
     }
@@ -112,6 +115,25 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
   return (uint64_t)((saddr & 0x3FFFF) >> 4) | (1ull << 16) | (kSbo << 32) | (1ull << 46) | (kLayout << 61);
 }
 
+struct TileCoord { int n_tile, tx, ty, tn; };
+__device__ __forceinline__ TileCoord decode_tile(const ConvParams& p, int tile, int n_tiles) {
+  TileCoord t;
+  if (p.pow2) {
+    t.n_tile = tile & (n_tiles - 1);
+    int m = tile >> p.sh_n;
+    t.tx = m & (p.tiles_x - 1); m >>= p.sh_x;
+    t.ty = m & (p.tiles_y - 1);
+    t.tn = m >> p.sh_y;
+  } else {
+    t.n_tile = tile % n_tiles;
+    int m = tile / n_tiles;
+    t.tx = m % p.tiles_x; m /= p.tiles_x;
+    t.ty = m % p.tiles_y;
+    t.tn = m / p.tiles_y;
+  }
+  return t;
+}
+
 constexpr int kEpiWarps = 8;
 constexpr int kEpiThreads = kEpiWarps * 32;
 constexpr int kNumParams = 6;   // scale, shift, oscale, rgb0, rgb1, rgb2
@@ -132,8 +154,11 @@ struct Cfg {
   static constexpr int kCopyBytes = (kHaloTH + 2) * kHaloTW * BK * 2;          // one dx-copy of the halo tile
   static constexpr int kStageBytes = MODE == 0 ? kABytes + kBBytes : 3 * kCopyBytes;
   static constexpr int kWBytes = MODE == 0 ? 0 : 9 * kBBytes;                  // resident taps (MODE 1)
-  static constexpr int kParamBytes = 2 * kNumParams * BN * 4;      // double-buffered per-tile epilogue parameters
-  static constexpr int kBudget = 222 * 1024 - kParamBytes - kWBytes;   // 227 KB/CTA minus alignment + barriers
+  // double-buffered per-tile epilogue parameters + 2 x 128 float4 for combining the two column halves' toRGB sums
+  static constexpr int kParamBytes = 2 * kNumParams * BN * 4 + 2 * 128 * 16;
+  // the 32-channel MODE-1 layers are bookkeeping/latency-bound, not smem-bound: run two CTAs per SM there
+  static constexpr int kMinBlocks = (MODE == 1 && BK == 32 && BN <= 64) ? 2 : 1;
+  static constexpr int kBudget = (kMinBlocks == 2 ? 110 : 222) * 1024 - kParamBytes - kWBytes;   // of 227 KB/SM
   static constexpr int kStagesRaw = kBudget / kStageBytes;
   static constexpr int kStages = kStagesRaw > 12 ? 12 : kStagesRaw;
   static_assert(kStages >= 2, "not enough shared memory for a double-buffered pipeline");
@@ -228,7 +253,7 @@ __device__ __forceinline__ void epilogue_fast16(const EpiParams& e, const float*
 }
 
 template <int BN, int BK, int MODE>
-__global__ void __launch_bounds__(kNumThreads, 1)
+__global__ void __launch_bounds__(kNumThreads, (Cfg<BN, BK, MODE>::kMinBlocks))
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                const ConvParams p) {
   using C = Cfg<BN, BK, MODE>;
@@ -236,6 +261,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   uint8_t* smem_w = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem = smem_w + C::kWBytes;       // pipeline stages
   float* params = reinterpret_cast<float*>(smem + C::kStages * C::kStageBytes);
+  float4* rgb_stage = reinterpret_cast<float4*>(params + 2 * kNumParams * BN);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::kStages * C::kStageBytes + C::kParamBytes);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + C::kStages;
@@ -289,12 +315,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           tma_load_3d(&map_b, smem_w + tap * C::kBBytes, w_bar, 0, n_tile * BN, tap);
       }
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int n_tile = tile % n_tiles;
-        int m = tile / n_tiles;
-        const int tx = m % p.tiles_x; m /= p.tiles_x;
-        const int ty = m % p.tiles_y;
-        const int tn = m / p.tiles_y;
-        const int x0 = tx * p.TW, y0 = ty * p.TH, i0 = tn * p.TN;
+        const TileCoord tc = decode_tile(p, tile, n_tiles);
+        const int n_tile = tc.n_tile;
+        const int x0 = tc.tx * p.TW, y0 = tc.ty * p.TH, i0 = tc.tn * p.TN;
         if (MODE == 1) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * C::kStageBytes;
@@ -396,21 +419,46 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     const float gain = (e.act == kActLrelu) ? kSqrt2 : 1.f;
     constexpr int kHalf = BN / 2;
     constexpr int kChunks = kHalf / 16;
+    const bool d2s = (e.store_mode == kStoreDepthToSpace);
+    const float nscale = (e.noise != nullptr) ? gain * __ldg(e.noise_strength) : 0.f;
+    // Noise of the NEXT tile is fetched while the current one is processed: the (L2/DRAM) latency of this
+    // scattered 4-byte load would otherwise sit on the critical path of every tile.
+    auto fetch_noise = [&](int t, float (&dst)[kChunks]) {
+#pragma unroll
+      for (int c = 0; c < kChunks; ++c) dst[c] = 0.f;
+      if (e.noise == nullptr || t >= total_tiles) return;
+      const TileCoord c2 = decode_tile(p, t, n_tiles);
+      const int img2 = c2.tn * p.TN + ri, y2 = c2.ty * p.TH + ry, x2 = c2.tx * p.TW + rx;
+      if (!(img2 < p.Nimg && y2 < p.H && x2 < p.W)) return;
+      const float* base = e.noise + (size_t)(img2 / e.noise_group_div) * e.noise_group_stride;
+      if (d2s) {
+#pragma unroll
+        for (int c = 0; c < kChunks; ++c) {
+          const int ph = (c2.n_tile * BN + half * kHalf + c * 16) / e.Cout;
+          dst[c] = __ldg(base + (size_t)(2 * y2 + (ph >> 1)) * (2 * p.W) + 2 * x2 + (ph & 1));
+        }
+      } else {
+        dst[0] = __ldg(base + (size_t)y2 * p.W + x2);
+      }
+    };
+    float nz_next[kChunks];
+    fetch_noise(blockIdx.x, nz_next);
     int it = 0;
     int staged_img = -1, staged_ntile = -1;
     int pbuf = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
-      const int n_tile = tile % n_tiles;
-      int m = tile / n_tiles;
-      const int tx = m % p.tiles_x; m /= p.tiles_x;
-      const int ty = m % p.tiles_y;
-      const int tn = m / p.tiles_y;
-      const int img = tn * p.TN + ri, y = ty * p.TH + ry, x = tx * p.TW + rx;
+      const TileCoord tc = decode_tile(p, tile, n_tiles);
+      const int n_tile = tc.n_tile, tn = tc.tn;
+      const int img = tn * p.TN + ri, y = tc.ty * p.TH + ry, x = tc.tx * p.TW + rx;
       const bool valid = img < p.Nimg && y < p.H && x < p.W;
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + as * BN + half * kHalf;
       float rgb[3] = {0.f, 0.f, 0.f};
+      float nz_cur[kChunks];
+#pragma unroll
+      for (int c = 0; c < kChunks; ++c) nz_cur[c] = nz_next[c];
+      if (fast) fetch_noise(tile + gridDim.x, nz_next);
 
       if (fast) {
         // ---- stage the per-(image, n_tile) parameters once; reuse while they do not change ----
@@ -452,12 +500,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             out_base = (((size_t)(img * (p.H >> 1) + (y >> 1)) * (p.W >> 1) + (x >> 1)) * 4 + ((y & 1) * 2 + (x & 1))) *
                            p.Ntot + n_first;
           }
-          if (e.noise != nullptr && e.store_mode != kStoreDepthToSpace) {
-            nz = gain * __ldg(e.noise_strength) *
-                 __ldg(e.noise + (size_t)(img / e.noise_group_div) * e.noise_group_stride + (size_t)y * p.W + x);
-          }
         }
         (void)chunk_stride;
+        (void)nz;
         mbar_wait(&tmem_full[as], aphase);
         tc_fence_after();
         uint32_t acc[2][16];
@@ -468,18 +513,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           if (c + 1 < kChunks) tc_ld16_issue(taddr + (c + 1) * 16, acc[(c + 1) & 1]);
           if (valid) {
             const int j0 = half * kHalf + c * 16;
-            float nzc = nz;
+            const float nzc = nscale * nz_cur[d2s ? c : 0];
             __half* optr = nullptr;
-            if (e.store_mode == kStoreDepthToSpace) {
+            if (d2s) {
               // column n -> phase (py,px) and channel o; output pixel (2y+py, 2x+px)
               const int n0 = n_tile * BN + j0;
               const int ph = n0 / e.Cout, o0 = n0 - ph * e.Cout;
               const int yo = 2 * y + (ph >> 1), xo = 2 * x + (ph & 1);
-              if (e.noise != nullptr) {
-                nzc = gain * __ldg(e.noise_strength) *
-                      __ldg(e.noise + (size_t)(img / e.noise_group_div) * e.noise_group_stride +
-                            (size_t)yo * (2 * p.W) + xo);
-              }
               if (e.out != nullptr) optr = e.out + ((size_t)(img * 2 * p.H + yo) * (2 * p.W) + xo) * e.Cout + o0;
             } else if (e.out != nullptr) {
               optr = e.out + out_base + c * 16;
@@ -500,9 +540,18 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           if (valid) epilogue_row16(p, img, y, x, n_tile * BN + half * kHalf + c * 16, v, rgb);
         }
       }
-      if (valid && e.rgb_w != nullptr) {
-        const size_t pix = ((size_t)img * p.H + y) * p.W + x;
-        e.rgb_out[(size_t)(n_tile * 2 + half) * p.Nimg * p.H * p.W + pix] = make_float4(rgb[0], rgb[1], rgb[2], 0.f);
+      if (e.rgb_w != nullptr) {
+        // the two warps of a lane quarter own different column halves of the same rows: combine their
+        // partial toRGB sums in shared memory so that one float4 per pixel goes to HBM
+        float4* stg = rgb_stage + (it & 1) * 128;
+        if (half == 1) stg[row] = make_float4(rgb[0], rgb[1], rgb[2], 0.f);
+        asm volatile("bar.sync %0, 64;" ::"r"(2 + q) : "memory");
+        if (half == 0 && valid) {
+          const float4 o = stg[row];
+          const size_t pix = ((size_t)img * p.H + y) * p.W + x;
+          e.rgb_out[(size_t)n_tile * p.Nimg * p.H * p.W + pix] =
+              make_float4(rgb[0] + o.x, rgb[1] + o.y, rgb[2] + o.z, 0.f);
+        }
       }
       tc_fence_before();
       __syncwarp();
@@ -531,7 +580,8 @@ cudaError_t launch_one(const ConvParams& p, const TmaMaps& maps, int num_sms, cu
   }
   const int n_tiles = p.Ntot / BN;
   const int total = p.tiles_n * p.tiles_y * p.tiles_x * n_tiles;
-  int grid = total < num_sms ? total : num_sms;
+  const int ctas = num_sms * C::kMinBlocks;
+  int grid = total < ctas ? total : ctas;
   if (MODE == 1) grid = (grid / n_tiles) * n_tiles;   // keeps tile % n_tiles constant per CTA (resident taps)
   if (grid <= 0) return cudaErrorInvalidValue;
   conv_tc_kernel<BN, BK, MODE><<<grid, kNumThreads, C::kSmemBytes, s>>>(maps.a, maps.b, p);
@@ -576,7 +626,7 @@ __global__ void conv_simt_kernel(const ConvParams p) {
     epilogue_row16(p, img, y, x, g * 16, acc, rgb);
     if (p.epi.rgb_w != nullptr) {
       const size_t opix = ((size_t)img * p.H + y) * p.W + x;
-      const int slab = (g * 16) / (p.BN / 2);   // same half-tile slabs as the tensor-core path
+      const int slab = (g * 16) / p.BN;
       float* dst = reinterpret_cast<float*>(p.epi.rgb_out + (size_t)slab * p.Nimg * p.H * p.W + opix);
       atomicAdd(dst + 0, rgb[0]);
       atomicAdd(dst + 1, rgb[1]);
@@ -614,7 +664,7 @@ cudaError_t launch_conv_simt(const ConvParams& p, cudaStream_t s) {
   if (p.epi.rgb_w != nullptr) {
     // bring-up path accumulates toRGB partials with atomics: clear the slabs first
     cudaError_t err = cudaMemsetAsync(p.epi.rgb_out, 0,
-                                      sizeof(float4) * (size_t)(2 * p.Ntot / p.BN) * p.Nimg * p.H * p.W, s);
+                                      sizeof(float4) * (size_t)(p.Ntot / p.BN) * p.Nimg * p.H * p.W, s);
     if (err != cudaSuccess) return err;
   }
   conv_simt_kernel<<<blocks, 128, 0, s>>>(p);

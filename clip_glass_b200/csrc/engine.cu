@@ -199,6 +199,12 @@ int make_conv(glass_engine* e, ConvLaunch* out, const __half* in, int Nimg, int 
     const int bn_cap = (Cin == 64) ? 64 : 128;         // 9 resident taps must leave room for >= 2 stages
     while (p.BN > bn_cap) p.BN /= 2;
   }
+  {
+    auto lg = [](int v) { int s = 0; while ((1 << s) < v) ++s; return ((1 << s) == v) ? s : -1; };
+    const int ln = lg(Ntot / p.BN), lx = lg(p.tiles_x), ly = lg(p.tiles_y);
+    p.pow2 = (ln >= 0 && lx >= 0 && ly >= 0) ? 1 : 0;
+    p.sh_n = ln; p.sh_x = lx; p.sh_y = ly;
+  }
   if (e->cfg.conv_impl != 0) return GLASS_OK;   // SIMT bring-up path needs no descriptors
   // activations: [C, W, H, N]; outermost extent rounded up to the box (buffers carry the slack)
   const uint64_t wdecl = gemm ? (uint64_t)p.tiles_x * 128 : (uint64_t)W;
@@ -384,7 +390,7 @@ void layout_workspace(glass_engine* e, Arena& a) {
   for (const GLayer& l : e->glayers) {
     act_elems = std::max(act_elems, P * (size_t)l.res * l.res * l.cout);
     const int bn = pick_bn(l.cout);
-    if (bn) slab_elems = std::max(slab_elems, (size_t)(2 * l.cout / bn) * P * l.res * l.res);   // half-tile slabs
+    if (bn) slab_elems = std::max(slab_elems, (size_t)(l.cout / 32) * P * l.res * l.res);   // worst case BN = 32
   }
   // every activation row is at least 32 channels wide; slack covers box overhang in the outermost dim
   const size_t slack = kSlackRows * 512;
@@ -624,7 +630,7 @@ int run_generator(glass_engine* e, const float* z, int P, const glass_noise* nz,
     if (last_in_block) {
       const bool final_block = (li + 1 == nl);
       snprintf(nm, sizeof nm, "g.rgb%d.bias", l.block);
-      const int n_slabs = 2 * cl.p.Ntot / cl.p.BN;   // each epilogue warp pair writes its own half-tile partial
+      const int n_slabs = cl.p.Ntot / cl.p.BN;
       LAUNCH(k_rgb_combine(have_y ? ybuf[ycur] : nullptr, e->slabs, n_slabs, tptr<float>(e, nm), ybuf[ycur ^ 1],
                            final_block ? images_out : nullptr, P, l.res, l.res, s));
       ycur ^= 1;
