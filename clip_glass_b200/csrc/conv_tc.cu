@@ -152,12 +152,13 @@ struct Cfg {
   static constexpr int kABytes = kBlockM * BK * 2;
   static constexpr int kBBytes = BN * BK * 2;
   static constexpr int kCopyBytes = (kHaloTH + 2) * kHaloTW * BK * 2;          // one dx-copy of the halo tile
-  static constexpr int kStageBytes = MODE == 0 ? kABytes + kBBytes : 3 * kCopyBytes;
-  static constexpr int kWBytes = MODE == 0 ? 0 : 9 * kBBytes;                  // resident taps (MODE 1)
+  // MODE 2 = MODE 1 for 1x1 convs: one resident tap, one un-haloed tile per stage
+  static constexpr int kStageBytes = MODE == 0 ? kABytes + kBBytes : (MODE == 1 ? 3 * kCopyBytes : kABytes);
+  static constexpr int kWBytes = MODE == 0 ? 0 : (MODE == 1 ? 9 : 1) * kBBytes;   // resident taps
   // double-buffered per-tile epilogue parameters + 2 x 128 float4 for combining the two column halves' toRGB sums
   static constexpr int kParamBytes = 2 * kNumParams * BN * 4 + 2 * 128 * 16;
   // the 32-channel MODE-1 layers are bookkeeping/latency-bound, not smem-bound: run two CTAs per SM there
-  static constexpr int kMinBlocks = (MODE == 1 && BK == 32 && BN <= 64) ? 2 : 1;
+  static constexpr int kMinBlocks = (MODE == 1 && BK == 32 && BN <= 32) ? 2 : 1;
   static constexpr int kBudget = (kMinBlocks == 2 ? 110 : 222) * 1024 - kParamBytes - kWBytes;   // of 227 KB/SM
   static constexpr int kStagesRaw = kBudget / kStageBytes;
   static constexpr int kStages = kStagesRaw > 12 ? 12 : kStagesRaw;
@@ -307,7 +308,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      if (MODE == 1) {
+      if (MODE != 0) {
         // resident filter taps of this CTA's n-tile (grid is a multiple of n_tiles, so n_tile is fixed)
         const int n_tile = blockIdx.x % n_tiles;
         mbar_expect_tx(w_bar, p.taps * C::kBBytes);
@@ -318,7 +319,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         const TileCoord tc = decode_tile(p, tile, n_tiles);
         const int n_tile = tc.n_tile;
         const int x0 = tc.tx * p.TW, y0 = tc.ty * p.TH, i0 = tc.tn * p.TN;
-        if (MODE == 1) {
+        if (MODE != 0) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * C::kStageBytes;
           if (p.taps == 9) {
@@ -354,7 +355,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
-      if (MODE == 1) {
+      if (MODE != 0) {
         mbar_wait(w_bar, 0);
         tc_fence_after();
       }
@@ -364,7 +365,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         mbar_wait(&tmem_empty[as], aphase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + as * BN;
-        if (MODE == 1) {
+        if (MODE != 0) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * C::kStageBytes);
@@ -582,7 +583,7 @@ cudaError_t launch_one(const ConvParams& p, const TmaMaps& maps, int num_sms, cu
   const int total = p.tiles_n * p.tiles_y * p.tiles_x * n_tiles;
   const int ctas = num_sms * C::kMinBlocks;
   int grid = total < ctas ? total : ctas;
-  if (MODE == 1) grid = (grid / n_tiles) * n_tiles;   // keeps tile % n_tiles constant per CTA (resident taps)
+  if (MODE != 0) grid = (grid / n_tiles) * n_tiles;   // keeps tile % n_tiles constant per CTA (resident taps)
   if (grid <= 0) return cudaErrorInvalidValue;
   conv_tc_kernel<BN, BK, MODE><<<grid, kNumThreads, C::kSmemBytes, s>>>(maps.a, maps.b, p);
   return cudaGetLastError();
@@ -653,6 +654,13 @@ cudaError_t launch_conv_tc(const ConvParams& p, const TmaMaps& maps, int num_sms
   GLASS_CASE(128, 32, 1)
   GLASS_CASE(32, 64, 1)
   GLASS_CASE(64, 64, 1)
+  GLASS_CASE(32, 32, 2)
+  GLASS_CASE(64, 32, 2)
+  GLASS_CASE(128, 32, 2)
+  GLASS_CASE(32, 64, 2)
+  GLASS_CASE(64, 64, 2)
+  GLASS_CASE(128, 64, 2)
+  GLASS_CASE(256, 64, 2)
 #undef GLASS_CASE
   return cudaErrorInvalidValue;
 }

@@ -195,9 +195,14 @@ int make_conv(glass_engine* e, ConvLaunch* out, const __half* in, int Nimg, int 
   // Small-channel layers (the whole K of a tap is one chunk) on full 16x8 tiles: resident taps + halo copies.
   p.mode = 0;
   if (!gemm && (Cin == 32 || Cin == 64) && p.TW == 16 && p.TH == 8 && p.TN == 1 && (taps == 9 || taps == 1)) {
-    p.mode = 1;
-    const int bn_cap = (Cin == 64) ? 64 : 128;         // 9 resident taps must leave room for >= 2 stages
-    while (p.BN > bn_cap) p.BN /= 2;
+    if (taps == 9) {
+      p.mode = 1;
+      const int bn_cap = (Cin == 64) ? 64 : 128;       // 9 resident taps must leave room for >= 2 stages
+      while (p.BN > bn_cap) p.BN /= 2;
+    } else {
+      p.mode = 2;                                      // 1x1: one resident tap, BN up to 256 (Cin 64) / 128 (Cin 32)
+      if (Cin == 32 && p.BN > 128) p.BN = 128;
+    }
   }
   {
     auto lg = [](int v) { int s = 0; while ((1 << s) < v) ++s; return ((1 << s) == v) ? s : -1; };
