@@ -43,6 +43,8 @@ struct EpiParams {
   __half* out;              // null => nothing stored (G's last conv only feeds toRGB)
   int store_mode;
   int Cout;                 // per-phase channel count (== Ntot unless depth-to-space)
+  int cout_shift;           // log2(Cout) when Cout is a power of two, else -1
+  int noise_div_shift;      // log2(noise_group_div) when it is a power of two, else -1
 };
 
 struct ConvParams {
@@ -53,6 +55,7 @@ struct ConvParams {
   int taps;                 // 9 or 1
   int Ntot;                 // multiple of BN
   int BN, BK;
+  int all_valid;            // H % TH == 0 && W % TW == 0 && Nimg % TN == 0: no row of any tile is out of range
   int pow2, sh_n, sh_x, sh_y;  // tile grid is a power of two in every dimension: decode with shifts
   int mode;                 // 0 = streamed taps, 1 = resident taps + halo copies (conv_tc.cu)
   const __half* in;         // [Nimg][H][W][Cin]   (SIMT bring-up path; the TC path reads through TMA)

@@ -259,7 +259,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                const ConvParams p) {
   using C = Cfg<BN, BK, MODE>;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem_w = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // (offset arithmetic on the extern array keeps the pointers in the shared address space: LDS/STS, not generic LD/ST)
+  uint8_t* smem_w = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* smem = smem_w + C::kWBytes;       // pipeline stages
   float* params = reinterpret_cast<float*>(smem + C::kStages * C::kStageBytes);
   float4* rgb_stage = reinterpret_cast<float4*>(params + 2 * kNumParams * BN);
@@ -421,37 +422,51 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     constexpr int kHalf = BN / 2;
     constexpr int kChunks = kHalf / 16;
     const bool d2s = (e.store_mode == kStoreDepthToSpace);
+    const bool s2d = (e.store_mode == kStoreSpaceToDepth);
+    const bool has_rgb = (e.rgb_w != nullptr);
     const float nscale = (e.noise != nullptr) ? gain * __ldg(e.noise_strength) : 0.f;
+    // All index math below is 32-bit pixel arithmetic (pixel counts stay < 2^31); one 64-bit multiply per tile
+    // turns a pixel index into an element offset.  Per-thread row offsets are loop invariants.
+    const int W = p.W, H = p.H;
+    const int row_reg = ry * W + rx;                                              // NHWC pixel offset inside the tile
+    const int row_d2s = (2 * ry) * (2 * W) + 2 * rx;                              // depth-to-space: top-left output pixel
+    const int row_s2d = (((ry >> 1) * (W >> 1) + (rx >> 1)) << 2) + ((ry & 1) * 2 + (rx & 1));
+    const int cout_sh = e.cout_shift;       // log2(Cout) or -1
+    const int ngrp_sh = e.noise_div_shift;  // log2(noise_group_div) or -1
+
     // Noise of the NEXT tile is fetched while the current one is processed: the (L2/DRAM) latency of this
     // scattered 4-byte load would otherwise sit on the critical path of every tile.
-    auto fetch_noise = [&](int t, float (&dst)[kChunks]) {
+    auto fetch_noise = [&](const TileCoord& c2, bool in_range, float (&dst)[kChunks]) {
 #pragma unroll
       for (int c = 0; c < kChunks; ++c) dst[c] = 0.f;
-      if (e.noise == nullptr || t >= total_tiles) return;
-      const TileCoord c2 = decode_tile(p, t, n_tiles);
+      if (e.noise == nullptr || !in_range) return;
       const int img2 = c2.tn * p.TN + ri, y2 = c2.ty * p.TH + ry, x2 = c2.tx * p.TW + rx;
-      if (!(img2 < p.Nimg && y2 < p.H && x2 < p.W)) return;
-      const float* base = e.noise + (size_t)(img2 / e.noise_group_div) * e.noise_group_stride;
+      if (!p.all_valid && !(img2 < p.Nimg && y2 < H && x2 < W)) return;
+      const int grp = ngrp_sh >= 0 ? (img2 >> ngrp_sh) : (img2 / e.noise_group_div);
+      const float* base = e.noise + (size_t)grp * e.noise_group_stride;
       if (d2s) {
+        const float* b2 = base + (size_t)(2 * y2) * (2 * W) + 2 * x2;
 #pragma unroll
         for (int c = 0; c < kChunks; ++c) {
-          const int ph = (c2.n_tile * BN + half * kHalf + c * 16) / e.Cout;
-          dst[c] = __ldg(base + (size_t)(2 * y2 + (ph >> 1)) * (2 * p.W) + 2 * x2 + (ph & 1));
+          const int n0 = c2.n_tile * BN + half * kHalf + c * 16;
+          const int ph = cout_sh >= 0 ? (n0 >> cout_sh) : (n0 / e.Cout);
+          dst[c] = __ldg(b2 + (ph >> 1) * (2 * W) + (ph & 1));
         }
       } else {
-        dst[0] = __ldg(base + (size_t)y2 * p.W + x2);
+        dst[0] = __ldg(base + y2 * W + x2);
       }
     };
     float nz_next[kChunks];
-    fetch_noise(blockIdx.x, nz_next);
+    TileCoord tc_next = decode_tile(p, blockIdx.x, n_tiles);
+    fetch_noise(tc_next, true, nz_next);
     int it = 0;
     int staged_img = -1, staged_ntile = -1;
     int pbuf = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
-      const TileCoord tc = decode_tile(p, tile, n_tiles);
+      const TileCoord tc = tc_next;
       const int n_tile = tc.n_tile, tn = tc.tn;
       const int img = tn * p.TN + ri, y = tc.ty * p.TH + ry, x = tc.tx * p.TW + rx;
-      const bool valid = img < p.Nimg && y < p.H && x < p.W;
+      const bool valid = p.all_valid || (img < p.Nimg && y < H && x < W);
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + as * BN + half * kHalf;
@@ -459,7 +474,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       float nz_cur[kChunks];
 #pragma unroll
       for (int c = 0; c < kChunks; ++c) nz_cur[c] = nz_next[c];
-      if (fast) fetch_noise(tile + gridDim.x, nz_next);
+      {
+        const int nt = tile + gridDim.x;
+        const bool more = nt < total_tiles;
+        if (more) tc_next = decode_tile(p, nt, n_tiles);
+        if (fast) fetch_noise(tc_next, more, nz_next);
+      }
 
       if (fast) {
         // ---- stage the per-(image, n_tile) parameters once; reuse while they do not change ----
@@ -469,14 +489,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           float* par = params + pbuf * (kNumParams * BN);
           if (et < BN) {
             const int n = n_tile * BN + et;
-            const int o = n % e.Cout;
+            const int o = cout_sh >= 0 ? (n & (e.Cout - 1)) : (n % e.Cout);
             const float d = e.dmod != nullptr ? __ldg(e.dmod + (size_t)timg * e.Cout + o) : 1.f;
             const float b = e.bias != nullptr ? __ldg(e.bias + o) : 0.f;
             const float osn = e.out_scale != nullptr ? __ldg(e.out_scale + (size_t)timg * e.out_scale_stride + o) : 1.f;
             par[0 * BN + et] = d * gain;
             par[1 * BN + et] = b * gain;
             par[2 * BN + et] = osn * e.post_scale;
-            if (e.rgb_w != nullptr) {
+            if (has_rgb) {
               const float* rw = e.rgb_w + (size_t)timg * 3 * e.Cout + o;
               par[3 * BN + et] = __ldg(rw);
               par[4 * BN + et] = __ldg(rw + e.Cout);
@@ -488,22 +508,21 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           epi_bar_sync();                    // all 8 epilogue warps take the same branch (uniform condition)
         }
         const float* par = params + pbuf * (kNumParams * BN);
-        // ---- per-row constants (issued before waiting for the accumulator) ----
+        // ---- per-tile addresses ----
         const int n_first = n_tile * BN + half * kHalf;
-        float nz = 0.f;
-        size_t out_base = 0, res_base = 0;
-        int chunk_stride = 16;               // elements between consecutive 16-column chunks in the output
-        if (valid) {
-          res_base = ((size_t)(img * p.H + y) * p.W + x) * p.Ntot + n_first;
-          if (e.store_mode == kStoreRegular) {
-            out_base = res_base;
-          } else if (e.store_mode == kStoreSpaceToDepth) {
-            out_base = (((size_t)(img * (p.H >> 1) + (y >> 1)) * (p.W >> 1) + (x >> 1)) * 4 + ((y & 1) * 2 + (x & 1))) *
-                           p.Ntot + n_first;
+        const int pix = (img * H + tc.ty * p.TH) * W + tc.tx * p.TW + row_reg;          // NHWC pixel index of this row
+        const __half* res_row = e.residual != nullptr ? e.residual + (size_t)pix * p.Ntot + n_first : nullptr;
+        __half* out_row = nullptr;           // regular / space-to-depth: contiguous columns
+        int d2s_pix = 0;
+        if (e.out != nullptr) {
+          if (s2d) {
+            const int org = ((img * (H >> 1) + ((tc.ty * p.TH) >> 1)) * (W >> 1) + ((tc.tx * p.TW) >> 1)) << 2;
+            out_row = e.out + (size_t)(org + row_s2d) * p.Ntot + n_first;
+          } else if (!d2s) {
+            out_row = e.out + (size_t)pix * p.Ntot + n_first;
           }
         }
-        (void)chunk_stride;
-        (void)nz;
+        if (d2s) d2s_pix = (img * 2 * H + 2 * tc.ty * p.TH) * (2 * W) + 2 * tc.tx * p.TW + row_d2s;
         mbar_wait(&tmem_full[as], aphase);
         tc_fence_after();
         uint32_t acc[2][16];
@@ -519,14 +538,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             if (d2s) {
               // column n -> phase (py,px) and channel o; output pixel (2y+py, 2x+px)
               const int n0 = n_tile * BN + j0;
-              const int ph = n0 / e.Cout, o0 = n0 - ph * e.Cout;
-              const int yo = 2 * y + (ph >> 1), xo = 2 * x + (ph & 1);
-              if (e.out != nullptr) optr = e.out + ((size_t)(img * 2 * p.H + yo) * (2 * p.W) + xo) * e.Cout + o0;
-            } else if (e.out != nullptr) {
-              optr = e.out + out_base + c * 16;
+              const int ph = cout_sh >= 0 ? (n0 >> cout_sh) : (n0 / e.Cout);
+              const int o0 = n0 - ph * e.Cout;
+              if (e.out != nullptr)
+                optr = e.out + (size_t)(d2s_pix + (ph >> 1) * (2 * W) + (ph & 1)) * e.Cout + o0;
+            } else if (out_row != nullptr) {
+              optr = out_row + c * 16;
             }
-            const __half* rptr = e.residual != nullptr ? e.residual + res_base + c * 16 : nullptr;
-            if (e.rgb_w != nullptr) epilogue_fast16<true>(e, par, BN, j0, acc[c & 1], nzc, rptr, optr, rgb);
+            const __half* rptr = res_row != nullptr ? res_row + c * 16 : nullptr;
+            if (has_rgb) epilogue_fast16<true>(e, par, BN, j0, acc[c & 1], nzc, rptr, optr, rgb);
             else epilogue_fast16<false>(e, par, BN, j0, acc[c & 1], nzc, rptr, optr, rgb);
           }
         }
@@ -541,7 +561,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           if (valid) epilogue_row16(p, img, y, x, n_tile * BN + half * kHalf + c * 16, v, rgb);
         }
       }
-      if (e.rgb_w != nullptr) {
+      if (has_rgb) {
         // the two warps of a lane quarter own different column halves of the same rows: combine their
         // partial toRGB sums in shared memory so that one float4 per pixel goes to HBM
         float4* stg = rgb_stage + (it & 1) * 128;
@@ -549,9 +569,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         asm volatile("bar.sync %0, 64;" ::"r"(2 + q) : "memory");
         if (half == 0 && valid) {
           const float4 o = stg[row];
-          const size_t pix = ((size_t)img * p.H + y) * p.W + x;
-          e.rgb_out[(size_t)n_tile * p.Nimg * p.H * p.W + pix] =
-              make_float4(rgb[0] + o.x, rgb[1] + o.y, rgb[2] + o.z, 0.f);
+          const size_t pix = ((size_t)img * H + y) * W + x;
+          e.rgb_out[(size_t)n_tile * p.Nimg * H * W + pix] = make_float4(rgb[0] + o.x, rgb[1] + o.y, rgb[2] + o.z, 0.f);
         }
       }
       tc_fence_before();

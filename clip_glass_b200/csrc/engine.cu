@@ -209,6 +209,9 @@ int make_conv(glass_engine* e, ConvLaunch* out, const __half* in, int Nimg, int 
     const int ln = lg(Ntot / p.BN), lx = lg(p.tiles_x), ly = lg(p.tiles_y);
     p.pow2 = (ln >= 0 && lx >= 0 && ly >= 0) ? 1 : 0;
     p.sh_n = ln; p.sh_x = lx; p.sh_y = ly;
+    p.all_valid = (H % p.TH == 0 && W % p.TW == 0 && Nimg % p.TN == 0) ? 1 : 0;
+    p.epi.cout_shift = lg(p.epi.Cout);
+    p.epi.noise_div_shift = lg(p.epi.noise_group_div);
   }
   if (e->cfg.conv_impl != 0) return GLASS_OK;   // SIMT bring-up path needs no descriptors
   // activations: [C, W, H, N]; outermost extent rounded up to the box (buffers carry the slack)
