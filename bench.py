@@ -90,6 +90,13 @@ class ClockSampler(threading.Thread):
                     reasons=sorted(reasons), samples=len(sm))
 
 
+def best_cpu_threads():
+    """Threads for the CPU arm.  One 4-candidate minibatch does not scale past ~32 threads: measured on the
+    128-core GPU box (tests/cpu_threads_probe.py): 8 -> 0.35, 16 -> 0.38, 32 -> 0.38, 64 -> 0.32, 128 -> 0.05
+    candidates/s.  Using every core would make the baseline 7x slower than it can be, so cap at 32."""
+    return min(os.cpu_count() or 1, 32)
+
+
 def cpu_oracle_step(pop, batch, use_d, seed, threads):
     """One bounded sample of the SAME workload on the host cores: the oracle port of
     problem.py:14-29 (full ffhq-config-f G + ViT-B/32 + D, fp32 G/D, CLIP fp16 as built)."""
@@ -115,7 +122,7 @@ def run_reference(args, rank, world):
     timed on the host cores with every thread it can use.  Rank 0 only."""
     if rank != 0:
         return
-    threads = os.cpu_count() or 1
+    threads = best_cpu_threads()
     use_d = args.variant == "_d"
     sample = args.cpu_sample
     budget_s = 270.0
@@ -141,6 +148,7 @@ def run_reference(args, rank, world):
                     population_per_step=sample, note="bounded sample of the same workload on host cores"),
         cpu_baseline=dict(value=value, unit=UNIT, cores=threads, kind="port",
                           sample=f"{sample} candidates per step x {len(times)} steps (oracle port of problem.py:14-29; "
+                                 f"{threads} of {os.cpu_count()} host threads, the fastest setting measured; "
                                  "steps stop early once ~4.5 min of wall time is used)"),
         e2e=dict(value=value, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0),
     )
@@ -299,13 +307,14 @@ def main():
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        threads = os.cpu_count() or 1
+        threads = best_cpu_threads()
         cpu_oracle_step(args.cpu_sample, args.batch, use_d, 3, threads)            # warm
         ts = [cpu_oracle_step(args.cpu_sample, args.batch, use_d, 4 + i, threads) for i in range(2)]
         v = args.cpu_sample / statistics.median(ts)
         cpu_baseline = dict(value=v, unit=UNIT, cores=threads, kind="port",
                             sample=f"{args.cpu_sample} candidates (one minibatch) x 2 timed repetitions, median; "
-                                   "oracle port of problem.py:14-29 on torch CPU")
+                                   f"oracle port of problem.py:14-29 on torch CPU; {threads} of {os.cpu_count()} host "
+                                   "threads (more threads are slower for a 4-candidate minibatch, see best_cpu_threads)")
 
     if rank == 0:
         ms = float(ms_dev.mean())

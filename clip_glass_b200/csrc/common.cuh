@@ -55,6 +55,7 @@ struct ConvParams {
   int taps;                 // 9 or 1
   int Ntot;                 // multiple of BN
   int BN, BK;
+  int debug_skip;           // profiling aid (env GLASS_DEBUG_SKIP): 1 = epilogue only drains TMEM (results invalid)
   int all_valid;            // H % TH == 0 && W % TW == 0 && Nimg % TN == 0: no row of any tile is out of range
   int pow2, sh_n, sh_x, sh_y;  // tile grid is a power of two in every dimension: decode with shifts
   int mode;                 // 0 = streamed taps, 1 = resident taps + halo copies (conv_tc.cu)

@@ -531,7 +531,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         for (int c = 0; c < kChunks; ++c) {
           tc_ld_wait();
           if (c + 1 < kChunks) tc_ld16_issue(taddr + (c + 1) * 16, acc[(c + 1) & 1]);
-          if (valid) {
+          if (valid && !p.debug_skip) {
             const int j0 = half * kHalf + c * 16;
             const float nzc = nscale * nz_cur[d2s ? c : 0];
             __half* optr = nullptr;

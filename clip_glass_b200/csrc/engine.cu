@@ -9,6 +9,7 @@
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <string>
@@ -210,6 +211,8 @@ int make_conv(glass_engine* e, ConvLaunch* out, const __half* in, int Nimg, int 
     p.pow2 = (ln >= 0 && lx >= 0 && ly >= 0) ? 1 : 0;
     p.sh_n = ln; p.sh_x = lx; p.sh_y = ly;
     p.all_valid = (H % p.TH == 0 && W % p.TW == 0 && Nimg % p.TN == 0) ? 1 : 0;
+    const char* dbg = getenv("GLASS_DEBUG_SKIP");     // timing experiments only; never set in tests or bench
+    p.debug_skip = dbg ? atoi(dbg) : 0;
     p.epi.cout_shift = lg(p.epi.Cout);
     p.epi.noise_div_shift = lg(p.epi.noise_group_div);
   }
