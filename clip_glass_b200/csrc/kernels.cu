@@ -68,9 +68,23 @@ __global__ void vecmat_kernel(const float* __restrict__ in, int in_stride, const
   __syncthreads();
   const int n = blockIdx.x * blockDim.x + threadIdx.x;
   if (n >= N) return;
-  float acc = 0.f;
-#pragma unroll 4
-  for (int k = 0; k < K; ++k) acc = fmaf(row[k], __ldg(Wt + (size_t)k * N + n), acc);
+  // four independent accumulators and 16 loads in flight per thread: the loop is L2-latency-bound otherwise
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+  int k = 0;
+  for (; k + 16 <= K; k += 16) {
+    float w[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) w[j] = __ldg(Wt + (size_t)(k + j) * N + n);
+#pragma unroll
+    for (int j = 0; j < 16; j += 4) {
+      a0 = fmaf(row[k + j], w[j], a0);
+      a1 = fmaf(row[k + j + 1], w[j + 1], a1);
+      a2 = fmaf(row[k + j + 2], w[j + 2], a2);
+      a3 = fmaf(row[k + j + 3], w[j + 3], a3);
+    }
+  }
+  for (; k < K; ++k) a0 = fmaf(row[k], __ldg(Wt + (size_t)k * N + n), a0);
+  float acc = (a0 + a1) + (a2 + a3);
   if (bias != nullptr) acc += bias[n];
   if (mode == 1) acc = (acc > 0.f ? acc : 0.2f * acc) * kSqrt2;
   if (mode == 2) acc = rsqrtf(acc + 1e-8f);
@@ -350,71 +364,90 @@ __global__ void from_rgb_kernel(const float* __restrict__ images, const float* _
   for (int i = threadIdx.x; i < 3 * C; i += blockDim.x) w[i] = Wt[i];
   for (int i = threadIdx.x; i < C; i += blockDim.x) w[3 * C + i] = bias[i];
   __syncthreads();
+  constexpr int G = C / 8;                       // 8-channel groups per pixel; consecutive threads -> consecutive 16 B
   const size_t plane = (size_t)R * R;
-  const size_t n = (size_t)P * plane;
+  const size_t n = (size_t)P * plane * G;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-    const size_t b = i / plane, pix = i - b * plane;
+    const int g = (int)(i % G);
+    const size_t pixi = i / G;
+    const size_t b = pixi / plane, pix = pixi - b * plane;
     const float* ip = images + b * 3 * plane + pix;
-    const float r = ip[0] * 2.f - 1.f, g = ip[plane] * 2.f - 1.f, bl = ip[2 * plane] * 2.f - 1.f;
-    __half* op = out + i * C;
+    const float r = __ldg(ip) * 2.f - 1.f, gg = __ldg(ip + plane) * 2.f - 1.f, bl = __ldg(ip + 2 * plane) * 2.f - 1.f;
+    uint4 pk;
+    __half2* h2 = reinterpret_cast<__half2*>(&pk);
 #pragma unroll
-    for (int c0 = 0; c0 < C; c0 += 8) {
-      uint4 pk;
-      __half2* h2 = reinterpret_cast<__half2*>(&pk);
+    for (int j = 0; j < 4; ++j) {
+      float a[2];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        float a[2];
-#pragma unroll
-        for (int u = 0; u < 2; ++u) {
-          const int c = c0 + 2 * j + u;
-          float t = fmaf(r, w[c], fmaf(g, w[C + c], fmaf(bl, w[2 * C + c], w[3 * C + c])));
-          a[u] = (t > 0.f ? t : 0.2f * t) * kSqrt2;
-        }
-        h2[j] = __floats2half2_rn(a[0], a[1]);
+      for (int u = 0; u < 2; ++u) {
+        const int c = g * 8 + 2 * j + u;
+        const float t = fmaf(r, w[c], fmaf(gg, w[C + c], fmaf(bl, w[2 * C + c], w[3 * C + c])));
+        a[u] = fmaxf(t, 0.2f * t) * kSqrt2;
       }
-      *reinterpret_cast<uint4*>(op + c0) = pk;
+      h2[j] = __floats2half2_rn(a[0], a[1]);
     }
+    *reinterpret_cast<uint4*>(out + pixi * C + g * 8) = pk;
   }
 }
 
-// 8 channels (one 16-byte vector) per thread; the 4x4 taps of neighbouring outputs overlap by half, so the
-// re-reads are L1/L2 hits and DRAM sees each input byte about once.
-__global__ void fir_down_kernel(const __half* __restrict__ x, __half* __restrict__ out, int N, int H, int W, int C) {
-  const int Ho = H >> 1, Wo = W >> 1, C8 = C >> 3;
-  const size_t n = (size_t)N * Ho * Wo * C8;
+// FIR (pad 1) sampled at stride 2.  One block = 8x16 outputs x 32 channels: the (18 x 34)-pixel input patch is
+// staged once in shared memory (coalesced 16-byte loads, pixel pitch padded to 80 B against bank conflicts), so
+// HBM/L2 see every input byte once and the 16 taps per output come from shared memory.
+constexpr int kFdTH = 8, kFdTW = 16, kFdC = 32, kFdPitch = 40;   // pitch in halfs (80 bytes)
+__global__ void __launch_bounds__(256) fir_down_kernel(const __half* __restrict__ x, __half* __restrict__ out, int N,
+                                                       int H, int W, int C) {
+  __shared__ __align__(16) __half tile[(2 * kFdTH + 2) * (2 * kFdTW + 2) * kFdPitch];
+  const int Ho = H >> 1, Wo = W >> 1;
+  const int tiles_x = (Wo + kFdTW - 1) / kFdTW, tiles_y = (Ho + kFdTH - 1) / kFdTH;
+  int t = blockIdx.x;
+  const int tx = t % tiles_x; t /= tiles_x;
+  const int ty = t % tiles_y;
+  const int b = t / tiles_y;
+  const int c0 = blockIdx.y * kFdC;
+  const int iy0 = 2 * ty * kFdTH - 1, ix0 = 2 * tx * kFdTW - 1;
+  constexpr int IW = 2 * kFdTW + 2, IH = 2 * kFdTH + 2;
+  for (int i = threadIdx.x; i < IH * IW * 4; i += blockDim.x) {
+    const int g = i & 3, pix = i >> 2;
+    const int py = pix / IW, px = pix - py * IW;
+    const int yy = iy0 + py, xx = ix0 + px;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (yy >= 0 && yy < H && xx >= 0 && xx < W)
+      v = __ldg(reinterpret_cast<const uint4*>(x + (((size_t)b * H + yy) * W + xx) * C + c0 + g * 8));
+    *reinterpret_cast<uint4*>(tile + pix * kFdPitch + g * 8) = v;
+  }
+  __syncthreads();
   const float f[4] = {0.125f, 0.375f, 0.375f, 0.125f};
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-    const int c8 = (int)(i % C8);
-    const int zx = (int)((i / C8) % Wo);
-    const int zy = (int)((i / ((size_t)C8 * Wo)) % Ho);
-    const int b = (int)(i / ((size_t)C8 * Wo * Ho));
+  const int g = threadIdx.x & 3;
+#pragma unroll
+  for (int pass = 0; pass < 2; ++pass) {
+    const int op = (threadIdx.x >> 2) + 64 * pass;
+    const int oy = op / kFdTW, ox = op - oy * kFdTW;
+    const int zy = ty * kFdTH + oy, zx = tx * kFdTW + ox;
     float acc[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[j] = 0.f;
 #pragma unroll
     for (int jy = 0; jy < 4; ++jy) {
-      const int yy = 2 * zy + jy - 1;
-      if (yy < 0 || yy >= H) continue;
 #pragma unroll
       for (int jx = 0; jx < 4; ++jx) {
-        const int xx = 2 * zx + jx - 1;
-        if (xx < 0 || xx >= W) continue;
-        const uint4 v = __ldg(reinterpret_cast<const uint4*>(x + (((size_t)b * H + yy) * W + xx) * C + 8 * c8));
+        const uint4 v = *reinterpret_cast<const uint4*>(tile + ((2 * oy + jy) * IW + 2 * ox + jx) * kFdPitch + g * 8);
         const __half2* h2 = reinterpret_cast<const __half2*>(&v);
         const float wgt = f[jy] * f[jx];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          const float2 t = __half22float2(h2[j]);
-          acc[2 * j] = fmaf(wgt, t.x, acc[2 * j]);
-          acc[2 * j + 1] = fmaf(wgt, t.y, acc[2 * j + 1]);
+          const float2 tt = __half22float2(h2[j]);
+          acc[2 * j] = fmaf(wgt, tt.x, acc[2 * j]);
+          acc[2 * j + 1] = fmaf(wgt, tt.y, acc[2 * j + 1]);
         }
       }
     }
-    uint4 o;
-    __half2* oh = reinterpret_cast<__half2*>(&o);
+    if (zy < Ho && zx < Wo) {
+      uint4 o;
+      __half2* oh = reinterpret_cast<__half2*>(&o);
 #pragma unroll
-    for (int j = 0; j < 4; ++j) oh[j] = __floats2half2_rn(acc[2 * j], acc[2 * j + 1]);
-    *reinterpret_cast<uint4*>(out + (((size_t)b * Ho + zy) * Wo + zx) * C + 8 * c8) = o;
+      for (int j = 0; j < 4; ++j) oh[j] = __floats2half2_rn(acc[2 * j], acc[2 * j + 1]);
+      *reinterpret_cast<uint4*>(out + (((size_t)b * Ho + zy) * Wo + zx) * C + c0 + g * 8) = o;
+    }
   }
 }
 
@@ -545,7 +578,7 @@ cudaError_t k_final_cosine(const __half* tokens, const float* lw, const float* l
 }
 cudaError_t k_from_rgb(const float* images, const float* Wt, const float* bias, __half* out, int P, int R, int C,
                        cudaStream_t s) {
-  const int blocks = blocks_for((size_t)P * R * R);
+  const int blocks = blocks_for((size_t)P * R * R * (C / 8), kThreads, 148 * 32);
   if (C == 32) from_rgb_kernel<32><<<blocks, kThreads, 0, s>>>(images, Wt, bias, out, P, R);
   else if (C == 64) from_rgb_kernel<64><<<blocks, kThreads, 0, s>>>(images, Wt, bias, out, P, R);
   else if (C == 128) from_rgb_kernel<128><<<blocks, kThreads, 0, s>>>(images, Wt, bias, out, P, R);
@@ -553,7 +586,11 @@ cudaError_t k_from_rgb(const float* images, const float* Wt, const float* bias, 
   GLASS_RET();
 }
 cudaError_t k_fir_down(const __half* x, __half* out, int N, int H, int W, int C, cudaStream_t s) {
-  fir_down_kernel<<<blocks_for((size_t)N * (H / 2) * (W / 2) * (C / 8), kThreads, 148 * 32), kThreads, 0, s>>>(x, out, N, H, W, C);
+  if (C % kFdC != 0) return cudaErrorInvalidValue;
+  const int Ho = H / 2, Wo = W / 2;
+  const int tiles = ((Wo + kFdTW - 1) / kFdTW) * ((Ho + kFdTH - 1) / kFdTH) * N;
+  dim3 grid(tiles, C / kFdC);
+  fir_down_kernel<<<grid, 256, 0, s>>>(x, out, N, H, W, C);
   GLASS_RET();
 }
 cudaError_t k_mbstd(const __half* x, __half* out, int P, int batch, int group, int C, int Cpad, cudaStream_t s) {
