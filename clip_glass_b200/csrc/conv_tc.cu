@@ -165,8 +165,11 @@ struct Cfg {
   static constexpr int kStagesRaw = kBudget / kStageBytes;
   static constexpr int kStages = kStagesRaw > 12 ? 12 : kStagesRaw;
   static_assert(kStages >= 2, "not enough shared memory for a double-buffered pipeline");
-  static constexpr int kTmemCols = (2 * BN < 32) ? 32 : 2 * BN;   // power of two for BN in {32,64,128,256}
-  static constexpr int kSmemBytes = kWBytes + kStages * kStageBytes + kParamBytes + 1024 /*align*/ + 256 /*barriers*/;
+  // accumulator stages in TMEM: each epilogue group owns every second stage, so with four stages a group can
+  // drain one accumulator while the MMA warp fills its other one (512 columns allow four only up to BN = 128)
+  static constexpr int kAccStages = (BN <= 128) ? 4 : 2;
+  static constexpr int kTmemCols = kAccStages * BN;               // power of two for BN in {32,64,128,256}
+  static constexpr int kSmemBytes = kWBytes + kStages * kStageBytes + kParamBytes + 1024 /*align*/ + 512 /*barriers*/;
   // instruction descriptor: D=f32 [4,6)=1, A=B=f16 (0), K-major both, N>>3 [17,23), M>>4 [24,29)
   static constexpr uint32_t kIdesc = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(kBlockM >> 4) << 24);
 };
@@ -269,8 +272,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + C::kStages;
   uint64_t* tmem_full = bars + 2 * C::kStages;
-  uint64_t* tmem_empty = tmem_full + 2;
-  uint64_t* w_bar = tmem_empty + 2;
+  uint64_t* tmem_empty = tmem_full + 4;
+  uint64_t* w_bar = tmem_empty + 4;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_bar + 1);
 
   const int warp = threadIdx.x >> 5;
@@ -288,7 +291,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
-    for (int s = 0; s < 2; ++s) {
+    for (int s = 0; s < C::kAccStages; ++s) {
       mbar_init(&tmem_full[s], 1);
       mbar_init(&tmem_empty[s], kEpiWarps / 2);   // the four warps of the group that owns this stage
     }
@@ -362,8 +365,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         tc_fence_after();
       }
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
-        const int as = it & 1;
-        const uint32_t aphase = (it >> 1) & 1;
+        const int as = it % C::kAccStages;
+        const uint32_t aphase = (it / C::kAccStages) & 1;
         mbar_wait(&tmem_empty[as], aphase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + as * BN;
@@ -468,13 +471,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     TileCoord tc_next = decode_tile(p, first_tile < total_tiles ? first_tile : 0, n_tiles);
     fetch_noise(tc_next, fast && first_tile < total_tiles, nz_next);
     int staged_img = -1, staged_ntile = -1;
-    uint32_t aphase = 0;
-    for (int tile = first_tile; tile < total_tiles; tile += stride2, aphase ^= 1) {
+    int it = grp;                            // CTA-local tile counter (this group handles it = grp, grp+2, ...)
+    for (int tile = first_tile; tile < total_tiles; tile += stride2, it += 2) {
       const TileCoord tc = tc_next;
       const int n_tile = tc.n_tile, tn = tc.tn;
       const int img = tn * p.TN + ri, y = tc.ty * p.TH + ry, x = tc.tx * p.TW + rx;
       const bool valid = p.all_valid || (img < p.Nimg && y < H && x < W);
-      const int as = grp;
+      const int as = it % C::kAccStages;
+      const uint32_t aphase = (it / C::kAccStages) & 1;
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + as * BN;
       float rgb[3] = {0.f, 0.f, 0.f};
       float nz_cur[kNz];
