@@ -153,23 +153,18 @@ struct Cfg {
   static constexpr int kBBytes = BN * BK * 2;
   static constexpr int kCopyBytes = (kHaloTH + 2) * kHaloTW * BK * 2;          // one dx-copy of the halo tile
   // MODE 2 = MODE 1 for 1x1 convs: one resident tap, one un-haloed tile per stage
-  // MODE 3 = MODE 1 compiled for two CTAs per SM (register cap 96, half the shared memory)
-  static constexpr bool kHalo = (MODE == 1 || MODE == 3);
-  static constexpr int kStageBytes = MODE == 0 ? kABytes + kBBytes : (kHalo ? 3 * kCopyBytes : kABytes);
-  static constexpr int kWBytes = MODE == 0 ? 0 : (kHalo ? 9 : 1) * kBBytes;   // resident taps
-  // per-tile epilogue parameters, one set per epilogue group
-  static constexpr int kParamBytes = 2 * kNumParams * BN * 4;
+  static constexpr int kStageBytes = MODE == 0 ? kABytes + kBBytes : (MODE == 1 ? 3 * kCopyBytes : kABytes);
+  static constexpr int kWBytes = MODE == 0 ? 0 : (MODE == 1 ? 9 : 1) * kBBytes;   // resident taps
+  // double-buffered per-tile epilogue parameters + 2 x 128 float4 for combining the two column halves' toRGB sums
+  static constexpr int kParamBytes = 2 * kNumParams * BN * 4 + 2 * 128 * 16;
   // the 32-channel MODE-1 layers are bookkeeping/latency-bound, not smem-bound: run two CTAs per SM there
-  static constexpr int kMinBlocks = (MODE == 3) ? 2 : 1;
+  static constexpr int kMinBlocks = (MODE == 1 && BK == 32 && BN <= 32) ? 2 : 1;
   static constexpr int kBudget = (kMinBlocks == 2 ? 110 : 222) * 1024 - kParamBytes - kWBytes;   // of 227 KB/SM
   static constexpr int kStagesRaw = kBudget / kStageBytes;
   static constexpr int kStages = kStagesRaw > 12 ? 12 : kStagesRaw;
   static_assert(kStages >= 2, "not enough shared memory for a double-buffered pipeline");
-  // accumulator stages in TMEM: each epilogue group owns every second stage, so with four stages a group can
-  // drain one accumulator while the MMA warp fills its other one (512 columns allow four only up to BN = 128)
-  static constexpr int kAccStages = (BN <= 128) ? 4 : 2;
-  static constexpr int kTmemCols = kAccStages * BN;               // power of two for BN in {32,64,128,256}
-  static constexpr int kSmemBytes = kWBytes + kStages * kStageBytes + kParamBytes + 1024 /*align*/ + 512 /*barriers*/;
+  static constexpr int kTmemCols = (2 * BN < 32) ? 32 : 2 * BN;   // power of two for BN in {32,64,128,256}
+  static constexpr int kSmemBytes = kWBytes + kStages * kStageBytes + kParamBytes + 1024 /*align*/ + 256 /*barriers*/;
   // instruction descriptor: D=f32 [4,6)=1, A=B=f16 (0), K-major both, N>>3 [17,23), M>>4 [24,29)
   static constexpr uint32_t kIdesc = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(kBlockM >> 4) << 24);
 };
@@ -268,12 +263,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   uint8_t* smem_w = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* smem = smem_w + C::kWBytes;       // pipeline stages
   float* params = reinterpret_cast<float*>(smem + C::kStages * C::kStageBytes);
+  float4* rgb_stage = reinterpret_cast<float4*>(params + 2 * kNumParams * BN);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::kStages * C::kStageBytes + C::kParamBytes);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + C::kStages;
   uint64_t* tmem_full = bars + 2 * C::kStages;
-  uint64_t* tmem_empty = tmem_full + 4;
-  uint64_t* w_bar = tmem_empty + 4;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint64_t* w_bar = tmem_empty + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_bar + 1);
 
   const int warp = threadIdx.x >> 5;
@@ -291,9 +287,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
-    for (int s = 0; s < C::kAccStages; ++s) {
+    for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full[s], 1);
-      mbar_init(&tmem_empty[s], kEpiWarps / 2);   // the four warps of the group that owns this stage
+      mbar_init(&tmem_empty[s], kEpiWarps);
     }
     mbar_init(w_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -365,8 +361,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         tc_fence_after();
       }
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
-        const int as = it % C::kAccStages;
-        const uint32_t aphase = (it / C::kAccStages) & 1;
+        const int as = it & 1;
+        const uint32_t aphase = (it >> 1) & 1;
         mbar_wait(&tmem_empty[as], aphase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + as * BN;
@@ -409,15 +405,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     }
   } else {
     // ===================== epilogue (warps 2..9) =====================
-    // Two groups of four warps.  Group g owns TMEM accumulator stage g, i.e. every second tile of this CTA, and
-    // within a group each warp owns one TMEM lane quarter (32 rows) and ALL columns of the tile.  Compared with
-    // splitting the columns between warp pairs this halves the per-tile bookkeeping per element, needs no
-    // exchange of toRGB partial sums, and gives every thread several independent 16-column chunks to overlap.
+    // Two warps per TMEM lane quarter; each owns half of the tile's columns.
     const EpiParams& e = p.epi;
     const int ew = warp - 2;
     const int q = warp & 3;                 // TMEM lane quarter this warp may access
-    const int grp = ew >> 2;                // accumulator stage / tile parity owned by this warp
-    const int gt = (ew & 3) * 32 + lane;    // thread index inside the group, 0..127
+    const int half = ew >> 2;               // column half
+    const int et = threadIdx.x - 64;        // 0..255
     const int row = q * 32 + lane;          // accumulator row == pixel within the tile
     const int thw = p.TH * p.TW;
     const int ri = row / thw;
@@ -426,8 +419,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     const int rx = rr - ry * p.TW;
     const bool fast = (p.TN == 1);          // every row of a tile belongs to one image
     const float gain = (e.act == kActLrelu) ? kSqrt2 : 1.f;
-    constexpr int kChunks = BN / 16;
-    constexpr int kNz = kChunks < 8 ? kChunks : 8;    // prefetched noise values (depth-to-space: one per chunk)
+    constexpr int kHalf = BN / 2;
+    constexpr int kChunks = kHalf / 16;
     const bool d2s = (e.store_mode == kStoreDepthToSpace);
     const bool s2d = (e.store_mode == kStoreSpaceToDepth);
     const bool has_rgb = (e.rgb_w != nullptr);
@@ -440,25 +433,22 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     const int row_s2d = (((ry >> 1) * (W >> 1) + (rx >> 1)) << 2) + ((ry & 1) * 2 + (rx & 1));
     const int cout_sh = e.cout_shift;       // log2(Cout) or -1
     const int ngrp_sh = e.noise_div_shift;  // log2(noise_group_div) or -1
-    float* gpar = params + grp * (kNumParams * BN);     // this group's staged parameters
-    const int stride2 = 2 * gridDim.x;
 
-    // Noise of this group's NEXT tile is fetched while the current one is processed: the (L2/DRAM) latency of
-    // this scattered 4-byte load would otherwise sit on the critical path of every tile.
-    auto fetch_noise = [&](const TileCoord& c2, bool in_range, float (&dst)[kNz]) {
+    // Noise of the NEXT tile is fetched while the current one is processed: the (L2/DRAM) latency of this
+    // scattered 4-byte load would otherwise sit on the critical path of every tile.
+    auto fetch_noise = [&](const TileCoord& c2, bool in_range, float (&dst)[kChunks]) {
 #pragma unroll
-      for (int c = 0; c < kNz; ++c) dst[c] = 0.f;
+      for (int c = 0; c < kChunks; ++c) dst[c] = 0.f;
       if (e.noise == nullptr || !in_range) return;
       const int img2 = c2.tn * p.TN + ri, y2 = c2.ty * p.TH + ry, x2 = c2.tx * p.TW + rx;
       if (!p.all_valid && !(img2 < p.Nimg && y2 < H && x2 < W)) return;
-      const int g2 = ngrp_sh >= 0 ? (img2 >> ngrp_sh) : (img2 / e.noise_group_div);
-      const float* base = e.noise + (size_t)g2 * e.noise_group_stride;
+      const int grp = ngrp_sh >= 0 ? (img2 >> ngrp_sh) : (img2 / e.noise_group_div);
+      const float* base = e.noise + (size_t)grp * e.noise_group_stride;
       if (d2s) {
-        // at most four distinct phases: chunk c of this tile belongs to phase (n_tile*BN + 16c) / Cout
         const float* b2 = base + (size_t)(2 * y2) * (2 * W) + 2 * x2;
 #pragma unroll
-        for (int c = 0; c < kNz; ++c) {
-          const int n0 = c2.n_tile * BN + c * (BN / kNz);
+        for (int c = 0; c < kChunks; ++c) {
+          const int n0 = c2.n_tile * BN + half * kHalf + c * 16;
           const int ph = cout_sh >= 0 ? (n0 >> cout_sh) : (n0 / e.Cout);
           dst[c] = __ldg(b2 + (ph >> 1) * (2 * W) + (ph & 1));
         }
@@ -466,58 +456,60 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         dst[0] = __ldg(base + y2 * W + x2);
       }
     };
-    float nz_next[kNz];
-    const int first_tile = blockIdx.x + grp * gridDim.x;
-    TileCoord tc_next = decode_tile(p, first_tile < total_tiles ? first_tile : 0, n_tiles);
-    fetch_noise(tc_next, fast && first_tile < total_tiles, nz_next);
+    float nz_next[kChunks];
+    TileCoord tc_next = decode_tile(p, blockIdx.x, n_tiles);
+    fetch_noise(tc_next, true, nz_next);
+    int it = 0;
     int staged_img = -1, staged_ntile = -1;
-    int it = grp;                            // CTA-local tile counter (this group handles it = grp, grp+2, ...)
-    for (int tile = first_tile; tile < total_tiles; tile += stride2, it += 2) {
+    int pbuf = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
       const TileCoord tc = tc_next;
       const int n_tile = tc.n_tile, tn = tc.tn;
       const int img = tn * p.TN + ri, y = tc.ty * p.TH + ry, x = tc.tx * p.TW + rx;
       const bool valid = p.all_valid || (img < p.Nimg && y < H && x < W);
-      const int as = it % C::kAccStages;
-      const uint32_t aphase = (it / C::kAccStages) & 1;
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + as * BN;
+      const int as = it & 1;
+      const uint32_t aphase = (it >> 1) & 1;
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + as * BN + half * kHalf;
       float rgb[3] = {0.f, 0.f, 0.f};
-      float nz_cur[kNz];
+      float nz_cur[kChunks];
 #pragma unroll
-      for (int c = 0; c < kNz; ++c) nz_cur[c] = nz_next[c];
+      for (int c = 0; c < kChunks; ++c) nz_cur[c] = nz_next[c];
       {
-        const int nt = tile + stride2;
+        const int nt = tile + gridDim.x;
         const bool more = nt < total_tiles;
         if (more) tc_next = decode_tile(p, nt, n_tiles);
         if (fast) fetch_noise(tc_next, more, nz_next);
       }
 
       if (fast) {
-        // ---- stage the per-(image, n_tile) parameters once per group; reuse while they do not change ----
+        // ---- stage the per-(image, n_tile) parameters once; reuse while they do not change ----
         const int timg = tn;                 // TN == 1
         if (timg != staged_img || n_tile != staged_ntile) {
-          asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");   // everyone is done with the old values
-          for (int j = gt; j < BN; j += 128) {
-            const int n = n_tile * BN + j;
+          pbuf ^= 1;
+          float* par = params + pbuf * (kNumParams * BN);
+          if (et < BN) {
+            const int n = n_tile * BN + et;
             const int o = cout_sh >= 0 ? (n & (e.Cout - 1)) : (n % e.Cout);
             const float d = e.dmod != nullptr ? __ldg(e.dmod + (size_t)timg * e.Cout + o) : 1.f;
             const float b = e.bias != nullptr ? __ldg(e.bias + o) : 0.f;
             const float osn = e.out_scale != nullptr ? __ldg(e.out_scale + (size_t)timg * e.out_scale_stride + o) : 1.f;
-            gpar[0 * BN + j] = d * gain;
-            gpar[1 * BN + j] = b * gain;
-            gpar[2 * BN + j] = osn * e.post_scale;
+            par[0 * BN + et] = d * gain;
+            par[1 * BN + et] = b * gain;
+            par[2 * BN + et] = osn * e.post_scale;
             if (has_rgb) {
               const float* rw = e.rgb_w + (size_t)timg * 3 * e.Cout + o;
-              gpar[3 * BN + j] = __ldg(rw);
-              gpar[4 * BN + j] = __ldg(rw + e.Cout);
-              gpar[5 * BN + j] = __ldg(rw + 2 * e.Cout);
+              par[3 * BN + et] = __ldg(rw);
+              par[4 * BN + et] = __ldg(rw + e.Cout);
+              par[5 * BN + et] = __ldg(rw + 2 * e.Cout);
             }
           }
           staged_img = timg;
           staged_ntile = n_tile;
-          asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");   // (uniform condition inside the group)
+          epi_bar_sync();                    // all 8 epilogue warps take the same branch (uniform condition)
         }
+        const float* par = params + pbuf * (kNumParams * BN);
         // ---- per-tile addresses ----
-        const int n_first = n_tile * BN;
+        const int n_first = n_tile * BN + half * kHalf;
         const int pix = (img * H + tc.ty * p.TH) * W + tc.tx * p.TW + row_reg;          // NHWC pixel index of this row
         const __half* res_row = e.residual != nullptr ? e.residual + (size_t)pix * p.Ntot + n_first : nullptr;
         __half* out_row = nullptr;           // regular / space-to-depth: contiguous columns
@@ -540,22 +532,22 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           tc_ld_wait();
           if (c + 1 < kChunks) tc_ld16_issue(taddr + (c + 1) * 16, acc[(c + 1) & 1]);
           if (valid && !p.debug_skip) {
-            const int j0 = c * 16;
-            const float nzc = nscale * nz_cur[d2s ? (c * kNz) / kChunks : 0];
+            const int j0 = half * kHalf + c * 16;
+            const float nzc = nscale * nz_cur[d2s ? c : 0];
             __half* optr = nullptr;
             if (d2s) {
               // column n -> phase (py,px) and channel o; output pixel (2y+py, 2x+px)
-              const int n0 = n_first + j0;
+              const int n0 = n_tile * BN + j0;
               const int ph = cout_sh >= 0 ? (n0 >> cout_sh) : (n0 / e.Cout);
               const int o0 = n0 - ph * e.Cout;
               if (e.out != nullptr)
                 optr = e.out + (size_t)(d2s_pix + (ph >> 1) * (2 * W) + (ph & 1)) * e.Cout + o0;
             } else if (out_row != nullptr) {
-              optr = out_row + j0;
+              optr = out_row + c * 16;
             }
-            const __half* rptr = res_row != nullptr ? res_row + j0 : nullptr;
-            if (has_rgb) epilogue_fast16<true>(e, gpar, BN, j0, acc[c & 1], nzc, rptr, optr, rgb);
-            else epilogue_fast16<false>(e, gpar, BN, j0, acc[c & 1], nzc, rptr, optr, rgb);
+            const __half* rptr = res_row != nullptr ? res_row + c * 16 : nullptr;
+            if (has_rgb) epilogue_fast16<true>(e, par, BN, j0, acc[c & 1], nzc, rptr, optr, rgb);
+            else epilogue_fast16<false>(e, par, BN, j0, acc[c & 1], nzc, rptr, optr, rgb);
           }
         }
       } else {
@@ -566,12 +558,20 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         for (int c = 0; c < kChunks; ++c) {
           float v[16];
           tc_ld16(taddr + c * 16, v);
-          if (valid) epilogue_row16(p, img, y, x, n_tile * BN + c * 16, v, rgb);
+          if (valid) epilogue_row16(p, img, y, x, n_tile * BN + half * kHalf + c * 16, v, rgb);
         }
       }
-      if (has_rgb && valid) {
-        const size_t pix = ((size_t)img * H + y) * W + x;
-        e.rgb_out[(size_t)n_tile * p.Nimg * H * W + pix] = make_float4(rgb[0], rgb[1], rgb[2], 0.f);
+      if (has_rgb) {
+        // the two warps of a lane quarter own different column halves of the same rows: combine their
+        // partial toRGB sums in shared memory so that one float4 per pixel goes to HBM
+        float4* stg = rgb_stage + (it & 1) * 128;
+        if (half == 1) stg[row] = make_float4(rgb[0], rgb[1], rgb[2], 0.f);
+        asm volatile("bar.sync %0, 64;" ::"r"(2 + q) : "memory");
+        if (half == 0 && valid) {
+          const float4 o = stg[row];
+          const size_t pix = ((size_t)img * H + y) * W + x;
+          e.rgb_out[(size_t)n_tile * p.Nimg * H * W + pix] = make_float4(rgb[0] + o.x, rgb[1] + o.y, rgb[2] + o.z, 0.f);
+        }
       }
       tc_fence_before();
       __syncwarp();
@@ -673,7 +673,6 @@ cudaError_t launch_conv_tc(const ConvParams& p, const TmaMaps& maps, int num_sms
   GLASS_CASE(128, 32, 1)
   GLASS_CASE(32, 64, 1)
   GLASS_CASE(64, 64, 1)
-  GLASS_CASE(32, 32, 3)
   GLASS_CASE(32, 32, 2)
   GLASS_CASE(64, 32, 2)
   GLASS_CASE(128, 32, 2)

@@ -200,8 +200,6 @@ int make_conv(glass_engine* e, ConvLaunch* out, const __half* in, int Nimg, int 
       p.mode = 1;
       const int bn_cap = (Cin == 64) ? 64 : 128;       // 9 resident taps must leave room for >= 2 stages
       while (p.BN > bn_cap) p.BN /= 2;
-      const char* two = getenv("GLASS_MODE1_2CTA");   // tuning knob: 32x32 halo kernel with two CTAs per SM
-      if (Cin == 32 && p.BN == 32 && two && atoi(two)) p.mode = 3;
     } else {
       p.mode = 2;                                      // 1x1: one resident tap, BN up to 256 (Cin 64) / 128 (Cin 32)
       if (Cin == 32 && p.BN > 128) p.BN = 128;
@@ -225,7 +223,7 @@ int make_conv(glass_engine* e, ConvLaunch* out, const __half* in, int Nimg, int 
   uint64_t dims[4] = {(uint64_t)Cin, wdecl, (uint64_t)H, ndecl};
   uint64_t strides[3] = {(uint64_t)Cin * 2, (uint64_t)Cin * 2 * wdecl, (uint64_t)Cin * 2 * wdecl * H};
   // mode 1 with 3x3 taps loads the tile plus one halo row above and below per horizontal shift
-  const uint32_t box_h = ((p.mode == 1 || p.mode == 3) && taps == 9) ? (uint32_t)p.TH + 2 : (uint32_t)p.TH;
+  const uint32_t box_h = (p.mode == 1 && taps == 9) ? (uint32_t)p.TH + 2 : (uint32_t)p.TH;
   uint32_t box[4] = {(uint32_t)p.BK, (uint32_t)p.TW, box_h, (uint32_t)p.TN};
   int rc = encode_map(e, &out->maps.a, in, 4, dims, strides, box, p.BK * 2);
   if (rc != GLASS_OK) return rc;
