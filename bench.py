@@ -90,6 +90,16 @@ class ClockSampler(threading.Thread):
                     reasons=sorted(reasons), samples=len(sm))
 
 
+def conv_launch_names(use_d):
+    """Short names of the tensor-core launches of one step, in launch order (G convs, CLIP GEMMs, D convs)."""
+    names = [f"G{i}" for i in range(17)] + ["Cpatch"] + [f"C{l}{n}" for l in range(12) for n in ("qkv", "out", "fc", "proj")]
+    if use_d:
+        for b in range(8):
+            names += [f"D{b}c0", f"D{b}proj", f"D{b}c1"]
+        names += ["Dfin", "Ddense0"]
+    return names
+
+
 def best_cpu_threads():
     """Threads for the CPU arm.  One 4-candidate minibatch does not scale past ~32 threads: measured on the
     128-core GPU box (tests/cpu_threads_probe.py): 8 -> 0.35, 16 -> 0.38, 32 -> 0.38, 64 -> 0.32, 128 -> 0.05
@@ -298,12 +308,30 @@ def main():
         if os.path.exists(tpath):
             with open(tpath) as f:
                 traffic = json.load(f).get("bytes_per_launch")
+        # exemplars: the most tensor-bound and the most HBM-bound launch of the step, each against its own roof
+        names = conv_launch_names(use_d)
+        detail = {}
+        for key, bound in (("G8", "tensor"), ("G16", "hbm")):
+            if key in names:
+                i = names.index(key)
+                if i < len(bd) and bd[i][0] > 0:
+                    m, f = bd[i]
+                    if bound == "tensor":
+                        a = f / (m * 1e-3) / 1e12
+                        detail[key] = dict(layer="G 3x3 512->512 @64^2", bound="tensor", achieved=a, unit="TFLOP/s",
+                                           peak=peak, frac=a / peak, ms=m)
+                    else:
+                        # algorithmic bytes: fp16 NHWC input read once + one float4 toRGB partial per pixel written
+                        byts = P_local * 1024 * 1024 * (32 * 2 + 16)
+                        a = byts / (m * 1e-3) / 1e9
+                        detail[key] = dict(layer="G 3x3 32->32 @1024^2 (+fused toRGB)", bound="hbm", achieved=a,
+                                           unit="GB/s", peak=peaks["hbm_gbs"], frac=a / peaks["hbm_gbs"], ms=m)
         roofline = dict(bound="tensor", kernel="conv_tc_kernel (all tcgen05 conv/GEMM launches of one step)",
                         achieved=achieved, peak=peak, unit="TFLOP/s", frac=achieved / peak, traffic=traffic,
                         peak_source=peaks["source"] + ", sustained bf16 figure (kernel timed inside a long step)",
                         launches_per_step=len(bd), kernel_ms_per_step=conv_ms,
                         share_of_step=conv_ms / float(ms_dev.mean()),
-                        algorithmic_gflop_per_step=conv_flops / 1e9)
+                        algorithmic_gflop_per_step=conv_flops / 1e9, exemplars=detail)
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
