@@ -39,6 +39,7 @@ class GlassConfig(ctypes.Structure):
         ("max_population", ctypes.c_int32),
         ("device", ctypes.c_int32),
         ("conv_impl", ctypes.c_int32),
+        ("flags", ctypes.c_int32),
     ]
 
 

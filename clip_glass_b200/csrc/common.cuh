@@ -51,8 +51,10 @@ struct ConvParams {
   int Nimg, H, W;           // accumulator grid
   int TN, TH, TW;           // tile box, TN*TH*TW == 128
   int tiles_n, tiles_y, tiles_x;
+  int in_H, in_W;           // input tensor extent (== H, W except for the exact polyphase forms)
   int Cin;                  // K per tap (multiple of BK)
-  int taps;                 // 9 or 1
+  int taps;                 // number of filter taps (9, 4 or 1)
+  signed char tap_dy[9], tap_dx[9];   // input offset of each tap (3x3: ky-1, kx-1)
   int Ntot;                 // multiple of BN
   int BN, BK;
   int debug_skip;           // profiling aid (env GLASS_DEBUG_SKIP): 1 = epilogue only drains TMEM (results invalid)

@@ -338,8 +338,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         for (int kit = 0; kit < kiters; ++kit) {
           const int tap = kit / kchunks;
           const int kc = kit - tap * kchunks;
-          int dy = 0, dx = 0;
-          if (p.taps == 9) { dy = tap / 3 - 1; dx = tap % 3 - 1; }
+          const int dy = p.tap_dy[tap], dx = p.tap_dx[tap];
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * C::kStageBytes;
           uint8_t* sb = sa + C::kABytes;
@@ -624,11 +623,9 @@ __global__ void conv_simt_kernel(const ConvParams p) {
 #pragma unroll
     for (int j = 0; j < 16; ++j) acc[j] = 0.f;
     for (int tap = 0; tap < p.taps; ++tap) {
-      int dy = 0, dx = 0;
-      if (p.taps == 9) { dy = tap / 3 - 1; dx = tap % 3 - 1; }
-      const int yy = y + dy, xx = x + dx;
-      if (yy < 0 || yy >= p.H || xx < 0 || xx >= p.W) continue;
-      const __half* a = p.in + ((size_t)(img * p.H + yy) * p.W + xx) * p.Cin;
+      const int yy = y + p.tap_dy[tap], xx = x + p.tap_dx[tap];
+      if (yy < 0 || yy >= p.in_H || xx < 0 || xx >= p.in_W) continue;
+      const __half* a = p.in + ((size_t)(img * p.in_H + yy) * p.in_W + xx) * p.Cin;
       const __half* w = p.wgt + ((size_t)tap * p.Ntot + g * 16) * p.Cin;
       for (int c = 0; c < p.Cin; c += 2) {
         const float2 av = __half22float2(*reinterpret_cast<const __half2*>(a + c));

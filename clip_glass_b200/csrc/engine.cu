@@ -91,7 +91,9 @@ struct glass_engine {
   float *z32 = nullptr, *wA = nullptr, *wB = nullptr, *styles = nullptr, *noise = nullptr;
   std::vector<float*> dmod;
   std::vector<float*> rgbw;
-  __half *actA = nullptr, *actB = nullptr;
+  __half *actA = nullptr, *actB = nullptr, *actC = nullptr;   // actC: intermediate of the exact polyphase forms
+  std::vector<int> g_exact;   // per G layer: 1 = exact polyphase up-conv
+  std::vector<int> d_exact;   // per D block: 1 = exact polyphase down-conv
   float4 *slabs = nullptr, *yA = nullptr, *yB = nullptr;
   float* images = nullptr;
   __half *patches = nullptr, *patch_emb = nullptr, *tokens = nullptr, *hbuf = nullptr, *qkv = nullptr, *att = nullptr,
@@ -173,11 +175,23 @@ int pick_bn(int ntot) {
 }
 
 // Build one implicit-GEMM launch.  gemm=true: plain [M x K] @ [Ntot x K]^T with M = W.
+// Tap tables of the exact polyphase forms (packing.py: UP_EXACT_TAPS / DOWN_EXACT_TAPS)
+const signed char kUpExactTaps[4][2] = {{-1, -1}, {-1, 0}, {0, -1}, {0, 0}};
+const signed char kDownExactTaps[4][2] = {{0, 0}, {0, 1}, {1, 0}, {1, 1}};
+
 int make_conv(glass_engine* e, ConvLaunch* out, const __half* in, int Nimg, int H, int W, int Cin, const __half* wgt,
-              int taps, int Ntot, const EpiParams& epi, bool gemm) {
+              int taps, int Ntot, const EpiParams& epi, bool gemm, const signed char (*table)[2] = nullptr,
+              int in_H = 0, int in_W = 0) {
   ConvParams& p = out->p;
   memset(&p, 0, sizeof(p));
   p.Nimg = Nimg; p.H = H; p.W = W; p.Cin = Cin; p.taps = taps; p.Ntot = Ntot;
+  p.in_H = in_H > 0 ? in_H : H;
+  p.in_W = in_W > 0 ? in_W : W;
+  for (int t = 0; t < taps; ++t) {
+    if (table != nullptr) { p.tap_dy[t] = table[t][0]; p.tap_dx[t] = table[t][1]; }
+    else if (taps == 9) { p.tap_dy[t] = (signed char)(t / 3 - 1); p.tap_dx[t] = (signed char)(t % 3 - 1); }
+    else { p.tap_dy[t] = 0; p.tap_dx[t] = 0; }
+  }
   p.in = in; p.wgt = wgt; p.epi = epi;
   if (gemm) {
     p.TW = 128; p.TH = 1; p.TN = 1;
@@ -195,7 +209,8 @@ int make_conv(glass_engine* e, ConvLaunch* out, const __half* in, int Nimg, int 
     return fail(GLASS_ERR_ARG, "unsupported conv shape Cin=%d Ntot=%d", Cin, Ntot);
   // Small-channel layers (the whole K of a tap is one chunk) on full 16x8 tiles: resident taps + halo copies.
   p.mode = 0;
-  if (!gemm && (Cin == 32 || Cin == 64) && p.TW == 16 && p.TH == 8 && p.TN == 1 && (taps == 9 || taps == 1)) {
+  if (!gemm && table == nullptr && (Cin == 32 || Cin == 64) && p.TW == 16 && p.TH == 8 && p.TN == 1 &&
+      (taps == 9 || taps == 1)) {
     if (taps == 9) {
       p.mode = 1;
       const int bn_cap = (Cin == 64) ? 64 : 128;       // 9 resident taps must leave room for >= 2 stages
@@ -218,10 +233,10 @@ int make_conv(glass_engine* e, ConvLaunch* out, const __half* in, int Nimg, int 
   }
   if (e->cfg.conv_impl != 0) return GLASS_OK;   // SIMT bring-up path needs no descriptors
   // activations: [C, W, H, N]; outermost extent rounded up to the box (buffers carry the slack)
-  const uint64_t wdecl = gemm ? (uint64_t)p.tiles_x * 128 : (uint64_t)W;
+  const uint64_t wdecl = gemm ? (uint64_t)p.tiles_x * 128 : (uint64_t)p.in_W;
   const uint64_t ndecl = (uint64_t)p.tiles_n * p.TN;
-  uint64_t dims[4] = {(uint64_t)Cin, wdecl, (uint64_t)H, ndecl};
-  uint64_t strides[3] = {(uint64_t)Cin * 2, (uint64_t)Cin * 2 * wdecl, (uint64_t)Cin * 2 * wdecl * H};
+  uint64_t dims[4] = {(uint64_t)Cin, wdecl, (uint64_t)p.in_H, ndecl};
+  uint64_t strides[3] = {(uint64_t)Cin * 2, (uint64_t)Cin * 2 * wdecl, (uint64_t)Cin * 2 * wdecl * p.in_H};
   // mode 1 with 3x3 taps loads the tile plus one halo row above and below per horizontal shift
   const uint32_t box_h = (p.mode == 1 && taps == 9) ? (uint32_t)p.TH + 2 : (uint32_t)p.TH;
   uint32_t box[4] = {(uint32_t)p.BK, (uint32_t)p.TW, box_h, (uint32_t)p.TN};
@@ -307,6 +322,11 @@ void derive_arch(glass_engine* e) {
   for (int b = 0; b < c.num_blocks; ++b) { e->rgb_off.push_back(off); off += e->gch[b]; }
   e->S = off;
   e->R = 4 << (c.num_blocks - 1);
+  const bool folded = (c.flags & GLASS_FLAG_FOLDED_RESAMPLE) != 0;
+  e->g_exact.clear();
+  for (const GLayer& l : e->glayers) e->g_exact.push_back((!folded && l.up && l.res / 2 >= 16) ? 1 : 0);
+  e->d_exact.clear();
+  for (int b = 0; b + 1 < c.num_blocks; ++b) e->d_exact.push_back((!folded && (e->R >> b) >= 32) ? 1 : 0);
   e->noise_layer_off.clear();
   size_t noff = 0;
   for (const GLayer& l : e->glayers) { e->noise_layer_off.push_back(noff); noff += (size_t)l.res * l.res; }
@@ -328,6 +348,7 @@ int validate_weights(glass_engine* e) {
     const GLayer& l = e->glayers[li];
     const int ntot = l.up ? 4 * l.cout : l.cout;
     snprintf(nm, sizeof nm, "g.conv%zu.w", li); RC(check_tensor(e, nm, (size_t)9 * ntot * l.cin * 2));
+    if (e->g_exact[li]) { snprintf(nm, sizeof nm, "g.conv%zu.wx", li); RC(check_tensor(e, nm, (size_t)4 * ntot * l.cin * 2)); }
     snprintf(nm, sizeof nm, "g.conv%zu.wsq", li); RC(check_tensor(e, nm, (size_t)l.cin * l.cout * 4));
     snprintf(nm, sizeof nm, "g.conv%zu.bias", li); RC(check_tensor(e, nm, (size_t)l.cout * 4));
     snprintf(nm, sizeof nm, "g.conv%zu.nstr", li); RC(check_tensor(e, nm, 4));
@@ -363,6 +384,7 @@ int validate_weights(glass_engine* e) {
       RC(check_tensor(e, nmf("c0.w"), (size_t)9 * dch(b) * dch(b) * 2));
       RC(check_tensor(e, nmf("c0.b"), (size_t)dch(b) * 4));
       RC(check_tensor(e, nmf("c1.w"), (size_t)9 * dch(b + 1) * 4 * dch(b) * 2));
+      if (e->d_exact[b]) RC(check_tensor(e, nmf("c1.wx"), (size_t)4 * dch(b + 1) * 4 * dch(b) * 2));
       RC(check_tensor(e, nmf("c1.b"), (size_t)dch(b + 1) * 4));
       RC(check_tensor(e, nmf("proj.w"), (size_t)dch(b + 1) * dch(b) * 2));
     }
@@ -407,6 +429,17 @@ void layout_workspace(glass_engine* e, Arena& a) {
   const size_t slack = kSlackRows * 512;
   e->actA = (__half*)a.take((act_elems + slack) * 2);
   e->actB = (__half*)a.take((act_elems + slack) * 2);
+  {
+    size_t c_elems = 0;
+    for (size_t li = 0; li < e->glayers.size(); ++li)
+      if (e->g_exact[li]) c_elems = std::max(c_elems, P * (size_t)(e->glayers[li].res + 2) * (e->glayers[li].res + 2) * e->glayers[li].cout);
+    for (size_t b = 0; b < e->d_exact.size(); ++b)
+      if (e->d_exact[b]) {
+        const size_t r2 = (size_t)(e->R >> b) / 2 + 1;
+        c_elems = std::max(c_elems, P * r2 * r2 * 4 * (size_t)e->gch[nb - 1 - b]);
+      }
+    e->actC = c_elems ? (__half*)a.take((c_elems + slack) * 2) : nullptr;
+  }
   e->slabs = (float4*)a.take(slab_elems * 16);
   e->yA = (float4*)a.take(P * (size_t)e->R * e->R * 16);
   e->yB = (float4*)a.take(P * (size_t)e->R * e->R * 16);
@@ -488,10 +521,23 @@ int build_plan(glass_engine* e, int P) {
     } else {
       ep.out = nullptr;
     }
-    snprintf(nm, sizeof nm, "g.conv%zu.w", li);
     ConvLaunch cl;
-    RC(make_conv(e, &cl, bufs[cur], P, in_res, in_res, l.cin, tptr<__half>(e, nm), 9, l.up ? 4 * l.cout : l.cout, ep,
-                 false));
+    if (e->g_exact[li]) {
+      // exact polyphase: transposed conv as a 2x2-tap conv on the (H+1)x(W+1) grid -> u (demodulated, fp16) in actC;
+      // FIR + noise + bias + activation + next-style pre-scale happen in k_upfir (run_generator)
+      EpiParams eu = epi_default();
+      eu.dmod = e->dmod[li];
+      eu.Cout = l.cout;
+      eu.store_mode = kStoreDepthToSpace;
+      eu.out = e->actC;
+      snprintf(nm, sizeof nm, "g.conv%zu.wx", li);
+      RC(make_conv(e, &cl, bufs[cur], P, in_res + 1, in_res + 1, l.cin, tptr<__half>(e, nm), 4, 4 * l.cout, eu, false,
+                   kUpExactTaps, in_res, in_res));
+    } else {
+      snprintf(nm, sizeof nm, "g.conv%zu.w", li);
+      RC(make_conv(e, &cl, bufs[cur], P, in_res, in_res, l.cin, tptr<__half>(e, nm), 9, l.up ? 4 * l.cout : l.cout, ep,
+                   false));
+    }
     // the noise tensor index inside a group is per-layer; stride between groups is noise_per_group
     cl.flops = 2.0 * 9.0 * (double)P * in_res * in_res * l.cin * l.cout;   // as written by the reference
     e->g_convs.push_back(cl);
@@ -542,21 +588,28 @@ int build_plan(glass_engine* e, int P) {
       const int Ci = dch(b), Co = dch(b + 1);
       auto nmf = [&](const char* suffix) { snprintf(nm, sizeof nm, "d.b%d.%s", b, suffix); return std::string(nm); };
       ConvLaunch cl;
-      // conv0: 3x3 Ci->Ci, bias, lrelu; stored space-to-depth for conv1
+      // conv0: 3x3 Ci->Ci, bias, lrelu; stored space-to-depth for the folded conv1, or plain NHWC for the blur pass
       EpiParams ep = epi_default();
       ep.Cout = Ci; ep.bias = tptr<float>(e, nmf("c0.b")); ep.act = kActLrelu; ep.out = e->actB;
-      ep.store_mode = kStoreSpaceToDepth;
+      ep.store_mode = e->d_exact[b] ? kStoreRegular : kStoreSpaceToDepth;
       RC(make_conv(e, &cl, x, P, res, res, Ci, tptr<__half>(e, nmf("c0.w")), 9, Ci, ep, false));
       cl.flops = 2.0 * 9.0 * (double)P * res * res * Ci * Ci; e->d_convs.push_back(cl);
       // projection: 1x1 on the FIR-downsampled input
       ep = epi_default(); ep.Cout = Co; ep.out = e->dR;
       RC(make_conv(e, &cl, e->dXd, P, res / 2, res / 2, Ci, tptr<__half>(e, nmf("proj.w")), 1, Co, ep, false));
       cl.flops = 2.0 * (double)P * (res / 2) * (res / 2) * Ci * Co; e->d_convs.push_back(cl);
-      // conv1: folded FIR + 3x3 stride 2 == 3x3 over the space-to-depth tensor (4*Ci channels)
+      // conv1
       ep = epi_default();
       ep.Cout = Co; ep.bias = tptr<float>(e, nmf("c1.b")); ep.act = kActLrelu; ep.residual = e->dR;
       ep.post_scale = kInvSqrt2; ep.out = outs[b & 1];
-      RC(make_conv(e, &cl, e->actB, P, res / 2, res / 2, 4 * Ci, tptr<__half>(e, nmf("c1.w")), 9, Co, ep, false));
+      if (e->d_exact[b]) {
+        // exact: blurred input (k_blur_s2d -> actC, [(res/2+1)^2][4*Ci]) then a 2x2-tap conv == 3x3 stride 2
+        RC(make_conv(e, &cl, e->actC, P, res / 2, res / 2, 4 * Ci, tptr<__half>(e, nmf("c1.wx")), 4, Co, ep, false,
+                     kDownExactTaps, res / 2 + 1, res / 2 + 1));
+      } else {
+        // folded FIR + 3x3 stride 2 == 3x3 over the space-to-depth tensor (4*Ci channels)
+        RC(make_conv(e, &cl, e->actB, P, res / 2, res / 2, 4 * Ci, tptr<__half>(e, nmf("c1.w")), 9, Co, ep, false));
+      }
       cl.flops = 2.0 * 9.0 * (double)P * (res / 2) * (res / 2) * Ci * Co; e->d_convs.push_back(cl);
       x = outs[b & 1];
       res /= 2;
@@ -633,9 +686,21 @@ int run_generator(glass_engine* e, const float* z, int P, const glass_noise* nz,
     const GLayer& l = e->glayers[li];
     const ConvLaunch& cl = e->g_convs[li];
     RC(run_conv(e, cl, s));
-    if (cl.p.epi.out != nullptr) {
+    const __half* layer_out = cl.p.epi.out;
+    if (e->g_exact[li]) {
+      snprintf(nm, sizeof nm, "u%zu", li);
+      RC(capture_f16(e, nm, e->actC, (size_t)P * (l.res + 2) * (l.res + 2) * l.cout, s));
+      __half* dst = (cl.p.in == e->actA) ? e->actB : e->actA;
+      snprintf(nm, sizeof nm, "g.conv%zu.bias", li);
+      const float* bias = tptr<float>(e, nm);
+      snprintf(nm, sizeof nm, "g.conv%zu.nstr", li);
+      LAUNCH(k_upfir(e->actC, dst, e->noise + e->noise_layer_off[li], e->noise_per_group, c.batch_size,
+                     tptr<float>(e, nm), bias, e->styles + e->conv_off[li + 1], e->S, P, l.res, l.res, l.cout, s));
+      layer_out = dst;
+    }
+    if (layer_out != nullptr) {
       snprintf(nm, sizeof nm, "xs%zu", li);
-      RC(capture_f16(e, nm, cl.p.epi.out, (size_t)P * l.res * l.res * l.cout, s));
+      RC(capture_f16(e, nm, layer_out, (size_t)P * l.res * l.res * l.cout, s));
     }
     const bool last_in_block = (li + 1 == nl) || (e->glayers[li + 1].block != l.block);
     if (last_in_block) {
@@ -695,7 +760,8 @@ int run_discriminator(glass_engine* e, const float* images, int P, float* logits
   size_t ci = 0;
   for (int b = 0; b < nb - 1; ++b) {
     LAUNCH(k_fir_down(x, e->dXd, P, res, res, dch(b), s));
-    RC(run_conv(e, e->d_convs[ci++], s));   // conv0 -> actB (space-to-depth)
+    RC(run_conv(e, e->d_convs[ci++], s));   // conv0 -> actB (space-to-depth, or NHWC for the exact form)
+    if (e->d_exact[b]) LAUNCH(k_blur_s2d(e->actB, e->actC, P, res, res, dch(b), s));
     RC(run_conv(e, e->d_convs[ci++], s));   // projection -> dR
     const ConvLaunch& c1 = e->d_convs[ci++];
     RC(run_conv(e, c1, s));                 // conv1 + residual

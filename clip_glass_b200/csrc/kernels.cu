@@ -451,6 +451,146 @@ __global__ void __launch_bounds__(256) fir_down_kernel(const __half* __restrict_
   }
 }
 
+// ---------------------------------------------------------------------------
+// exact polyphase helpers (streaming, HBM-bound)
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void ld8(const __half* p, float (&v)[8]) {
+  const uint4 q = __ldg(reinterpret_cast<const uint4*>(p));
+  const __half2* h2 = reinterpret_cast<const __half2*>(&q);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float2 t = __half22float2(h2[j]);
+    v[2 * j] = t.x;
+    v[2 * j + 1] = t.y;
+  }
+}
+__device__ __forceinline__ void st8(__half* p, const float (&v)[8]) {
+  uint4 o;
+  __half2* oh = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) oh[j] = __floats2half2_rn(v[2 * j], v[2 * j + 1]);
+  *reinterpret_cast<uint4*>(p) = o;
+}
+
+// One thread: 8 channels x 4 consecutive output rows of one output column.  Horizontal taps first (7 input rows x
+// 4 columns = 28 vector loads for 4 outputs), then the vertical taps: v[Z] = sum_j f[j] u[Z+j-1].
+__global__ void upfir_kernel(const __half* __restrict__ u, __half* __restrict__ out, const float* __restrict__ noise,
+                             size_t noise_group_stride, int noise_group_div, const float* __restrict__ noise_strength,
+                             const float* __restrict__ bias, const float* __restrict__ out_scale, int out_scale_stride,
+                             int P, int Hout, int Wout, int C) {
+  const int C8 = C >> 3, Hq = Hout >> 2;
+  const int Hu = Hout + 2, Wu = Wout + 2;
+  const size_t n = (size_t)P * Hq * Wout * C8;
+  const float f[4] = {0.25f, 0.75f, 0.75f, 0.25f};
+  const float nstr = noise != nullptr ? __ldg(noise_strength) : 0.f;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const int c8 = (int)(i % C8);
+    const int X = (int)((i / C8) % Wout);
+    const int zq = (int)((i / ((size_t)C8 * Wout)) % Hq);
+    const int b = (int)(i / ((size_t)C8 * Wout * Hq));
+    const int Z0 = zq * 4;
+    float hrow[7][8];
+#pragma unroll
+    for (int r = 0; r < 7; ++r) {
+      const int Y = Z0 + r - 1;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) hrow[r][j] = 0.f;
+      if (Y < 0 || Y >= Hu) continue;
+      const __half* rowp = u + (((size_t)b * Hu + Y) * Wu) * C + c8 * 8;
+#pragma unroll
+      for (int jx = 0; jx < 4; ++jx) {
+        const int Xu = X + jx - 1;
+        if (Xu < 0 || Xu >= Wu) continue;
+        float t[8];
+        ld8(rowp + (size_t)Xu * C, t);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) hrow[r][j] = fmaf(f[jx], t[j], hrow[r][j]);
+      }
+    }
+    float bs[8], sc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      bs[j] = __ldg(bias + c8 * 8 + j);
+      sc[j] = __ldg(out_scale + (size_t)b * out_scale_stride + c8 * 8 + j);
+    }
+    const float* nz = noise != nullptr ? noise + (size_t)(b / noise_group_div) * noise_group_stride : nullptr;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int Z = Z0 + k;
+      const float nv = nz != nullptr ? nstr * __ldg(nz + (size_t)Z * Wout + X) : 0.f;
+      float v[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float t = f[0] * hrow[k][j];
+        t = fmaf(f[1], hrow[k + 1][j], t);
+        t = fmaf(f[2], hrow[k + 2][j], t);
+        t = fmaf(f[3], hrow[k + 3][j], t);
+        t = t + nv + bs[j];
+        t = fmaxf(t, 0.2f * t) * kSqrt2;
+        v[j] = t * sc[j];
+      }
+      st8(out + (((size_t)b * Hout + Z) * Wout + X) * C + c8 * 8, v);
+    }
+  }
+}
+
+// One thread: 8 channels of the four phases of one space-to-depth cell: a 5x5 input patch (25 vector loads).
+// u[Y][X] = sum_{jy,jx} f[jy] f[jx] a[Y+jy-2][X+jx-2];  cell (z,w) holds u[2z+py][2w+px].
+__global__ void blur_s2d_kernel(const __half* __restrict__ a, __half* __restrict__ out, int P, int H, int W, int C) {
+  const int C8 = C >> 3, Hs = (H >> 1) + 1, Ws = (W >> 1) + 1;
+  const size_t n = (size_t)P * Hs * Ws * C8;
+  const float f[4] = {0.125f, 0.375f, 0.375f, 0.125f};
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const int c8 = (int)(i % C8);
+    const int w = (int)((i / C8) % Ws);
+    const int z = (int)((i / ((size_t)C8 * Ws)) % Hs);
+    const int b = (int)(i / ((size_t)C8 * Ws * Hs));
+    float hx[5][2][8];     // horizontally filtered rows 2z-2 .. 2z+2, for px = 0,1
+#pragma unroll
+    for (int r = 0; r < 5; ++r) {
+#pragma unroll
+      for (int px = 0; px < 2; ++px)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) hx[r][px][j] = 0.f;
+      const int yy = 2 * z + r - 2;
+      if (yy < 0 || yy >= H) continue;
+      const __half* rowp = a + (((size_t)b * H + yy) * W) * C + c8 * 8;
+#pragma unroll
+      for (int cix = 0; cix < 5; ++cix) {
+        const int xx = 2 * w + cix - 2;
+        if (xx < 0 || xx >= W) continue;
+        float t[8];
+        ld8(rowp + (size_t)xx * C, t);
+        // column cix contributes to px=0 with tap jx = cix (X = 2w: xx = X + jx - 2) and to px=1 with jx = cix-1
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          if (cix < 4) hx[r][0][j] = fmaf(f[cix], t[j], hx[r][0][j]);
+          if (cix > 0) hx[r][1][j] = fmaf(f[cix - 1], t[j], hx[r][1][j]);
+        }
+      }
+    }
+    __half* op = out + (((size_t)b * Hs + z) * Ws + w) * (4 * C) + c8 * 8;
+#pragma unroll
+    for (int py = 0; py < 2; ++py) {
+#pragma unroll
+      for (int px = 0; px < 2; ++px) {
+        float v[8];
+        const bool inside = (2 * z + py <= H) && (2 * w + px <= W);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          // row r contributes to py with tap jy = r - py
+          float t = f[0] * hx[py][px][j];
+          t = fmaf(f[1], hx[py + 1][px][j], t);
+          t = fmaf(f[2], hx[py + 2][px][j], t);
+          t = fmaf(f[3], hx[py + 3][px][j], t);
+          v[j] = inside ? t : 0.f;
+        }
+        st8(op + (py * 2 + px) * C, v);
+      }
+    }
+  }
+}
+
 // one block per (minibatch, member m in [0, batch/group)); samples mb*batch + gi*(batch/group) + m
 __global__ void mbstd_kernel(const __half* __restrict__ x, __half* __restrict__ out, int batch, int group, int C,
                              int Cpad) {
@@ -591,6 +731,22 @@ cudaError_t k_fir_down(const __half* x, __half* out, int N, int H, int W, int C,
   const int tiles = ((Wo + kFdTW - 1) / kFdTW) * ((Ho + kFdTH - 1) / kFdTH) * N;
   dim3 grid(tiles, C / kFdC);
   fir_down_kernel<<<grid, 256, 0, s>>>(x, out, N, H, W, C);
+  GLASS_RET();
+}
+cudaError_t k_upfir(const __half* u, __half* out, const float* noise, size_t noise_group_stride, int noise_group_div,
+                    const float* noise_strength, const float* bias, const float* out_scale, int out_scale_stride,
+                    int P, int Hout, int Wout, int C, cudaStream_t s) {
+  if (C % 8 != 0 || Hout % 4 != 0) return cudaErrorInvalidValue;
+  const size_t n = (size_t)P * (Hout / 4) * Wout * (C / 8);
+  upfir_kernel<<<blocks_for(n, kThreads, 148 * 32), kThreads, 0, s>>>(u, out, noise, noise_group_stride, noise_group_div,
+                                                                     noise_strength, bias, out_scale, out_scale_stride,
+                                                                     P, Hout, Wout, C);
+  GLASS_RET();
+}
+cudaError_t k_blur_s2d(const __half* a, __half* out, int P, int H, int W, int C, cudaStream_t s) {
+  if (C % 8 != 0 || (H & 1) || (W & 1)) return cudaErrorInvalidValue;
+  const size_t n = (size_t)P * (H / 2 + 1) * (W / 2 + 1) * (C / 8);
+  blur_s2d_kernel<<<blocks_for(n, kThreads, 148 * 32), kThreads, 0, s>>>(a, out, P, H, W, C);
   GLASS_RET();
 }
 cudaError_t k_mbstd(const __half* x, __half* out, int P, int batch, int group, int C, int Cpad, cudaStream_t s) {

@@ -23,6 +23,16 @@ cudaError_t k_rgb_combine(const float4* yprev, const float4* slabs, int n_slabs,
 // noise: Philox4x32-10 + Box-Muller, n floats
 cudaError_t k_noise(float* out, size_t n, uint64_t seed, uint64_t offset, cudaStream_t s);
 
+// Exact up-conv, second half (stylegan2/modules.py:1131-1132 FilterLayer + :414-453 noise + :276-297 bias/act):
+// u [P][2H+2][2W+2][C] fp16 (transposed-conv output, demodulated) -> FIR [1,3,3,1]x[1,3,3,1]/16 (pad 1)
+// -> + strength*noise + bias -> lrelu*sqrt2 -> * next style -> fp16 NHWC [P][2H][2W][C]
+cudaError_t k_upfir(const __half* u, __half* out, const float* noise, size_t noise_group_stride, int noise_group_div,
+                    const float* noise_strength, const float* bias, const float* out_scale, int out_scale_stride,
+                    int P, int Hout, int Wout, int C, cudaStream_t s);
+// Exact down-conv, first half (modules.py:1243-1246 FilterLayer pad 2): a [P][H][W][C] -> blurred (H+1)x(W+1),
+// written space-to-depth as [P][H/2+1][W/2+1][4C] (phase-major channels), zeros beyond row/col H
+cudaError_t k_blur_s2d(const __half* a, __half* out, int P, int H, int W, int C, cudaStream_t s);
+
 // ---- CLIP tower ----
 // generator.py:45 (bilinear 1024->224, align_corners=False) fused with the im2col of
 // clip/model.py:219 conv1 (k=32,s=32): patches[b*g*g + gy*g+gx][c*p*p + py*p + px] fp16

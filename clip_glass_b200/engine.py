@@ -28,7 +28,7 @@ def flatten_noise(noise: Sequence[Sequence[torch.Tensor]]) -> np.ndarray:
 class GlassEngine:
     def __init__(self, gan: GanSpec, clip: ClipSpec, g_sd: Dict[str, torch.Tensor],
                  d_sd: Optional[Dict[str, torch.Tensor]], clip_sd: Dict[str, torch.Tensor],
-                 batch_size: int, max_population: int, device: int = 0, conv_impl: int = 0):
+                 batch_size: int, max_population: int, device: int = 0, conv_impl: int = 0, flags: int = 0):
         self.lib = load_library()
         self.gan, self.clip = gan, clip
         self.batch_size = batch_size
@@ -49,6 +49,7 @@ class GlassEngine:
         cfg.max_population = max_population
         cfg.device = device
         cfg.conv_impl = conv_impl
+        cfg.flags = flags
         self._h = ctypes.c_void_p()
         check(self.lib.glass_create(ctypes.byref(cfg), ctypes.byref(self._h)))
         packed = {}

@@ -111,6 +111,54 @@ def fold_downconv(w: torch.Tensor) -> torch.Tensor:
     return out
 
 
+# Tap tables of the exact polyphase forms (dy, dx per tap); see DESIGN.md section 3.
+UP_EXACT_TAPS = [(-1, -1), (-1, 0), (0, -1), (0, 0)]
+DOWN_EXACT_TAPS = [(0, 0), (0, 1), (1, 0), (1, 1)]
+
+
+def exact_upconv(w: torch.Tensor) -> torch.Tensor:
+    """conv_transpose2d(stride 2, 3x3) WITHOUT the FIR, as a 2x2-tap conv with 4*O phase columns.
+
+    u[2z+py, 2w+px] = sum over (y,ky): 2y+ky = 2z+py  ->  y = z (ky = py)  or  y = z-1 (ky = 2, only py = 0);
+    same along x.  w [O,I,3,3] (already * coef) -> [4 taps][4*O][I], tap order UP_EXACT_TAPS,
+    column (py*2+px)*O + o.  9 of the 16 (tap, phase) blocks are non-zero: the 9 MACs/pixel of the
+    transposed conv as the reference writes it."""
+    O, I = w.shape[:2]
+    out = torch.zeros(4, 4 * O, I, dtype=w.dtype)
+    for t, (dy, dx) in enumerate(UP_EXACT_TAPS):
+        for py in range(2):
+            ky = py if dy == 0 else (2 if py == 0 else None)
+            if ky is None:
+                continue
+            for px in range(2):
+                kx = px if dx == 0 else (2 if px == 0 else None)
+                if kx is None:
+                    continue
+                ph = py * 2 + px
+                out[t, ph * O:(ph + 1) * O] = w[:, :, ky, kx]
+    return out
+
+
+def exact_downconv(w: torch.Tensor) -> torch.Tensor:
+    """3x3 stride-2 conv (no FIR) over the space-to-depth(2) of the blurred input: out[z] = sum_k w[k] u[2z+k]
+    = sum_{a,p: 2a+p=k} w[2a+p] U[z+a, p].  w [O,I,3,3] -> [4 taps][O][4*I], tap order DOWN_EXACT_TAPS,
+    k index (py*2+px)*I + i."""
+    O, I = w.shape[:2]
+    out = torch.zeros(4, O, 4 * I, dtype=w.dtype)
+    for t, (a, b) in enumerate(DOWN_EXACT_TAPS):
+        for py in range(2):
+            ky = 2 * a + py
+            if ky > 2:
+                continue
+            for px in range(2):
+                kx = 2 * b + px
+                if kx > 2:
+                    continue
+                ph = py * 2 + px
+                out[t, :, ph * I:(ph + 1) * I] = w[:, :, ky, kx]
+    return out
+
+
 def taps_plain(w: torch.Tensor) -> torch.Tensor:
     """w [O,I,k,k] -> [k*k][O][I]."""
     O, I, k, _ = w.shape
@@ -145,6 +193,8 @@ def pack_generator(sd: Dict[str, torch.Tensor], spec: GanSpec) -> Dict[str, np.n
         wc = w * _coef(w.shape)
         out[f"g.conv{li}.wsq"] = _f32((wc ** 2).sum(dim=(2, 3)).t())       # [cin][cout]
         out[f"g.conv{li}.w"] = _f16(fold_upconv(wc) if ly["up"] else taps_plain(wc))
+        if ly["up"]:
+            out[f"g.conv{li}.wx"] = _f16(exact_upconv(wc))      # exact polyphase form (used from 16x16 inputs up)
         out[f"g.conv{li}.bias"] = _f32(sd[p + ".bias"])
         out[f"g.conv{li}.nstr"] = _f32(sd[p + ".layer.weight"].reshape(1))
     ch = list(spec.channels)[::-1]
@@ -180,6 +230,7 @@ def pack_discriminator(sd: Dict[str, torch.Tensor], spec: GanSpec) -> Dict[str, 
         out[f"d.b{b}.c0.b"] = _f32(sd[p + ".conv_block.0.bias"])
         w1 = sd[p + ".conv_block.1.layer.weight"].float()
         out[f"d.b{b}.c1.w"] = _f16(fold_downconv(w1 * _coef(w1.shape)))
+        out[f"d.b{b}.c1.wx"] = _f16(exact_downconv(w1 * _coef(w1.shape)))
         out[f"d.b{b}.c1.b"] = _f32(sd[p + ".conv_block.1.bias"])
         wp = sd[p + ".projection.weight"].float()
         out[f"d.b{b}.proj.w"] = _f16(taps_plain(wp * _coef(wp.shape)))

@@ -55,7 +55,12 @@ typedef struct glass_config {
   int32_t device;                         /* CUDA ordinal                        */
   int32_t conv_impl;                      /* 0 = tcgen05 tensor-core path (product);
                                              1 = SIMT bring-up kernels (same epilogues; tests only) */
+  int32_t flags;                          /* GLASS_FLAG_* */
 } glass_config;
+
+/* Use the FIR-folded 3x3 forms for every up/down conv (4x the MACs, no separate FIR pass) instead of the
+ * exact polyphase forms (2x2-tap conv + streaming FIR pass) that are the default from 16x16 inputs up. */
+#define GLASS_FLAG_FOLDED_RESAMPLE 1
 
 /* -- lifetime ------------------------------------------------------------- */
 /* Replaces Generator.__init__ (generator.py:12-27): allocate the engine. */

@@ -42,6 +42,31 @@ def conv_taps(x_nhwc: torch.Tensor, w_taps: torch.Tensor) -> torch.Tensor:
     return y.permute(0, 2, 3, 1)
 
 
+def conv_taps_table(x_nhwc: torch.Tensor, w_taps: torch.Tensor, table, out_hw) -> torch.Tensor:
+    """Generic tap-table conv: out[n,y,x,:] = sum_t W[t] @ x[n, y+dy_t, x+dx_t, :] (zero outside the input).
+    x [N,Hin,Win,C]; out grid out_hw = (H, W)."""
+    n, hin, win, c = x_nhwc.shape
+    H, Wd = out_hw
+    ntot = w_taps.shape[1]
+    out = torch.zeros(n, H, Wd, ntot)
+    pad = 2
+    xp = F.pad(x_nhwc, [0, 0, pad, pad + max(0, Wd - win) + 2, pad, pad + max(0, H - hin) + 2])
+    for t, (dy, dx) in enumerate(table):
+        patch = xp[:, pad + dy:pad + dy + H, pad + dx:pad + dx + Wd, :]
+        out += patch @ w_taps[t].float().t()
+    return out
+
+
+def fir_same(u: torch.Tensor, f1: torch.Tensor, out_hw, shift: int) -> torch.Tensor:
+    """v[Z,X] = sum_{jy,jx} f[jy] f[jx] u[Z+jy-shift, X+jx-shift] (zero outside u). u [N,Hu,Wu,C]."""
+    n, hu, wu, c = u.shape
+    H, Wd = out_hw
+    k = (f1[:, None] * f1[None, :])
+    up = F.pad(u.permute(0, 3, 1, 2), [shift, 4, shift, 4])
+    v = F.conv2d(up, k[None, None].repeat(c, 1, 1, 1), groups=c)
+    return v[:, :, :H, :Wd].permute(0, 2, 3, 1)
+
+
 def depth_to_space(y: torch.Tensor, cout: int) -> torch.Tensor:
     """[N,H,W,4*C] with n=(py*2+px)*C+o -> [N,2H,2W,C]"""
     n, hh, ww, _ = y.shape
@@ -84,7 +109,7 @@ def emu_mapping(pk, spec, z):
     return x
 
 
-def emu_generator(pk, spec, z, noise, batch, capture=None, fp16=True):
+def emu_generator(pk, spec, z, noise, batch, capture=None, fp16=True, exact=True):
     """z [P,L] fp32; noise list per group of list per layer [1,1,H,W] or None.
     Returns images [P,3,R,R] in [0,1]."""
     r = h if fp16 else (lambda t: t)
@@ -106,10 +131,19 @@ def emu_generator(pk, spec, z, noise, batch, capture=None, fp16=True):
         cin, cout = ly["cin"], ly["cout"]
         s = styles[:, conv_off[li]:conv_off[li] + cin]
         d = torch.rsqrt((s * s) @ T(pk[f"g.conv{li}.wsq"]) + 1e-8)            # [P,cout]
-        acc = conv_taps(x, T(pk[f"g.conv{li}.w"]))
-        if ly["up"]:
-            acc = depth_to_space(acc, cout)
-        v = acc * d[:, None, None, :]
+        in_res = x.shape[1]
+        if ly["up"] and exact and in_res >= 16:
+            # exact polyphase transposed conv on the (H+1)x(W+1) grid -> u (fp16), then the FIR pass
+            acc = conv_taps_table(x, T(pk[f"g.conv{li}.wx"]), packing.UP_EXACT_TAPS, (in_res + 1, in_res + 1))
+            u = r(depth_to_space(acc * d[:, None, None, :].repeat(1, 1, 1, 4), cout))      # [(2H+2)^2], fp16 storage
+            if capture is not None:
+                capture[f"u{li}"] = u
+            v = fir_same(u, packing.F1_UP, (2 * in_res, 2 * in_res), 1)
+        else:
+            acc = conv_taps(x, T(pk[f"g.conv{li}.w"]))
+            if ly["up"]:
+                acc = depth_to_space(acc, cout)
+            v = acc * d[:, None, None, :]
         if noise is not None:
             nz = torch.cat([noise[g][li].reshape(1, ly["res"], ly["res"], 1).expand(batch, -1, -1, -1)
                             for g in range(P // batch)])
@@ -135,7 +169,7 @@ def emu_generator(pk, spec, z, noise, batch, capture=None, fp16=True):
     return img.permute(0, 3, 1, 2).contiguous()
 
 
-def emu_discriminator(pk, spec, images, batch, capture=None, fp16=True):
+def emu_discriminator(pk, spec, images, batch, capture=None, fp16=True, exact=True):
     """images [P,3,R,R] in [0,1] -> logits [P]."""
     r = h if fp16 else (lambda t: t)
     ch = list(spec.channels)
@@ -147,14 +181,22 @@ def emu_discriminator(pk, spec, images, batch, capture=None, fp16=True):
     blur = (f1[:, None] * f1[None, :])
     for b in range(spec.num_blocks - 1):
         a = r(lrelu_gain(conv_taps(x, T(pk[f"d.b{b}.c0.w"])) + T(pk[f"d.b{b}.c0.b"])))
-        a_s2d = space_to_depth(a)
+        res = a.shape[1]
+        use_exact = exact and res >= 32
         # projection path: FIR(pad 1) sampled at even positions, then 1x1
         c = x.shape[-1]
         xp = F.pad(x.permute(0, 3, 1, 2), [1, 1, 1, 1])
         xd = F.conv2d(xp, blur[None, None].repeat(c, 1, 1, 1), stride=2, groups=c)
         xd = r(xd.permute(0, 2, 3, 1))
         proj = r(conv_taps(xd, T(pk[f"d.b{b}.proj.w"])))
-        acc = conv_taps(a_s2d, T(pk[f"d.b{b}.c1.w"]))
+        if use_exact:
+            # blur (FIR pad 2) -> (H+1)^2, stored space-to-depth as [(H/2+1)^2][4C] fp16; then the 2x2-tap conv
+            u = fir_same(a, packing.F1_DOWN, (res + 1, res + 1), 2)
+            up = F.pad(u, [0, 0, 0, 1, 0, 1])                                    # pad to (H+2)^2 (zeros)
+            u_s2d = r(space_to_depth(up))
+            acc = conv_taps_table(u_s2d, T(pk[f"d.b{b}.c1.wx"]), packing.DOWN_EXACT_TAPS, (res // 2, res // 2))
+        else:
+            acc = conv_taps(space_to_depth(a), T(pk[f"d.b{b}.c1.w"]))
         x = r((lrelu_gain(acc + T(pk[f"d.b{b}.c1.b"])) + proj) * (1.0 / SQRT2))
         if capture is not None:
             capture[f"d{b}"] = x

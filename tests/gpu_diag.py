@@ -43,6 +43,7 @@ def main():
     ap.add_argument("--config", default="tiny")
     ap.add_argument("--impl", type=int, default=0)
     ap.add_argument("--no-capture", action="store_true")
+    ap.add_argument("--flags", type=int, default=0, help="glass_config.flags (1 = folded up/down convs)")
     ap.add_argument("--json", default=None)
     args = ap.parse_args()
 
@@ -57,7 +58,7 @@ def main():
 
     t0 = time.time()
     eng = GlassEngine(gan, clip, inp["g_sd"], inp["d_sd"], inp["c_sd"], batch_size=B, max_population=P,
-                      conv_impl=args.impl)
+                      conv_impl=args.impl, flags=args.flags)
     eng.set_text_features(text)
     eng.set_debug(capture=not args.no_capture)
     print(f"engine ready in {time.time() - t0:.1f}s", flush=True)
@@ -70,13 +71,16 @@ def main():
     print("generate done", flush=True)
 
     cap = {}
-    emu_img = E.emu_generator(pk, gan, z, inp["noise"], B, capture=cap)
+    exact = (args.flags & 1) == 0
+    emu_img = E.emu_generator(pk, gan, z, inp["noise"], B, capture=cap, exact=exact)
     layers = packing.g_layers(gan)
     if not args.no_capture:
         lines.append(err_line("w", eng.debug_read("w"), cap["w"]))
         lines.append(err_line("styles", eng.debug_read("styles"), cap["styles"]))
         lines.append(err_line("x0", eng.debug_read("x0"), cap["x0"]))
         for li in range(len(layers) - 1):
+            if f"u{li}" in cap:
+                lines.append(err_line(f"u{li}", eng.debug_read(f"u{li}"), cap[f"u{li}"]))
             lines.append(err_line(f"xs{li}", eng.debug_read(f"xs{li}"), cap[f"xs{li}"]))
         for b in range(gan.num_blocks):
             got = eng.debug_read(f"rgb{b}").reshape(-1, 4)[:, :3]
@@ -99,7 +103,7 @@ def main():
     torch.cuda.synchronize()
     print("discriminate done", flush=True)
     dcap = {}
-    emu_logits = E.emu_discriminator(pk, gan, images.cpu(), B, capture=dcap)
+    emu_logits = E.emu_discriminator(pk, gan, images.cpu(), B, capture=dcap, exact=exact)
     if not args.no_capture:
         for b in range(gan.num_blocks - 1):
             lines.append(err_line(f"d{b}", eng.debug_read(f"d{b}"), dcap[f"d{b}"]))

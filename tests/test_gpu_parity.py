@@ -26,9 +26,9 @@ pytestmark = pytest.mark.gpu
 REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def run_diag(config, impl, timeout):
+def run_diag(config, impl, timeout, flags=0):
     """gpu_diag in a subprocess with a timeout: a trapped or hung kernel fails one test, not the session."""
-    cmd = [sys.executable, "-m", "tests.gpu_diag", "--config", config, "--impl", str(impl)]
+    cmd = [sys.executable, "-m", "tests.gpu_diag", "--config", config, "--impl", str(impl), "--flags", str(flags)]
     r = subprocess.run(cmd, cwd=REPO, capture_output=True, text=True, timeout=timeout)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     return {d["name"]: d for d in (json.loads(l) for l in r.stdout.splitlines() if l.startswith("{"))}
@@ -54,6 +54,12 @@ def test_tiny_layerwise_tcgen05_path():
 
 def test_tiny_layerwise_simt_bringup_path():
     check_diag(run_diag("tiny", 1, 600))
+
+
+def test_tiny_layerwise_folded_resampling_variant():
+    """GLASS_FLAG_FOLDED_RESAMPLE: every up/down conv in its FIR-folded 3x3 form (the default uses the exact
+    polyphase form from 16x16 inputs up); both must match the emulation and the oracle."""
+    check_diag(run_diag("tiny", 0, 600, flags=1))
 
 
 @pytest.fixture(scope="module")

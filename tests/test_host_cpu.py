@@ -95,7 +95,7 @@ def test_library_exports_every_declared_symbol():
     for name in sorted(declared):
         assert hasattr(lib, name), name
     assert declared == set(_lib.SYMBOLS), declared ^ set(_lib.SYMBOLS)
-    assert ctypes.sizeof(_lib.GlassConfig) == 4 * (1 + 12 + 13)
+    assert ctypes.sizeof(_lib.GlassConfig) == 4 * (1 + 12 + 14)
     assert ctypes.sizeof(_lib.GlassNoise) == 32
 
 
