@@ -18,11 +18,12 @@ def main():
     ap.add_argument("--evals", type=int, default=2)
     ap.add_argument("--nod", action="store_true")
     ap.add_argument("--timing", action="store_true")
+    ap.add_argument("--flags", type=int, default=0)
     args = ap.parse_args()
     gan, clip = W.FFHQ, W.VIT_B32
     eng = GlassEngine(gan, clip, W.make_generator_weights(gan, 1000),
                       None if args.nod else W.make_discriminator_weights(gan, 1001),
-                      W.make_clip_visual_weights(clip, 1002), batch_size=4, max_population=args.pop)
+                      W.make_clip_visual_weights(clip, 1002), batch_size=4, max_population=args.pop, flags=args.flags)
     eng.set_text_features(torch.randn(1, 512, generator=torch.Generator().manual_seed(5)))
     z = torch.from_numpy(W.make_latents(args.pop, 512, 50)).float().cuda()
     if args.timing:
@@ -42,7 +43,7 @@ def main():
             names += ["D:fin", "D:dense0"]
         bd = eng.conv_breakdown()
         tot = sum(m for m, _ in bd)
-        print(f"pop={args.pop} conv launches={len(bd)} total conv ms={tot:.3f}")
+        print(f"pop={args.pop} flags={args.flags} conv launches={len(bd)} total conv ms={tot:.3f}")
         for n, (ms, fl) in zip(names, bd):
             print(f"{n:28s} {ms:9.4f} ms  {fl/1e9:10.2f} GFLOP  {fl/ms/1e9 if ms > 0 else 0:9.1f} TFLOP/s")
     eng.close()
