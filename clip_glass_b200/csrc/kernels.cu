@@ -472,13 +472,30 @@ __device__ __forceinline__ void st8(__half* p, const float (&v)[8]) {
   *reinterpret_cast<uint4*>(p) = o;
 }
 
-// One thread: 8 channels x 4 consecutive output rows of one output column.  Horizontal taps first (7 input rows x
-// 4 columns = 28 vector loads for 4 outputs), then the vertical taps: v[Z] = sum_j f[j] u[Z+j-1].
-__global__ void upfir_kernel(const __half* __restrict__ u, __half* __restrict__ out, const float* __restrict__ noise,
-                             size_t noise_group_stride, int noise_group_div, const float* __restrict__ noise_strength,
-                             const float* __restrict__ bias, const float* __restrict__ out_scale, int out_scale_stride,
-                             int P, int Hout, int Wout, int C) {
-  const int C8 = C >> 3, Hq = Hout >> 2;
+// fp16 pair sums (one rounding of <= 1/2 ulp each), everything after that in fp32: ~30 % fewer instructions than
+// converting every tap, without letting fp16 accumulate the filter.
+__device__ __forceinline__ void pair_sum8(const uint4& p, const uint4& q, float (&v)[8]) {
+  const __half2* a = reinterpret_cast<const __half2*>(&p);
+  const __half2* b = reinterpret_cast<const __half2*>(&q);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float2 t = __half22float2(__hadd2(a[j], b[j]));
+    v[2 * j] = t.x;
+    v[2 * j + 1] = t.y;
+  }
+}
+
+// One thread: 8 channels x kUpRows consecutive output rows of one output column.  Input rows stream through a
+// sliding window of four row accumulators: row Y = Z0+r-1 is filtered horizontally once,
+//   h = 1/4 (u[X-1] + u[X+2]) + 3/4 (u[X] + u[X+1]),
+// and added to the (up to four) outputs Z = Y-2 .. Y+1 with the vertical taps; a finished output gets noise, bias,
+// lrelu*sqrt2 and the next layer's style and is stored as fp16.
+constexpr int kUpRows = 8;
+__global__ void __launch_bounds__(256) upfir_kernel(
+    const __half* __restrict__ u, __half* __restrict__ out, const float* __restrict__ noise, size_t noise_group_stride,
+    int noise_group_div, const float* __restrict__ noise_strength, const float* __restrict__ bias,
+    const float* __restrict__ out_scale, int out_scale_stride, int P, int Hout, int Wout, int C) {
+  const int C8 = C >> 3, Hq = Hout / kUpRows;
   const int Hu = Hout + 2, Wu = Wout + 2;
   const size_t n = (size_t)P * Hq * Wout * C8;
   const float f[4] = {0.25f, 0.75f, 0.75f, 0.25f};
@@ -488,25 +505,7 @@ __global__ void upfir_kernel(const __half* __restrict__ u, __half* __restrict__ 
     const int X = (int)((i / C8) % Wout);
     const int zq = (int)((i / ((size_t)C8 * Wout)) % Hq);
     const int b = (int)(i / ((size_t)C8 * Wout * Hq));
-    const int Z0 = zq * 4;
-    float hrow[7][8];
-#pragma unroll
-    for (int r = 0; r < 7; ++r) {
-      const int Y = Z0 + r - 1;
-#pragma unroll
-      for (int j = 0; j < 8; ++j) hrow[r][j] = 0.f;
-      if (Y < 0 || Y >= Hu) continue;
-      const __half* rowp = u + (((size_t)b * Hu + Y) * Wu) * C + c8 * 8;
-#pragma unroll
-      for (int jx = 0; jx < 4; ++jx) {
-        const int Xu = X + jx - 1;
-        if (Xu < 0 || Xu >= Wu) continue;
-        float t[8];
-        ld8(rowp + (size_t)Xu * C, t);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) hrow[r][j] = fmaf(f[jx], t[j], hrow[r][j]);
-      }
-    }
+    const int Z0 = zq * kUpRows;
     float bs[8], sc[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -514,77 +513,119 @@ __global__ void upfir_kernel(const __half* __restrict__ u, __half* __restrict__ 
       sc[j] = __ldg(out_scale + (size_t)b * out_scale_stride + c8 * 8 + j);
     }
     const float* nz = noise != nullptr ? noise + (size_t)(b / noise_group_div) * noise_group_stride : nullptr;
+    const __half* ub = u + ((size_t)b * Hu * Wu) * C + c8 * 8;
+    // X-1 >= 0 always holds except at X == 0; X+2 <= Wout+1 = Wu-1 always holds
+    const bool left = X > 0;
+    float acc[kUpRows][8];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const int Z = Z0 + k;
-      const float nv = nz != nullptr ? nstr * __ldg(nz + (size_t)Z * Wout + X) : 0.f;
-      float v[8];
+    for (int k = 0; k < kUpRows; ++k)
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        float t = f[0] * hrow[k][j];
-        t = fmaf(f[1], hrow[k + 1][j], t);
-        t = fmaf(f[2], hrow[k + 2][j], t);
-        t = fmaf(f[3], hrow[k + 3][j], t);
-        t = t + nv + bs[j];
-        t = fmaxf(t, 0.2f * t) * kSqrt2;
-        v[j] = t * sc[j];
+      for (int j = 0; j < 8; ++j) acc[k][j] = 0.f;
+#pragma unroll
+    for (int r = 0; r < kUpRows + 3; ++r) {
+      const int Y = Z0 + r - 1;
+      if (Y >= 0 && Y < Hu) {
+        const __half* rp = ub + ((size_t)Y * Wu + X) * C;
+        const uint4 zero = make_uint4(0, 0, 0, 0);
+        const uint4 ua = left ? __ldg(reinterpret_cast<const uint4*>(rp - C)) : zero;
+        const uint4 ubv = __ldg(reinterpret_cast<const uint4*>(rp));
+        const uint4 uc = __ldg(reinterpret_cast<const uint4*>(rp + C));
+        const uint4 ud = __ldg(reinterpret_cast<const uint4*>(rp + 2 * C));
+        float so[8], si[8];
+        pair_sum8(ua, ud, so);
+        pair_sum8(ubv, uc, si);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float hv = fmaf(0.75f, si[j], 0.25f * so[j]);
+          // row r feeds output k = r - jv with vertical tap jv (v[Z] = sum_jv f[jv] u[Z + jv - 1])
+#pragma unroll
+          for (int jv = 0; jv < 4; ++jv) {
+            const int k = r - jv;
+            if (k >= 0 && k < kUpRows) acc[k][j] = fmaf(f[jv], hv, acc[k][j]);
+          }
+        }
       }
-      st8(out + (((size_t)b * Hout + Z) * Wout + X) * C + c8 * 8, v);
+      const int kdone = r - 3;       // output row whose last input row was just added
+      if (kdone >= 0) {
+        const int Z = Z0 + kdone;
+        const float nv = nz != nullptr ? nstr * __ldg(nz + (size_t)Z * Wout + X) : 0.f;
+        float v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float t = acc[kdone][j] + nv + bs[j];
+          t = fmaxf(t, 0.2f * t) * kSqrt2;
+          v[j] = t * sc[j];
+        }
+        st8(out + (((size_t)b * Hout + Z) * Wout + X) * C + c8 * 8, v);
+      }
     }
   }
 }
 
-// One thread: 8 channels of the four phases of one space-to-depth cell: a 5x5 input patch (25 vector loads).
-// u[Y][X] = sum_{jy,jx} f[jy] f[jx] a[Y+jy-2][X+jx-2];  cell (z,w) holds u[2z+py][2w+px].
-__global__ void blur_s2d_kernel(const __half* __restrict__ a, __half* __restrict__ out, int P, int H, int W, int C) {
-  const int C8 = C >> 3, Hs = (H >> 1) + 1, Ws = (W >> 1) + 1;
-  const size_t n = (size_t)P * Hs * Ws * C8;
+// One thread: 8 channels of two vertically adjacent space-to-depth cells (8 outputs) from a 7x5 input patch.
+// u[Y][X] = sum_{jy,jx} f[jy] f[jx] a[Y+jy-2][X+jx-2];  cell (z,w) holds u[2z+py][2w+px];  f = [1,3,3,1]/8.
+__global__ void __launch_bounds__(256) blur_s2d_kernel(const __half* __restrict__ a, __half* __restrict__ out, int P,
+                                                       int H, int W, int C) {
+  const int C8 = C >> 3, Hs = (H >> 1) + 1, Ws = (W >> 1) + 1, Hp = (Hs + 1) >> 1;
+  const size_t n = (size_t)P * Hp * Ws * C8;
   const float f[4] = {0.125f, 0.375f, 0.375f, 0.125f};
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
     const int c8 = (int)(i % C8);
     const int w = (int)((i / C8) % Ws);
-    const int z = (int)((i / ((size_t)C8 * Ws)) % Hs);
-    const int b = (int)(i / ((size_t)C8 * Ws * Hs));
-    float hx[5][2][8];     // horizontally filtered rows 2z-2 .. 2z+2, for px = 0,1
+    const int zp = (int)((i / ((size_t)C8 * Ws)) % Hp);
+    const int b = (int)(i / ((size_t)C8 * Ws * Hp));
+    const int z0 = 2 * zp;                       // cells z0 and z0+1: output rows Y = 2*z0 .. 2*z0+3
+    const __half* ab = a + ((size_t)b * H * W) * C + c8 * 8;
+    float acc[4][2][8];                          // [output row 0..3][px][channel]
 #pragma unroll
-    for (int r = 0; r < 5; ++r) {
+    for (int k = 0; k < 4; ++k)
 #pragma unroll
       for (int px = 0; px < 2; ++px)
 #pragma unroll
-        for (int j = 0; j < 8; ++j) hx[r][px][j] = 0.f;
-      const int yy = 2 * z + r - 2;
+        for (int j = 0; j < 8; ++j) acc[k][px][j] = 0.f;
+    const int x0 = 2 * w - 2;                    // input columns x0 .. x0+4
+#pragma unroll
+    for (int r = 0; r < 7; ++r) {
+      const int yy = 2 * z0 + r - 2;             // input row; feeds output row k = r - jy
       if (yy < 0 || yy >= H) continue;
-      const __half* rowp = a + (((size_t)b * H + yy) * W) * C + c8 * 8;
+      const __half* rp = ab + ((size_t)yy * W) * C;
+      uint4 c[5];
 #pragma unroll
-      for (int cix = 0; cix < 5; ++cix) {
-        const int xx = 2 * w + cix - 2;
-        if (xx < 0 || xx >= W) continue;
-        float t[8];
-        ld8(rowp + (size_t)xx * C, t);
-        // column cix contributes to px=0 with tap jx = cix (X = 2w: xx = X + jx - 2) and to px=1 with jx = cix-1
+      for (int q = 0; q < 5; ++q) {
+        const int xx = x0 + q;
+        c[q] = (xx >= 0 && xx < W) ? __ldg(reinterpret_cast<const uint4*>(rp + (size_t)xx * C)) : make_uint4(0, 0, 0, 0);
+      }
+      // px = 0: taps on columns 0..3; px = 1: taps on columns 1..4
+      float o0[8], i0[8], o1[8], i1[8];
+      pair_sum8(c[0], c[3], o0);
+      pair_sum8(c[1], c[2], i0);
+      pair_sum8(c[1], c[4], o1);
+      pair_sum8(c[2], c[3], i1);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          if (cix < 4) hx[r][0][j] = fmaf(f[cix], t[j], hx[r][0][j]);
-          if (cix > 0) hx[r][1][j] = fmaf(f[cix - 1], t[j], hx[r][1][j]);
+      for (int j = 0; j < 8; ++j) {
+        const float h0 = fmaf(0.375f, i0[j], 0.125f * o0[j]);
+        const float h1 = fmaf(0.375f, i1[j], 0.125f * o1[j]);
+#pragma unroll
+        for (int jy = 0; jy < 4; ++jy) {
+          const int k = r - jy;
+          if (k >= 0 && k < 4) {
+            acc[k][0][j] = fmaf(f[jy], h0, acc[k][0][j]);
+            acc[k][1][j] = fmaf(f[jy], h1, acc[k][1][j]);
+          }
         }
       }
     }
-    __half* op = out + (((size_t)b * Hs + z) * Ws + w) * (4 * C) + c8 * 8;
 #pragma unroll
-    for (int py = 0; py < 2; ++py) {
+    for (int k = 0; k < 4; ++k) {
+      const int z = z0 + (k >> 1), py = k & 1;
+      if (z >= Hs) continue;
+      __half* op = out + (((size_t)b * Hs + z) * Ws + w) * (4 * C) + c8 * 8;
 #pragma unroll
       for (int px = 0; px < 2; ++px) {
-        float v[8];
         const bool inside = (2 * z + py <= H) && (2 * w + px <= W);
+        float v[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          // row r contributes to py with tap jy = r - py
-          float t = f[0] * hx[py][px][j];
-          t = fmaf(f[1], hx[py + 1][px][j], t);
-          t = fmaf(f[2], hx[py + 2][px][j], t);
-          t = fmaf(f[3], hx[py + 3][px][j], t);
-          v[j] = inside ? t : 0.f;
-        }
+        for (int j = 0; j < 8; ++j) v[j] = inside ? acc[k][px][j] : 0.f;
         st8(op + (py * 2 + px) * C, v);
       }
     }
@@ -736,8 +777,8 @@ cudaError_t k_fir_down(const __half* x, __half* out, int N, int H, int W, int C,
 cudaError_t k_upfir(const __half* u, __half* out, const float* noise, size_t noise_group_stride, int noise_group_div,
                     const float* noise_strength, const float* bias, const float* out_scale, int out_scale_stride,
                     int P, int Hout, int Wout, int C, cudaStream_t s) {
-  if (C % 8 != 0 || Hout % 4 != 0) return cudaErrorInvalidValue;
-  const size_t n = (size_t)P * (Hout / 4) * Wout * (C / 8);
+  if (C % 8 != 0 || Hout % kUpRows != 0) return cudaErrorInvalidValue;
+  const size_t n = (size_t)P * (Hout / kUpRows) * Wout * (C / 8);
   upfir_kernel<<<blocks_for(n, kThreads, 148 * 32), kThreads, 0, s>>>(u, out, noise, noise_group_stride, noise_group_div,
                                                                      noise_strength, bias, out_scale, out_scale_stride,
                                                                      P, Hout, Wout, C);
@@ -745,7 +786,7 @@ cudaError_t k_upfir(const __half* u, __half* out, const float* noise, size_t noi
 }
 cudaError_t k_blur_s2d(const __half* a, __half* out, int P, int H, int W, int C, cudaStream_t s) {
   if (C % 8 != 0 || (H & 1) || (W & 1)) return cudaErrorInvalidValue;
-  const size_t n = (size_t)P * (H / 2 + 1) * (W / 2 + 1) * (C / 8);
+  const size_t n = (size_t)P * ((H / 2 + 2) / 2) * (W / 2 + 1) * (C / 8);
   blur_s2d_kernel<<<blocks_for(n, kThreads, 148 * 32), kThreads, 0, s>>>(a, out, P, H, W, C);
   GLASS_RET();
 }
