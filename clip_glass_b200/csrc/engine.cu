@@ -322,11 +322,22 @@ void derive_arch(glass_engine* e) {
   for (int b = 0; b < c.num_blocks; ++b) { e->rgb_off.push_back(off); off += e->gch[b]; }
   e->S = off;
   e->R = 4 << (c.num_blocks - 1);
+  // Which up/down convs run in the exact polyphase form.  Cost model from profiles/r01_fir_passes_p64.txt: the
+  // exact form saves 3/4 of the tensor work of the layer but adds a streaming pass over its output, so it pays
+  // where the layer is tensor-bound (wide channels), not where it is HBM/epilogue-bound (32..256 channels).
   const bool folded = (c.flags & GLASS_FLAG_FOLDED_RESAMPLE) != 0;
+  const bool exact_all = (c.flags & GLASS_FLAG_EXACT_RESAMPLE) != 0;
   e->g_exact.clear();
-  for (const GLayer& l : e->glayers) e->g_exact.push_back((!folded && l.up && l.res / 2 >= 16) ? 1 : 0);
+  for (const GLayer& l : e->glayers) {
+    const int in_res = l.res / 2;
+    const bool possible = !folded && l.up && in_res >= 16;
+    e->g_exact.push_back((possible && (exact_all || (l.cin >= 512 && in_res >= 64))) ? 1 : 0);
+  }
   e->d_exact.clear();
-  for (int b = 0; b + 1 < c.num_blocks; ++b) e->d_exact.push_back((!folded && (e->R >> b) >= 32) ? 1 : 0);
+  for (int b = 0; b + 1 < c.num_blocks; ++b) {
+    const bool possible = !folded && (e->R >> b) >= 32;
+    e->d_exact.push_back((possible && (exact_all || e->gch[c.num_blocks - 1 - b] >= 128)) ? 1 : 0);
+  }
   e->noise_layer_off.clear();
   size_t noff = 0;
   for (const GLayer& l : e->glayers) { e->noise_layer_off.push_back(noff); noff += (size_t)l.res * l.res; }

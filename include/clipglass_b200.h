@@ -58,9 +58,11 @@ typedef struct glass_config {
   int32_t flags;                          /* GLASS_FLAG_* */
 } glass_config;
 
-/* Use the FIR-folded 3x3 forms for every up/down conv (4x the MACs, no separate FIR pass) instead of the
- * exact polyphase forms (2x2-tap conv + streaming FIR pass) that are the default from 16x16 inputs up. */
-#define GLASS_FLAG_FOLDED_RESAMPLE 1
+/* Up/down convs exist in two forms: FIR-folded 3x3 (4x the MACs, everything in one tensor-core launch) and
+ * exact polyphase (2x2-tap conv + one streaming FIR pass).  By default the engine picks per layer with a
+ * measured cost model (exact where the layer is tensor-bound: Cin >= 512 at >= 64x64 in G, Cin >= 128 in D). */
+#define GLASS_FLAG_FOLDED_RESAMPLE 1   /* folded form everywhere */
+#define GLASS_FLAG_EXACT_RESAMPLE 2    /* exact form wherever it is defined (inputs >= 16x16) */
 
 /* -- lifetime ------------------------------------------------------------- */
 /* Replaces Generator.__init__ (generator.py:12-27): allocate the engine. */

@@ -43,7 +43,7 @@ def main():
     ap.add_argument("--config", default="tiny")
     ap.add_argument("--impl", type=int, default=0)
     ap.add_argument("--no-capture", action="store_true")
-    ap.add_argument("--flags", type=int, default=0, help="glass_config.flags (1 = folded up/down convs)")
+    ap.add_argument("--flags", type=int, default=0, help="glass_config.flags (1 = folded up/down convs everywhere, 2 = exact everywhere)")
     ap.add_argument("--json", default=None)
     args = ap.parse_args()
 
@@ -71,7 +71,7 @@ def main():
     print("generate done", flush=True)
 
     cap = {}
-    exact = (args.flags & 1) == 0
+    exact = (args.flags & 2) != 0      # tiny config: the default cost model keeps every layer folded
     emu_img = E.emu_generator(pk, gan, z, inp["noise"], B, capture=cap, exact=exact)
     layers = packing.g_layers(gan)
     if not args.no_capture:

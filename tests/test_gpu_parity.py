@@ -56,10 +56,11 @@ def test_tiny_layerwise_simt_bringup_path():
     check_diag(run_diag("tiny", 1, 600))
 
 
-def test_tiny_layerwise_folded_resampling_variant():
-    """GLASS_FLAG_FOLDED_RESAMPLE: every up/down conv in its FIR-folded 3x3 form (the default uses the exact
-    polyphase form from 16x16 inputs up); both must match the emulation and the oracle."""
-    check_diag(run_diag("tiny", 0, 600, flags=1))
+def test_tiny_layerwise_exact_resampling_variant():
+    """GLASS_FLAG_EXACT_RESAMPLE: every up/down conv from 16x16 inputs up in its exact polyphase form (2x2-tap conv
+    + k_upfir / k_blur_s2d).  With the tiny config's 32/64 channels the default cost model keeps every layer in
+    the folded form, so this is the test that exercises the exact kernels."""
+    check_diag(run_diag("tiny", 0, 600, flags=2))
 
 
 @pytest.fixture(scope="module")
@@ -72,6 +73,22 @@ def full_engine():
     eng.set_text_features(torch.from_numpy(gold["text_features"]))
     yield eng, inp, gold
     eng.close()
+
+
+@pytest.mark.parametrize("flags", [1, 2])
+def test_full_size_resampling_variants_agree(flags):
+    """ffhq-f at full size with every resampling conv folded (1) / exact (2): same scores as the fixture."""
+    from clip_glass_b200.engine import GlassEngine
+    inp = build_inputs("full")
+    gold = load_golden("full")
+    eng = GlassEngine(inp["gan"], inp["clip"], inp["g_sd"], inp["d_sd"], inp["c_sd"], batch_size=inp["batch"],
+                      max_population=4, flags=flags)
+    eng.set_text_features(torch.from_numpy(gold["text_features"]))
+    neg_sim, hinge = eng.evaluate(inp["x"], noise=inp["noise"])
+    eng.close()
+    sim32 = gold["sim_oracle_fp32"]
+    assert np.abs(-neg_sim - sim32).max() / np.abs(sim32).min() <= 1e-3, (-neg_sim, sim32)
+    np.testing.assert_allclose(hinge, gold["F"][:, 1], atol=2e-3)
 
 
 def test_full_size_against_reference_fixture(full_engine):
