@@ -176,6 +176,7 @@ def main():
     ap.add_argument("--variant", default="_d", choices=["_d", "_nod"])
     ap.add_argument("--cpu-sample", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--flags", type=int, default=0, help="glass_config.flags (tuning experiments; 0 = product default)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -206,7 +207,7 @@ def main():
     text = torch.randn(1, 512, generator=torch.Generator().manual_seed(5))
     config = make_namespace(cfg_name, device=f"cuda:{local_rank}", target="synthetic", pop_size=P,
                             batch_size=args.batch, max_population=P_local, synthetic_seed=1000,
-                            text_features=text, noise_seed=7)
+                            text_features=text, noise_seed=7, engine_flags=args.flags)
     problem = GenerationProblem(config)
     eng = problem.generator.engine
     stream = torch.cuda.current_stream()

@@ -472,9 +472,11 @@ __device__ __forceinline__ void st8(__half* p, const float (&v)[8]) {
   *reinterpret_cast<uint4*>(p) = o;
 }
 
-// fp16 pair sums (one rounding of <= 1/2 ulp each), everything after that in fp32: ~30 % fewer instructions than
-// converting every tap, without letting fp16 accumulate the filter.
-__device__ __forceinline__ void pair_sum8(const uint4& p, const uint4& q, float (&v)[8]) {
+// The FIR [1,3,3,1] is the binomial [1,1]*[1,1]*[1,1]: three cascaded adjacent sums per axis (3 adds per output
+// instead of 4 multiply-adds), with only three running vectors of vertical state.  Each thread produces two
+// adjacent output columns from five loaded columns.  The first level of adjacent sums is taken in fp16 (one
+// rounding of <= 1/2 ulp per sum) so that only four vectors per row need converting; everything else is fp32.
+__device__ __forceinline__ void adj_sum8(const uint4& p, const uint4& q, float (&v)[8]) {
   const __half2* a = reinterpret_cast<const __half2*>(&p);
   const __half2* b = reinterpret_cast<const __half2*>(&q);
 #pragma unroll
@@ -484,149 +486,150 @@ __device__ __forceinline__ void pair_sum8(const uint4& p, const uint4& q, float 
     v[2 * j + 1] = t.y;
   }
 }
+// five columns c[0..4] (x0-1 .. x0+3) -> unnormalised horizontal FIR at x0 and x0+1: h = [1,3,3,1] . c
+__device__ __forceinline__ void hfir2(const uint4 (&c)[5], float (&h0)[8], float (&h1)[8]) {
+  float p0[8], p1[8], p2[8], p3[8];
+  adj_sum8(c[0], c[1], p0);
+  adj_sum8(c[1], c[2], p1);
+  adj_sum8(c[2], c[3], p2);
+  adj_sum8(c[3], c[4], p3);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float s0 = p0[j] + p1[j], s1 = p1[j] + p2[j], s2 = p2[j] + p3[j];
+    h0[j] = s0 + s1;
+    h1[j] = s1 + s2;
+  }
+}
 
-// One thread: 8 channels x kUpRows consecutive output rows of one output column.  Input rows stream through a
-// sliding window of four row accumulators: row Y = Z0+r-1 is filtered horizontally once,
-//   h = 1/4 (u[X-1] + u[X+2]) + 3/4 (u[X] + u[X+1]),
-// and added to the (up to four) outputs Z = Y-2 .. Y+1 with the vertical taps; a finished output gets noise, bias,
-// lrelu*sqrt2 and the next layer's style and is stored as fp16.
+// k_upfir: one thread = 8 channels x 2 output columns x kUpRows output rows.  v[Z][X] = sum f f u[Z+jy-1][X+jx-1]
+// with f = [1,3,3,1]/4; then + noise + bias, lrelu*sqrt2, * next style.
 constexpr int kUpRows = 8;
 __global__ void __launch_bounds__(256) upfir_kernel(
     const __half* __restrict__ u, __half* __restrict__ out, const float* __restrict__ noise, size_t noise_group_stride,
     int noise_group_div, const float* __restrict__ noise_strength, const float* __restrict__ bias,
     const float* __restrict__ out_scale, int out_scale_stride, int P, int Hout, int Wout, int C) {
-  const int C8 = C >> 3, Hq = Hout / kUpRows;
+  const int C8 = C >> 3, Hq = Hout / kUpRows, Wp = Wout >> 1;
   const int Hu = Hout + 2, Wu = Wout + 2;
-  const size_t n = (size_t)P * Hq * Wout * C8;
-  const float f[4] = {0.25f, 0.75f, 0.75f, 0.25f};
+  const size_t n = (size_t)P * Hq * Wp * C8;
   const float nstr = noise != nullptr ? __ldg(noise_strength) : 0.f;
+  const uint4 zero4 = make_uint4(0, 0, 0, 0);
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
     const int c8 = (int)(i % C8);
-    const int X = (int)((i / C8) % Wout);
-    const int zq = (int)((i / ((size_t)C8 * Wout)) % Hq);
-    const int b = (int)(i / ((size_t)C8 * Wout * Hq));
-    const int Z0 = zq * kUpRows;
+    const int xp = (int)((i / C8) % Wp);
+    const int zq = (int)((i / ((size_t)C8 * Wp)) % Hq);
+    const int b = (int)(i / ((size_t)C8 * Wp * Hq));
+    const int Z0 = zq * kUpRows, X0 = 2 * xp;
     float bs[8], sc[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       bs[j] = __ldg(bias + c8 * 8 + j);
-      sc[j] = __ldg(out_scale + (size_t)b * out_scale_stride + c8 * 8 + j);
+      sc[j] = kSqrt2 * __ldg(out_scale + (size_t)b * out_scale_stride + c8 * 8 + j);
     }
     const float* nz = noise != nullptr ? noise + (size_t)(b / noise_group_div) * noise_group_stride : nullptr;
     const __half* ub = u + ((size_t)b * Hu * Wu) * C + c8 * 8;
-    // X-1 >= 0 always holds except at X == 0; X+2 <= Wout+1 = Wu-1 always holds
-    const bool left = X > 0;
-    float acc[kUpRows][8];
+    // columns X0-1 .. X0+3: X0-1 >= 0 unless X0 == 0; X0+3 <= Wout+1 = Wu-1 always
+    float sa[2][8], sb[2][8], sc3[2][8];      // vertical cascade state: previous h, previous p, previous s
 #pragma unroll
-    for (int k = 0; k < kUpRows; ++k)
+    for (int x = 0; x < 2; ++x)
 #pragma unroll
-      for (int j = 0; j < 8; ++j) acc[k][j] = 0.f;
+      for (int j = 0; j < 8; ++j) sa[x][j] = sb[x][j] = sc3[x][j] = 0.f;
 #pragma unroll
     for (int r = 0; r < kUpRows + 3; ++r) {
       const int Y = Z0 + r - 1;
+      float h[2][8];
       if (Y >= 0 && Y < Hu) {
-        const __half* rp = ub + ((size_t)Y * Wu + X) * C;
-        const uint4 zero = make_uint4(0, 0, 0, 0);
-        const uint4 ua = left ? __ldg(reinterpret_cast<const uint4*>(rp - C)) : zero;
-        const uint4 ubv = __ldg(reinterpret_cast<const uint4*>(rp));
-        const uint4 uc = __ldg(reinterpret_cast<const uint4*>(rp + C));
-        const uint4 ud = __ldg(reinterpret_cast<const uint4*>(rp + 2 * C));
-        float so[8], si[8];
-        pair_sum8(ua, ud, so);
-        pair_sum8(ubv, uc, si);
+        const __half* rp = ub + ((size_t)Y * Wu + X0) * C;
+        uint4 c[5];
+        c[0] = X0 > 0 ? __ldg(reinterpret_cast<const uint4*>(rp - C)) : zero4;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float hv = fmaf(0.75f, si[j], 0.25f * so[j]);
-          // row r feeds output k = r - jv with vertical tap jv (v[Z] = sum_jv f[jv] u[Z + jv - 1])
+        for (int q = 1; q < 5; ++q) c[q] = __ldg(reinterpret_cast<const uint4*>(rp + (size_t)(q - 1) * C));
+        hfir2(c, h[0], h[1]);
+      } else {
 #pragma unroll
-          for (int jv = 0; jv < 4; ++jv) {
-            const int k = r - jv;
-            if (k >= 0 && k < kUpRows) acc[k][j] = fmaf(f[jv], hv, acc[k][j]);
-          }
-        }
+        for (int j = 0; j < 8; ++j) h[0][j] = h[1][j] = 0.f;
       }
-      const int kdone = r - 3;       // output row whose last input row was just added
-      if (kdone >= 0) {
-        const int Z = Z0 + kdone;
-        const float nv = nz != nullptr ? nstr * __ldg(nz + (size_t)Z * Wout + X) : 0.f;
+      const int kdone = r - 3;                 // after this row, output row Z0 + kdone is complete
+      const int Z = Z0 + kdone;
+#pragma unroll
+      for (int x = 0; x < 2; ++x) {
         float v[8];
+        const float nv = (kdone >= 0 && nz != nullptr) ? nstr * __ldg(nz + (size_t)Z * Wout + X0 + x) : 0.f;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          float t = acc[kdone][j] + nv + bs[j];
-          t = fmaxf(t, 0.2f * t) * kSqrt2;
-          v[j] = t * sc[j];
+          const float p = sa[x][j] + h[x][j];
+          const float q = sb[x][j] + p;
+          const float t = sc3[x][j] + q;        // = h[r-3] + 3 h[r-2] + 3 h[r-1] + h[r]
+          sa[x][j] = h[x][j];
+          sb[x][j] = p;
+          sc3[x][j] = q;
+          float o = fmaf(t, 1.f / 16.f, bs[j]) + nv;
+          o = fmaxf(o, 0.2f * o);
+          v[j] = o * sc[j];
         }
-        st8(out + (((size_t)b * Hout + Z) * Wout + X) * C + c8 * 8, v);
+        if (kdone >= 0) st8(out + (((size_t)b * Hout + Z) * Wout + X0 + x) * C + c8 * 8, v);
       }
     }
   }
 }
 
-// One thread: 8 channels of two vertically adjacent space-to-depth cells (8 outputs) from a 7x5 input patch.
-// u[Y][X] = sum_{jy,jx} f[jy] f[jx] a[Y+jy-2][X+jx-2];  cell (z,w) holds u[2z+py][2w+px];  f = [1,3,3,1]/8.
+// k_blur_s2d: one thread = 8 channels x one space-to-depth cell column (2 output columns) x kBlurCells cells
+// vertically (2*kBlurCells output rows).  u[Y][X] = sum f f a[Y+jy-2][X+jx-2], f = [1,3,3,1]/8, for Y,X in [0,H];
+// cell (z,w), phase (py,px) holds u[2z+py][2w+px]; positions beyond H are written as zeros.
+constexpr int kBlurCells = 4;
 __global__ void __launch_bounds__(256) blur_s2d_kernel(const __half* __restrict__ a, __half* __restrict__ out, int P,
                                                        int H, int W, int C) {
-  const int C8 = C >> 3, Hs = (H >> 1) + 1, Ws = (W >> 1) + 1, Hp = (Hs + 1) >> 1;
+  const int C8 = C >> 3, Hs = (H >> 1) + 1, Ws = (W >> 1) + 1, Hp = (Hs + kBlurCells - 1) / kBlurCells;
   const size_t n = (size_t)P * Hp * Ws * C8;
-  const float f[4] = {0.125f, 0.375f, 0.375f, 0.125f};
+  const uint4 zero4 = make_uint4(0, 0, 0, 0);
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
     const int c8 = (int)(i % C8);
     const int w = (int)((i / C8) % Ws);
     const int zp = (int)((i / ((size_t)C8 * Ws)) % Hp);
     const int b = (int)(i / ((size_t)C8 * Ws * Hp));
-    const int z0 = 2 * zp;                       // cells z0 and z0+1: output rows Y = 2*z0 .. 2*z0+3
+    const int z0 = zp * kBlurCells;              // output rows Y = 2*z0 .. 2*z0 + 2*kBlurCells - 1
     const __half* ab = a + ((size_t)b * H * W) * C + c8 * 8;
-    float acc[4][2][8];                          // [output row 0..3][px][channel]
-#pragma unroll
-    for (int k = 0; k < 4; ++k)
-#pragma unroll
-      for (int px = 0; px < 2; ++px)
-#pragma unroll
-        for (int j = 0; j < 8; ++j) acc[k][px][j] = 0.f;
     const int x0 = 2 * w - 2;                    // input columns x0 .. x0+4
+    float sa[2][8], sb[2][8], sc3[2][8];
 #pragma unroll
-    for (int r = 0; r < 7; ++r) {
-      const int yy = 2 * z0 + r - 2;             // input row; feeds output row k = r - jy
-      if (yy < 0 || yy >= H) continue;
-      const __half* rp = ab + ((size_t)yy * W) * C;
-      uint4 c[5];
+    for (int x = 0; x < 2; ++x)
 #pragma unroll
-      for (int q = 0; q < 5; ++q) {
-        const int xx = x0 + q;
-        c[q] = (xx >= 0 && xx < W) ? __ldg(reinterpret_cast<const uint4*>(rp + (size_t)xx * C)) : make_uint4(0, 0, 0, 0);
-      }
-      // px = 0: taps on columns 0..3; px = 1: taps on columns 1..4
-      float o0[8], i0[8], o1[8], i1[8];
-      pair_sum8(c[0], c[3], o0);
-      pair_sum8(c[1], c[2], i0);
-      pair_sum8(c[1], c[4], o1);
-      pair_sum8(c[2], c[3], i1);
+      for (int j = 0; j < 8; ++j) sa[x][j] = sb[x][j] = sc3[x][j] = 0.f;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float h0 = fmaf(0.375f, i0[j], 0.125f * o0[j]);
-        const float h1 = fmaf(0.375f, i1[j], 0.125f * o1[j]);
+    for (int r = 0; r < 2 * kBlurCells + 3; ++r) {
+      const int yy = 2 * z0 + r - 2;             // input row; output row 2*z0 + (r-3) completes with it
+      float h[2][8];
+      if (yy >= 0 && yy < H) {
+        const __half* rp = ab + ((size_t)yy * W) * C;
+        uint4 c[5];
 #pragma unroll
-        for (int jy = 0; jy < 4; ++jy) {
-          const int k = r - jy;
-          if (k >= 0 && k < 4) {
-            acc[k][0][j] = fmaf(f[jy], h0, acc[k][0][j]);
-            acc[k][1][j] = fmaf(f[jy], h1, acc[k][1][j]);
-          }
+        for (int q = 0; q < 5; ++q) {
+          const int xx = x0 + q;
+          c[q] = (xx >= 0 && xx < W) ? __ldg(reinterpret_cast<const uint4*>(rp + (size_t)xx * C)) : zero4;
         }
+        hfir2(c, h[0], h[1]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) h[0][j] = h[1][j] = 0.f;
       }
-    }
+      const int kdone = r - 3;
+      const int Y = 2 * z0 + kdone;
+      const int z = Y >> 1, py = Y & 1;
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const int z = z0 + (k >> 1), py = k & 1;
-      if (z >= Hs) continue;
-      __half* op = out + (((size_t)b * Hs + z) * Ws + w) * (4 * C) + c8 * 8;
-#pragma unroll
-      for (int px = 0; px < 2; ++px) {
-        const bool inside = (2 * z + py <= H) && (2 * w + px <= W);
+      for (int x = 0; x < 2; ++x) {
         float v[8];
+        const bool inside = (Y <= H) && (2 * w + x <= W);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] = inside ? acc[k][px][j] : 0.f;
-        st8(op + (py * 2 + px) * C, v);
+        for (int j = 0; j < 8; ++j) {
+          const float p = sa[x][j] + h[x][j];
+          const float q = sb[x][j] + p;
+          const float t = sc3[x][j] + q;
+          sa[x][j] = h[x][j];
+          sb[x][j] = p;
+          sc3[x][j] = q;
+          v[j] = inside ? t * (1.f / 64.f) : 0.f;
+        }
+        if (kdone >= 0 && z < Hs)
+          st8(out + (((size_t)b * Hs + z) * Ws + w) * (4 * C) + (py * 2 + x) * C + c8 * 8, v);
       }
     }
   }
@@ -777,8 +780,8 @@ cudaError_t k_fir_down(const __half* x, __half* out, int N, int H, int W, int C,
 cudaError_t k_upfir(const __half* u, __half* out, const float* noise, size_t noise_group_stride, int noise_group_div,
                     const float* noise_strength, const float* bias, const float* out_scale, int out_scale_stride,
                     int P, int Hout, int Wout, int C, cudaStream_t s) {
-  if (C % 8 != 0 || Hout % kUpRows != 0) return cudaErrorInvalidValue;
-  const size_t n = (size_t)P * (Hout / kUpRows) * Wout * (C / 8);
+  if (C % 8 != 0 || Hout % kUpRows != 0 || (Wout & 1)) return cudaErrorInvalidValue;
+  const size_t n = (size_t)P * (Hout / kUpRows) * (Wout / 2) * (C / 8);
   upfir_kernel<<<blocks_for(n, kThreads, 148 * 32), kThreads, 0, s>>>(u, out, noise, noise_group_stride, noise_group_div,
                                                                      noise_strength, bias, out_scale, out_scale_stride,
                                                                      P, Hout, Wout, C);
@@ -786,7 +789,7 @@ cudaError_t k_upfir(const __half* u, __half* out, const float* noise, size_t noi
 }
 cudaError_t k_blur_s2d(const __half* a, __half* out, int P, int H, int W, int C, cudaStream_t s) {
   if (C % 8 != 0 || (H & 1) || (W & 1)) return cudaErrorInvalidValue;
-  const size_t n = (size_t)P * ((H / 2 + 2) / 2) * (W / 2 + 1) * (C / 8);
+  const size_t n = (size_t)P * ((H / 2 + 1 + kBlurCells - 1) / kBlurCells) * (W / 2 + 1) * (C / 8);
   blur_s2d_kernel<<<blocks_for(n, kThreads, 148 * 32), kThreads, 0, s>>>(a, out, P, H, W, C);
   GLASS_RET();
 }

@@ -71,7 +71,8 @@ class Generator:
         max_pop = (max_pop + config.batch_size - 1) // config.batch_size * config.batch_size
         self.engine = GlassEngine(gan, clip, g_sd, d_sd, c_sd, batch_size=config.batch_size,
                                   max_population=max_pop, device=index,
-                                  conv_impl=int(getattr(config, "conv_impl", 0)))
+                                  conv_impl=int(getattr(config, "conv_impl", 0)),
+                                  flags=int(getattr(config, "engine_flags", 0)))
         tf = getattr(config, "text_features", None)
         if tf is None:
             raise GlassError("config.text_features ([1,512], CLIP.encode_text of the target) is required")
