@@ -21,7 +21,9 @@ constexpr float kInvSqrt2 = 0.7071067811865476f;
 enum StoreMode : int {
   kStoreRegular = 0,       // out[pix][Ntot]
   kStoreDepthToSpace = 1,  // Ntot = 4*Cout, column (py*2+px)*Cout+o -> out[2y+py][2x+px][o]   (G up-conv)
-  kStoreSpaceToDepth = 2   // out[y/2][x/2][(y&1)*2+(x&1)][Ntot]                               (D conv0 -> conv1 input)
+  kStoreSpaceToDepth = 2,  // out[y/2][x/2][(y&1)*2+(x&1)][Ntot]                               (D conv0 -> conv1 input)
+  kStoreSpaceToDepthY = 3  // pixel-pair rows (x_phases == 2): out[y/2][x][(y&1)][Ntot], i.e. space-to-depth of the
+                           // underlying full-width image, because a row already holds the two x phases
 };
 enum Act : int { kActNone = 0, kActLrelu = 1, kActQuickGelu = 2 };
 
@@ -43,6 +45,8 @@ struct EpiParams {
   __half* out;              // null => nothing stored (G's last conv only feeds toRGB)
   int store_mode;
   int Cout;                 // per-phase channel count (== Ntot unless depth-to-space)
+  int x_phases;             // 1, or 2 for pixel-pair rows: columns [k*Cout, (k+1)*Cout) belong to pixel 2x+k
+                            // (requires BN == Ntot == 2*Cout, so that an epilogue warp's column half is one pixel)
   int cout_shift;           // log2(Cout) when Cout is a power of two, else -1
   int noise_div_shift;      // log2(noise_group_div) when it is a power of two, else -1
 };

@@ -422,6 +422,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     constexpr int kChunks = kHalf / 16;
     const bool d2s = (e.store_mode == kStoreDepthToSpace);
     const bool s2d = (e.store_mode == kStoreSpaceToDepth);
+    const bool s2dy = (e.store_mode == kStoreSpaceToDepthY);
+    const bool paired = (e.x_phases == 2);   // pixel-pair rows: this warp's column half IS pixel 2x+half
     const bool has_rgb = (e.rgb_w != nullptr);
     const float nscale = (e.noise != nullptr) ? gain * __ldg(e.noise_strength) : 0.f;
     // All index math below is 32-bit pixel arithmetic (pixel counts stay < 2^31); one 64-bit multiply per tile
@@ -451,6 +453,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           const int ph = cout_sh >= 0 ? (n0 >> cout_sh) : (n0 / e.Cout);
           dst[c] = __ldg(b2 + (ph >> 1) * (2 * W) + (ph & 1));
         }
+      } else if (paired) {
+        dst[0] = __ldg(base + (size_t)y2 * (2 * W) + 2 * x2 + half);
       } else {
         dst[0] = __ldg(base + y2 * W + x2);
       }
@@ -517,6 +521,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           if (s2d) {
             const int org = ((img * (H >> 1) + ((tc.ty * p.TH) >> 1)) * (W >> 1) + ((tc.tx * p.TW) >> 1)) << 2;
             out_row = e.out + (size_t)(org + row_s2d) * p.Ntot + n_first;
+          } else if (s2dy) {
+            const int org = (img * (H >> 1) + ((tc.ty * p.TH + ry) >> 1)) * W + tc.tx * p.TW + rx;
+            out_row = e.out + ((size_t)org * 2 + (ry & 1)) * p.Ntot + n_first;
           } else if (!d2s) {
             out_row = e.out + (size_t)pix * p.Ntot + n_first;
           }
@@ -560,7 +567,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           if (valid) epilogue_row16(p, img, y, x, n_tile * BN + half * kHalf + c * 16, v, rgb);
         }
       }
-      if (has_rgb) {
+      if (has_rgb && paired) {
+        // pixel-pair rows: the two column halves are two different pixels, each warp stores its own
+        if (valid) {
+          const size_t pix2 = ((size_t)img * H + y) * (2 * W) + 2 * x + half;
+          e.rgb_out[pix2] = make_float4(rgb[0], rgb[1], rgb[2], 0.f);
+        }
+      } else if (has_rgb) {
         // the two warps of a lane quarter own different column halves of the same rows: combine their
         // partial toRGB sums in shared memory so that one float4 per pixel goes to HBM
         float4* stg = rgb_stage + (it & 1) * 128;

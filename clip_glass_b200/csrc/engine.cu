@@ -94,6 +94,8 @@ struct glass_engine {
   __half *actA = nullptr, *actB = nullptr, *actC = nullptr;   // actC: intermediate of the exact polyphase forms
   std::vector<int> g_exact;   // per G layer: 1 = exact polyphase up-conv
   std::vector<int> d_exact;   // per D block: 1 = exact polyphase down-conv
+  std::vector<int> g_pair;    // per G layer: 1 = 32-channel conv on horizontally paired pixels
+  std::vector<int> d_pair;    // per D block: conv0 likewise
   float4 *slabs = nullptr, *yA = nullptr, *yB = nullptr;
   float* images = nullptr;
   __half *patches = nullptr, *patch_emb = nullptr, *tokens = nullptr, *hbuf = nullptr, *qkv = nullptr, *att = nullptr,
@@ -338,6 +340,13 @@ void derive_arch(glass_engine* e) {
     const bool possible = !folded && (e->R >> b) >= 32;
     e->d_exact.push_back((possible && (exact_all || e->gch[c.num_blocks - 1 - b] >= 128)) ? 1 : 0);
   }
+  const bool pair_ok = (c.flags & GLASS_FLAG_NO_PAIR_PACK) == 0 && c.conv_impl == 0;
+  e->g_pair.clear();
+  for (const GLayer& l : e->glayers)
+    e->g_pair.push_back((pair_ok && !l.up && l.cin == 32 && l.cout == 32 && l.res >= 32) ? 1 : 0);
+  e->d_pair.clear();
+  for (int b = 0; b + 1 < c.num_blocks; ++b)
+    e->d_pair.push_back((pair_ok && e->gch[c.num_blocks - 1 - b] == 32 && (e->R >> b) >= 32) ? 1 : 0);
   e->noise_layer_off.clear();
   size_t noff = 0;
   for (const GLayer& l : e->glayers) { e->noise_layer_off.push_back(noff); noff += (size_t)l.res * l.res; }
@@ -360,6 +369,7 @@ int validate_weights(glass_engine* e) {
     const int ntot = l.up ? 4 * l.cout : l.cout;
     snprintf(nm, sizeof nm, "g.conv%zu.w", li); RC(check_tensor(e, nm, (size_t)9 * ntot * l.cin * 2));
     if (e->g_exact[li]) { snprintf(nm, sizeof nm, "g.conv%zu.wx", li); RC(check_tensor(e, nm, (size_t)4 * ntot * l.cin * 2)); }
+    if (e->g_pair[li]) { snprintf(nm, sizeof nm, "g.conv%zu.wp", li); RC(check_tensor(e, nm, (size_t)9 * 2 * l.cout * 2 * l.cin * 2)); }
     snprintf(nm, sizeof nm, "g.conv%zu.wsq", li); RC(check_tensor(e, nm, (size_t)l.cin * l.cout * 4));
     snprintf(nm, sizeof nm, "g.conv%zu.bias", li); RC(check_tensor(e, nm, (size_t)l.cout * 4));
     snprintf(nm, sizeof nm, "g.conv%zu.nstr", li); RC(check_tensor(e, nm, 4));
@@ -396,6 +406,7 @@ int validate_weights(glass_engine* e) {
       RC(check_tensor(e, nmf("c0.b"), (size_t)dch(b) * 4));
       RC(check_tensor(e, nmf("c1.w"), (size_t)9 * dch(b + 1) * 4 * dch(b) * 2));
       if (e->d_exact[b]) RC(check_tensor(e, nmf("c1.wx"), (size_t)4 * dch(b + 1) * 4 * dch(b) * 2));
+      if (e->d_pair[b]) RC(check_tensor(e, nmf("c0.wp"), (size_t)9 * 2 * dch(b) * 2 * dch(b) * 2));
       RC(check_tensor(e, nmf("c1.b"), (size_t)dch(b + 1) * 4));
       RC(check_tensor(e, nmf("proj.w"), (size_t)dch(b + 1) * dch(b) * 2));
     }
@@ -491,6 +502,7 @@ EpiParams epi_default() {
   memset(&ep, 0, sizeof(ep));
   ep.post_scale = 1.f;
   ep.noise_group_div = 1;
+  ep.x_phases = 1;
   return ep;
 }
 
@@ -544,6 +556,11 @@ int build_plan(glass_engine* e, int P) {
       snprintf(nm, sizeof nm, "g.conv%zu.wx", li);
       RC(make_conv(e, &cl, bufs[cur], P, in_res + 1, in_res + 1, l.cin, tptr<__half>(e, nm), 4, 4 * l.cout, eu, false,
                    kUpExactTaps, in_res, in_res));
+    } else if (e->g_pair[li]) {
+      // 32-channel layer on paired pixels: [H][W/2][64] view, N = 2*Cout, the epilogue's column halves are pixels
+      ep.x_phases = 2;
+      snprintf(nm, sizeof nm, "g.conv%zu.wp", li);
+      RC(make_conv(e, &cl, bufs[cur], P, in_res, in_res / 2, 2 * l.cin, tptr<__half>(e, nm), 9, 2 * l.cout, ep, false));
     } else {
       snprintf(nm, sizeof nm, "g.conv%zu.w", li);
       RC(make_conv(e, &cl, bufs[cur], P, in_res, in_res, l.cin, tptr<__half>(e, nm), 9, l.up ? 4 * l.cout : l.cout, ep,
@@ -603,7 +620,13 @@ int build_plan(glass_engine* e, int P) {
       EpiParams ep = epi_default();
       ep.Cout = Ci; ep.bias = tptr<float>(e, nmf("c0.b")); ep.act = kActLrelu; ep.out = e->actB;
       ep.store_mode = e->d_exact[b] ? kStoreRegular : kStoreSpaceToDepth;
-      RC(make_conv(e, &cl, x, P, res, res, Ci, tptr<__half>(e, nmf("c0.w")), 9, Ci, ep, false));
+      if (e->d_pair[b]) {
+        ep.x_phases = 2;
+        if (ep.store_mode == kStoreSpaceToDepth) ep.store_mode = kStoreSpaceToDepthY;
+        RC(make_conv(e, &cl, x, P, res, res / 2, 2 * Ci, tptr<__half>(e, nmf("c0.wp")), 9, 2 * Ci, ep, false));
+      } else {
+        RC(make_conv(e, &cl, x, P, res, res, Ci, tptr<__half>(e, nmf("c0.w")), 9, Ci, ep, false));
+      }
       cl.flops = 2.0 * 9.0 * (double)P * res * res * Ci * Ci; e->d_convs.push_back(cl);
       // projection: 1x1 on the FIR-downsampled input
       ep = epi_default(); ep.Cout = Co; ep.out = e->dR;

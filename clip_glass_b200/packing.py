@@ -159,6 +159,25 @@ def exact_downconv(w: torch.Tensor) -> torch.Tensor:
     return out
 
 
+def pair_pack(w: torch.Tensor) -> torch.Tensor:
+    """3x3 conv over horizontally PAIRED pixels: the NHWC tensor [H][W][C] is read as [H][W/2][2C] and written as
+    [H][W/2][2*O] (the same bytes).  Row xp of the GEMM holds pixels 2xp, 2xp+1; tap (ky, kxp) reads pair xp+kxp-1.
+    w [O,I,3,3] (already * coef) -> [9 taps][2*O][2*I] with
+        W[(ky,kxp)][px_out*O + o][px_in*I + i] = w[o,i,ky,kx],  kx = 2*(kxp-1) + px_in - px_out + 1  (if 0 <= kx <= 2).
+    Half of the blocks are zero (2x the MACs), in exchange for 128-byte TMA rows and 256-pixel tiles on the
+    32-channel layers, which are bound by TMA row rate and per-tile bookkeeping, not by math."""
+    O, I = w.shape[:2]
+    out = torch.zeros(9, 2 * O, 2 * I, dtype=w.dtype)
+    for ky in range(3):
+        for kxp in range(3):
+            for po in range(2):
+                for pi in range(2):
+                    kx = 2 * (kxp - 1) + pi - po + 1
+                    if 0 <= kx <= 2:
+                        out[ky * 3 + kxp, po * O:(po + 1) * O, pi * I:(pi + 1) * I] = w[:, :, ky, kx]
+    return out
+
+
 def taps_plain(w: torch.Tensor) -> torch.Tensor:
     """w [O,I,k,k] -> [k*k][O][I]."""
     O, I, k, _ = w.shape
@@ -195,6 +214,8 @@ def pack_generator(sd: Dict[str, torch.Tensor], spec: GanSpec) -> Dict[str, np.n
         out[f"g.conv{li}.w"] = _f16(fold_upconv(wc) if ly["up"] else taps_plain(wc))
         if ly["up"]:
             out[f"g.conv{li}.wx"] = _f16(exact_upconv(wc))      # exact polyphase form (used from 16x16 inputs up)
+        elif ly["cin"] == 32 and ly["res"] >= 32:
+            out[f"g.conv{li}.wp"] = _f16(pair_pack(wc))         # pixel-pair form of the 32-channel layers
         out[f"g.conv{li}.bias"] = _f32(sd[p + ".bias"])
         out[f"g.conv{li}.nstr"] = _f32(sd[p + ".layer.weight"].reshape(1))
     ch = list(spec.channels)[::-1]
@@ -227,6 +248,8 @@ def pack_discriminator(sd: Dict[str, torch.Tensor], spec: GanSpec) -> Dict[str, 
         p = f"conv_blocks.{b}"
         w0 = sd[p + ".conv_block.0.layer.weight"].float()
         out[f"d.b{b}.c0.w"] = _f16(taps_plain(w0 * _coef(w0.shape)))
+        if ch[b] == 32 and (spec.resolution >> b) >= 32:
+            out[f"d.b{b}.c0.wp"] = _f16(pair_pack(w0 * _coef(w0.shape)))
         out[f"d.b{b}.c0.b"] = _f32(sd[p + ".conv_block.0.bias"])
         w1 = sd[p + ".conv_block.1.layer.weight"].float()
         out[f"d.b{b}.c1.w"] = _f16(fold_downconv(w1 * _coef(w1.shape)))

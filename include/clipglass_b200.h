@@ -63,6 +63,9 @@ typedef struct glass_config {
  * measured cost model (exact where the layer is tensor-bound: Cin >= 512 at >= 64x64 in G, Cin >= 128 in D). */
 #define GLASS_FLAG_FOLDED_RESAMPLE 1   /* folded form everywhere */
 #define GLASS_FLAG_EXACT_RESAMPLE 2    /* exact form wherever it is defined (inputs >= 16x16) */
+/* The 32-channel 3x3 convs normally run on horizontally paired pixels ([H][W/2][64] view of the same bytes:
+ * 128-byte TMA rows, 256-pixel tiles, 2x the MACs of a layer that is not math-bound). */
+#define GLASS_FLAG_NO_PAIR_PACK 4      /* keep them on single pixels */
 
 /* -- lifetime ------------------------------------------------------------- */
 /* Replaces Generator.__init__ (generator.py:12-27): allocate the engine. */

@@ -63,6 +63,12 @@ def test_tiny_layerwise_exact_resampling_variant():
     check_diag(run_diag("tiny", 0, 600, flags=2))
 
 
+def test_tiny_layerwise_single_pixel_variant():
+    """GLASS_FLAG_NO_PAIR_PACK: the 32-channel convs on single pixels (resident-tap MODE 1 with 64-byte rows)
+    instead of the default horizontally paired pixels."""
+    check_diag(run_diag("tiny", 0, 600, flags=4))
+
+
 @pytest.fixture(scope="module")
 def full_engine():
     from clip_glass_b200.engine import GlassEngine
@@ -75,9 +81,10 @@ def full_engine():
     eng.close()
 
 
-@pytest.mark.parametrize("flags", [1, 2])
+@pytest.mark.parametrize("flags", [1, 2, 4])
 def test_full_size_resampling_variants_agree(flags):
-    """ffhq-f at full size with every resampling conv folded (1) / exact (2): same scores as the fixture."""
+    """ffhq-f at full size with every resampling conv folded (1) / exact (2), or without pixel pairing (4):
+    same scores as the fixture."""
     from clip_glass_b200.engine import GlassEngine
     inp = build_inputs("full")
     gold = load_golden("full")

@@ -67,6 +67,35 @@ def test_fold_downconv_is_exact_in_fp32():
     np.testing.assert_allclose(got.numpy(), ref.numpy(), atol=1e-4)
 
 
+def test_pair_packed_conv_is_the_same_conv():
+    """[H][W][C] read as [H][W/2][2C] with packing.pair_pack weights == the plain 3x3 conv."""
+    torch.manual_seed(2)
+    x = torch.randn(2, 6, 8, 4)                       # NHWC
+    w = torch.randn(5, 4, 3, 3)
+    ref = E.conv_taps(x, packing.taps_plain(w))       # [2,6,8,5]
+    got = E.conv_taps(x.reshape(2, 6, 4, 8), packing.pair_pack(w)).reshape(2, 6, 8, 5)
+    np.testing.assert_allclose(got.numpy(), ref.numpy(), atol=1e-5)
+
+
+def test_exact_polyphase_forms_match_reference_ops():
+    from oracle import stylegan2_oracle as so
+    torch.manual_seed(3)
+    x = torch.randn(2, 8, 16, 16)
+    w = torch.randn(6, 8, 3, 3)
+    ref = so.fir(torch.nn.functional.conv_transpose2d(x, w.transpose(0, 1), stride=2), so.fir_kernel(1.0, 2), 1, 1)
+    u = E.depth_to_space(E.conv_taps_table(x.permute(0, 2, 3, 1), packing.exact_upconv(w), packing.UP_EXACT_TAPS,
+                                           (17, 17)), 6)
+    got = E.fir_same(u, packing.F1_UP, (32, 32), 1).permute(0, 3, 1, 2)
+    np.testing.assert_allclose(got.numpy(), ref.numpy(), atol=1e-4)
+    a = torch.randn(2, 4, 32, 32)
+    wd = torch.randn(6, 4, 3, 3)
+    refd = torch.nn.functional.conv2d(so.fir(a, so.fir_kernel(1.0, 1), 2, 2), wd, stride=2)
+    ub = E.fir_same(a.permute(0, 2, 3, 1), packing.F1_DOWN, (33, 33), 2)
+    us = E.space_to_depth(torch.nn.functional.pad(ub, [0, 0, 0, 1, 0, 1]))
+    gotd = E.conv_taps_table(us, packing.exact_downconv(wd), packing.DOWN_EXACT_TAPS, (16, 16)).permute(0, 3, 1, 2)
+    np.testing.assert_allclose(gotd.numpy(), refd.numpy(), atol=1e-4)
+
+
 def test_skip_upsample_polyphase_matches_reference_upsample():
     from oracle import stylegan2_oracle as so
     y = torch.randn(2, 3, 6, 6)
