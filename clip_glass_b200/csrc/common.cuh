@@ -45,6 +45,7 @@ struct EpiParams {
   __half* out;              // null => nothing stored (G's last conv only feeds toRGB)
   int store_mode;
   int Cout;                 // per-phase channel count (== Ntot unless depth-to-space)
+  int out_i8;               // store channel-group-interleaved: out[n][y][c/8][x][8] (regular and depth-to-space)
   int x_phases;             // 1, or 2 for pixel-pair rows: columns [k*Cout, (k+1)*Cout) belong to pixel 2x+k
                             // (requires BN == Ntot == 2*Cout, so that an epilogue warp's column half is one pixel)
   int cout_shift;           // log2(Cout) when Cout is a power of two, else -1
@@ -61,7 +62,8 @@ struct ConvParams {
   signed char tap_dy[9], tap_dx[9];   // input offset of each tap (3x3: ky-1, kx-1)
   int Ntot;                 // multiple of BN
   int BN, BK;
-  int debug_skip;           // profiling aid (env GLASS_DEBUG_SKIP): 1 = epilogue only drains TMEM (results invalid)
+  int debug_skip;           // bring-up aid (env GLASS_DEBUG_SKIP): bit 0 = epilogue only drains TMEM (results
+                            // invalid, timing experiments); bit 1 = MODE 4 with LBO/SBO roles swapped
   int all_valid;            // H % TH == 0 && W % TW == 0 && Nimg % TN == 0: no row of any tile is out of range
   int pow2, sh_n, sh_x, sh_y;  // tile grid is a power of two in every dimension: decode with shifts
   int mode;                 // 0 = streamed taps, 1 = resident taps + halo copies (conv_tc.cu)

@@ -147,14 +147,32 @@ constexpr int kNumParams = 6;   // scale, shift, oscale, rgb0, rgb1, rgb2
 //                    producer issues 3 TMA ops per tile instead of 18.
 constexpr int kHaloTH = 8, kHaloTW = 16;
 
+// Un-swizzled K-major descriptor: 8x16B core matrices; LBO = byte distance between the two core matrices of one
+// K=16 step, SBO = byte distance between consecutive 8-row groups (cute::UMMA canonical INTERLEAVE layout).
+__device__ __forceinline__ uint64_t make_smem_desc_noswz(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) |
+         (1ull << 46);
+}
+
 template <int BN, int BK, int MODE>
 struct Cfg {
   static constexpr int kABytes = kBlockM * BK * 2;
   static constexpr int kBBytes = BN * BK * 2;
   static constexpr int kCopyBytes = (kHaloTH + 2) * kHaloTW * BK * 2;          // one dx-copy of the halo tile
   // MODE 2 = MODE 1 for 1x1 convs: one resident tap, one un-haloed tile per stage
-  static constexpr int kStageBytes = MODE == 0 ? kABytes + kBBytes : (MODE == 1 ? 3 * kCopyBytes : kABytes);
-  static constexpr int kWBytes = MODE == 0 ? 0 : (MODE == 1 ? 9 : 1) * kBBytes;   // resident taps
+  // MODE 4 ("I8"): the input tensor is stored channel-group-interleaved, [N][H][C/8][W][8].  One TMA box of
+  //   (TW+2)*8 contiguous elements x C/8 groups x (TH+2) rows lands in shared memory as [row][group][pixel][8ch]:
+  //   exactly the un-swizzled K-major core-matrix layout (8 pixels x 16 B contiguous; next 8-channel group at
+  //   LBO = (TW+2)*16 B; next image row at SBO = (C/8)*(TW+2)*16 B; tile = 8 wide x 16 tall).  A filter tap is just
+  //   a different start address (16-byte granularity), so ONE copy of the haloed tile serves all nine taps:
+  //   1.4x the tile in L2->SM bytes (MODE 1: 3.75x, MODE 0: 9x) and (TH+2)*C/8 long TMA rows instead of hundreds
+  //   of 64/128-byte ones (TMA issues ~0.41 rows/cycle/SM regardless of their length).
+  static constexpr int kI8TW = 8, kI8TH = 16;
+  static constexpr int kI8RowBytes = (kI8TW + 2) * 16;                          // one (row, group): 10 pixels x 16 B
+  static constexpr int kI8StageBytes = (kI8TH + 2) * (BK / 8) * kI8RowBytes;
+  static constexpr int kStageBytes = MODE == 0 ? kABytes + kBBytes
+                                     : (MODE == 1 ? 3 * kCopyBytes : (MODE == 4 ? kI8StageBytes : kABytes));
+  static constexpr int kWBytes = MODE == 0 ? 0 : ((MODE == 1 || MODE == 4) ? 9 : 1) * kBBytes;   // resident taps
   // double-buffered per-tile epilogue parameters + 2 x 128 float4 for combining the two column halves' toRGB sums
   static constexpr int kParamBytes = 2 * kNumParams * BN * 4 + 2 * 128 * 16;
   // the 32-channel MODE-1 layers are bookkeeping/latency-bound, not smem-bound: run two CTAs per SM there
@@ -185,7 +203,7 @@ __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" 
 template <bool kRgb>
 __device__ __forceinline__ void epilogue_fast16(const EpiParams& e, const float* __restrict__ par, int BN, int j0,
                                                 const uint32_t (&acc)[16], float nz, const __half* res_ptr,
-                                                __half* out_ptr, float (&rgb)[3]) {
+                                                __half* out_ptr, size_t out_half_stride, float (&rgb)[3]) {
   const float4* sc = reinterpret_cast<const float4*>(par + 0 * BN + j0);
   const float4* sh = reinterpret_cast<const float4*>(par + 1 * BN + j0);
   const float4* os = reinterpret_cast<const float4*>(par + 2 * BN + j0);
@@ -247,9 +265,9 @@ __device__ __forceinline__ void epilogue_fast16(const EpiParams& e, const float*
       h1[2 * g] = __floats2half2_rn(t[8 + 4 * g] * b.x, t[8 + 4 * g + 1] * b.y);
       h1[2 * g + 1] = __floats2half2_rn(t[8 + 4 * g + 2] * b.z, t[8 + 4 * g + 3] * b.w);
     }
-    uint4* op = reinterpret_cast<uint4*>(out_ptr);
-    op[0] = w0;
-    op[1] = w1;
+    // channels [0,8) and [8,16) of the chunk: adjacent in NHWC, one channel-group plane apart in the I8 layout
+    *reinterpret_cast<uint4*>(out_ptr) = w0;
+    *reinterpret_cast<uint4*>(out_ptr + out_half_stride) = w1;
   }
 }
 
@@ -323,7 +341,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         if (MODE != 0) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * C::kStageBytes;
-          if (p.taps == 9) {
+          if (MODE == 4) {
+            mbar_expect_tx(&full_bar[stage], C::kI8StageBytes);
+            // coordinates: ((x0-1)*8 elements, group 0, row y0-1, image); out-of-image parts are zero-filled
+            tma_load_4d(&map_a, sa, &full_bar[stage], (x0 - 1) * 8, 0, y0 - 1, i0);
+          } else if (p.taps == 9) {
             mbar_expect_tx(&full_bar[stage], 3 * C::kCopyBytes);
 #pragma unroll
             for (int c = 0; c < 3; ++c)
@@ -370,6 +392,26 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * C::kStageBytes);
           const uint32_t sw = smem_u32(smem_w);
+          if (MODE == 4) {
+            constexpr uint32_t kLbo = C::kI8RowBytes;                 // next 8-channel group
+            constexpr uint32_t kSbo = (BK / 8) * C::kI8RowBytes;      // next image row (= next 8-pixel group)
+            const uint32_t lbo = (p.debug_skip & 2) ? kSbo : kLbo;    // (bring-up knob: swapped roles)
+            const uint32_t sbo = (p.debug_skip & 2) ? kLbo : kSbo;
+            for (int tap = 0; tap < 9; ++tap) {
+              const int ky = tap / 3, kx = tap - ky * 3;
+              const uint32_t a_addr = sa + ky * kSbo + kx * 16;       // pixel (ry+ky, rx+kx) of the haloed tile
+              const uint64_t db = make_smem_desc<BK>(sw + tap * C::kBBytes);
+#pragma unroll
+              for (int k = 0; k < BK / 16; ++k) {
+                const uint64_t da = make_smem_desc_noswz(a_addr + k * 2 * kLbo, lbo, sbo);
+                tc_mma_f16(d_tmem, da, db + (uint64_t)(k * 2), C::kIdesc, (tap | k) != 0);
+              }
+            }
+            tc_commit(&empty_bar[stage]);
+            if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+            tc_commit(&tmem_full[as]);
+            continue;
+          }
           for (int tap = 0; tap < p.taps; ++tap) {
             // tap (ky,kx): copy kx holds the tile shifted by dx = kx-1; row offset ky*TW pixels shifts by dy = ky-1
             const int ky = tap / 3, kx = tap - ky * 3;
@@ -524,11 +566,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           } else if (s2dy) {
             const int org = (img * (H >> 1) + ((tc.ty * p.TH + ry) >> 1)) * W + tc.tx * p.TW + rx;
             out_row = e.out + ((size_t)org * 2 + (ry & 1)) * p.Ntot + n_first;
-          } else if (!d2s) {
+          } else if (!d2s && !e.out_i8) {
             out_row = e.out + (size_t)pix * p.Ntot + n_first;
           }
         }
         if (d2s) d2s_pix = (img * 2 * H + 2 * tc.ty * p.TH) * (2 * W) + 2 * tc.tx * p.TW + row_d2s;
+        // I8 layout [n][y][c/8][x][8]: (row index) * (C/8) * Wo + x, in units of 8-channel vectors
+        const int i8_groups = e.Cout >> 3;
+        const int i8_row = img * H + tc.ty * p.TH + ry;          // regular store: image row of this pixel
+        const int i8_x = tc.tx * p.TW + rx;
         mbar_wait(&tmem_full[as], aphase);
         tc_fence_after();
         uint32_t acc[2][16];
@@ -537,23 +583,35 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         for (int c = 0; c < kChunks; ++c) {
           tc_ld_wait();
           if (c + 1 < kChunks) tc_ld16_issue(taddr + (c + 1) * 16, acc[(c + 1) & 1]);
-          if (valid && !p.debug_skip) {
+          if (valid && !(p.debug_skip & 1)) {
             const int j0 = half * kHalf + c * 16;
             const float nzc = nscale * nz_cur[d2s ? c : 0];
             __half* optr = nullptr;
+            size_t half_stride = 8;
             if (d2s) {
               // column n -> phase (py,px) and channel o; output pixel (2y+py, 2x+px)
               const int n0 = n_tile * BN + j0;
               const int ph = cout_sh >= 0 ? (n0 >> cout_sh) : (n0 / e.Cout);
               const int o0 = n0 - ph * e.Cout;
-              if (e.out != nullptr)
-                optr = e.out + (size_t)(d2s_pix + (ph >> 1) * (2 * W) + (ph & 1)) * e.Cout + o0;
+              if (e.out != nullptr) {
+                if (e.out_i8) {
+                  const int yo = 2 * (tc.ty * p.TH + ry) + (ph >> 1), xo = 2 * i8_x + (ph & 1);
+                  half_stride = (size_t)(2 * W) * 8;
+                  optr = e.out + (((size_t)(img * 2 * H + yo) * i8_groups + (o0 >> 3)) * (2 * W) + xo) * 8;
+                } else {
+                  optr = e.out + (size_t)(d2s_pix + (ph >> 1) * (2 * W) + (ph & 1)) * e.Cout + o0;
+                }
+              }
+            } else if (e.out_i8 && e.out != nullptr) {
+              const int o0 = n_first + c * 16;                     // regular store: Ntot == Cout
+              half_stride = (size_t)W * 8;
+              optr = e.out + (((size_t)i8_row * i8_groups + (o0 >> 3)) * W + i8_x) * 8;
             } else if (out_row != nullptr) {
               optr = out_row + c * 16;
             }
             const __half* rptr = res_row != nullptr ? res_row + c * 16 : nullptr;
-            if (has_rgb) epilogue_fast16<true>(e, par, BN, j0, acc[c & 1], nzc, rptr, optr, rgb);
-            else epilogue_fast16<false>(e, par, BN, j0, acc[c & 1], nzc, rptr, optr, rgb);
+            if (has_rgb) epilogue_fast16<true>(e, par, BN, j0, acc[c & 1], nzc, rptr, optr, half_stride, rgb);
+            else epilogue_fast16<false>(e, par, BN, j0, acc[c & 1], nzc, rptr, optr, half_stride, rgb);
           }
         }
       } else {
@@ -683,6 +741,12 @@ cudaError_t launch_conv_tc(const ConvParams& p, const TmaMaps& maps, int num_sms
   GLASS_CASE(128, 32, 1)
   GLASS_CASE(32, 64, 1)
   GLASS_CASE(64, 64, 1)
+  GLASS_CASE(32, 32, 4)
+  GLASS_CASE(64, 32, 4)
+  GLASS_CASE(128, 32, 4)
+  GLASS_CASE(32, 64, 4)
+  GLASS_CASE(64, 64, 4)
+  GLASS_CASE(128, 64, 4)
   GLASS_CASE(32, 32, 2)
   GLASS_CASE(64, 32, 2)
   GLASS_CASE(128, 32, 2)

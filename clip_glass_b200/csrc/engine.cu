@@ -94,6 +94,8 @@ struct glass_engine {
   __half *actA = nullptr, *actB = nullptr, *actC = nullptr;   // actC: intermediate of the exact polyphase forms
   std::vector<int> g_exact;   // per G layer: 1 = exact polyphase up-conv
   std::vector<int> d_exact;   // per D block: 1 = exact polyphase down-conv
+  std::vector<int> g_in_i8;   // per G layer: its INPUT activation is stored [N][H][C/8][W][8]
+  std::vector<int> d_in_i8;   // per D block: its input activation likewise
   std::vector<int> g_pair;    // per G layer: 1 = 32-channel conv on horizontally paired pixels
   std::vector<int> d_pair;    // per D block: conv0 likewise
   float4 *slabs = nullptr, *yA = nullptr, *yB = nullptr;
@@ -154,10 +156,12 @@ int encode_map(glass_engine* e, CUtensorMap* map, const void* ptr, int rank, con
     estr[i] = 1;
     if (i > 0) gstr[i - 1] = strides_bytes[i - 1];
   }
+  // inner_bytes 128 / 64 select the matching swizzle; 0 = un-swizzled box (conv_tc MODE 4)
   CUtensorMapSwizzle sw = inner_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
                         : inner_bytes == 64  ? CU_TENSOR_MAP_SWIZZLE_64B
                                              : CU_TENSOR_MAP_SWIZZLE_NONE;
-  if (sw == CU_TENSOR_MAP_SWIZZLE_NONE) return fail(GLASS_ERR_ARG, "unsupported TMA inner box of %d bytes", inner_bytes);
+  if (sw == CU_TENSOR_MAP_SWIZZLE_NONE && inner_bytes != 0)
+    return fail(GLASS_ERR_ARG, "unsupported TMA inner box of %d bytes", inner_bytes);
   CUresult r = e->encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, rank, const_cast<void*>(ptr), gdim, gstr, bdim, estr,
                          CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -183,7 +187,7 @@ const signed char kDownExactTaps[4][2] = {{0, 0}, {0, 1}, {1, 0}, {1, 1}};
 
 int make_conv(glass_engine* e, ConvLaunch* out, const __half* in, int Nimg, int H, int W, int Cin, const __half* wgt,
               int taps, int Ntot, const EpiParams& epi, bool gemm, const signed char (*table)[2] = nullptr,
-              int in_H = 0, int in_W = 0) {
+              int in_H = 0, int in_W = 0, bool in_i8 = false) {
   ConvParams& p = out->p;
   memset(&p, 0, sizeof(p));
   p.Nimg = Nimg; p.H = H; p.W = W; p.Cin = Cin; p.taps = taps; p.Ntot = Ntot;
@@ -211,8 +215,16 @@ int make_conv(glass_engine* e, ConvLaunch* out, const __half* in, int Nimg, int 
     return fail(GLASS_ERR_ARG, "unsupported conv shape Cin=%d Ntot=%d", Cin, Ntot);
   // Small-channel layers (the whole K of a tap is one chunk) on full 16x8 tiles: resident taps + halo copies.
   p.mode = 0;
-  if (!gemm && table == nullptr && (Cin == 32 || Cin == 64) && p.TW == 16 && p.TH == 8 && p.TN == 1 &&
-      (taps == 9 || taps == 1)) {
+  if (in_i8) {
+    // channel-group-interleaved input: 8-wide x 16-tall tiles, one un-swizzled haloed box per tile (MODE 4)
+    if (gemm || table != nullptr || taps != 9 || (Cin != 32 && Cin != 64) || H < 16 || W < 8 || H % 16 || W % 8)
+      return fail(GLASS_ERR_ARG, "I8 input layout needs a 3x3 conv with 32/64 channels on a >=16x8 grid");
+    p.mode = 4;
+    p.TW = 8; p.TH = 16; p.TN = 1;
+    p.tiles_x = W / 8; p.tiles_y = H / 16; p.tiles_n = Nimg;
+    while (p.BN > 128) p.BN /= 2;
+  } else if (!gemm && table == nullptr && (Cin == 32 || Cin == 64) && p.TW == 16 && p.TH == 8 && p.TN == 1 &&
+             (taps == 9 || taps == 1)) {
     if (taps == 9) {
       p.mode = 1;
       const int bn_cap = (Cin == 64) ? 64 : 128;       // 9 resident taps must leave room for >= 2 stages
@@ -239,6 +251,19 @@ int make_conv(glass_engine* e, ConvLaunch* out, const __half* in, int Nimg, int 
   const uint64_t ndecl = (uint64_t)p.tiles_n * p.TN;
   uint64_t dims[4] = {(uint64_t)Cin, wdecl, (uint64_t)p.in_H, ndecl};
   uint64_t strides[3] = {(uint64_t)Cin * 2, (uint64_t)Cin * 2 * wdecl, (uint64_t)Cin * 2 * wdecl * p.in_H};
+  if (p.mode == 4) {
+    // [N][H][G][W][8] seen as dims (W*8, G, H, N); box ((TW+2)*8, G, TH+2, 1), no swizzle
+    const uint64_t G = Cin / 8;
+    uint64_t d4[4] = {(uint64_t)W * 8, G, (uint64_t)H, (uint64_t)Nimg};
+    uint64_t s4[3] = {(uint64_t)W * 16, G * W * 16, (uint64_t)H * G * W * 16};
+    uint32_t b4[4] = {(uint32_t)(p.TW + 2) * 8, (uint32_t)G, (uint32_t)p.TH + 2, 1};
+    int rc4 = encode_map(e, &out->maps.a, in, 4, d4, s4, b4, 0);
+    if (rc4 != GLASS_OK) return rc4;
+    uint64_t wd4[3] = {(uint64_t)Cin, (uint64_t)Ntot, (uint64_t)taps};
+    uint64_t ws4[2] = {(uint64_t)Cin * 2, (uint64_t)Cin * 2 * Ntot};
+    uint32_t wb4[3] = {(uint32_t)p.BK, (uint32_t)p.BN, 1};
+    return encode_map(e, &out->maps.b, wgt, 3, wd4, ws4, wb4, p.BK * 2);
+  }
   // mode 1 with 3x3 taps loads the tile plus one halo row above and below per horizontal shift
   const uint32_t box_h = (p.mode == 1 && taps == 9) ? (uint32_t)p.TH + 2 : (uint32_t)p.TH;
   uint32_t box[4] = {(uint32_t)p.BK, (uint32_t)p.TW, box_h, (uint32_t)p.TN};
@@ -290,14 +315,25 @@ int capture_f32(glass_engine* e, const std::string& name, const float* dev, size
   CUDA_OK(cudaMemcpy(v.data(), dev, n * sizeof(float), cudaMemcpyDeviceToHost));
   return GLASS_OK;
 }
-int capture_f16(glass_engine* e, const std::string& name, const __half* dev, size_t n, cudaStream_t s) {
+// i8_w/i8_c > 0: the device tensor is [rows][C/8][W][8]; captured as NHWC [rows][W][C]
+int capture_f16(glass_engine* e, const std::string& name, const __half* dev, size_t n, cudaStream_t s, int i8_w = 0,
+                int i8_c = 0) {
   if (!e->capture) return GLASS_OK;
   std::vector<__half> tmp(n);
   CUDA_OK(cudaStreamSynchronize(s));
   CUDA_OK(cudaMemcpy(tmp.data(), dev, n * sizeof(__half), cudaMemcpyDeviceToHost));
   std::vector<float>& v = e->captured[name];
   v.resize(n);
-  for (size_t i = 0; i < n; ++i) v[i] = __half2float(tmp[i]);
+  if (i8_w > 0) {
+    const size_t G = i8_c / 8, rows = n / ((size_t)i8_w * i8_c);
+    for (size_t r = 0; r < rows; ++r)
+      for (size_t g = 0; g < G; ++g)
+        for (size_t x = 0; x < (size_t)i8_w; ++x)
+          for (size_t j = 0; j < 8; ++j)
+            v[(r * i8_w + x) * i8_c + g * 8 + j] = __half2float(tmp[((r * G + g) * i8_w + x) * 8 + j]);
+  } else {
+    for (size_t i = 0; i < n; ++i) v[i] = __half2float(tmp[i]);
+  }
   return GLASS_OK;
 }
 
@@ -340,13 +376,31 @@ void derive_arch(glass_engine* e) {
     const bool possible = !folded && (e->R >> b) >= 32;
     e->d_exact.push_back((possible && (exact_all || e->gch[c.num_blocks - 1 - b] >= 128)) ? 1 : 0);
   }
+  // activations feeding a 32/64-channel 3x3 conv: channel-group-interleaved (MODE 4), written by the producing
+  // conv's epilogue (not by k_upfir) or by k_from_rgb
+  const bool i8_ok = (c.flags & GLASS_FLAG_NO_I8_LAYOUT) == 0 && c.conv_impl == 0;
+  e->g_in_i8.clear();
+  for (size_t li = 0; li < e->glayers.size(); ++li) {
+    const GLayer& l = e->glayers[li];
+    const int in_res = l.up ? l.res / 2 : l.res;
+    const bool ok = i8_ok && li >= 1 && !e->g_exact[li] && !e->g_exact[li - 1] && (l.cin == 32 || l.cin == 64) &&
+                    in_res >= 16 && (l.up ? 4 * l.cout : l.cout) % 32 == 0;
+    e->g_in_i8.push_back(ok ? 1 : 0);
+  }
+  e->d_in_i8.clear();
+  for (int b = 0; b + 1 < c.num_blocks; ++b) {
+    const int Ci = e->gch[c.num_blocks - 1 - b];
+    e->d_in_i8.push_back((i8_ok && (Ci == 32 || Ci == 64) && (e->R >> b) >= 16) ? 1 : 0);
+  }
   const bool pair_ok = (c.flags & GLASS_FLAG_NO_PAIR_PACK) == 0 && c.conv_impl == 0;
   e->g_pair.clear();
-  for (const GLayer& l : e->glayers)
-    e->g_pair.push_back((pair_ok && !l.up && l.cin == 32 && l.cout == 32 && l.res >= 32) ? 1 : 0);
+  for (size_t li = 0; li < e->glayers.size(); ++li) {
+    const GLayer& l = e->glayers[li];
+    e->g_pair.push_back((pair_ok && !e->g_in_i8[li] && !l.up && l.cin == 32 && l.cout == 32 && l.res >= 32) ? 1 : 0);
+  }
   e->d_pair.clear();
   for (int b = 0; b + 1 < c.num_blocks; ++b)
-    e->d_pair.push_back((pair_ok && e->gch[c.num_blocks - 1 - b] == 32 && (e->R >> b) >= 32) ? 1 : 0);
+    e->d_pair.push_back((pair_ok && !e->d_in_i8[b] && e->gch[c.num_blocks - 1 - b] == 32 && (e->R >> b) >= 32) ? 1 : 0);
   e->noise_layer_off.clear();
   size_t noff = 0;
   for (const GLayer& l : e->glayers) { e->noise_layer_off.push_back(noff); noff += (size_t)l.res * l.res; }
@@ -541,6 +595,7 @@ int build_plan(glass_engine* e, int P) {
       ep.out_scale = e->styles + e->conv_off[li + 1];
       ep.out_scale_stride = e->S;
       ep.out = bufs[cur ^ 1];
+      ep.out_i8 = e->g_in_i8[li + 1];
     } else {
       ep.out = nullptr;
     }
@@ -556,6 +611,10 @@ int build_plan(glass_engine* e, int P) {
       snprintf(nm, sizeof nm, "g.conv%zu.wx", li);
       RC(make_conv(e, &cl, bufs[cur], P, in_res + 1, in_res + 1, l.cin, tptr<__half>(e, nm), 4, 4 * l.cout, eu, false,
                    kUpExactTaps, in_res, in_res));
+    } else if (e->g_in_i8[li]) {
+      snprintf(nm, sizeof nm, "g.conv%zu.w", li);
+      RC(make_conv(e, &cl, bufs[cur], P, in_res, in_res, l.cin, tptr<__half>(e, nm), 9, l.up ? 4 * l.cout : l.cout, ep,
+                   false, nullptr, 0, 0, true));
     } else if (e->g_pair[li]) {
       // 32-channel layer on paired pixels: [H][W/2][64] view, N = 2*Cout, the epilogue's column halves are pixels
       ep.x_phases = 2;
@@ -620,7 +679,9 @@ int build_plan(glass_engine* e, int P) {
       EpiParams ep = epi_default();
       ep.Cout = Ci; ep.bias = tptr<float>(e, nmf("c0.b")); ep.act = kActLrelu; ep.out = e->actB;
       ep.store_mode = e->d_exact[b] ? kStoreRegular : kStoreSpaceToDepth;
-      if (e->d_pair[b]) {
+      if (e->d_in_i8[b]) {
+        RC(make_conv(e, &cl, x, P, res, res, Ci, tptr<__half>(e, nmf("c0.w")), 9, Ci, ep, false, nullptr, 0, 0, true));
+      } else if (e->d_pair[b]) {
         ep.x_phases = 2;
         if (ep.store_mode == kStoreSpaceToDepth) ep.store_mode = kStoreSpaceToDepthY;
         RC(make_conv(e, &cl, x, P, res, res / 2, 2 * Ci, tptr<__half>(e, nmf("c0.wp")), 9, 2 * Ci, ep, false));
@@ -636,6 +697,7 @@ int build_plan(glass_engine* e, int P) {
       ep = epi_default();
       ep.Cout = Co; ep.bias = tptr<float>(e, nmf("c1.b")); ep.act = kActLrelu; ep.residual = e->dR;
       ep.post_scale = kInvSqrt2; ep.out = outs[b & 1];
+      ep.out_i8 = (b + 1 < nb - 1) ? e->d_in_i8[b + 1] : 0;
       if (e->d_exact[b]) {
         // exact: blurred input (k_blur_s2d -> actC, [(res/2+1)^2][4*Ci]) then a 2x2-tap conv == 3x3 stride 2
         RC(make_conv(e, &cl, e->actC, P, res / 2, res / 2, 4 * Ci, tptr<__half>(e, nmf("c1.wx")), 4, Co, ep, false,
@@ -734,7 +796,8 @@ int run_generator(glass_engine* e, const float* z, int P, const glass_noise* nz,
     }
     if (layer_out != nullptr) {
       snprintf(nm, sizeof nm, "xs%zu", li);
-      RC(capture_f16(e, nm, layer_out, (size_t)P * l.res * l.res * l.cout, s));
+      const bool i8 = li + 1 < nl && e->g_in_i8[li + 1];
+      RC(capture_f16(e, nm, layer_out, (size_t)P * l.res * l.res * l.cout, s, i8 ? l.res : 0, i8 ? l.cout : 0));
     }
     const bool last_in_block = (li + 1 == nl) || (e->glayers[li + 1].block != l.block);
     if (last_in_block) {
@@ -788,12 +851,13 @@ int run_discriminator(glass_engine* e, const float* images, int P, float* logits
   const int nb = c.num_blocks;
   auto dch = [&](int i) { return e->gch[nb - 1 - i]; };
   char nm[64];
-  LAUNCH(k_from_rgb(images, tptr<float>(e, "d.frgb.w"), tptr<float>(e, "d.frgb.b"), e->actA, P, e->R, dch(0), s));
+  LAUNCH(k_from_rgb(images, tptr<float>(e, "d.frgb.w"), tptr<float>(e, "d.frgb.b"), e->actA, P, e->R, dch(0),
+                    e->d_in_i8[0], s));
   const __half* x = e->actA;
   int res = e->R;
   size_t ci = 0;
   for (int b = 0; b < nb - 1; ++b) {
-    LAUNCH(k_fir_down(x, e->dXd, P, res, res, dch(b), s));
+    LAUNCH(k_fir_down(x, e->dXd, P, res, res, dch(b), e->d_in_i8[b], s));
     RC(run_conv(e, e->d_convs[ci++], s));   // conv0 -> actB (space-to-depth, or NHWC for the exact form)
     if (e->d_exact[b]) LAUNCH(k_blur_s2d(e->actB, e->actC, P, res, res, dch(b), s));
     RC(run_conv(e, e->d_convs[ci++], s));   // projection -> dR
@@ -802,7 +866,8 @@ int run_discriminator(glass_engine* e, const float* images, int P, float* logits
     x = c1.p.epi.out;
     res /= 2;
     snprintf(nm, sizeof nm, "d%d", b);
-    RC(capture_f16(e, nm, x, (size_t)P * res * res * dch(b + 1), s));
+    const bool i8 = (b + 1 < nb - 1) && e->d_in_i8[b + 1];
+    RC(capture_f16(e, nm, x, (size_t)P * res * res * dch(b + 1), s, i8 ? res : 0, i8 ? dch(b + 1) : 0));
   }
   const int C = dch(nb - 1);
   const int cpad = ((C + 1 + 63) / 64) * 64;

@@ -359,7 +359,7 @@ __global__ void final_cosine_kernel(const __half* __restrict__ tokens, const flo
 // ---------------------------------------------------------------------------
 template <int C>
 __global__ void from_rgb_kernel(const float* __restrict__ images, const float* __restrict__ Wt,
-                                const float* __restrict__ bias, __half* __restrict__ out, int P, int R) {
+                                const float* __restrict__ bias, __half* __restrict__ out, int P, int R, int out_i8) {
   __shared__ float w[3 * C + C];
   for (int i = threadIdx.x; i < 3 * C; i += blockDim.x) w[i] = Wt[i];
   for (int i = threadIdx.x; i < C; i += blockDim.x) w[3 * C + i] = bias[i];
@@ -386,7 +386,12 @@ __global__ void from_rgb_kernel(const float* __restrict__ images, const float* _
       }
       h2[j] = __floats2half2_rn(a[0], a[1]);
     }
-    *reinterpret_cast<uint4*>(out + pixi * C + g * 8) = pk;
+    if (out_i8) {
+      const size_t y = pix / R, x = pix - y * R;
+      *reinterpret_cast<uint4*>(out + ((((b * R + y) * G + g) * R) + x) * 8) = pk;
+    } else {
+      *reinterpret_cast<uint4*>(out + pixi * C + g * 8) = pk;
+    }
   }
 }
 
@@ -395,7 +400,7 @@ __global__ void from_rgb_kernel(const float* __restrict__ images, const float* _
 // HBM/L2 see every input byte once and the 16 taps per output come from shared memory.
 constexpr int kFdTH = 8, kFdTW = 16, kFdC = 32, kFdPitch = 40;   // pitch in halfs (80 bytes)
 __global__ void __launch_bounds__(256) fir_down_kernel(const __half* __restrict__ x, __half* __restrict__ out, int N,
-                                                       int H, int W, int C) {
+                                                       int H, int W, int C, int in_i8) {
   __shared__ __align__(16) __half tile[(2 * kFdTH + 2) * (2 * kFdTW + 2) * kFdPitch];
   const int Ho = H >> 1, Wo = W >> 1;
   const int tiles_x = (Wo + kFdTW - 1) / kFdTW, tiles_y = (Ho + kFdTH - 1) / kFdTH;
@@ -411,8 +416,11 @@ __global__ void __launch_bounds__(256) fir_down_kernel(const __half* __restrict_
     const int py = pix / IW, px = pix - py * IW;
     const int yy = iy0 + py, xx = ix0 + px;
     uint4 v = make_uint4(0, 0, 0, 0);
-    if (yy >= 0 && yy < H && xx >= 0 && xx < W)
-      v = __ldg(reinterpret_cast<const uint4*>(x + (((size_t)b * H + yy) * W + xx) * C + c0 + g * 8));
+    if (yy >= 0 && yy < H && xx >= 0 && xx < W) {
+      const size_t off = in_i8 ? ((((size_t)b * H + yy) * (C >> 3) + (c0 >> 3) + g) * W + xx) * 8
+                               : (((size_t)b * H + yy) * W + xx) * C + c0 + g * 8;
+      v = __ldg(reinterpret_cast<const uint4*>(x + off));
+    }
     *reinterpret_cast<uint4*>(tile + pix * kFdPitch + g * 8) = v;
   }
   __syncthreads();
@@ -761,20 +769,20 @@ cudaError_t k_final_cosine(const __half* tokens, const float* lw, const float* l
   GLASS_RET();
 }
 cudaError_t k_from_rgb(const float* images, const float* Wt, const float* bias, __half* out, int P, int R, int C,
-                       cudaStream_t s) {
+                       int out_i8, cudaStream_t s) {
   const int blocks = blocks_for((size_t)P * R * R * (C / 8), kThreads, 148 * 32);
-  if (C == 32) from_rgb_kernel<32><<<blocks, kThreads, 0, s>>>(images, Wt, bias, out, P, R);
-  else if (C == 64) from_rgb_kernel<64><<<blocks, kThreads, 0, s>>>(images, Wt, bias, out, P, R);
-  else if (C == 128) from_rgb_kernel<128><<<blocks, kThreads, 0, s>>>(images, Wt, bias, out, P, R);
+  if (C == 32) from_rgb_kernel<32><<<blocks, kThreads, 0, s>>>(images, Wt, bias, out, P, R, out_i8);
+  else if (C == 64) from_rgb_kernel<64><<<blocks, kThreads, 0, s>>>(images, Wt, bias, out, P, R, out_i8);
+  else if (C == 128) from_rgb_kernel<128><<<blocks, kThreads, 0, s>>>(images, Wt, bias, out, P, R, out_i8);
   else return cudaErrorInvalidValue;
   GLASS_RET();
 }
-cudaError_t k_fir_down(const __half* x, __half* out, int N, int H, int W, int C, cudaStream_t s) {
+cudaError_t k_fir_down(const __half* x, __half* out, int N, int H, int W, int C, int in_i8, cudaStream_t s) {
   if (C % kFdC != 0) return cudaErrorInvalidValue;
   const int Ho = H / 2, Wo = W / 2;
   const int tiles = ((Wo + kFdTW - 1) / kFdTW) * ((Ho + kFdTH - 1) / kFdTH) * N;
   dim3 grid(tiles, C / kFdC);
-  fir_down_kernel<<<grid, 256, 0, s>>>(x, out, N, H, W, C);
+  fir_down_kernel<<<grid, 256, 0, s>>>(x, out, N, H, W, C, in_i8);
   GLASS_RET();
 }
 cudaError_t k_upfir(const __half* u, __half* out, const float* noise, size_t noise_group_stride, int noise_group_div,

@@ -51,10 +51,12 @@ cudaError_t k_final_cosine(const __half* tokens, const float* lw, const float* l
 
 // ---- discriminator ----
 // utils.py:19-21 denorm + models.py:1121-1144 fromRGB 1x1 + bias + lrelu*sqrt2 -> NHWC fp16
+// out_i8: write the channel-group-interleaved layout [P][R][C/8][R][8] instead of NHWC
 cudaError_t k_from_rgb(const float* images, const float* Wt, const float* bias, __half* out, int P, int R, int C,
-                       cudaStream_t s);
+                       int out_i8, cudaStream_t s);
 // projection path FIR (pad 1) sampled at stride 2 (modules.py:1204-1220, 1243-1246): [N,H,W,C] -> [N,H/2,W/2,C]
-cudaError_t k_fir_down(const __half* x, __half* out, int N, int H, int W, int C, cudaStream_t s);
+// in_i8: x is channel-group-interleaved [N][H][C/8][W][8]; the output is always NHWC
+cudaError_t k_fir_down(const __half* x, __half* out, int N, int H, int W, int C, int in_i8, cudaStream_t s);
 // modules.py:701-747 incl. the in-place centring; x [P,16,C] -> out [P,16,Cpad] (channel C = std feature)
 cudaError_t k_mbstd(const __half* x, __half* out, int P, int batch, int group, int C, int Cpad, cudaStream_t s);
 // models.py:1224-1225 last dense + problem.py:23 hinge

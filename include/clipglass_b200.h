@@ -66,6 +66,9 @@ typedef struct glass_config {
 /* The 32-channel 3x3 convs normally run on horizontally paired pixels ([H][W/2][64] view of the same bytes:
  * 128-byte TMA rows, 256-pixel tiles, 2x the MACs of a layer that is not math-bound). */
 #define GLASS_FLAG_NO_PAIR_PACK 4      /* keep them on single pixels */
+/* Activations that feed a 32/64-channel 3x3 conv are normally stored channel-group-interleaved
+ * ([N][H][C/8][W][8]) so that one un-swizzled haloed TMA box per tile serves all nine taps (conv_tc MODE 4). */
+#define GLASS_FLAG_NO_I8_LAYOUT 8      /* keep every activation NHWC (MODE 1 / pixel pairs for those layers) */
 
 /* -- lifetime ------------------------------------------------------------- */
 /* Replaces Generator.__init__ (generator.py:12-27): allocate the engine. */
