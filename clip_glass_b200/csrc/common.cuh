@@ -103,7 +103,12 @@ __device__ __forceinline__ void epilogue_row16(const ConvParams& p, int img, int
          __ldg(e.noise + (size_t)(img / e.noise_group_div) * e.noise_group_stride + (size_t)yo * Wo + xo);
   }
   size_t out_idx;
-  if (e.store_mode == kStoreRegular) {
+  size_t half_stride = 8;     // distance between channels [0,8) and [8,16) of the chunk
+  if (e.out_i8) {
+    // channel-group-interleaved [n][yo][Cout/8][xo][8] (regular and depth-to-space stores)
+    out_idx = (((size_t)(img * Ho + yo) * (Cout >> 3) + (o0 >> 3)) * Wo + xo) * 8;
+    half_stride = (size_t)Wo * 8;
+  } else if (e.store_mode == kStoreRegular) {
     out_idx = ((size_t)(img * p.H + y) * p.W + x) * p.Ntot + n0;
   } else if (e.store_mode == kStoreDepthToSpace) {
     out_idx = ((size_t)(img * Ho + yo) * Wo + xo) * Cout + o0;
@@ -152,9 +157,8 @@ __device__ __forceinline__ void epilogue_row16(const ConvParams& p, int img, int
       h0[j] = __floats2half2_rn(v[2 * j], v[2 * j + 1]);
       h1[j] = __floats2half2_rn(v[8 + 2 * j], v[8 + 2 * j + 1]);
     }
-    uint4* op = reinterpret_cast<uint4*>(e.out + out_idx);
-    op[0] = w0;
-    op[1] = w1;
+    *reinterpret_cast<uint4*>(e.out + out_idx) = w0;
+    *reinterpret_cast<uint4*>(e.out + out_idx + half_stride) = w1;
   }
 }
 
