@@ -176,7 +176,7 @@ struct Cfg {
   // double-buffered per-tile epilogue parameters + 2 x 128 float4 for combining the two column halves' toRGB sums
   static constexpr int kParamBytes = 2 * kNumParams * BN * 4 + 2 * 128 * 16;
   // the 32-channel MODE-1 layers are bookkeeping/latency-bound, not smem-bound: run two CTAs per SM there
-  static constexpr int kMinBlocks = (MODE == 1 && BK == 32 && BN <= 32) ? 2 : 1;
+  static constexpr int kMinBlocks = ((MODE == 1 || MODE == 4) && BK == 32 && BN <= 32) ? 2 : 1;
   static constexpr int kBudget = (kMinBlocks == 2 ? 110 : 222) * 1024 - kParamBytes - kWBytes;   // of 227 KB/SM
   static constexpr int kStagesRaw = kBudget / kStageBytes;
   static constexpr int kStages = kStagesRaw > 12 ? 12 : kStagesRaw;
