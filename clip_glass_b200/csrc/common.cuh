@@ -104,7 +104,12 @@ __device__ __forceinline__ void epilogue_row16(const ConvParams& p, int img, int
   }
   size_t out_idx;
   size_t half_stride = 8;     // distance between channels [0,8) and [8,16) of the chunk
-  if (e.out_i8) {
+  if (e.out_i8 && e.store_mode == kStoreSpaceToDepth) {
+    // space-to-depth + I8: [n][y/2][(phase*Ntot + o)/8][x/2][8]
+    const int k0 = ((y & 1) * 2 + (x & 1)) * p.Ntot + n0;
+    out_idx = (((size_t)(img * (p.H >> 1) + (y >> 1)) * (p.Ntot >> 1) + (k0 >> 3)) * (p.W >> 1) + (x >> 1)) * 8;
+    half_stride = (size_t)(p.W >> 1) * 8;
+  } else if (e.out_i8) {
     // channel-group-interleaved [n][yo][Cout/8][xo][8] (regular and depth-to-space stores)
     out_idx = (((size_t)(img * Ho + yo) * (Cout >> 3) + (o0 >> 3)) * Wo + xo) * 8;
     half_stride = (size_t)Wo * 8;

@@ -167,6 +167,10 @@ struct Cfg {
   //   a different start address (16-byte granularity), so ONE copy of the haloed tile serves all nine taps:
   //   1.4x the tile in L2->SM bytes (MODE 1: 3.75x, MODE 0: 9x) and (TH+2)*C/8 long TMA rows instead of hundreds
   //   of 64/128-byte ones (TMA issues ~0.41 rows/cycle/SM regardless of their length).
+  // resident weights are kept in 64-channel (128-byte, swizzled) K chunks: [tap][chunk][BN x kBKc]
+  static constexpr int kBKc = BK > 64 ? 64 : BK;
+  static constexpr int kKChunks = BK / kBKc;
+  static constexpr int kBChunkBytes = BN * kBKc * 2;
   static constexpr int kI8TW = 8, kI8TH = 16;
   static constexpr int kI8RowBytes = (kI8TW + 2) * 16;                          // one (row, group): 10 pixels x 16 B
   static constexpr int kI8StageBytes = (kI8TH + 2) * (BK / 8) * kI8RowBytes;
@@ -332,7 +336,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         const int n_tile = blockIdx.x % n_tiles;
         mbar_expect_tx(w_bar, p.taps * C::kBBytes);
         for (int tap = 0; tap < p.taps; ++tap)
-          tma_load_3d(&map_b, smem_w + tap * C::kBBytes, w_bar, 0, n_tile * BN, tap);
+          for (int ch = 0; ch < C::kKChunks; ++ch)
+            tma_load_3d(&map_b, smem_w + (tap * C::kKChunks + ch) * C::kBChunkBytes, w_bar, ch * C::kBKc, n_tile * BN,
+                        tap);
       }
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const TileCoord tc = decode_tile(p, tile, n_tiles);
@@ -400,11 +406,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             for (int tap = 0; tap < 9; ++tap) {
               const int ky = tap / 3, kx = tap - ky * 3;
               const uint32_t a_addr = sa + ky * kSbo + kx * 16;       // pixel (ry+ky, rx+kx) of the haloed tile
-              const uint64_t db = make_smem_desc<BK>(sw + tap * C::kBBytes);
 #pragma unroll
               for (int k = 0; k < BK / 16; ++k) {
+                constexpr int kPerChunk = C::kBKc / 16;
+                const int ch = k / kPerChunk, kk = k - ch * kPerChunk;
+                const uint64_t db = make_smem_desc<C::kBKc>(sw + (tap * C::kKChunks + ch) * C::kBChunkBytes);
                 const uint64_t da = make_smem_desc_noswz(a_addr + k * 2 * kLbo, lbo, sbo);
-                tc_mma_f16(d_tmem, da, db + (uint64_t)(k * 2), C::kIdesc, (tap | k) != 0);
+                tc_mma_f16(d_tmem, da, db + (uint64_t)(kk * 2), C::kIdesc, (tap | k) != 0);
               }
             }
             tc_commit(&empty_bar[stage]);
@@ -560,7 +568,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         __half* out_row = nullptr;           // regular / space-to-depth: contiguous columns
         int d2s_pix = 0;
         if (e.out != nullptr) {
-          if (s2d) {
+          if (s2d && !e.out_i8) {
             const int org = ((img * (H >> 1) + ((tc.ty * p.TH) >> 1)) * (W >> 1) + ((tc.tx * p.TW) >> 1)) << 2;
             out_row = e.out + (size_t)(org + row_s2d) * p.Ntot + n_first;
           } else if (s2dy) {
@@ -602,6 +610,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                   optr = e.out + (size_t)(d2s_pix + (ph >> 1) * (2 * W) + (ph & 1)) * e.Cout + o0;
                 }
               }
+            } else if (e.out_i8 && s2d && e.out != nullptr) {
+              // space-to-depth + I8: [n][y/2][(phase*Ntot + o)/8][x/2][8] with 4*Ntot channels per cell
+              const int yy = tc.ty * p.TH + ry;
+              const int k0 = ((yy & 1) * 2 + (i8_x & 1)) * p.Ntot + n_first + c * 16;
+              half_stride = (size_t)(W >> 1) * 8;
+              optr = e.out + (((size_t)(img * (H >> 1) + (yy >> 1)) * (p.Ntot >> 1) + (k0 >> 3)) * (W >> 1) + (i8_x >> 1)) * 8;
             } else if (e.out_i8 && e.out != nullptr) {
               const int o0 = n_first + c * 16;                     // regular store: Ntot == Cout
               half_stride = (size_t)W * 8;
@@ -747,6 +761,7 @@ cudaError_t launch_conv_tc(const ConvParams& p, const TmaMaps& maps, int num_sms
   GLASS_CASE(32, 64, 4)
   GLASS_CASE(64, 64, 4)
   GLASS_CASE(128, 64, 4)
+  GLASS_CASE(32, 128, 4)
   GLASS_CASE(32, 32, 2)
   GLASS_CASE(64, 32, 2)
   GLASS_CASE(128, 32, 2)

@@ -96,6 +96,7 @@ struct glass_engine {
   std::vector<int> d_exact;   // per D block: 1 = exact polyphase down-conv
   std::vector<int> g_in_i8;   // per G layer: its INPUT activation is stored [N][H][C/8][W][8]
   std::vector<int> d_in_i8;   // per D block: its input activation likewise
+  std::vector<int> d_c1_i8;   // per D block: the space-to-depth tensor between conv0 and the folded conv1 likewise
   std::vector<int> g_pair;    // per G layer: 1 = 32-channel conv on horizontally paired pixels
   std::vector<int> d_pair;    // per D block: conv0 likewise
   float4 *slabs = nullptr, *yA = nullptr, *yB = nullptr;
@@ -217,12 +218,14 @@ int make_conv(glass_engine* e, ConvLaunch* out, const __half* in, int Nimg, int 
   p.mode = 0;
   if (in_i8) {
     // channel-group-interleaved input: 8-wide x 16-tall tiles, one un-swizzled haloed box per tile (MODE 4)
-    if (gemm || table != nullptr || taps != 9 || (Cin != 32 && Cin != 64) || H < 16 || W < 8 || H % 16 || W % 8)
-      return fail(GLASS_ERR_ARG, "I8 input layout needs a 3x3 conv with 32/64 channels on a >=16x8 grid");
+    if (gemm || table != nullptr || taps != 9 || (Cin != 32 && Cin != 64 && Cin != 128) || H < 16 || W < 8 || H % 16 ||
+        W % 8)
+      return fail(GLASS_ERR_ARG, "I8 input layout needs a 3x3 conv with 32/64/128 channels on a >=16x8 grid");
     p.mode = 4;
+    p.BK = Cin;                        // whole K of a tap in one stage
     p.TW = 8; p.TH = 16; p.TN = 1;
     p.tiles_x = W / 8; p.tiles_y = H / 16; p.tiles_n = Nimg;
-    while (p.BN > 128) p.BN /= 2;
+    while (p.BN > (Cin == 128 ? 32 : 128)) p.BN /= 2;      // nine resident taps must leave room for >= 2 stages
   } else if (!gemm && table == nullptr && (Cin == 32 || Cin == 64) && p.TW == 16 && p.TH == 8 && p.TN == 1 &&
              (taps == 9 || taps == 1)) {
     if (taps == 9) {
@@ -261,8 +264,9 @@ int make_conv(glass_engine* e, ConvLaunch* out, const __half* in, int Nimg, int 
     if (rc4 != GLASS_OK) return rc4;
     uint64_t wd4[3] = {(uint64_t)Cin, (uint64_t)Ntot, (uint64_t)taps};
     uint64_t ws4[2] = {(uint64_t)Cin * 2, (uint64_t)Cin * 2 * Ntot};
-    uint32_t wb4[3] = {(uint32_t)p.BK, (uint32_t)p.BN, 1};
-    return encode_map(e, &out->maps.b, wgt, 3, wd4, ws4, wb4, p.BK * 2);
+    const int bkc = p.BK > 64 ? 64 : p.BK;            // resident weights are loaded in 64-channel swizzled chunks
+    uint32_t wb4[3] = {(uint32_t)bkc, (uint32_t)p.BN, 1};
+    return encode_map(e, &out->maps.b, wgt, 3, wd4, ws4, wb4, bkc * 2);
   }
   // mode 1 with 3x3 taps loads the tile plus one halo row above and below per horizontal shift
   const uint32_t box_h = (p.mode == 1 && taps == 9) ? (uint32_t)p.TH + 2 : (uint32_t)p.TH;
@@ -391,6 +395,11 @@ void derive_arch(glass_engine* e) {
   for (int b = 0; b + 1 < c.num_blocks; ++b) {
     const int Ci = e->gch[c.num_blocks - 1 - b];
     e->d_in_i8.push_back((i8_ok && (Ci == 32 || Ci == 64) && (e->R >> b) >= 16) ? 1 : 0);
+  }
+  e->d_c1_i8.clear();
+  for (int b = 0; b + 1 < c.num_blocks; ++b) {
+    const int Ci = e->gch[c.num_blocks - 1 - b];
+    e->d_c1_i8.push_back((i8_ok && !e->d_exact[b] && Ci == 32 && (e->R >> b) / 2 >= 16) ? 1 : 0);
   }
   const bool pair_ok = (c.flags & GLASS_FLAG_NO_PAIR_PACK) == 0 && c.conv_impl == 0;
   e->g_pair.clear();
@@ -679,6 +688,7 @@ int build_plan(glass_engine* e, int P) {
       EpiParams ep = epi_default();
       ep.Cout = Ci; ep.bias = tptr<float>(e, nmf("c0.b")); ep.act = kActLrelu; ep.out = e->actB;
       ep.store_mode = e->d_exact[b] ? kStoreRegular : kStoreSpaceToDepth;
+      ep.out_i8 = e->d_c1_i8[b];
       if (e->d_in_i8[b]) {
         RC(make_conv(e, &cl, x, P, res, res, Ci, tptr<__half>(e, nmf("c0.w")), 9, Ci, ep, false, nullptr, 0, 0, true));
       } else if (e->d_pair[b]) {
@@ -704,7 +714,8 @@ int build_plan(glass_engine* e, int P) {
                      kDownExactTaps, res / 2 + 1, res / 2 + 1));
       } else {
         // folded FIR + 3x3 stride 2 == 3x3 over the space-to-depth tensor (4*Ci channels)
-        RC(make_conv(e, &cl, e->actB, P, res / 2, res / 2, 4 * Ci, tptr<__half>(e, nmf("c1.w")), 9, Co, ep, false));
+        RC(make_conv(e, &cl, e->actB, P, res / 2, res / 2, 4 * Ci, tptr<__half>(e, nmf("c1.w")), 9, Co, ep, false,
+                     nullptr, 0, 0, e->d_c1_i8[b] != 0));
       }
       cl.flops = 2.0 * 9.0 * (double)P * (res / 2) * (res / 2) * Ci * Co; e->d_convs.push_back(cl);
       x = outs[b & 1];
