@@ -399,7 +399,10 @@ void derive_arch(glass_engine* e) {
   e->d_c1_i8.clear();
   for (int b = 0; b + 1 < c.num_blocks; ++b) {
     const int Ci = e->gch[c.num_blocks - 1 - b];
-    e->d_c1_i8.push_back((i8_ok && !e->d_exact[b] && Ci == 32 && (e->R >> b) / 2 >= 16) ? 1 : 0);
+    // Measured slower (D0:c1 5.35 ms vs 4.45 ms at P=64): the nine resident 128-channel taps only leave room for
+    // BN = 32, which doubles the tile count of an epilogue-bound layer.  Kept behind GLASS_DEBUG_C1_I8 for round 2.
+    const char* c1i8 = getenv("GLASS_DEBUG_C1_I8");
+    e->d_c1_i8.push_back((i8_ok && c1i8 && atoi(c1i8) && !e->d_exact[b] && Ci == 32 && (e->R >> b) / 2 >= 16) ? 1 : 0);
   }
   const bool pair_ok = (c.flags & GLASS_FLAG_NO_PAIR_PACK) == 0 && c.conv_impl == 0;
   e->g_pair.clear();
