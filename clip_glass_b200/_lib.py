@@ -12,7 +12,8 @@ import os
 
 GLASS_MAX_BLOCKS = 12
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libclipglass_b200.so")
+# CLIPGLASS_LIB: load another build of the same ABI (A/B timing of kernel variants; never set in tests or bench)
+LIB_PATH = os.environ.get("CLIPGLASS_LIB") or os.path.join(_HERE, "libclipglass_b200.so")
 
 SYMBOLS = [
     "glass_create", "glass_set_tensor", "glass_finalize", "glass_set_text_features", "glass_destroy",

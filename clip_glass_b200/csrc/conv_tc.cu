@@ -22,7 +22,7 @@ namespace glass {
 namespace {
 
 constexpr int kBlockM = 128;
-constexpr int kNumThreads = 64 + 8 * 32;   // TMA warp, MMA warp, 8 epilogue warps
+constexpr int kMaxThreads = 64 + 16 * 32;   // TMA warp, MMA warp, up to 16 epilogue warps
 constexpr long long kWaitLimitCycles = 4000000000ll;   // ~2 s at 1.9 GHz
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -134,8 +134,6 @@ __device__ __forceinline__ TileCoord decode_tile(const ConvParams& p, int tile, 
   return t;
 }
 
-constexpr int kEpiWarps = 8;
-constexpr int kEpiThreads = kEpiWarps * 32;
 constexpr int kNumParams = 6;   // scale, shift, oscale, rgb0, rgb1, rgb2
 
 // MODE 0 ("stream"): one pipeline stage per (filter tap, 64-channel chunk): A box + B box per stage.
@@ -177,8 +175,14 @@ struct Cfg {
   static constexpr int kStageBytes = MODE == 0 ? kABytes + kBBytes
                                      : (MODE == 1 ? 3 * kCopyBytes : (MODE == 4 ? kI8StageBytes : kABytes));
   static constexpr int kWBytes = MODE == 0 ? 0 : ((MODE == 1 || MODE == 4) ? 9 : 1) * kBBytes;   // resident taps
-  // double-buffered per-tile epilogue parameters + 2 x 128 float4 for combining the two column halves' toRGB sums
-  static constexpr int kParamBytes = 2 * kNumParams * BN * 4 + 2 * 128 * 16;
+  // Epilogue warps: the epilogue is latency-bound (TMEM load -> parameter loads -> math -> store chains with little
+  // to overlap), so it gets as many warps as the register file allows: four per TMEM lane quarter (each owning a
+  // quarter of the columns) from BN = 64 up, two per quarter for BN = 32 (its hot instances run two CTAs per SM).
+  static constexpr int kEpiWarps = BN >= 64 ? 16 : 8;
+  static constexpr int kParts = kEpiWarps / 4;                      // column parts per lane quarter
+  static constexpr int kThreads = 64 + 32 * kEpiWarps;
+  // double-buffered per-tile epilogue parameters + double-buffered staging of the non-leading parts' toRGB sums
+  static constexpr int kParamBytes = 2 * kNumParams * BN * 4 + 2 * (kParts - 1) * 128 * 16;
   // the 32-channel MODE-1 layers are bookkeeping/latency-bound, not smem-bound: run two CTAs per SM there
   static constexpr int kMinBlocks = ((MODE == 1 || MODE == 4) && BK == 32 && BN <= 32) ? 2 : 1;
   static constexpr int kBudget = (kMinBlocks == 2 ? 110 : 222) * 1024 - kParamBytes - kWBytes;   // of 227 KB/SM
@@ -199,7 +203,8 @@ __device__ __forceinline__ void tc_ld16_issue(uint32_t taddr, uint32_t (&r)[16])
       : "r"(taddr));
 }
 __device__ __forceinline__ void tc_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory"); }
+template <int kThreads>
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kThreads) : "memory"); }
 
 // Fast epilogue for one row and 16 columns with the per-tile parameters staged in shared memory.
 //   t = act(acc*scale + shift + nz) ; rgb += t*rgbw ; t = (t + residual) * oscale ; store fp16
@@ -276,7 +281,7 @@ __device__ __forceinline__ void epilogue_fast16(const EpiParams& e, const float*
 }
 
 template <int BN, int BK, int MODE>
-__global__ void __launch_bounds__(kNumThreads, (Cfg<BN, BK, MODE>::kMinBlocks))
+__global__ void __launch_bounds__((Cfg<BN, BK, MODE>::kThreads), (Cfg<BN, BK, MODE>::kMinBlocks))
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                const ConvParams p) {
   using C = Cfg<BN, BK, MODE>;
@@ -311,7 +316,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full[s], 1);
-      mbar_init(&tmem_empty[s], kEpiWarps);
+      mbar_init(&tmem_empty[s], C::kEpiWarps);
     }
     mbar_init(w_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -454,12 +459,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     }
   } else {
     // ===================== epilogue (warps 2..9) =====================
-    // Two warps per TMEM lane quarter; each owns half of the tile's columns.
+    // kParts warps per TMEM lane quarter; each owns 1/kParts of the tile's columns.
     const EpiParams& e = p.epi;
     const int ew = warp - 2;
     const int q = warp & 3;                 // TMEM lane quarter this warp may access
-    const int half = ew >> 2;               // column half
-    const int et = threadIdx.x - 64;        // 0..255
+    const int half = ew >> 2;               // column part owned by this warp (0 .. kParts-1)
+    const int et = threadIdx.x - 64;        // 0 .. 32*kEpiWarps-1
     const int row = q * 32 + lane;          // accumulator row == pixel within the tile
     const int thw = p.TH * p.TW;
     const int ri = row / thw;
@@ -468,12 +473,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     const int rx = rr - ry * p.TW;
     const bool fast = (p.TN == 1);          // every row of a tile belongs to one image
     const float gain = (e.act == kActLrelu) ? kSqrt2 : 1.f;
-    constexpr int kHalf = BN / 2;
+    constexpr int kParts = C::kParts;
+    constexpr int kHalf = BN / kParts;      // columns per warp
     constexpr int kChunks = kHalf / 16;
+    static_assert(kHalf % 16 == 0, "a warp's column part must be whole 16-column chunks");
     const bool d2s = (e.store_mode == kStoreDepthToSpace);
     const bool s2d = (e.store_mode == kStoreSpaceToDepth);
     const bool s2dy = (e.store_mode == kStoreSpaceToDepthY);
-    const bool paired = (e.x_phases == 2);   // pixel-pair rows: this warp's column half IS pixel 2x+half
+    const bool paired = (e.x_phases == 2);   // pixel-pair rows: the low/high half of the columns is pixel 2x / 2x+1
+    const int ppx = paired ? (half * 2) / kParts : 0;           // pixel of this warp's columns
+    const int parts_per_sum = paired ? kParts / 2 : kParts;     // warps whose toRGB partial sums belong together
     const bool has_rgb = (e.rgb_w != nullptr);
     const float nscale = (e.noise != nullptr) ? gain * __ldg(e.noise_strength) : 0.f;
     // All index math below is 32-bit pixel arithmetic (pixel counts stay < 2^31); one 64-bit multiply per tile
@@ -504,7 +513,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           dst[c] = __ldg(b2 + (ph >> 1) * (2 * W) + (ph & 1));
         }
       } else if (paired) {
-        dst[0] = __ldg(base + (size_t)y2 * (2 * W) + 2 * x2 + half);
+        dst[0] = __ldg(base + (size_t)y2 * (2 * W) + 2 * x2 + ppx);
       } else {
         dst[0] = __ldg(base + y2 * W + x2);
       }
@@ -540,7 +549,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         if (timg != staged_img || n_tile != staged_ntile) {
           pbuf ^= 1;
           float* par = params + pbuf * (kNumParams * BN);
-          if (et < BN) {
+          if (et < BN) {                      // (32*kEpiWarps >= BN for every instantiation)
             const int n = n_tile * BN + et;
             const int o = cout_sh >= 0 ? (n & (e.Cout - 1)) : (n % e.Cout);
             const float d = e.dmod != nullptr ? __ldg(e.dmod + (size_t)timg * e.Cout + o) : 1.f;
@@ -558,7 +567,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           }
           staged_img = timg;
           staged_ntile = n_tile;
-          epi_bar_sync();                    // all 8 epilogue warps take the same branch (uniform condition)
+          epi_bar_sync<32 * C::kEpiWarps>();  // all epilogue warps take the same branch (uniform condition)
         }
         const float* par = params + pbuf * (kNumParams * BN);
         // ---- per-tile addresses ----
@@ -639,22 +648,29 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           if (valid) epilogue_row16(p, img, y, x, n_tile * BN + half * kHalf + c * 16, v, rgb);
         }
       }
-      if (has_rgb && paired) {
-        // pixel-pair rows: the two column halves are two different pixels, each warp stores its own
-        if (valid) {
-          const size_t pix2 = ((size_t)img * H + y) * (2 * W) + 2 * x + half;
-          e.rgb_out[pix2] = make_float4(rgb[0], rgb[1], rgb[2], 0.f);
+      if (has_rgb) {
+        // The warps of a lane quarter own different column parts of the same rows: the non-leading parts stage
+        // their partial toRGB sums in shared memory and the leading part of each sum group adds them, so that one
+        // float4 per pixel goes to HBM.  (Pixel-pair rows: two sum groups, one per pixel.)
+        const int lead = (half / parts_per_sum) * parts_per_sum;
+        float4* stg = rgb_stage + (it & 1) * ((kParts - 1) * 128);
+        if (parts_per_sum > 1) {
+          if (half != lead) stg[(half - 1) * 128 + row] = make_float4(rgb[0], rgb[1], rgb[2], 0.f);
+          asm volatile("bar.sync %0, %1;" ::"r"(2 + q), "n"(32 * kParts) : "memory");
         }
-      } else if (has_rgb) {
-        // the two warps of a lane quarter own different column halves of the same rows: combine their
-        // partial toRGB sums in shared memory so that one float4 per pixel goes to HBM
-        float4* stg = rgb_stage + (it & 1) * 128;
-        if (half == 1) stg[row] = make_float4(rgb[0], rgb[1], rgb[2], 0.f);
-        asm volatile("bar.sync %0, 64;" ::"r"(2 + q) : "memory");
-        if (half == 0 && valid) {
-          const float4 o = stg[row];
-          const size_t pix = ((size_t)img * H + y) * W + x;
-          e.rgb_out[(size_t)n_tile * p.Nimg * H * W + pix] = make_float4(rgb[0] + o.x, rgb[1] + o.y, rgb[2] + o.z, 0.f);
+        if (half == lead && valid) {
+          float r0 = rgb[0], r1 = rgb[1], r2 = rgb[2];
+          for (int o = 1; o < parts_per_sum; ++o) {
+            const float4 t = stg[(lead + o - 1) * 128 + row];
+            r0 += t.x; r1 += t.y; r2 += t.z;
+          }
+          if (paired) {
+            const size_t pix2 = ((size_t)img * H + y) * (2 * W) + 2 * x + ppx;
+            e.rgb_out[pix2] = make_float4(r0, r1, r2, 0.f);
+          } else {
+            const size_t pix = ((size_t)img * H + y) * W + x;
+            e.rgb_out[(size_t)n_tile * p.Nimg * H * W + pix] = make_float4(r0, r1, r2, 0.f);
+          }
         }
       }
       tc_fence_before();
@@ -688,7 +704,7 @@ cudaError_t launch_one(const ConvParams& p, const TmaMaps& maps, int num_sms, cu
   int grid = total < ctas ? total : ctas;
   if (MODE != 0) grid = (grid / n_tiles) * n_tiles;   // keeps tile % n_tiles constant per CTA (resident taps)
   if (grid <= 0) return cudaErrorInvalidValue;
-  conv_tc_kernel<BN, BK, MODE><<<grid, kNumThreads, C::kSmemBytes, s>>>(maps.a, maps.b, p);
+  conv_tc_kernel<BN, BK, MODE><<<grid, C::kThreads, C::kSmemBytes, s>>>(maps.a, maps.b, p);
   return cudaGetLastError();
 }
 
