@@ -175,10 +175,10 @@ struct Cfg {
   static constexpr int kStageBytes = MODE == 0 ? kABytes + kBBytes
                                      : (MODE == 1 ? 3 * kCopyBytes : (MODE == 4 ? kI8StageBytes : kABytes));
   static constexpr int kWBytes = MODE == 0 ? 0 : ((MODE == 1 || MODE == 4) ? 9 : 1) * kBBytes;   // resident taps
-  // Epilogue warps: the epilogue is latency-bound (TMEM load -> parameter loads -> math -> store chains with little
-  // to overlap), so it gets as many warps as the register file allows: four per TMEM lane quarter (each owning a
-  // quarter of the columns) from BN = 64 up, two per quarter for BN = 32 (its hot instances run two CTAs per SM).
-  static constexpr int kEpiWarps = BN >= 64 ? 16 : 8;
+  // Epilogue warps: two per TMEM lane quarter (each owning half of the columns).  Four per quarter (16 warps, 96
+  // registers/thread) was measured at P=64: it helps the wide resident-tap instance (G up 64->32 @1024^2: 4.23 ->
+  // 3.56 ms) and costs 5-25 % on the streamed large-K instances (spills), so only that instance uses it.
+  static constexpr int kEpiWarps = (MODE == 4 && BN == 128) ? 16 : 8;
   static constexpr int kParts = kEpiWarps / 4;                      // column parts per lane quarter
   static constexpr int kThreads = 64 + 32 * kEpiWarps;
   // double-buffered per-tile epilogue parameters + double-buffered staging of the non-leading parts' toRGB sums
