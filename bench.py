@@ -162,10 +162,32 @@ def run_reference(args, rank, world):
                                  "steps stop early once ~4.5 min of wall time is used)"),
         e2e=dict(value=value, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0),
     )
-    print(json.dumps(line), flush=True)
+    emit(line)
+
+
+_JSON_FD = None
+
+
+def _guard_stdout():
+    """Route fd 1 to stderr for the whole run (NCCL and torchrun children print banners on stdout) and keep the
+    original stdout for the ONE JSON line of the contract."""
+    global _JSON_FD
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)
+
+
+def emit(line):
+    sys.stdout.flush()
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        os.write(1, data)
+    else:
+        os.write(_JSON_FD, data)
 
 
 def main():
+    _guard_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
@@ -364,7 +386,7 @@ def main():
             gflop_per_candidate=GFLOP_PER_CAND[args.variant],
             roofline=roofline, cpu_baseline=cpu_baseline,
         )
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         tdist.destroy_process_group()
 

@@ -21,6 +21,9 @@ namespace glass {
 
 namespace {
 
+#ifndef GLASS_BN32_CTAS
+#define GLASS_BN32_CTAS 4
+#endif
 constexpr int kBlockM = 128;
 constexpr int kMaxThreads = 64 + 16 * 32;   // TMA warp, MMA warp, up to 16 epilogue warps
 constexpr long long kWaitLimitCycles = 4000000000ll;   // ~2 s at 1.9 GHz
@@ -178,14 +181,19 @@ struct Cfg {
   // Epilogue warps: two per TMEM lane quarter (each owning half of the columns).  Four per quarter (16 warps, 96
   // registers/thread) was measured at P=64: it helps the wide resident-tap instance (G up 64->32 @1024^2: 4.23 ->
   // 3.56 ms) and costs 5-25 % on the streamed large-K instances (spills), so only that instance uses it.
-  static constexpr int kEpiWarps = (MODE == 4 && BN == 128) ? 16 : 8;
+  // The 32->32 I8 instances (G 1024^2 conv, D 1024^2 conv) are bound by per-(warp, tile) bookkeeping: there one
+  // warp per lane quarter owns all 32 columns (half the bookkeeping per element, no cross-warp toRGB combine)
+  // and GLASS_BN32_CTAS small CTAs per SM supply the warps that hide latency.
+  static constexpr bool kSmallN = (MODE == 4 && BK == 32 && BN == 32 && GLASS_BN32_CTAS > 2);
+  static constexpr int kEpiWarps = (MODE == 4 && BN == 128) ? 16 : (kSmallN ? 4 : 8);
   static constexpr int kParts = kEpiWarps / 4;                      // column parts per lane quarter
   static constexpr int kThreads = 64 + 32 * kEpiWarps;
   // double-buffered per-tile epilogue parameters + double-buffered staging of the non-leading parts' toRGB sums
   static constexpr int kParamBytes = 2 * kNumParams * BN * 4 + 2 * (kParts - 1) * 128 * 16;
   // the 32-channel MODE-1 layers are bookkeeping/latency-bound, not smem-bound: run two CTAs per SM there
-  static constexpr int kMinBlocks = ((MODE == 1 || MODE == 4) && BK == 32 && BN <= 32) ? 2 : 1;
-  static constexpr int kBudget = (kMinBlocks == 2 ? 110 : 222) * 1024 - kParamBytes - kWBytes;   // of 227 KB/SM
+  static constexpr int kMinBlocks = kSmallN ? GLASS_BN32_CTAS : (((MODE == 1 || MODE == 4) && BK == 32 && BN <= 32) ? 2 : 1);
+  static constexpr int kBudget = (kMinBlocks == 4 ? 54 : (kMinBlocks == 3 ? 73 : (kMinBlocks == 2 ? 110 : 222))) * 1024 -
+                                 kParamBytes - kWBytes;   // of 227 KB/SM (+1 KB reserved per CTA)
   static constexpr int kStagesRaw = kBudget / kStageBytes;
   static constexpr int kStages = kStagesRaw > 12 ? 12 : kStagesRaw;
   static_assert(kStages >= 2, "not enough shared memory for a double-buffered pipeline");

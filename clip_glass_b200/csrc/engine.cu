@@ -865,13 +865,20 @@ int run_discriminator(glass_engine* e, const float* images, int P, float* logits
   const int nb = c.num_blocks;
   auto dch = [&](int i) { return e->gch[nb - 1 - i]; };
   char nm[64];
-  LAUNCH(k_from_rgb(images, tptr<float>(e, "d.frgb.w"), tptr<float>(e, "d.frgb.b"), e->actA, P, e->R, dch(0),
-                    e->d_in_i8[0], s));
+  // fromRGB + the first block's projection FIR in one pass (GLASS_DEBUG_SPLIT_FRGB: the two-kernel route)
+  static const bool split_frgb = getenv("GLASS_DEBUG_SPLIT_FRGB") != nullptr;
+  const bool fused_frgb = !split_frgb && dch(0) % 32 == 0;
+  if (fused_frgb)
+    LAUNCH(k_from_rgb_fir(images, tptr<float>(e, "d.frgb.w"), tptr<float>(e, "d.frgb.b"), e->actA, e->dXd, P, e->R,
+                          dch(0), e->d_in_i8[0], s));
+  else
+    LAUNCH(k_from_rgb(images, tptr<float>(e, "d.frgb.w"), tptr<float>(e, "d.frgb.b"), e->actA, P, e->R, dch(0),
+                      e->d_in_i8[0], s));
   const __half* x = e->actA;
   int res = e->R;
   size_t ci = 0;
   for (int b = 0; b < nb - 1; ++b) {
-    LAUNCH(k_fir_down(x, e->dXd, P, res, res, dch(b), e->d_in_i8[b], s));
+    if (b > 0 || !fused_frgb) LAUNCH(k_fir_down(x, e->dXd, P, res, res, dch(b), e->d_in_i8[b], s));
     RC(run_conv(e, e->d_convs[ci++], s));   // conv0 -> actB (space-to-depth, or NHWC for the exact form)
     if (e->d_exact[b]) LAUNCH(k_blur_s2d(e->actB, e->actC, P, res, res, dch(b), s));
     RC(run_conv(e, e->d_convs[ci++], s));   // projection -> dR

@@ -399,31 +399,10 @@ __global__ void from_rgb_kernel(const float* __restrict__ images, const float* _
 // staged once in shared memory (coalesced 16-byte loads, pixel pitch padded to 80 B against bank conflicts), so
 // HBM/L2 see every input byte once and the 16 taps per output come from shared memory.
 constexpr int kFdTH = 8, kFdTW = 16, kFdC = 32, kFdPitch = 40;   // pitch in halfs (80 bytes)
-__global__ void __launch_bounds__(256) fir_down_kernel(const __half* __restrict__ x, __half* __restrict__ out, int N,
-                                                       int H, int W, int C, int in_i8) {
-  __shared__ __align__(16) __half tile[(2 * kFdTH + 2) * (2 * kFdTW + 2) * kFdPitch];
-  const int Ho = H >> 1, Wo = W >> 1;
-  const int tiles_x = (Wo + kFdTW - 1) / kFdTW, tiles_y = (Ho + kFdTH - 1) / kFdTH;
-  int t = blockIdx.x;
-  const int tx = t % tiles_x; t /= tiles_x;
-  const int ty = t % tiles_y;
-  const int b = t / tiles_y;
-  const int c0 = blockIdx.y * kFdC;
-  const int iy0 = 2 * ty * kFdTH - 1, ix0 = 2 * tx * kFdTW - 1;
-  constexpr int IW = 2 * kFdTW + 2, IH = 2 * kFdTH + 2;
-  for (int i = threadIdx.x; i < IH * IW * 4; i += blockDim.x) {
-    const int g = i & 3, pix = i >> 2;
-    const int py = pix / IW, px = pix - py * IW;
-    const int yy = iy0 + py, xx = ix0 + px;
-    uint4 v = make_uint4(0, 0, 0, 0);
-    if (yy >= 0 && yy < H && xx >= 0 && xx < W) {
-      const size_t off = in_i8 ? ((((size_t)b * H + yy) * (C >> 3) + (c0 >> 3) + g) * W + xx) * 8
-                               : (((size_t)b * H + yy) * W + xx) * C + c0 + g * 8;
-      v = __ldg(reinterpret_cast<const uint4*>(x + off));
-    }
-    *reinterpret_cast<uint4*>(tile + pix * kFdPitch + g * 8) = v;
-  }
-  __syncthreads();
+// Shared second half of fir_down_kernel / from_rgb_fir_kernel: 4x4 FIR taps from the staged tile, stride 2.
+__device__ __forceinline__ void fir_down_from_tile(const __half* tile, __half* __restrict__ out, int b, int ty, int tx,
+                                                   int Ho, int Wo, int C, int c0) {
+  constexpr int IW = 2 * kFdTW + 2;
   const float f[4] = {0.125f, 0.375f, 0.375f, 0.125f};
   const int g = threadIdx.x & 3;
 #pragma unroll
@@ -457,6 +436,123 @@ __global__ void __launch_bounds__(256) fir_down_kernel(const __half* __restrict_
       *reinterpret_cast<uint4*>(out + (((size_t)b * Ho + zy) * Wo + zx) * C + c0 + g * 8) = o;
     }
   }
+}
+
+constexpr int kFdTileBytes = (2 * kFdTH + 2) * (2 * kFdTW + 2) * kFdPitch * 2;
+constexpr int kFdItems = (2 * kFdTH + 2) * (2 * kFdTW + 2) * 4;       // (pixel, 8-channel group) items per tile
+constexpr int kFdPerThread = (kFdItems + 255) / 256;
+
+__global__ void __launch_bounds__(256) fir_down_kernel(const __half* __restrict__ x, __half* __restrict__ out, int N,
+                                                       int H, int W, int C, int in_i8) {
+  __shared__ __align__(16) __half tile[(2 * kFdTH + 2) * (2 * kFdTW + 2) * kFdPitch];
+  const int Ho = H >> 1, Wo = W >> 1;
+  const int tiles_x = (Wo + kFdTW - 1) / kFdTW, tiles_y = (Ho + kFdTH - 1) / kFdTH;
+  int t = blockIdx.x;
+  const int tx = t % tiles_x; t /= tiles_x;
+  const int ty = t % tiles_y;
+  const int b = t / tiles_y;
+  const int c0 = blockIdx.y * kFdC;
+  const int iy0 = 2 * ty * kFdTH - 1, ix0 = 2 * tx * kFdTW - 1;
+  constexpr int IW = 2 * kFdTW + 2;
+  // all of a thread's loads are issued before the first one is consumed (ten 16-byte loads in flight per thread)
+  uint4 v[kFdPerThread];
+#pragma unroll
+  for (int k = 0; k < kFdPerThread; ++k) {
+    const int i = threadIdx.x + k * 256;
+    const int g = i & 3, pix = i >> 2;
+    const int py = pix / IW, px = pix - py * IW;
+    const int yy = iy0 + py, xx = ix0 + px;
+    v[k] = make_uint4(0, 0, 0, 0);
+    if (i < kFdItems && yy >= 0 && yy < H && xx >= 0 && xx < W) {
+      const size_t off = in_i8 ? ((((size_t)b * H + yy) * (C >> 3) + (c0 >> 3) + g) * W + xx) * 8
+                               : (((size_t)b * H + yy) * W + xx) * C + c0 + g * 8;
+      v[k] = __ldg(reinterpret_cast<const uint4*>(x + off));
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < kFdPerThread; ++k) {
+    const int i = threadIdx.x + k * 256;
+    if (i < kFdItems) *reinterpret_cast<uint4*>(tile + (i >> 2) * kFdPitch + (i & 3) * 8) = v[k];
+  }
+  __syncthreads();
+  fir_down_from_tile(tile, out, b, ty, tx, Ho, Wo, C, c0);
+}
+
+// fromRGB fused with the first block's projection FIR: the tile of x = lrelu(W.rgb + b)*sqrt2 is computed once from
+// the image (halo pixels are recomputed by the neighbouring block: 19 % extra arithmetic, no extra HBM traffic),
+// written to HBM for conv0 (interior pixels only) and filtered from shared memory, so the 32-channel 1024^2
+// tensor is never read back for the FIR.  Same fp16 values and the same summation order as k_from_rgb followed by
+// k_fir_down: the two routes are bit-identical.
+__global__ void __launch_bounds__(256) from_rgb_fir_kernel(const float* __restrict__ images,
+                                                           const float* __restrict__ Wt, const float* __restrict__ bias,
+                                                           __half* __restrict__ xout, __half* __restrict__ down, int P,
+                                                           int R, int C, int out_i8) {
+  extern __shared__ __align__(16) uint8_t fr_smem[];      // tile + weights: 49.5 KB, above the static limit
+  __half* tile = reinterpret_cast<__half*>(fr_smem);
+  float* w = reinterpret_cast<float*>(fr_smem + kFdTileBytes);
+  const int c0 = blockIdx.y * kFdC;
+  if (threadIdx.x < 4 * kFdC) {
+    const int r = threadIdx.x / kFdC, c = threadIdx.x - r * kFdC;
+    w[threadIdx.x] = r < 3 ? Wt[r * C + c0 + c] : bias[c0 + c];
+  }
+  const int Ho = R >> 1, Wo = R >> 1;
+  const int tiles_x = (Wo + kFdTW - 1) / kFdTW, tiles_y = (Ho + kFdTH - 1) / kFdTH;
+  int t = blockIdx.x;
+  const int tx = t % tiles_x; t /= tiles_x;
+  const int ty = t % tiles_y;
+  const int b = t / tiles_y;
+  const int iy0 = 2 * ty * kFdTH - 1, ix0 = 2 * tx * kFdTW - 1;
+  constexpr int IW = 2 * kFdTW + 2, IH = 2 * kFdTH + 2;
+  const size_t plane = (size_t)R * R;
+  const float* img = images + (size_t)b * 3 * plane;
+  float rgb[kFdPerThread][3];
+#pragma unroll
+  for (int k = 0; k < kFdPerThread; ++k) {
+    const int i = threadIdx.x + k * 256;
+    const int pix = i >> 2;
+    const int py = pix / IW, px = pix - py * IW;
+    const int yy = iy0 + py, xx = ix0 + px;
+    rgb[k][0] = rgb[k][1] = rgb[k][2] = 0.f;
+    if (i < kFdItems && yy >= 0 && yy < R && xx >= 0 && xx < R) {
+      const float* ip = img + (size_t)yy * R + xx;
+      rgb[k][0] = __ldg(ip); rgb[k][1] = __ldg(ip + plane); rgb[k][2] = __ldg(ip + 2 * plane);
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < kFdPerThread; ++k) {
+    const int i = threadIdx.x + k * 256;
+    if (i >= kFdItems) continue;
+    const int g = i & 3, pix = i >> 2;
+    const int py = pix / IW, px = pix - py * IW;
+    const int yy = iy0 + py, xx = ix0 + px;
+    uint4 pk = make_uint4(0, 0, 0, 0);                 // outside the image: the FIR's zero padding
+    const bool inside = yy >= 0 && yy < R && xx >= 0 && xx < R;
+    if (inside) {
+      const float r = rgb[k][0] * 2.f - 1.f, gg = rgb[k][1] * 2.f - 1.f, bl = rgb[k][2] * 2.f - 1.f;
+      __half2* h2 = reinterpret_cast<__half2*>(&pk);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float a[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          const int c = g * 8 + 2 * j + u;
+          const float tt = fmaf(r, w[c], fmaf(gg, w[kFdC + c], fmaf(bl, w[2 * kFdC + c], w[3 * kFdC + c])));
+          a[u] = fmaxf(tt, 0.2f * tt) * kSqrt2;
+        }
+        h2[j] = __floats2half2_rn(a[0], a[1]);
+      }
+      // interior pixels of the tile (rows/cols 1 .. IH-2 / IW-2) belong to this block
+      if (py >= 1 && py < IH - 1 && px >= 1 && px < IW - 1) {
+        const size_t off = out_i8 ? ((((size_t)b * R + yy) * (C >> 3) + (c0 >> 3) + g) * R + xx) * 8
+                                  : (((size_t)b * R + yy) * R + xx) * C + c0 + g * 8;
+        *reinterpret_cast<uint4*>(xout + off) = pk;
+      }
+    }
+    *reinterpret_cast<uint4*>(tile + pix * kFdPitch + g * 8) = pk;
+  }
+  __syncthreads();
+  fir_down_from_tile(tile, down, b, ty, tx, Ho, Wo, C, c0);
 }
 
 // ---------------------------------------------------------------------------
@@ -775,6 +871,22 @@ cudaError_t k_from_rgb(const float* images, const float* Wt, const float* bias, 
   else if (C == 64) from_rgb_kernel<64><<<blocks, kThreads, 0, s>>>(images, Wt, bias, out, P, R, out_i8);
   else if (C == 128) from_rgb_kernel<128><<<blocks, kThreads, 0, s>>>(images, Wt, bias, out, P, R, out_i8);
   else return cudaErrorInvalidValue;
+  GLASS_RET();
+}
+cudaError_t k_from_rgb_fir(const float* images, const float* Wt, const float* bias, __half* xout, __half* down, int P,
+                           int R, int C, int out_i8, cudaStream_t s) {
+  if (C % kFdC != 0 || (R & 1)) return cudaErrorInvalidValue;
+  const int Ho = R / 2;
+  const int tiles = ((Ho + kFdTW - 1) / kFdTW) * ((Ho + kFdTH - 1) / kFdTH) * P;
+  dim3 grid(tiles, C / kFdC);
+  constexpr int kSmem = kFdTileBytes + 4 * kFdC * 4;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t err = cudaFuncSetAttribute(from_rgb_fir_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
+    if (err != cudaSuccess) return err;
+    configured = true;
+  }
+  from_rgb_fir_kernel<<<grid, 256, kSmem, s>>>(images, Wt, bias, xout, down, P, R, C, out_i8);
   GLASS_RET();
 }
 cudaError_t k_fir_down(const __half* x, __half* out, int N, int H, int W, int C, int in_i8, cudaStream_t s) {

@@ -28,9 +28,15 @@ def main():
     z = torch.from_numpy(W.make_latents(args.pop, 512, 50)).float().cuda()
     if args.timing:
         eng.set_debug(timing=True)
+    step_ms = []
     for i in range(args.evals):
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0.record()
         eng.evaluate_device(z, seed=1 + i)
+        t1.record()
         torch.cuda.synchronize()
+        step_ms.append(t0.elapsed_time(t1))
+    print("step ms per eval:", " ".join(f"{m:.2f}" for m in step_ms), f"(lib {os.environ.get('CLIPGLASS_LIB', 'default')})")
     if args.timing:
         layers = packing.g_layers(gan)
         names = [f"G{li}:{'up' if l['up'] else 'cv'}{l['cin']}->{l['cout']}@{l['res']}" for li, l in enumerate(layers)]
