@@ -15,6 +15,7 @@
 // shares the epilogue: it exists for bring-up and as the in-library cross-check
 // (glass_config.conv_impl = 1); it is never used by the product path.
 #include <cstdio>
+#include <cstdlib>
 #include "common.cuh"
 
 namespace glass {
@@ -22,7 +23,7 @@ namespace glass {
 namespace {
 
 #ifndef GLASS_BN32_CTAS
-#define GLASS_BN32_CTAS 4
+#define GLASS_BN32_CTAS 2
 #endif
 constexpr int kBlockM = 128;
 constexpr int kMaxThreads = 64 + 16 * 32;   // TMA warp, MMA warp, up to 16 epilogue warps
@@ -119,9 +120,10 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
 }
 
 struct TileCoord { int n_tile, tx, ty, tn; };
+template <bool kPow2 = false>
 __device__ __forceinline__ TileCoord decode_tile(const ConvParams& p, int tile, int n_tiles) {
   TileCoord t;
-  if (p.pow2) {
+  if (kPow2 || p.pow2) {
     t.n_tile = tile & (n_tiles - 1);
     int m = tile >> p.sh_n;
     t.tx = m & (p.tiles_x - 1); m >>= p.sh_x;
@@ -138,6 +140,26 @@ __device__ __forceinline__ TileCoord decode_tile(const ConvParams& p, int tile, 
 }
 
 constexpr int kNumParams = 6;   // scale, shift, oscale, rgb0, rgb1, rgb2
+
+// Compile-time epilogue specialisations.  Spec 0 reads every feature switch from EpiParams at run time (any layer);
+// the others fix the switches of one hot small-channel layer family, which removes ~150 uniform loads / compares /
+// branches per (warp, tile) and shrinks the unrolled chunk bodies from ~2600 to a few hundred SASS instructions
+// (the epilogue of these layers is issue/latency-bound).  pick_epi_spec() selects a spec only
+// when the layer matches it exactly; everything else runs spec 0.
+enum { kStNone = 0, kStRegular = 1, kStD2S = 2, kStS2D = 3 };
+struct EpiSpec {
+  bool generic, noise, rgb, residual;
+  int store;
+  bool i8;
+};
+constexpr EpiSpec kEpiSpecs[] = {
+    {true, false, false, false, kStNone, false},      // 0: run-time switches
+    {false, true, true, false, kStRegular, true},     // 1: G conv + toRGB, I8 store          (G 64->64 @512^2)
+    {false, true, false, false, kStD2S, true},        // 2: G folded up-conv, depth-to-space I8 (G up 64->32 @1024^2)
+    {false, true, true, false, kStNone, false},       // 3: last G conv: toRGB only            (G 32->32 @1024^2)
+    {false, false, false, false, kStS2D, false},      // 4: D conv0, space-to-depth NHWC       (D 32@1024^2, 64@512^2)
+};
+constexpr int kNumEpiSpecs = sizeof(kEpiSpecs) / sizeof(kEpiSpecs[0]);
 
 // MODE 0 ("stream"): one pipeline stage per (filter tap, 64-channel chunk): A box + B box per stage.
 // MODE 1 ("halo"):   for layers whose whole K per tap is one chunk (Cin == BK in {32,64}): the filter taps of the
@@ -172,8 +194,13 @@ struct Cfg {
   static constexpr int kBKc = BK > 64 ? 64 : BK;
   static constexpr int kKChunks = BK / kBKc;
   static constexpr int kBChunkBytes = BN * kBKc * 2;
+  // Tile pairs (kPairM = 2): two horizontally adjacent 8x16 tiles share ONE haloed box (18 pixels wide) and one
+  // trip through the producer / MMA / epilogue bookkeeping; their accumulators sit side by side in TMEM.  Halves the
+  // per-element bookkeeping of the epilogue-bound small-channel layers and gives every epilogue warp two independent
+  // chunks to overlap.
+  static constexpr int kPairM = (MODE == 4 && BK <= 64) ? 2 : 1;
   static constexpr int kI8TW = 8, kI8TH = 16;
-  static constexpr int kI8RowBytes = (kI8TW + 2) * 16;                          // one (row, group): 10 pixels x 16 B
+  static constexpr int kI8RowBytes = (kI8TW * kPairM + 2) * 16;                 // one (row, group): 10 or 18 pixels x 16 B
   static constexpr int kI8StageBytes = (kI8TH + 2) * (BK / 8) * kI8RowBytes;
   static constexpr int kStageBytes = MODE == 0 ? kABytes + kBBytes
                                      : (MODE == 1 ? 3 * kCopyBytes : (MODE == 4 ? kI8StageBytes : kABytes));
@@ -184,12 +211,12 @@ struct Cfg {
   // The 32->32 I8 instances (G 1024^2 conv, D 1024^2 conv) are bound by per-(warp, tile) bookkeeping: there one
   // warp per lane quarter owns all 32 columns (half the bookkeeping per element, no cross-warp toRGB combine)
   // and GLASS_BN32_CTAS small CTAs per SM supply the warps that hide latency.
-  static constexpr bool kSmallN = (MODE == 4 && BK == 32 && BN == 32 && GLASS_BN32_CTAS > 2);
+  static constexpr bool kSmallN = (MODE == 4 && BK == 32 && BN == 32 && GLASS_BN32_CTAS > 2);   // measured slower
   static constexpr int kEpiWarps = (MODE == 4 && BN == 128) ? 16 : (kSmallN ? 4 : 8);
   static constexpr int kParts = kEpiWarps / 4;                      // column parts per lane quarter
   static constexpr int kThreads = 64 + 32 * kEpiWarps;
   // double-buffered per-tile epilogue parameters + double-buffered staging of the non-leading parts' toRGB sums
-  static constexpr int kParamBytes = 2 * kNumParams * BN * 4 + 2 * (kParts - 1) * 128 * 16;
+  static constexpr int kParamBytes = 2 * kNumParams * BN * 4 + 2 * (kParts - 1) * kPairM * 128 * 16;
   // the 32-channel MODE-1 layers are bookkeeping/latency-bound, not smem-bound: run two CTAs per SM there
   static constexpr int kMinBlocks = kSmallN ? GLASS_BN32_CTAS : (((MODE == 1 || MODE == 4) && BK == 32 && BN <= 32) ? 2 : 1);
   static constexpr int kBudget = (kMinBlocks == 4 ? 54 : (kMinBlocks == 3 ? 73 : (kMinBlocks == 2 ? 110 : 222))) * 1024 -
@@ -197,7 +224,9 @@ struct Cfg {
   static constexpr int kStagesRaw = kBudget / kStageBytes;
   static constexpr int kStages = kStagesRaw > 12 ? 12 : kStagesRaw;
   static_assert(kStages >= 2, "not enough shared memory for a double-buffered pipeline");
-  static constexpr int kTmemCols = (2 * BN < 32) ? 32 : 2 * BN;   // power of two for BN in {32,64,128,256}
+  static constexpr int kAccCols = kPairM * BN;                     // TMEM columns of one accumulator stage
+  static constexpr int kTmemCols = (2 * kAccCols < 32) ? 32 : 2 * kAccCols;   // power of two for BN in {32,..,256}
+  static_assert(kTmemCols <= 512, "TMEM has 512 columns");
   static constexpr int kSmemBytes = kWBytes + kStages * kStageBytes + kParamBytes + 1024 /*align*/ + 256 /*barriers*/;
   // instruction descriptor: D=f32 [4,6)=1, A=B=f16 (0), K-major both, N>>3 [17,23), M>>4 [24,29)
   static constexpr uint32_t kIdesc = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(kBlockM >> 4) << 24);
@@ -217,7 +246,7 @@ __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" 
 // Fast epilogue for one row and 16 columns with the per-tile parameters staged in shared memory.
 //   t = act(acc*scale + shift + nz) ; rgb += t*rgbw ; t = (t + residual) * oscale ; store fp16
 // (the sqrt(2) gain of lrelu is folded into scale/shift/nz: lrelu(a)*g == lrelu(a*g) for g > 0)
-template <bool kRgb>
+template <bool kRgb, bool kLean = false>
 __device__ __forceinline__ void epilogue_fast16(const EpiParams& e, const float* __restrict__ par, int BN, int j0,
                                                 const uint32_t (&acc)[16], float nz, const __half* res_ptr,
                                                 __half* out_ptr, size_t out_half_stride, float (&rgb)[3]) {
@@ -233,11 +262,11 @@ __device__ __forceinline__ void epilogue_fast16(const EpiParams& e, const float*
     t[4 * g + 2] = fmaf(__uint_as_float(acc[4 * g + 2]), a.z, b.z + nz);
     t[4 * g + 3] = fmaf(__uint_as_float(acc[4 * g + 3]), a.w, b.w + nz);
   }
-  if (e.round_fp16_before_act) {
+  if (!kLean && e.round_fp16_before_act) {
 #pragma unroll
     for (int j = 0; j < 16; ++j) t[j] = __half2float(__float2half_rn(t[j]));
   }
-  if (e.act == kActLrelu) {
+  if (kLean || e.act == kActLrelu) {
 #pragma unroll
     for (int j = 0; j < 16; ++j) t[j] = fmaxf(t[j], 0.2f * t[j]);
   } else if (e.act == kActQuickGelu) {
@@ -288,11 +317,13 @@ __device__ __forceinline__ void epilogue_fast16(const EpiParams& e, const float*
   }
 }
 
-template <int BN, int BK, int MODE>
+template <int BN, int BK, int MODE, int EPI>
 __global__ void __launch_bounds__((Cfg<BN, BK, MODE>::kThreads), (Cfg<BN, BK, MODE>::kMinBlocks))
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                const ConvParams p) {
   using C = Cfg<BN, BK, MODE>;
+  constexpr EpiSpec S = kEpiSpecs[EPI];
+  constexpr bool kPow2 = !S.generic;        // specialised layers have power-of-two tile grids and channel counts
   extern __shared__ uint8_t smem_raw[];
   // (offset arithmetic on the extern array keeps the pointers in the shared address space: LDS/STS, not generic LD/ST)
   uint8_t* smem_w = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -306,6 +337,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   uint64_t* tmem_empty = tmem_full + 2;
   uint64_t* w_bar = tmem_empty + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_bar + 1);
+  float* nscale_slot = reinterpret_cast<float*>(tmem_slot + 1);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -354,7 +386,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                         tap);
       }
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const TileCoord tc = decode_tile(p, tile, n_tiles);
+        const TileCoord tc = decode_tile<kPow2>(p, tile, n_tiles);
         const int n_tile = tc.n_tile;
         const int x0 = tc.tx * p.TW, y0 = tc.ty * p.TH, i0 = tc.tn * p.TN;
         if (MODE != 0) {
@@ -405,7 +437,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         const uint32_t aphase = (it >> 1) & 1;
         mbar_wait(&tmem_empty[as], aphase ^ 1);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + as * BN;
+        const uint32_t d_tmem = tmem_base + as * C::kAccCols;
         if (MODE != 0) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
@@ -416,16 +448,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             constexpr uint32_t kSbo = (BK / 8) * C::kI8RowBytes;      // next image row (= next 8-pixel group)
             const uint32_t lbo = (p.debug_skip & 2) ? kSbo : kLbo;    // (bring-up knob: swapped roles)
             const uint32_t sbo = (p.debug_skip & 2) ? kLbo : kSbo;
-            for (int tap = 0; tap < 9; ++tap) {
-              const int ky = tap / 3, kx = tap - ky * 3;
-              const uint32_t a_addr = sa + ky * kSbo + kx * 16;       // pixel (ry+ky, rx+kx) of the haloed tile
 #pragma unroll
-              for (int k = 0; k < BK / 16; ++k) {
-                constexpr int kPerChunk = C::kBKc / 16;
-                const int ch = k / kPerChunk, kk = k - ch * kPerChunk;
-                const uint64_t db = make_smem_desc<C::kBKc>(sw + (tap * C::kKChunks + ch) * C::kBChunkBytes);
-                const uint64_t da = make_smem_desc_noswz(a_addr + k * 2 * kLbo, lbo, sbo);
-                tc_mma_f16(d_tmem, da, db + (uint64_t)(kk * 2), C::kIdesc, (tap | k) != 0);
+            for (int h = 0; h < C::kPairM; ++h) {                     // tile h of the pair: 8 pixels further right
+              for (int tap = 0; tap < 9; ++tap) {
+                const int ky = tap / 3, kx = tap - ky * 3;
+                const uint32_t a_addr = sa + ky * kSbo + (kx + 8 * h) * 16;   // pixel (ry+ky, rx+kx) of the haloed tile
+#pragma unroll
+                for (int k = 0; k < BK / 16; ++k) {
+                  constexpr int kPerChunk = C::kBKc / 16;
+                  const int ch = k / kPerChunk, kk = k - ch * kPerChunk;
+                  const uint64_t db = make_smem_desc<C::kBKc>(sw + (tap * C::kKChunks + ch) * C::kBChunkBytes);
+                  const uint64_t da = make_smem_desc_noswz(a_addr + k * 2 * kLbo, lbo, sbo);
+                  tc_mma_f16(d_tmem + h * BN, da, db + (uint64_t)(kk * 2), C::kIdesc, (tap | k) != 0);
+                }
               }
             }
             tc_commit(&empty_bar[stage]);
@@ -466,33 +501,44 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       }
     }
   } else {
-    // ===================== epilogue (warps 2..9) =====================
-    // kParts warps per TMEM lane quarter; each owns 1/kParts of the tile's columns.
+    // ===================== epilogue (warps 2..) =====================
+    // kParts warps per TMEM lane quarter; each owns 1/kParts of the tile's columns (of both tiles of a pair).
     const EpiParams& e = p.epi;
     const int ew = warp - 2;
     const int q = warp & 3;                 // TMEM lane quarter this warp may access
     const int half = ew >> 2;               // column part owned by this warp (0 .. kParts-1)
     const int et = threadIdx.x - 64;        // 0 .. 32*kEpiWarps-1
-    const int row = q * 32 + lane;          // accumulator row == pixel within the tile
-    const int thw = p.TH * p.TW;
+    const int row = q * 32 + lane;          // accumulator row == pixel within the (first) tile
+    constexpr int kPairM = C::kPairM;
+    const int geo_w = (kPairM == 2) ? C::kI8TW : p.TW;     // width of ONE 128-pixel tile
+    const int thw = p.TH * geo_w;
     const int ri = row / thw;
     const int rr = row - ri * thw;
-    const int ry = rr / p.TW;
-    const int rx = rr - ry * p.TW;
-    const bool fast = (p.TN == 1);          // every row of a tile belongs to one image
-    const float gain = (e.act == kActLrelu) ? kSqrt2 : 1.f;
+    const int ry = rr / geo_w;
+    const int rx = rr - ry * geo_w;         // tile h of a pair: pixel column rx + 8h
+    const bool fast = (MODE == 4) ? true : (p.TN == 1);   // every row of a tile belongs to one image (I8 tiles: always)
+    const float gain = (!S.generic || e.act == kActLrelu) ? kSqrt2 : 1.f;
     constexpr int kParts = C::kParts;
     constexpr int kHalf = BN / kParts;      // columns per warp
     constexpr int kChunks = kHalf / 16;
     static_assert(kHalf % 16 == 0, "a warp's column part must be whole 16-column chunks");
-    const bool d2s = (e.store_mode == kStoreDepthToSpace);
-    const bool s2d = (e.store_mode == kStoreSpaceToDepth);
-    const bool s2dy = (e.store_mode == kStoreSpaceToDepthY);
-    const bool paired = (e.x_phases == 2);   // pixel-pair rows: the low/high half of the columns is pixel 2x / 2x+1
+    // feature switches: run-time for spec 0, compile-time constants otherwise
+    const bool d2s = S.generic ? (e.store_mode == kStoreDepthToSpace) : (S.store == kStD2S);
+    const bool s2d = S.generic ? (e.store_mode == kStoreSpaceToDepth) : (S.store == kStS2D);
+    const bool s2dy = S.generic ? (e.store_mode == kStoreSpaceToDepthY) : false;
+    const bool out_i8 = S.generic ? (e.out_i8 != 0) : S.i8;
+    const bool has_out = S.generic ? (e.out != nullptr) : (S.store != kStNone);
+    const bool has_noise = S.generic ? (e.noise != nullptr) : S.noise;
+    const bool has_res = S.generic ? (e.residual != nullptr) : S.residual;
+    const bool all_valid = S.generic ? (p.all_valid != 0) : true;
+    const bool paired = S.generic ? (e.x_phases == 2) : false;   // pixel-pair rows: columns' halves are pixels 2x / 2x+1
     const int ppx = paired ? (half * 2) / kParts : 0;           // pixel of this warp's columns
     const int parts_per_sum = paired ? kParts / 2 : kParts;     // warps whose toRGB partial sums belong together
-    const bool has_rgb = (e.rgb_w != nullptr);
-    const float nscale = (e.noise != nullptr) ? gain * __ldg(e.noise_strength) : 0.f;
+    const bool has_rgb = S.generic ? (e.rgb_w != nullptr) : S.rgb;
+    // (kept in shared memory: as a loop-invariant register it is spilled and reloaded from local memory on the
+    // critical path of every tile)
+    if (et == 0) *nscale_slot = has_noise ? gain * __ldg(e.noise_strength) : 0.f;
+    epi_bar_sync<32 * C::kEpiWarps>();
     // All index math below is 32-bit pixel arithmetic (pixel counts stay < 2^31); one 64-bit multiply per tile
     // turns a pixel index into an element offset.  Per-thread row offsets are loop invariants.
     const int W = p.W, H = p.H;
@@ -501,33 +547,40 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     const int row_s2d = (((ry >> 1) * (W >> 1) + (rx >> 1)) << 2) + ((ry & 1) * 2 + (rx & 1));
     const int cout_sh = e.cout_shift;       // log2(Cout) or -1
     const int ngrp_sh = e.noise_div_shift;  // log2(noise_group_div) or -1
+    const bool cout_p2 = S.generic ? (cout_sh >= 0) : true;
+    const bool ngrp_p2 = S.generic ? (ngrp_sh >= 0) : true;
 
     // Noise of the NEXT tile is fetched while the current one is processed: the (L2/DRAM) latency of this
     // scattered 4-byte load would otherwise sit on the critical path of every tile.
-    auto fetch_noise = [&](const TileCoord& c2, bool in_range, float (&dst)[kChunks]) {
+    auto fetch_noise = [&](const TileCoord& c2, bool in_range, float (&dst)[kPairM][kChunks]) {
 #pragma unroll
-      for (int c = 0; c < kChunks; ++c) dst[c] = 0.f;
-      if (e.noise == nullptr || !in_range) return;
+      for (int h = 0; h < kPairM; ++h)
+#pragma unroll
+        for (int c = 0; c < kChunks; ++c) dst[h][c] = 0.f;
+      if (!has_noise || !in_range) return;
       const int img2 = c2.tn * p.TN + ri, y2 = c2.ty * p.TH + ry, x2 = c2.tx * p.TW + rx;
-      if (!p.all_valid && !(img2 < p.Nimg && y2 < H && x2 < W)) return;
-      const int grp = ngrp_sh >= 0 ? (img2 >> ngrp_sh) : (img2 / e.noise_group_div);
+      if (!all_valid && !(img2 < p.Nimg && y2 < H && x2 < W)) return;
+      const int grp = ngrp_p2 ? (img2 >> ngrp_sh) : (img2 / e.noise_group_div);
       const float* base = e.noise + (size_t)grp * e.noise_group_stride;
       if (d2s) {
         const float* b2 = base + (size_t)(2 * y2) * (2 * W) + 2 * x2;
 #pragma unroll
-        for (int c = 0; c < kChunks; ++c) {
-          const int n0 = c2.n_tile * BN + half * kHalf + c * 16;
-          const int ph = cout_sh >= 0 ? (n0 >> cout_sh) : (n0 / e.Cout);
-          dst[c] = __ldg(b2 + (ph >> 1) * (2 * W) + (ph & 1));
-        }
+        for (int h = 0; h < kPairM; ++h)
+#pragma unroll
+          for (int c = 0; c < kChunks; ++c) {
+            const int n0 = c2.n_tile * BN + half * kHalf + c * 16;
+            const int ph = cout_p2 ? (n0 >> cout_sh) : (n0 / e.Cout);
+            dst[h][c] = __ldg(b2 + 16 * h + (ph >> 1) * (2 * W) + (ph & 1));
+          }
       } else if (paired) {
-        dst[0] = __ldg(base + (size_t)y2 * (2 * W) + 2 * x2 + ppx);
+        dst[0][0] = __ldg(base + (size_t)y2 * (2 * W) + 2 * x2 + ppx);
       } else {
-        dst[0] = __ldg(base + y2 * W + x2);
+#pragma unroll
+        for (int h = 0; h < kPairM; ++h) dst[h][0] = __ldg(base + y2 * W + x2 + 8 * h);
       }
     };
-    float nz_next[kChunks];
-    TileCoord tc_next = decode_tile(p, blockIdx.x, n_tiles);
+    float nz_next[kPairM][kChunks];
+    TileCoord tc_next = decode_tile<kPow2>(p, blockIdx.x, n_tiles);
     fetch_noise(tc_next, true, nz_next);
     int it = 0;
     int staged_img = -1, staged_ntile = -1;
@@ -536,18 +589,22 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       const TileCoord tc = tc_next;
       const int n_tile = tc.n_tile, tn = tc.tn;
       const int img = tn * p.TN + ri, y = tc.ty * p.TH + ry, x = tc.tx * p.TW + rx;
-      const bool valid = p.all_valid || (img < p.Nimg && y < H && x < W);
+      const bool valid = all_valid || (img < p.Nimg && y < H && x < W);
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + as * BN + half * kHalf;
-      float rgb[3] = {0.f, 0.f, 0.f};
-      float nz_cur[kChunks];
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + as * C::kAccCols + half * kHalf;
+      float rgb[kPairM][3];
+      float nz_cur[kPairM][kChunks];
 #pragma unroll
-      for (int c = 0; c < kChunks; ++c) nz_cur[c] = nz_next[c];
+      for (int h = 0; h < kPairM; ++h) {
+        rgb[h][0] = rgb[h][1] = rgb[h][2] = 0.f;
+#pragma unroll
+        for (int c = 0; c < kChunks; ++c) nz_cur[h][c] = nz_next[h][c];
+      }
       {
         const int nt = tile + gridDim.x;
         const bool more = nt < total_tiles;
-        if (more) tc_next = decode_tile(p, nt, n_tiles);
+        if (more) tc_next = decode_tile<kPow2>(p, nt, n_tiles);
         if (fast) fetch_noise(tc_next, more, nz_next);
       }
 
@@ -559,7 +616,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           float* par = params + pbuf * (kNumParams * BN);
           if (et < BN) {                      // (32*kEpiWarps >= BN for every instantiation)
             const int n = n_tile * BN + et;
-            const int o = cout_sh >= 0 ? (n & (e.Cout - 1)) : (n % e.Cout);
+            const int o = cout_p2 ? (n & (e.Cout - 1)) : (n % e.Cout);
             const float d = e.dmod != nullptr ? __ldg(e.dmod + (size_t)timg * e.Cout + o) : 1.f;
             const float b = e.bias != nullptr ? __ldg(e.bias + o) : 0.f;
             const float osn = e.out_scale != nullptr ? __ldg(e.out_scale + (size_t)timg * e.out_scale_stride + o) : 1.f;
@@ -578,82 +635,97 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           epi_bar_sync<32 * C::kEpiWarps>();  // all epilogue warps take the same branch (uniform condition)
         }
         const float* par = params + pbuf * (kNumParams * BN);
-        // ---- per-tile addresses ----
+        // ---- per-tile addresses (tile 0 of a pair; tile h adds 8 pixel columns) ----
         const int n_first = n_tile * BN + half * kHalf;
         const int pix = (img * H + tc.ty * p.TH) * W + tc.tx * p.TW + row_reg;          // NHWC pixel index of this row
-        const __half* res_row = e.residual != nullptr ? e.residual + (size_t)pix * p.Ntot + n_first : nullptr;
+        const __half* res_row = has_res ? e.residual + (size_t)pix * p.Ntot + n_first : nullptr;
         __half* out_row = nullptr;           // regular / space-to-depth: contiguous columns
+        size_t out_row_hstep = 0;            // element offset of the pair's second tile
         int d2s_pix = 0;
-        if (e.out != nullptr) {
-          if (s2d && !e.out_i8) {
+        if (has_out) {
+          if (s2d && !out_i8) {
             const int org = ((img * (H >> 1) + ((tc.ty * p.TH) >> 1)) * (W >> 1) + ((tc.tx * p.TW) >> 1)) << 2;
             out_row = e.out + (size_t)(org + row_s2d) * p.Ntot + n_first;
+            out_row_hstep = (size_t)16 * p.Ntot;      // 8 pixels right = 4 cells x 4 phases
           } else if (s2dy) {
             const int org = (img * (H >> 1) + ((tc.ty * p.TH + ry) >> 1)) * W + tc.tx * p.TW + rx;
             out_row = e.out + ((size_t)org * 2 + (ry & 1)) * p.Ntot + n_first;
-          } else if (!d2s && !e.out_i8) {
+            out_row_hstep = (size_t)16 * p.Ntot;
+          } else if (!d2s && !out_i8) {
             out_row = e.out + (size_t)pix * p.Ntot + n_first;
+            out_row_hstep = (size_t)8 * p.Ntot;
           }
         }
         if (d2s) d2s_pix = (img * 2 * H + 2 * tc.ty * p.TH) * (2 * W) + 2 * tc.tx * p.TW + row_d2s;
         // I8 layout [n][y][c/8][x][8]: (row index) * (C/8) * Wo + x, in units of 8-channel vectors
         const int i8_groups = e.Cout >> 3;
         const int i8_row = img * H + tc.ty * p.TH + ry;          // regular store: image row of this pixel
-        const int i8_x = tc.tx * p.TW + rx;
+        const int i8_x0 = tc.tx * p.TW + rx;
+        float nscale;
+        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(nscale) : "r"(smem_u32(nscale_slot)));
         mbar_wait(&tmem_full[as], aphase);
         tc_fence_after();
         uint32_t acc[2][16];
         tc_ld16_issue(taddr, acc[0]);
 #pragma unroll
-        for (int c = 0; c < kChunks; ++c) {
-          tc_ld_wait();
-          if (c + 1 < kChunks) tc_ld16_issue(taddr + (c + 1) * 16, acc[(c + 1) & 1]);
-          if (valid && !(p.debug_skip & 1)) {
-            const int j0 = half * kHalf + c * 16;
-            const float nzc = nscale * nz_cur[d2s ? c : 0];
-            __half* optr = nullptr;
-            size_t half_stride = 8;
-            if (d2s) {
-              // column n -> phase (py,px) and channel o; output pixel (2y+py, 2x+px)
-              const int n0 = n_tile * BN + j0;
-              const int ph = cout_sh >= 0 ? (n0 >> cout_sh) : (n0 / e.Cout);
-              const int o0 = n0 - ph * e.Cout;
-              if (e.out != nullptr) {
-                if (e.out_i8) {
-                  const int yo = 2 * (tc.ty * p.TH + ry) + (ph >> 1), xo = 2 * i8_x + (ph & 1);
-                  half_stride = (size_t)(2 * W) * 8;
-                  optr = e.out + (((size_t)(img * 2 * H + yo) * i8_groups + (o0 >> 3)) * (2 * W) + xo) * 8;
-                } else {
-                  optr = e.out + (size_t)(d2s_pix + (ph >> 1) * (2 * W) + (ph & 1)) * e.Cout + o0;
-                }
-              }
-            } else if (e.out_i8 && s2d && e.out != nullptr) {
-              // space-to-depth + I8: [n][y/2][(phase*Ntot + o)/8][x/2][8] with 4*Ntot channels per cell
-              const int yy = tc.ty * p.TH + ry;
-              const int k0 = ((yy & 1) * 2 + (i8_x & 1)) * p.Ntot + n_first + c * 16;
-              half_stride = (size_t)(W >> 1) * 8;
-              optr = e.out + (((size_t)(img * (H >> 1) + (yy >> 1)) * (p.Ntot >> 1) + (k0 >> 3)) * (W >> 1) + (i8_x >> 1)) * 8;
-            } else if (e.out_i8 && e.out != nullptr) {
-              const int o0 = n_first + c * 16;                     // regular store: Ntot == Cout
-              half_stride = (size_t)W * 8;
-              optr = e.out + (((size_t)i8_row * i8_groups + (o0 >> 3)) * W + i8_x) * 8;
-            } else if (out_row != nullptr) {
-              optr = out_row + c * 16;
+        for (int h = 0; h < kPairM; ++h) {
+          const int i8_x = i8_x0 + 8 * h;
+#pragma unroll
+          for (int c = 0; c < kChunks; ++c) {
+            constexpr int kTotal = kPairM * kChunks;
+            const int ci = h * kChunks + c;            // position in the LDTM pipeline
+            tc_ld_wait();
+            if (ci + 1 < kTotal) {
+              const int h2 = (ci + 1) / kChunks, c2 = (ci + 1) - h2 * kChunks;
+              tc_ld16_issue(taddr + h2 * BN + c2 * 16, acc[(ci + 1) & 1]);
             }
-            const __half* rptr = res_row != nullptr ? res_row + c * 16 : nullptr;
-            if (has_rgb) epilogue_fast16<true>(e, par, BN, j0, acc[c & 1], nzc, rptr, optr, half_stride, rgb);
-            else epilogue_fast16<false>(e, par, BN, j0, acc[c & 1], nzc, rptr, optr, half_stride, rgb);
+            if (valid && !(p.debug_skip & 1)) {
+              const int j0 = half * kHalf + c * 16;
+              const float nzc = nscale * nz_cur[h][d2s ? c : 0];
+              __half* optr = nullptr;
+              size_t half_stride = 8;
+              if (d2s) {
+                // column n -> phase (py,px) and channel o; output pixel (2y+py, 2x+px)
+                const int n0 = n_tile * BN + j0;
+                const int ph = cout_p2 ? (n0 >> cout_sh) : (n0 / e.Cout);
+                const int o0 = n0 - ph * e.Cout;
+                if (has_out) {
+                  if (out_i8) {
+                    const int yo = 2 * (tc.ty * p.TH + ry) + (ph >> 1), xo = 2 * i8_x + (ph & 1);
+                    half_stride = (size_t)(2 * W) * 8;
+                    optr = e.out + (((size_t)(img * 2 * H + yo) * i8_groups + (o0 >> 3)) * (2 * W) + xo) * 8;
+                  } else {
+                    optr = e.out + (size_t)(d2s_pix + 16 * h + (ph >> 1) * (2 * W) + (ph & 1)) * e.Cout + o0;
+                  }
+                }
+              } else if (out_i8 && s2d && has_out) {
+                // space-to-depth + I8: [n][y/2][(phase*Ntot + o)/8][x/2][8] with 4*Ntot channels per cell
+                const int yy = tc.ty * p.TH + ry;
+                const int k0 = ((yy & 1) * 2 + (i8_x & 1)) * p.Ntot + n_first + c * 16;
+                half_stride = (size_t)(W >> 1) * 8;
+                optr = e.out + (((size_t)(img * (H >> 1) + (yy >> 1)) * (p.Ntot >> 1) + (k0 >> 3)) * (W >> 1) + (i8_x >> 1)) * 8;
+              } else if (out_i8 && has_out) {
+                const int o0 = n_first + c * 16;                     // regular store: Ntot == Cout
+                half_stride = (size_t)W * 8;
+                optr = e.out + (((size_t)i8_row * i8_groups + (o0 >> 3)) * W + i8_x) * 8;
+              } else if (out_row != nullptr) {
+                optr = out_row + h * out_row_hstep + c * 16;
+              }
+              const __half* rptr = res_row != nullptr ? res_row + (size_t)(8 * h) * p.Ntot + c * 16 : nullptr;
+              if (has_rgb) epilogue_fast16<true, !S.generic>(e, par, BN, j0, acc[ci & 1], nzc, rptr, optr, half_stride, rgb[h]);
+              else epilogue_fast16<false, !S.generic>(e, par, BN, j0, acc[ci & 1], nzc, rptr, optr, half_stride, rgb[h]);
+            }
           }
         }
       } else {
-        // ---- generic path (tiles that span several images: 4x4 / 8x8 layers) ----
+        // ---- generic path (tiles that span several images: 4x4 / 8x8 layers; never a tile pair) ----
         mbar_wait(&tmem_full[as], aphase);
         tc_fence_after();
 #pragma unroll 1
         for (int c = 0; c < kChunks; ++c) {
           float v[16];
           tc_ld16(taddr + c * 16, v);
-          if (valid) epilogue_row16(p, img, y, x, n_tile * BN + half * kHalf + c * 16, v, rgb);
+          if (valid) epilogue_row16(p, img, y, x, n_tile * BN + half * kHalf + c * 16, v, rgb[0]);
         }
       }
       if (has_rgb) {
@@ -661,23 +733,30 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         // their partial toRGB sums in shared memory and the leading part of each sum group adds them, so that one
         // float4 per pixel goes to HBM.  (Pixel-pair rows: two sum groups, one per pixel.)
         const int lead = (half / parts_per_sum) * parts_per_sum;
-        float4* stg = rgb_stage + (it & 1) * ((kParts - 1) * 128);
+        float4* stg = rgb_stage + (it & 1) * ((kParts - 1) * kPairM * 128);
         if (parts_per_sum > 1) {
-          if (half != lead) stg[(half - 1) * 128 + row] = make_float4(rgb[0], rgb[1], rgb[2], 0.f);
+          if (half != lead) {
+#pragma unroll
+            for (int h = 0; h < kPairM; ++h)
+              stg[((half - 1) * kPairM + h) * 128 + row] = make_float4(rgb[h][0], rgb[h][1], rgb[h][2], 0.f);
+          }
           asm volatile("bar.sync %0, %1;" ::"r"(2 + q), "n"(32 * kParts) : "memory");
         }
         if (half == lead && valid) {
-          float r0 = rgb[0], r1 = rgb[1], r2 = rgb[2];
-          for (int o = 1; o < parts_per_sum; ++o) {
-            const float4 t = stg[(lead + o - 1) * 128 + row];
-            r0 += t.x; r1 += t.y; r2 += t.z;
-          }
-          if (paired) {
-            const size_t pix2 = ((size_t)img * H + y) * (2 * W) + 2 * x + ppx;
-            e.rgb_out[pix2] = make_float4(r0, r1, r2, 0.f);
-          } else {
-            const size_t pix = ((size_t)img * H + y) * W + x;
-            e.rgb_out[(size_t)n_tile * p.Nimg * H * W + pix] = make_float4(r0, r1, r2, 0.f);
+#pragma unroll
+          for (int h = 0; h < kPairM; ++h) {
+            float r0 = rgb[h][0], r1 = rgb[h][1], r2 = rgb[h][2];
+            for (int o = 1; o < parts_per_sum; ++o) {
+              const float4 t = stg[((lead + o - 1) * kPairM + h) * 128 + row];
+              r0 += t.x; r1 += t.y; r2 += t.z;
+            }
+            if (paired) {
+              const size_t pix2 = ((size_t)img * H + y) * (2 * W) + 2 * x + ppx;
+              e.rgb_out[pix2] = make_float4(r0, r1, r2, 0.f);
+            } else {
+              const size_t pix = ((size_t)img * H + y) * W + x + 8 * h;
+              e.rgb_out[(size_t)n_tile * p.Nimg * H * W + pix] = make_float4(r0, r1, r2, 0.f);
+            }
           }
         }
       }
@@ -696,13 +775,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   }
 }
 
-template <int BN, int BK, int MODE>
+template <int BN, int BK, int MODE, int EPI = 0>
 cudaError_t launch_one(const ConvParams& p, const TmaMaps& maps, int num_sms, cudaStream_t s) {
   using C = Cfg<BN, BK, MODE>;
   static bool configured = false;
   if (!configured) {
-    cudaError_t err = cudaFuncSetAttribute(conv_tc_kernel<BN, BK, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           C::kSmemBytes);
+    cudaError_t err = cudaFuncSetAttribute(conv_tc_kernel<BN, BK, MODE, EPI>,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes);
     if (err != cudaSuccess) return err;
     configured = true;
   }
@@ -712,7 +791,7 @@ cudaError_t launch_one(const ConvParams& p, const TmaMaps& maps, int num_sms, cu
   int grid = total < ctas ? total : ctas;
   if (MODE != 0) grid = (grid / n_tiles) * n_tiles;   // keeps tile % n_tiles constant per CTA (resident taps)
   if (grid <= 0) return cudaErrorInvalidValue;
-  conv_tc_kernel<BN, BK, MODE><<<grid, C::kThreads, C::kSmemBytes, s>>>(maps.a, maps.b, p);
+  conv_tc_kernel<BN, BK, MODE, EPI><<<grid, C::kThreads, C::kSmemBytes, s>>>(maps.a, maps.b, p);
   return cudaGetLastError();
 }
 
@@ -763,7 +842,39 @@ __global__ void conv_simt_kernel(const ConvParams p) {
 
 }  // namespace
 
+// The specialised epilogue whose compile-time switches equal this layer's run-time ones, or 0.
+static int pick_epi_spec(const ConvParams& p) {
+  const EpiParams& e = p.epi;
+  static const bool off = getenv("GLASS_DEBUG_GENERIC_EPI") != nullptr;     // A/B knob: always the run-time spec
+  if (off || p.mode != 4 || p.TN != 1 || !p.pow2 || !p.all_valid || p.debug_skip != 0) return 0;
+  if (e.act != kActLrelu || e.round_fp16_before_act || e.x_phases == 2 || e.cout_shift < 0) return 0;
+  if (e.noise != nullptr && e.noise_div_shift < 0) return 0;
+  int store = kStNone;
+  if (e.out != nullptr) {
+    if (e.store_mode == kStoreRegular) store = kStRegular;
+    else if (e.store_mode == kStoreDepthToSpace) store = kStD2S;
+    else if (e.store_mode == kStoreSpaceToDepth) store = kStS2D;
+    else return 0;
+  }
+  for (int i = 1; i < kNumEpiSpecs; ++i) {
+    const EpiSpec& sp = kEpiSpecs[i];
+    if (sp.noise == (e.noise != nullptr) && sp.rgb == (e.rgb_w != nullptr) && sp.residual == (e.residual != nullptr) &&
+        sp.store == store && (store == kStNone || sp.i8 == (e.out_i8 != 0)))
+      return i;
+  }
+  return 0;
+}
+
 cudaError_t launch_conv_tc(const ConvParams& p, const TmaMaps& maps, int num_sms, cudaStream_t s) {
+  const int spec = pick_epi_spec(p);
+#define GLASS_SPEC(bn, bk, md, sp) \
+  if (p.BN == bn && p.BK == bk && p.mode == md && spec == sp) return launch_one<bn, bk, md, sp>(p, maps, num_sms, s);
+  GLASS_SPEC(64, 64, 4, 1)
+  GLASS_SPEC(64, 64, 4, 2)
+  GLASS_SPEC(32, 32, 4, 3)
+  GLASS_SPEC(32, 32, 4, 4)
+  GLASS_SPEC(64, 64, 4, 4)
+#undef GLASS_SPEC
 #define GLASS_CASE(bn, bk, md) \
   if (p.BN == bn && p.BK == bk && p.mode == md) return launch_one<bn, bk, md>(p, maps, num_sms, s);
   GLASS_CASE(32, 32, 0)
@@ -784,7 +895,6 @@ cudaError_t launch_conv_tc(const ConvParams& p, const TmaMaps& maps, int num_sms
   GLASS_CASE(128, 32, 4)
   GLASS_CASE(32, 64, 4)
   GLASS_CASE(64, 64, 4)
-  GLASS_CASE(128, 64, 4)
   GLASS_CASE(32, 128, 4)
   GLASS_CASE(32, 32, 2)
   GLASS_CASE(64, 32, 2)

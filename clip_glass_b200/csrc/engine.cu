@@ -218,14 +218,16 @@ int make_conv(glass_engine* e, ConvLaunch* out, const __half* in, int Nimg, int 
   p.mode = 0;
   if (in_i8) {
     // channel-group-interleaved input: 8-wide x 16-tall tiles, one un-swizzled haloed box per tile (MODE 4)
-    if (gemm || table != nullptr || taps != 9 || (Cin != 32 && Cin != 64 && Cin != 128) || H < 16 || W < 8 || H % 16 ||
-        W % 8)
-      return fail(GLASS_ERR_ARG, "I8 input layout needs a 3x3 conv with 32/64/128 channels on a >=16x8 grid");
+    // Cin <= 64: tile pairs (two 8x16 tiles side by side share one box; conv_tc.cu Cfg::kPairM)
+    const int tw = Cin <= 64 ? 16 : 8;
+    if (gemm || table != nullptr || taps != 9 || (Cin != 32 && Cin != 64 && Cin != 128) || H < 16 || W < tw || H % 16 ||
+        W % tw)
+      return fail(GLASS_ERR_ARG, "I8 input layout needs a 3x3 conv with 32/64/128 channels on a >=16x16 grid");
     p.mode = 4;
     p.BK = Cin;                        // whole K of a tap in one stage
-    p.TW = 8; p.TH = 16; p.TN = 1;
-    p.tiles_x = W / 8; p.tiles_y = H / 16; p.tiles_n = Nimg;
-    while (p.BN > (Cin == 128 ? 32 : 128)) p.BN /= 2;      // nine resident taps must leave room for >= 2 stages
+    p.TW = tw; p.TH = 16; p.TN = 1;
+    p.tiles_x = W / tw; p.tiles_y = H / 16; p.tiles_n = Nimg;
+    while (p.BN > (Cin == 128 ? 32 : (Cin == 64 ? 64 : 128))) p.BN /= 2;   // nine resident taps + >= 2 stages must fit
   } else if (!gemm && table == nullptr && (Cin == 32 || Cin == 64) && p.TW == 16 && p.TH == 8 && p.TN == 1 &&
              (taps == 9 || taps == 1)) {
     if (taps == 9) {

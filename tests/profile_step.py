@@ -29,6 +29,7 @@ def main():
     if args.timing:
         eng.set_debug(timing=True)
     step_ms = []
+    best = None
     for i in range(args.evals):
         t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t0.record()
@@ -36,6 +37,9 @@ def main():
         t1.record()
         torch.cuda.synchronize()
         step_ms.append(t0.elapsed_time(t1))
+        if args.timing and i > 0:        # per-layer minimum over the evaluations after the first (warm-up)
+            bd = eng.conv_breakdown()
+            best = bd if best is None else [(min(a[0], b[0]), a[1]) for a, b in zip(best, bd)]
     print("step ms per eval:", " ".join(f"{m:.2f}" for m in step_ms), f"(lib {os.environ.get('CLIPGLASS_LIB', 'default')})")
     if args.timing:
         layers = packing.g_layers(gan)
@@ -47,7 +51,7 @@ def main():
                 r = gan.resolution >> b
                 names += [f"D{b}:c0 {ch[b]}@{r}", f"D{b}:proj {ch[b]}->{ch[b+1]}@{r//2}", f"D{b}:c1 {ch[b]}->{ch[b+1]}@{r//2}"]
             names += ["D:fin", "D:dense0"]
-        bd = eng.conv_breakdown()
+        bd = best if best is not None else eng.conv_breakdown()
         tot = sum(m for m, _ in bd)
         print(f"pop={args.pop} flags={args.flags} conv launches={len(bd)} total conv ms={tot:.3f}")
         for n, (ms, fl) in zip(names, bd):
