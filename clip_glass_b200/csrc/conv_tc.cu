@@ -151,13 +151,20 @@ struct EpiSpec {
   bool generic, noise, rgb, residual;
   int store;
   bool i8;
+  int act;      // kActNone / kActLrelu (specialised specs never round to fp16 before the activation)
 };
 constexpr EpiSpec kEpiSpecs[] = {
-    {true, false, false, false, kStNone, false},      // 0: run-time switches
-    {false, true, true, false, kStRegular, true},     // 1: G conv + toRGB, I8 store          (G 64->64 @512^2)
-    {false, true, false, false, kStD2S, true},        // 2: G folded up-conv, depth-to-space I8 (G up 64->32 @1024^2)
-    {false, true, true, false, kStNone, false},       // 3: last G conv: toRGB only            (G 32->32 @1024^2)
-    {false, false, false, false, kStS2D, false},      // 4: D conv0, space-to-depth NHWC       (D 32@1024^2, 64@512^2)
+    {true, false, false, false, kStNone, false, 0},               // 0: run-time switches
+    {false, true, true, false, kStRegular, true, kActLrelu},      // 1: G conv + toRGB, I8 store
+    {false, true, false, false, kStD2S, true, kActLrelu},         // 2: G folded up-conv, depth-to-space I8
+    {false, true, true, false, kStNone, false, kActLrelu},        // 3: last G conv: toRGB only
+    {false, false, false, false, kStS2D, false, kActLrelu},       // 4: D conv0, space-to-depth NHWC
+    {false, true, true, false, kStRegular, false, kActLrelu},     // 5: G conv + toRGB, NHWC store
+    {false, true, false, false, kStD2S, false, kActLrelu},        // 6: G folded up-conv, depth-to-space NHWC
+    {false, false, false, true, kStRegular, true, kActLrelu},     // 7: D conv1 + residual, I8 store
+    {false, false, false, true, kStRegular, false, kActLrelu},    // 8: D conv1 + residual, NHWC store
+    {false, false, false, false, kStRegular, false, kActNone},    // 9: D projection (1x1, linear)
+    {false, false, false, false, kStRegular, false, kActLrelu},   // 10: D conv0 of the exact form, NHWC store
 };
 constexpr int kNumEpiSpecs = sizeof(kEpiSpecs) / sizeof(kEpiSpecs[0]);
 
@@ -246,7 +253,8 @@ __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" 
 // Fast epilogue for one row and 16 columns with the per-tile parameters staged in shared memory.
 //   t = act(acc*scale + shift + nz) ; rgb += t*rgbw ; t = (t + residual) * oscale ; store fp16
 // (the sqrt(2) gain of lrelu is folded into scale/shift/nz: lrelu(a)*g == lrelu(a*g) for g > 0)
-template <bool kRgb, bool kLean = false>
+// kActT: -1 = activation and fp16 pre-rounding from EpiParams at run time; kActNone / kActLrelu = fixed, no rounding
+template <bool kRgb, int kActT = -1>
 __device__ __forceinline__ void epilogue_fast16(const EpiParams& e, const float* __restrict__ par, int BN, int j0,
                                                 const uint32_t (&acc)[16], float nz, const __half* res_ptr,
                                                 __half* out_ptr, size_t out_half_stride, float (&rgb)[3]) {
@@ -262,14 +270,14 @@ __device__ __forceinline__ void epilogue_fast16(const EpiParams& e, const float*
     t[4 * g + 2] = fmaf(__uint_as_float(acc[4 * g + 2]), a.z, b.z + nz);
     t[4 * g + 3] = fmaf(__uint_as_float(acc[4 * g + 3]), a.w, b.w + nz);
   }
-  if (!kLean && e.round_fp16_before_act) {
+  if (kActT < 0 && e.round_fp16_before_act) {
 #pragma unroll
     for (int j = 0; j < 16; ++j) t[j] = __half2float(__float2half_rn(t[j]));
   }
-  if (kLean || e.act == kActLrelu) {
+  if (kActT == kActLrelu || (kActT < 0 && e.act == kActLrelu)) {
 #pragma unroll
     for (int j = 0; j < 16; ++j) t[j] = fmaxf(t[j], 0.2f * t[j]);
-  } else if (e.act == kActQuickGelu) {
+  } else if (kActT < 0 && e.act == kActQuickGelu) {
 #pragma unroll
     for (int j = 0; j < 16; ++j) t[j] = t[j] / (1.f + __expf(-1.702f * t[j]));
   }
@@ -516,8 +524,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     const int rr = row - ri * thw;
     const int ry = rr / geo_w;
     const int rx = rr - ry * geo_w;         // tile h of a pair: pixel column rx + 8h
-    const bool fast = (MODE == 4) ? true : (p.TN == 1);   // every row of a tile belongs to one image (I8 tiles: always)
-    const float gain = (!S.generic || e.act == kActLrelu) ? kSqrt2 : 1.f;
+    // every row of a tile belongs to one image (always for I8 tiles and for the specialised layers)
+    const bool fast = (MODE == 4 || !S.generic) ? true : (p.TN == 1);
+    const float gain = (S.generic ? (e.act == kActLrelu) : (S.act == kActLrelu)) ? kSqrt2 : 1.f;
     constexpr int kParts = C::kParts;
     constexpr int kHalf = BN / kParts;      // columns per warp
     constexpr int kChunks = kHalf / 16;
@@ -712,8 +721,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 optr = out_row + h * out_row_hstep + c * 16;
               }
               const __half* rptr = res_row != nullptr ? res_row + (size_t)(8 * h) * p.Ntot + c * 16 : nullptr;
-              if (has_rgb) epilogue_fast16<true, !S.generic>(e, par, BN, j0, acc[ci & 1], nzc, rptr, optr, half_stride, rgb[h]);
-              else epilogue_fast16<false, !S.generic>(e, par, BN, j0, acc[ci & 1], nzc, rptr, optr, half_stride, rgb[h]);
+              constexpr int kActT = S.generic ? -1 : S.act;
+              if (has_rgb) epilogue_fast16<true, kActT>(e, par, BN, j0, acc[ci & 1], nzc, rptr, optr, half_stride, rgb[h]);
+              else epilogue_fast16<false, kActT>(e, par, BN, j0, acc[ci & 1], nzc, rptr, optr, half_stride, rgb[h]);
             }
           }
         }
@@ -846,8 +856,8 @@ __global__ void conv_simt_kernel(const ConvParams p) {
 static int pick_epi_spec(const ConvParams& p) {
   const EpiParams& e = p.epi;
   static const bool off = getenv("GLASS_DEBUG_GENERIC_EPI") != nullptr;     // A/B knob: always the run-time spec
-  if (off || p.mode != 4 || p.TN != 1 || !p.pow2 || !p.all_valid || p.debug_skip != 0) return 0;
-  if (e.act != kActLrelu || e.round_fp16_before_act || e.x_phases == 2 || e.cout_shift < 0) return 0;
+  if (off || p.TN != 1 || !p.pow2 || !p.all_valid || p.debug_skip != 0) return 0;
+  if ((e.act != kActLrelu && e.act != kActNone) || e.round_fp16_before_act || e.x_phases == 2 || e.cout_shift < 0) return 0;
   if (e.noise != nullptr && e.noise_div_shift < 0) return 0;
   int store = kStNone;
   if (e.out != nullptr) {
@@ -859,7 +869,7 @@ static int pick_epi_spec(const ConvParams& p) {
   for (int i = 1; i < kNumEpiSpecs; ++i) {
     const EpiSpec& sp = kEpiSpecs[i];
     if (sp.noise == (e.noise != nullptr) && sp.rgb == (e.rgb_w != nullptr) && sp.residual == (e.residual != nullptr) &&
-        sp.store == store && (store == kStNone || sp.i8 == (e.out_i8 != 0)))
+        sp.store == store && (store == kStNone || sp.i8 == (e.out_i8 != 0)) && sp.act == e.act)
       return i;
   }
   return 0;
@@ -867,6 +877,10 @@ static int pick_epi_spec(const ConvParams& p) {
 
 cudaError_t launch_conv_tc(const ConvParams& p, const TmaMaps& maps, int num_sms, cudaStream_t s) {
   const int spec = pick_epi_spec(p);
+  static const bool log_spec = getenv("GLASS_DEBUG_SPEC_LOG") != nullptr;
+  if (log_spec)
+    fprintf(stderr, "conv_tc: H=%d W=%d Cin=%d taps=%d Ntot=%d BN=%d BK=%d mode=%d spec=%d\n", p.H, p.W, p.Cin, p.taps,
+            p.Ntot, p.BN, p.BK, p.mode, spec);
 #define GLASS_SPEC(bn, bk, md, sp) \
   if (p.BN == bn && p.BK == bk && p.mode == md && spec == sp) return launch_one<bn, bk, md, sp>(p, maps, num_sms, s);
   GLASS_SPEC(64, 64, 4, 1)
@@ -874,6 +888,16 @@ cudaError_t launch_conv_tc(const ConvParams& p, const TmaMaps& maps, int num_sms
   GLASS_SPEC(32, 32, 4, 3)
   GLASS_SPEC(32, 32, 4, 4)
   GLASS_SPEC(64, 64, 4, 4)
+  GLASS_SPEC(128, 64, 0, 5)
+  GLASS_SPEC(256, 64, 0, 2)
+  GLASS_SPEC(256, 64, 0, 6)
+  GLASS_SPEC(64, 64, 0, 7)
+  GLASS_SPEC(128, 64, 0, 8)
+  GLASS_SPEC(256, 64, 0, 8)
+  GLASS_SPEC(64, 32, 2, 9)
+  GLASS_SPEC(128, 64, 2, 9)
+  GLASS_SPEC(256, 64, 0, 9)
+  GLASS_SPEC(128, 64, 0, 10)
 #undef GLASS_SPEC
 #define GLASS_CASE(bn, bk, md) \
   if (p.BN == bn && p.BK == bk && p.mode == md) return launch_one<bn, bk, md>(p, maps, num_sms, s);
