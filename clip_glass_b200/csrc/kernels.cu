@@ -337,8 +337,15 @@ __global__ void final_cosine_kernel(const __half* __restrict__ tokens, const flo
   __syncthreads();
   float dot = 0.f, nf = 0.f, nt = 0.f;
   for (int e = threadIdx.x; e < E; e += blockDim.x) {
-    float acc = 0.f;
-    for (int i = 0; i < W; ++i) acc = fmaf(c[i], __ldg(proj + (size_t)i * E + e), acc);
+    // four independent partial sums (the serial 768-long dependent chain was 0.3 ms of pure latency)
+    float a4[4] = {0.f, 0.f, 0.f, 0.f};
+    int i = 0;
+    for (; i + 4 <= W; i += 4) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) a4[u] = fmaf(c[i + u], __ldg(proj + (size_t)(i + u) * E + e), a4[u]);
+    }
+    for (; i < W; ++i) a4[0] = fmaf(c[i], __ldg(proj + (size_t)i * E + e), a4[0]);
+    float acc = (a4[0] + a4[1]) + (a4[2] + a4[3]);
     acc = rh(acc);
     if (features != nullptr) features[(size_t)b * E + e] = acc;
     const float t = text[e];
@@ -398,41 +405,51 @@ __global__ void from_rgb_kernel(const float* __restrict__ images, const float* _
 // FIR (pad 1) sampled at stride 2.  One block = 8x16 outputs x 32 channels: the (18 x 34)-pixel input patch is
 // staged once in shared memory (coalesced 16-byte loads, pixel pitch padded to 80 B against bank conflicts), so
 // HBM/L2 see every input byte once and the 16 taps per output come from shared memory.
+#ifndef GLASS_FIR_MINB
+#define GLASS_FIR_MINB 2   // 2 and 4 blocks/SM measured equal; 2 needs no spills
+#endif
 constexpr int kFdTH = 8, kFdTW = 16, kFdC = 32, kFdPitch = 40;   // pitch in halfs (80 bytes)
-// Shared second half of fir_down_kernel / from_rgb_fir_kernel: 4x4 FIR taps from the staged tile, stride 2.
+// Shared second half of fir_down_kernel / from_rgb_fir_kernel: separable [1,3,3,1]/8 FIR at stride 2 from the staged
+// tile.  One thread = one output column, 8 channels, two vertically adjacent outputs: six input rows are filtered
+// horizontally once ((a+d) + 3(b+c): two adds and one FMA per channel instead of four FMAs) and shared by both.
 __device__ __forceinline__ void fir_down_from_tile(const __half* tile, __half* __restrict__ out, int b, int ty, int tx,
                                                    int Ho, int Wo, int C, int c0) {
   constexpr int IW = 2 * kFdTW + 2;
-  const float f[4] = {0.125f, 0.375f, 0.375f, 0.125f};
+  static_assert(kFdTH == 8 && kFdTW == 16, "thread mapping below: 4 groups x 16 columns x 4 row pairs = 256 threads");
   const int g = threadIdx.x & 3;
+  const int ox = (threadIdx.x >> 2) & 15;
+  const int oyp = threadIdx.x >> 6;                 // output rows 2*oyp, 2*oyp+1 <- input rows 4*oyp .. 4*oyp+5
+  float hrow[6][8];
 #pragma unroll
-  for (int pass = 0; pass < 2; ++pass) {
-    const int op = (threadIdx.x >> 2) + 64 * pass;
-    const int oy = op / kFdTW, ox = op - oy * kFdTW;
-    const int zy = ty * kFdTH + oy, zx = tx * kFdTW + ox;
-    float acc[8];
+  for (int r = 0; r < 6; ++r) {
+    float v[4][8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    for (int jx = 0; jx < 4; ++jx) {
+      const uint4 q = *reinterpret_cast<const uint4*>(tile + ((4 * oyp + r) * IW + 2 * ox + jx) * kFdPitch + g * 8);
+      const __half2* h2 = reinterpret_cast<const __half2*>(&q);
 #pragma unroll
-    for (int jy = 0; jy < 4; ++jy) {
-#pragma unroll
-      for (int jx = 0; jx < 4; ++jx) {
-        const uint4 v = *reinterpret_cast<const uint4*>(tile + ((2 * oy + jy) * IW + 2 * ox + jx) * kFdPitch + g * 8);
-        const __half2* h2 = reinterpret_cast<const __half2*>(&v);
-        const float wgt = f[jy] * f[jx];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float2 tt = __half22float2(h2[j]);
-          acc[2 * j] = fmaf(wgt, tt.x, acc[2 * j]);
-          acc[2 * j + 1] = fmaf(wgt, tt.y, acc[2 * j + 1]);
-        }
+      for (int j = 0; j < 4; ++j) {
+        const float2 tt = __half22float2(h2[j]);
+        v[jx][2 * j] = tt.x;
+        v[jx][2 * j + 1] = tt.y;
       }
     }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) hrow[r][j] = fmaf(3.f, v[1][j] + v[2][j], v[0][j] + v[3][j]);
+  }
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    const int zy = ty * kFdTH + 2 * oyp + k, zx = tx * kFdTW + ox;
     if (zy < Ho && zx < Wo) {
       uint4 o;
       __half2* oh = reinterpret_cast<__half2*>(&o);
 #pragma unroll
-      for (int j = 0; j < 4; ++j) oh[j] = __floats2half2_rn(acc[2 * j], acc[2 * j + 1]);
+      for (int j = 0; j < 4; ++j) {
+        const float e0 = fmaf(3.f, hrow[2 * k + 1][2 * j] + hrow[2 * k + 2][2 * j], hrow[2 * k][2 * j] + hrow[2 * k + 3][2 * j]);
+        const float e1 = fmaf(3.f, hrow[2 * k + 1][2 * j + 1] + hrow[2 * k + 2][2 * j + 1],
+                              hrow[2 * k][2 * j + 1] + hrow[2 * k + 3][2 * j + 1]);
+        oh[j] = __floats2half2_rn(e0 * (1.f / 64.f), e1 * (1.f / 64.f));
+      }
       *reinterpret_cast<uint4*>(out + (((size_t)b * Ho + zy) * Wo + zx) * C + c0 + g * 8) = o;
     }
   }
@@ -442,7 +459,7 @@ constexpr int kFdTileBytes = (2 * kFdTH + 2) * (2 * kFdTW + 2) * kFdPitch * 2;
 constexpr int kFdItems = (2 * kFdTH + 2) * (2 * kFdTW + 2) * 4;       // (pixel, 8-channel group) items per tile
 constexpr int kFdPerThread = (kFdItems + 255) / 256;
 
-__global__ void __launch_bounds__(256) fir_down_kernel(const __half* __restrict__ x, __half* __restrict__ out, int N,
+__global__ void __launch_bounds__(256, GLASS_FIR_MINB) fir_down_kernel(const __half* __restrict__ x, __half* __restrict__ out, int N,
                                                        int H, int W, int C, int in_i8) {
   __shared__ __align__(16) __half tile[(2 * kFdTH + 2) * (2 * kFdTW + 2) * kFdPitch];
   const int Ho = H >> 1, Wo = W >> 1;
@@ -481,9 +498,9 @@ __global__ void __launch_bounds__(256) fir_down_kernel(const __half* __restrict_
 // fromRGB fused with the first block's projection FIR: the tile of x = lrelu(W.rgb + b)*sqrt2 is computed once from
 // the image (halo pixels are recomputed by the neighbouring block: 19 % extra arithmetic, no extra HBM traffic),
 // written to HBM for conv0 (interior pixels only) and filtered from shared memory, so the 32-channel 1024^2
-// tensor is never read back for the FIR.  Same fp16 values and the same summation order as k_from_rgb followed by
-// k_fir_down: the two routes are bit-identical.
-__global__ void __launch_bounds__(256) from_rgb_fir_kernel(const float* __restrict__ images,
+// tensor is never read back for the FIR.  (k_from_rgb + k_fir_down is the same computation up to the fp32 rounding
+// of the folded fromRGB constants.)
+__global__ void __launch_bounds__(256, GLASS_FIR_MINB) from_rgb_fir_kernel(const float* __restrict__ images,
                                                            const float* __restrict__ Wt, const float* __restrict__ bias,
                                                            __half* __restrict__ xout, __half* __restrict__ down, int P,
                                                            int R, int C, int out_i8) {
@@ -491,9 +508,11 @@ __global__ void __launch_bounds__(256) from_rgb_fir_kernel(const float* __restri
   __half* tile = reinterpret_cast<__half*>(fr_smem);
   float* w = reinterpret_cast<float*>(fr_smem + kFdTileBytes);
   const int c0 = blockIdx.y * kFdC;
+  // x = lrelu(W.(2 rgb - 1) + b) * sqrt2 = lrelu((2 sqrt2 W).rgb + sqrt2 (b - sum W)): constants folded once per block
   if (threadIdx.x < 4 * kFdC) {
     const int r = threadIdx.x / kFdC, c = threadIdx.x - r * kFdC;
-    w[threadIdx.x] = r < 3 ? Wt[r * C + c0 + c] : bias[c0 + c];
+    w[threadIdx.x] = r < 3 ? 2.f * kSqrt2 * Wt[r * C + c0 + c]
+                           : kSqrt2 * (bias[c0 + c] - Wt[c0 + c] - Wt[C + c0 + c] - Wt[2 * C + c0 + c]);
   }
   const int Ho = R >> 1, Wo = R >> 1;
   const int tiles_x = (Wo + kFdTW - 1) / kFdTW, tiles_y = (Ho + kFdTH - 1) / kFdTH;
@@ -529,7 +548,7 @@ __global__ void __launch_bounds__(256) from_rgb_fir_kernel(const float* __restri
     uint4 pk = make_uint4(0, 0, 0, 0);                 // outside the image: the FIR's zero padding
     const bool inside = yy >= 0 && yy < R && xx >= 0 && xx < R;
     if (inside) {
-      const float r = rgb[k][0] * 2.f - 1.f, gg = rgb[k][1] * 2.f - 1.f, bl = rgb[k][2] * 2.f - 1.f;
+      const float r = rgb[k][0], gg = rgb[k][1], bl = rgb[k][2];
       __half2* h2 = reinterpret_cast<__half2*>(&pk);
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
@@ -538,7 +557,7 @@ __global__ void __launch_bounds__(256) from_rgb_fir_kernel(const float* __restri
         for (int u = 0; u < 2; ++u) {
           const int c = g * 8 + 2 * j + u;
           const float tt = fmaf(r, w[c], fmaf(gg, w[kFdC + c], fmaf(bl, w[2 * kFdC + c], w[3 * kFdC + c])));
-          a[u] = fmaxf(tt, 0.2f * tt) * kSqrt2;
+          a[u] = fmaxf(tt, 0.2f * tt);
         }
         h2[j] = __floats2half2_rn(a[0], a[1]);
       }
