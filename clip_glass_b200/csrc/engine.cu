@@ -820,7 +820,9 @@ int run_generator(glass_engine* e, const float* z, int P, const glass_noise* nz,
       const bool final_block = (li + 1 == nl);
       snprintf(nm, sizeof nm, "g.rgb%d.bias", l.block);
       const int n_slabs = cl.p.Ntot / cl.p.BN;
-      LAUNCH(k_rgb_combine(have_y ? ybuf[ycur] : nullptr, e->slabs, n_slabs, tptr<float>(e, nm), ybuf[ycur ^ 1],
+      // the last block's skip sum only feeds the image: its fp32 copy is written for debug captures only
+      LAUNCH(k_rgb_combine(have_y ? ybuf[ycur] : nullptr, e->slabs, n_slabs, tptr<float>(e, nm),
+                           (final_block && !e->capture) ? nullptr : ybuf[ycur ^ 1],
                            final_block ? images_out : nullptr, P, l.res, l.res, s));
       ycur ^= 1;
       have_y = true;
@@ -846,7 +848,8 @@ int run_clip(glass_engine* e, const float* images, int P, float* sim_out, float*
     auto nmf = [&](const char* suffix) { snprintf(nm, sizeof nm, "c.l%d.%s", l, suffix); return std::string(nm); };
     LAUNCH(k_layernorm(e->tokens, tptr<float>(e, nmf("ln1.w")), tptr<float>(e, nmf("ln1.b")), e->hbuf, P * T, Wd, s));
     RC(run_conv(e, e->c_convs[ci++], s));   // qkv
-    LAUNCH(k_attention(e->qkv, e->att, P, T, Wd, s));
+    if (c.flags & GLASS_FLAG_SIMT_ATTENTION) LAUNCH(k_attention(e->qkv, e->att, P, T, Wd, s));
+    else LAUNCH(k_attention_tc(e->qkv, e->att, P, T, Wd, s));
     RC(run_conv(e, e->c_convs[ci++], s));   // out + residual
     LAUNCH(k_layernorm(e->tokens, tptr<float>(e, nmf("ln2.w")), tptr<float>(e, nmf("ln2.b")), e->hbuf, P * T, Wd, s));
     RC(run_conv(e, e->c_convs[ci++], s));   // fc

@@ -43,7 +43,10 @@ cudaError_t k_embed_lnpre(const __half* patch_emb, const float* cls, const float
 // clip/model.py:152-158
 cudaError_t k_layernorm(const __half* x, const float* w, const float* b, __half* out, int M, int W, cudaStream_t s);
 // nn.MultiheadAttention core (clip/model.py:180-182): qkv [P*T][3W] -> out [P*T][W]; heads of 64
+// k_attention_tc (attention_tc.cu): QK^T and PV as tcgen05.mma with the softmax between them out of TMEM -- the
+// product path; k_attention is the SIMT bring-up / cross-check version (GLASS_FLAG_SIMT_ATTENTION)
 cudaError_t k_attention(const __half* qkv, __half* out, int P, int T, int W, cudaStream_t s);
+cudaError_t k_attention_tc(const __half* qkv, __half* out, int P, int T, int W, cudaStream_t s);
 // clip/model.py:230-233 + generator.py:51: ln_post(cls) @ proj -> features; cosine vs text
 cudaError_t k_final_cosine(const __half* tokens, const float* lw, const float* lb, const float* proj,
                            const float* text, float* features, float* sim, float* neg_sim, int P, int T, int W, int E,

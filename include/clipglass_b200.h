@@ -69,6 +69,8 @@ typedef struct glass_config {
 /* Activations that feed a 32/64-channel 3x3 conv are normally stored channel-group-interleaved
  * ([N][H][C/8][W][8]) so that one un-swizzled haloed TMA box per tile serves all nine taps (conv_tc MODE 4). */
 #define GLASS_FLAG_NO_I8_LAYOUT 8      /* keep every activation NHWC (MODE 1 / pixel pairs for those layers) */
+/* The ViT attention core (QK^T, softmax, PV) runs as tcgen05.mma out of TMEM (attention_tc.cu). */
+#define GLASS_FLAG_SIMT_ATTENTION 16   /* use the scalar shared-memory kernel instead (cross-check) */
 
 /* -- lifetime ------------------------------------------------------------- */
 /* Replaces Generator.__init__ (generator.py:12-27): allocate the engine. */
