@@ -211,6 +211,10 @@ int make_conv(glass_engine* e, ConvLaunch* out, const __half* in, int Nimg, int 
   p.tiles_y = (H + p.TH - 1) / p.TH;
   p.tiles_n = (Nimg + p.TN - 1) / p.TN;
   p.BN = pick_bn(Ntot);
+  if (gemm) {
+    static const char* cap = getenv("GLASS_DEBUG_GEMM_BN");      // A/B knob for the plain GEMMs' tile width
+    if (cap != nullptr && atoi(cap) >= 32 && p.BN > atoi(cap) && Ntot % atoi(cap) == 0) p.BN = atoi(cap);
+  }
   p.BK = (Cin % 64 == 0) ? 64 : 32;
   if (p.BN == 0 || Cin % 32 != 0 || Ntot % 16 != 0)
     return fail(GLASS_ERR_ARG, "unsupported conv shape Cin=%d Ntot=%d", Cin, Ntot);
@@ -778,11 +782,16 @@ int run_generator(glass_engine* e, const float* z, int P, const glass_noise* nz,
   // all style affines in one pass (same dlatent for every layer, models.py:427-430)
   LAUNCH(k_vecmat(cur, L, tptr<float>(e, "g.style.w"), tptr<float>(e, "g.style.b"), e->styles, e->S, P, L, e->S, 0, s));
   RC(capture_f32(e, "styles", e->styles, (size_t)P * e->S, s));
-  for (size_t li = 0; li < e->glayers.size(); ++li) {
-    const GLayer& l = e->glayers[li];
-    snprintf(nm, sizeof nm, "g.conv%zu.wsq", li);
-    LAUNCH(k_vecmat(e->styles + e->conv_off[li], e->S, tptr<float>(e, nm), nullptr, e->dmod[li], l.cout, P, l.cin,
-                    l.cout, 2, s));
+  // demodulation coefficients of every layer (modules.py:945-954): independent GEMVs, kMaxVecmatJobs per launch
+  for (size_t l0 = 0; l0 < e->glayers.size(); l0 += kMaxVecmatJobs) {
+    VecmatBatch vb;
+    vb.n = 0;
+    for (size_t li = l0; li < e->glayers.size() && vb.n < kMaxVecmatJobs; ++li) {
+      const GLayer& l = e->glayers[li];
+      snprintf(nm, sizeof nm, "g.conv%zu.wsq", li);
+      vb.job[vb.n++] = VecmatJob{e->styles + e->conv_off[li], tptr<float>(e, nm), e->dmod[li], l.cin, l.cout};
+    }
+    LAUNCH(k_vecmat_batched(vb, e->S, P, 2, s));
   }
   for (int b = 0; b < c.num_blocks; ++b) {
     snprintf(nm, sizeof nm, "g.rgb%d.w", b);

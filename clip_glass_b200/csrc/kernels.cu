@@ -91,6 +91,42 @@ __global__ void vecmat_kernel(const float* __restrict__ in, int in_stride, const
   out[(size_t)b * out_stride + n] = acc;
 }
 
+// Several independent vecmat jobs (the 17 demodulation GEMVs of one generator pass) in ONE launch: blockIdx.z = job.
+__global__ void vecmat_batched_kernel(const VecmatBatch jobs, int in_stride, int mode) {
+  extern __shared__ float row[];
+  const VecmatJob& jb = jobs.job[blockIdx.z];
+  const int K = jb.K, N = jb.N;
+  if ((int)(blockIdx.x * blockDim.x) >= N) return;
+  const int b = blockIdx.y;
+  for (int k = threadIdx.x; k < K; k += blockDim.x) {
+    const float v = jb.in[(size_t)b * in_stride + k];
+    row[k] = (mode == 2) ? v * v : v;
+  }
+  __syncthreads();
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  const float* __restrict__ Wt = jb.Wt;
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+  int k = 0;
+  for (; k + 16 <= K; k += 16) {
+    float w[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) w[j] = __ldg(Wt + (size_t)(k + j) * N + n);
+#pragma unroll
+    for (int j = 0; j < 16; j += 4) {
+      a0 = fmaf(row[k + j], w[j], a0);
+      a1 = fmaf(row[k + j + 1], w[j + 1], a1);
+      a2 = fmaf(row[k + j + 2], w[j + 2], a2);
+      a3 = fmaf(row[k + j + 3], w[j + 3], a3);
+    }
+  }
+  for (; k < K; ++k) a0 = fmaf(row[k], __ldg(Wt + (size_t)k * N + n), a0);
+  float acc = (a0 + a1) + (a2 + a3);
+  if (mode == 1) acc = (acc > 0.f ? acc : 0.2f * acc) * kSqrt2;
+  if (mode == 2) acc = rsqrtf(acc + 1e-8f);
+  jb.out[(size_t)b * N + n] = acc;
+}
+
 __global__ void const_input_kernel(const float* cst, const float* styles, int stride, __half* out, int P, int C) {
   const size_t n = (size_t)P * 16 * C;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
@@ -213,6 +249,24 @@ __global__ void resize_patches_kernel(const float* __restrict__ images, __half* 
   }
 }
 
+__device__ __forceinline__ void ld8(const __half* p, float (&v)[8]) {
+  const uint4 q = __ldg(reinterpret_cast<const uint4*>(p));
+  const __half2* h2 = reinterpret_cast<const __half2*>(&q);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float2 t = __half22float2(h2[j]);
+    v[2 * j] = t.x;
+    v[2 * j + 1] = t.y;
+  }
+}
+__device__ __forceinline__ void st8(__half* p, const float (&v)[8]) {
+  uint4 o;
+  __half2* oh = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) oh[j] = __floats2half2_rn(v[2 * j], v[2 * j + 1]);
+  *reinterpret_cast<uint4*>(p) = o;
+}
+
 constexpr int kMaxPerLane = 32;   // rows up to 1024 wide
 
 __device__ __forceinline__ void warp_layernorm_store(float (&v)[kMaxPerLane], int W, const float* lw, const float* lb,
@@ -254,18 +308,48 @@ __global__ void embed_lnpre_kernel(const __half* __restrict__ emb, const float* 
   warp_layernorm_store(v, W, lw, lb, tokens + (size_t)row * W);
 }
 
-__global__ void layernorm_kernel(const __half* __restrict__ x, const float* lw, const float* lb,
+// One warp per row; a lane owns 8 contiguous channels of every 256-channel chunk (16-byte loads and stores; the
+// per-element mapping of warp_layernorm_store costs 24 two-byte loads per lane at W = 768 and was latency-bound).
+__global__ void layernorm_kernel(const __half* __restrict__ x, const float* __restrict__ lw, const float* __restrict__ lb,
                                  __half* __restrict__ out, int M, int W) {
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= M) return;
   const int lane = threadIdx.x & 31;
-  float v[kMaxPerLane];
+  constexpr int kChunks = kMaxPerLane / 8;       // rows up to 1024 wide
+  float v[kChunks][8];
+  float s = 0.f;
 #pragma unroll
-  for (int j = 0; j < kMaxPerLane; ++j) {
-    const int i = lane + 32 * j;
-    v[j] = (i < W) ? __half2float(x[(size_t)row * W + i]) : 0.f;
+  for (int j = 0; j < kChunks; ++j) {
+    const int i0 = j * 256 + lane * 8;
+    if (i0 < W) {
+      ld8(x + (size_t)row * W + i0, v[j]);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) s += v[j][u];
+    }
   }
-  warp_layernorm_store(v, W, lw, lb, out + (size_t)row * W);
+  const float mean = warp_sum(s) / (float)W;
+  float q = 0.f;
+#pragma unroll
+  for (int j = 0; j < kChunks; ++j)
+    if (j * 256 + lane * 8 < W) {
+#pragma unroll
+      for (int u = 0; u < 8; ++u) { const float d = v[j][u] - mean; q += d * d; }
+    }
+  const float rstd = rsqrtf(warp_sum(q) / (float)W + 1e-5f);
+#pragma unroll
+  for (int j = 0; j < kChunks; ++j) {
+    const int i0 = j * 256 + lane * 8;
+    if (i0 < W) {
+      const float4 w0 = __ldg(reinterpret_cast<const float4*>(lw + i0)), w1 = __ldg(reinterpret_cast<const float4*>(lw + i0 + 4));
+      const float4 b0 = __ldg(reinterpret_cast<const float4*>(lb + i0)), b1 = __ldg(reinterpret_cast<const float4*>(lb + i0 + 4));
+      const float ww[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+      const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+      float o[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) o[u] = (v[j][u] - mean) * rstd * ww[u] + bb[u];
+      st8(out + (size_t)row * W + i0, o);
+    }
+  }
 }
 
 // one block per (image, head); T <= 64 tokens, head dim 64
@@ -577,24 +661,6 @@ __global__ void __launch_bounds__(256, GLASS_FIR_MINB) from_rgb_fir_kernel(const
 // ---------------------------------------------------------------------------
 // exact polyphase helpers (streaming, HBM-bound)
 // ---------------------------------------------------------------------------
-__device__ __forceinline__ void ld8(const __half* p, float (&v)[8]) {
-  const uint4 q = __ldg(reinterpret_cast<const uint4*>(p));
-  const __half2* h2 = reinterpret_cast<const __half2*>(&q);
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const float2 t = __half22float2(h2[j]);
-    v[2 * j] = t.x;
-    v[2 * j + 1] = t.y;
-  }
-}
-__device__ __forceinline__ void st8(__half* p, const float (&v)[8]) {
-  uint4 o;
-  __half2* oh = reinterpret_cast<__half2*>(&o);
-#pragma unroll
-  for (int j = 0; j < 4; ++j) oh[j] = __floats2half2_rn(v[2 * j], v[2 * j + 1]);
-  *reinterpret_cast<uint4*>(p) = o;
-}
-
 // The FIR [1,3,3,1] is the binomial [1,1]*[1,1]*[1,1]: three cascaded adjacent sums per axis (3 adds per output
 // instead of 4 multiply-adds), with only three running vectors of vertical state.  Each thread produces two
 // adjacent output columns from five loaded columns.  The first level of adjacent sums is taken in fp16 (one
@@ -860,8 +926,15 @@ cudaError_t k_embed_lnpre(const __half* patch_emb, const float* cls, const float
   embed_lnpre_kernel<<<(rows + 7) / 8, 256, 0, s>>>(patch_emb, cls, pos, lw, lb, tokens, P, T, W);
   GLASS_RET();
 }
+cudaError_t k_vecmat_batched(const VecmatBatch& jobs, int in_stride, int P, int mode, cudaStream_t s) {
+  if (jobs.n <= 0 || jobs.n > kMaxVecmatJobs) return cudaErrorInvalidValue;
+  int maxN = 0, maxK = 0;
+  for (int i = 0; i < jobs.n; ++i) { maxN = jobs.job[i].N > maxN ? jobs.job[i].N : maxN; maxK = jobs.job[i].K > maxK ? jobs.job[i].K : maxK; }
+  vecmat_batched_kernel<<<dim3((maxN + 127) / 128, P, jobs.n), 128, maxK * sizeof(float), s>>>(jobs, in_stride, mode);
+  GLASS_RET();
+}
 cudaError_t k_layernorm(const __half* x, const float* w, const float* b, __half* out, int M, int W, cudaStream_t s) {
-  if (W > 32 * kMaxPerLane) return cudaErrorInvalidValue;
+  if (W > 32 * kMaxPerLane || W % 8 != 0) return cudaErrorInvalidValue;
   layernorm_kernel<<<(M + 7) / 8, 256, 0, s>>>(x, w, b, out, M, W);
   GLASS_RET();
 }

@@ -12,6 +12,11 @@ cudaError_t k_pixelnorm(const float* z, float* out, int P, int L, cudaStream_t s
 //   mode 0: linear; 1: lrelu(0.2)*sqrt2; 2: g = square, f = rsqrt(. + 1e-8) (demodulation, modules.py:945-954)
 cudaError_t k_vecmat(const float* in, int in_stride, const float* Wt, const float* bias, float* out, int out_stride,
                      int P, int K, int N, int mode, cudaStream_t s);
+// the same for up to kMaxVecmatJobs independent (in, Wt, out) triples in one launch; out row stride = N, no bias
+constexpr int kMaxVecmatJobs = 32;
+struct VecmatJob { const float* in; const float* Wt; float* out; int K, N; };
+struct VecmatBatch { VecmatJob job[kMaxVecmatJobs]; int n; };
+cudaError_t k_vecmat_batched(const VecmatBatch& jobs, int in_stride, int P, int mode, cudaStream_t s);
 // x0[b][pix][c] = fp16(const[pix][c] * s[b*stride + c])   (models.py:987 + pre-scale by the first style)
 cudaError_t k_const_input(const float* cst, const float* styles, int stride, __half* out, int P, int C, cudaStream_t s);
 // wr[b][c][o] = W[c][o] * styles[b*stride + off + o]   (toRGB modulated 1x1 weights, no demod; models.py:848-871)
