@@ -113,8 +113,17 @@ struct glass_engine {
   int plan_pop = -1;
   std::vector<ConvLaunch> g_convs, c_convs, d_convs;
 
+  std::vector<float> frgb_folded;   // host copy of the folded fromRGB constants [4][C] (k_from_rgb_fir)
   int max_groups = 0;        // noise buffer capacity in minibatch groups
   int64_t launches = 0;
+  // CUDA graph of one fitness evaluation (everything after the noise fill; fixed engine-owned pointers), replayed
+  // on the caller's stream.  Built on the second evaluation of a plan (the first runs eagerly and configures the
+  // kernels' attributes); dropped whenever the plan is rebuilt.
+  cudaStream_t cap_stream = nullptr, side_stream = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  cudaGraphExec_t graph_exec = nullptr;
+  int graph_evals = 0;       // evaluations since the plan was built
+  int64_t graph_launches = 0;   // kernel launches inside the graph
   // timing of tensor-core launches
   bool timing = false;
   std::vector<cudaEvent_t> ev;
@@ -581,7 +590,14 @@ EpiParams epi_default() {
 // ---------------------------------------------------------------------------
 // plan: all conv/GEMM launches for a population of P candidates
 // ---------------------------------------------------------------------------
+void drop_graph(glass_engine* e) {
+  if (e->graph_exec) cudaGraphExecDestroy(e->graph_exec);
+  e->graph_exec = nullptr;
+  e->graph_evals = 0;
+}
+
 int build_plan(glass_engine* e, int P) {
+  drop_graph(e);
   const glass_config& c = e->cfg;
   e->g_convs.clear();
   e->c_convs.clear();
@@ -686,6 +702,18 @@ int build_plan(glass_engine* e, int P) {
   if (c.use_discriminator) {
     const int nb = c.num_blocks;
     auto dch = [&](int i) { return e->gch[nb - 1 - i]; };
+    {
+      // folded fromRGB constants (kernels.cu: from_rgb_fir_kernel) on the host: they travel as kernel parameters
+      const int C0 = dch(0);
+      std::vector<float> w(3 * (size_t)C0), bs(C0);
+      CUDA_OK(cudaMemcpy(w.data(), tptr<float>(e, "d.frgb.w"), w.size() * 4, cudaMemcpyDeviceToHost));
+      CUDA_OK(cudaMemcpy(bs.data(), tptr<float>(e, "d.frgb.b"), bs.size() * 4, cudaMemcpyDeviceToHost));
+      e->frgb_folded.assign(4 * (size_t)C0, 0.f);
+      for (int ch = 0; ch < C0; ++ch) {
+        for (int r = 0; r < 3; ++r) e->frgb_folded[r * C0 + ch] = 2.f * kSqrt2 * w[r * C0 + ch];
+        e->frgb_folded[3 * C0 + ch] = kSqrt2 * (bs[ch] - w[ch] - w[C0 + ch] - w[2 * C0 + ch]);
+      }
+    }
     __half* x = e->actA;          // fromRGB output
     __half* outs[2] = {e->dOut, e->actA};
     int res = e->R;
@@ -762,11 +790,12 @@ int fill_noise(glass_engine* e, int P, const glass_noise* nz, cudaStream_t s) {
   return GLASS_OK;
 }
 
-int run_generator(glass_engine* e, const float* z, int P, const glass_noise* nz, float* images_out, cudaStream_t s) {
+int run_generator(glass_engine* e, const float* z, int P, const glass_noise* nz, float* images_out, cudaStream_t s,
+                  bool noise_ready = false) {
   const glass_config& c = e->cfg;
   const int L = c.latent_size;
   char nm[64];
-  RC(fill_noise(e, P, nz, s));
+  if (!noise_ready) RC(fill_noise(e, P, nz, s));
   // mapping (stylegan2/models.py:590-627)
   LAUNCH(k_pixelnorm(z, e->wA, P, L, s));
   float* cur = e->wA;
@@ -883,8 +912,7 @@ int run_discriminator(glass_engine* e, const float* images, int P, float* logits
   static const bool split_frgb = getenv("GLASS_DEBUG_SPLIT_FRGB") != nullptr;
   const bool fused_frgb = !split_frgb && dch(0) % 32 == 0;
   if (fused_frgb)
-    LAUNCH(k_from_rgb_fir(images, tptr<float>(e, "d.frgb.w"), tptr<float>(e, "d.frgb.b"), e->actA, e->dXd, P, e->R,
-                          dch(0), e->d_in_i8[0], s));
+    LAUNCH(k_from_rgb_fir(images, e->frgb_folded.data(), e->actA, e->dXd, P, e->R, dch(0), e->d_in_i8[0], s));
   else
     LAUNCH(k_from_rgb(images, tptr<float>(e, "d.frgb.w"), tptr<float>(e, "d.frgb.b"), e->actA, P, e->R, dch(0),
                       e->d_in_i8[0], s));
@@ -926,6 +954,27 @@ int check_pop(glass_engine* e, int pop) {
     return fail(GLASS_ERR_ARG, "population %d / batch_size %d needs more noise groups than the %d allocated", pop,
                 e->cfg.batch_size, e->max_groups);
   if (e->plan_pop != pop) RC(build_plan(e, pop));
+  return GLASS_OK;
+}
+
+// The graph body: one evaluation from e->z32 / e->noise to e->neg_sim / e->hinge on stream `s` (in capture).  The
+// CLIP tower and the discriminator both depend only on the images, so they are captured as parallel branches
+// (CLIP on the side stream): its small GEMMs fill the SMs that the discriminator's kernel tails leave idle.
+int evaluate_body(glass_engine* e, int pop, cudaStream_t s) {
+  static const bool no_fork = getenv("GLASS_DEBUG_NO_FORK") != nullptr;
+  RC(run_generator(e, e->z32, pop, nullptr, e->images, s, true));
+  const bool fork = e->cfg.use_discriminator && !no_fork;
+  cudaStream_t cs = fork ? e->side_stream : s;
+  if (fork) {
+    CUDA_OK(cudaEventRecord(e->ev_fork, s));
+    CUDA_OK(cudaStreamWaitEvent(cs, e->ev_fork, 0));
+  }
+  RC(run_clip(e, e->images, pop, e->sim, e->neg_sim, cs));
+  if (e->cfg.use_discriminator) RC(run_discriminator(e, e->images, pop, e->dlogits, e->hinge, s));
+  if (fork) {
+    CUDA_OK(cudaEventRecord(e->ev_join, cs));
+    CUDA_OK(cudaStreamWaitEvent(s, e->ev_join, 0));
+  }
   return GLASS_OK;
 }
 
@@ -1024,6 +1073,10 @@ int glass_finalize(glass_engine* e) {
   layout_workspace(e, e->arena);
   e->ev.resize(512);
   for (auto& ev : e->ev) CUDA_OK(cudaEventCreate(&ev));
+  CUDA_OK(cudaStreamCreateWithFlags(&e->cap_stream, cudaStreamNonBlocking));
+  CUDA_OK(cudaStreamCreateWithFlags(&e->side_stream, cudaStreamNonBlocking));
+  CUDA_OK(cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming));
+  CUDA_OK(cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming));
   e->finalized = true;
   return GLASS_OK;
 }
@@ -1042,6 +1095,11 @@ int glass_destroy(glass_engine* e) {
   for (auto& kv : e->tensors) cudaFree(kv.second.ptr);
   if (e->arena.base) cudaFree(e->arena.base);
   for (auto& ev : e->ev) cudaEventDestroy(ev);
+  drop_graph(e);
+  if (e->ev_fork) cudaEventDestroy(e->ev_fork);
+  if (e->ev_join) cudaEventDestroy(e->ev_join);
+  if (e->cap_stream) cudaStreamDestroy(e->cap_stream);
+  if (e->side_stream) cudaStreamDestroy(e->side_stream);
   delete e;
   return GLASS_OK;
 }
@@ -1076,11 +1134,47 @@ int glass_evaluate_device(glass_engine* e, const float* z_dev, int32_t pop, cons
   RC(check_pop(e, pop));
   if (e->cfg.use_discriminator && hinge_dev == nullptr) return fail(GLASS_ERR_ARG, "hinge output is required");
   cudaStream_t s = (cudaStream_t)stream;
-  timing_begin(e);
-  RC(run_generator(e, z_dev, pop, noise, e->images, s));
-  RC(run_clip(e, e->images, pop, e->sim, neg_sim_dev, s));
-  if (e->cfg.use_discriminator) RC(run_discriminator(e, e->images, pop, e->dlogits, hinge_dev, s));
-  return timing_end(e, s);
+  static const bool no_graph_env = getenv("GLASS_DEBUG_NO_GRAPH") != nullptr;
+  const bool use_graph = !no_graph_env && !(e->cfg.flags & GLASS_FLAG_NO_GRAPH) && e->cfg.conv_impl == 0 &&
+                         !e->timing && !e->capture;
+  if (!use_graph || e->graph_evals++ == 0) {
+    timing_begin(e);
+    RC(run_generator(e, z_dev, pop, noise, e->images, s));
+    RC(run_clip(e, e->images, pop, e->sim, neg_sim_dev, s));
+    if (e->cfg.use_discriminator) RC(run_discriminator(e, e->images, pop, e->dlogits, hinge_dev, s));
+    return timing_end(e, s);
+  }
+  // per-call inputs go to the engine's fixed buffers on the caller's stream; the graph reads only those
+  RC(fill_noise(e, pop, noise, s));
+  if (z_dev != e->z32)
+    CUDA_OK(cudaMemcpyAsync(e->z32, z_dev, (size_t)pop * e->cfg.latent_size * 4, cudaMemcpyDeviceToDevice, s));
+  if (e->graph_exec == nullptr) {
+    const int64_t before = e->launches;
+    cudaGraph_t graph = nullptr;
+    CUDA_OK(cudaStreamBeginCapture(e->cap_stream, cudaStreamCaptureModeThreadLocal));
+    int rc = evaluate_body(e, pop, e->cap_stream);
+    cudaError_t err = cudaStreamEndCapture(e->cap_stream, &graph);
+    e->graph_launches = e->launches - before;
+    e->launches = before;
+    if (rc != GLASS_OK) {
+      if (graph) cudaGraphDestroy(graph);
+      return rc;
+    }
+    if (err != cudaSuccess) return fail(GLASS_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(err));
+    err = cudaGraphInstantiate(&e->graph_exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (err != cudaSuccess) {
+      e->graph_exec = nullptr;
+      return fail(GLASS_ERR_CUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(err));
+    }
+  }
+  CUDA_OK(cudaGraphLaunch(e->graph_exec, s));
+  e->launches += e->graph_launches;
+  if (neg_sim_dev != e->neg_sim)
+    CUDA_OK(cudaMemcpyAsync(neg_sim_dev, e->neg_sim, (size_t)pop * 4, cudaMemcpyDeviceToDevice, s));
+  if (e->cfg.use_discriminator && hinge_dev != e->hinge)
+    CUDA_OK(cudaMemcpyAsync(hinge_dev, e->hinge, (size_t)pop * 4, cudaMemcpyDeviceToDevice, s));
+  return GLASS_OK;
 }
 
 int glass_evaluate_host(glass_engine* e, const double* x, int32_t pop, const glass_noise* noise, float* neg_sim,

@@ -62,9 +62,11 @@ cudaError_t k_final_cosine(const __half* tokens, const float* lw, const float* l
 // out_i8: write the channel-group-interleaved layout [P][R][C/8][R][8] instead of NHWC
 cudaError_t k_from_rgb(const float* images, const float* Wt, const float* bias, __half* out, int P, int R, int C,
                        int out_i8, cudaStream_t s);
-// k_from_rgb fused with k_fir_down of the first block (same values bit for bit): writes x AND its FIR/stride-2 copy
-cudaError_t k_from_rgb_fir(const float* images, const float* Wt, const float* bias, __half* xout, __half* down, int P,
-                           int R, int C, int out_i8, cudaStream_t s);
+// k_from_rgb fused with k_fir_down of the first block: writes x AND its FIR/stride-2 copy.  folded_host: HOST array
+// [4][C] = {2 sqrt2 W_r, 2 sqrt2 W_g, 2 sqrt2 W_b, sqrt2 (bias - sum W)} (passed to the kernel by value: the weights
+// are constant-bank operands of the FFMAs)
+cudaError_t k_from_rgb_fir(const float* images, const float* folded_host, __half* xout, __half* down, int P, int R,
+                           int C, int out_i8, cudaStream_t s);
 // projection path FIR (pad 1) sampled at stride 2 (modules.py:1204-1220, 1243-1246): [N,H,W,C] -> [N,H/2,W/2,C]
 // in_i8: x is channel-group-interleaved [N][H][C/8][W][8]; the output is always NHWC
 cudaError_t k_fir_down(const __half* x, __half* out, int N, int H, int W, int C, int in_i8, cudaStream_t s);

@@ -71,6 +71,9 @@ typedef struct glass_config {
 #define GLASS_FLAG_NO_I8_LAYOUT 8      /* keep every activation NHWC (MODE 1 / pixel pairs for those layers) */
 /* The ViT attention core (QK^T, softmax, PV) runs as tcgen05.mma out of TMEM (attention_tc.cu). */
 #define GLASS_FLAG_SIMT_ATTENTION 16   /* use the scalar shared-memory kernel instead (cross-check) */
+/* glass_evaluate_device / glass_evaluate_host replay one CUDA graph per launch plan (built on the second evaluation;
+ * CLIP and the discriminator as parallel branches).  The facade calls always launch eagerly. */
+#define GLASS_FLAG_NO_GRAPH 32         /* launch every kernel eagerly */
 
 /* -- lifetime ------------------------------------------------------------- */
 /* Replaces Generator.__init__ (generator.py:12-27): allocate the engine. */
