@@ -104,7 +104,7 @@ attention_tc_kernel(const __half* __restrict__ qkv, __half* __restrict__ out, in
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (tid == 0) {
+  if (warp == 0 && elect_one()) {
 #pragma unroll
     for (int k = 0; k < kAtHd / 16; ++k) {
       const uint64_t da = make_smem_desc_noswz(smem_u32(sQ) + k * 2 * kAtLbo, kAtLbo, kAtSbo64);
@@ -158,7 +158,7 @@ attention_tc_kernel(const __half* __restrict__ qkv, __half* __restrict__ out, in
   __syncthreads();
   tc_fence_after();
 
-  if (tid == 0) {
+  if (warp == 0 && elect_one()) {
 #pragma unroll
     for (int k = 0; k < 128 / 16; ++k) {
       const uint64_t da = make_smem_desc_noswz(smem_u32(sP) + k * 2 * kAtLbo, kAtLbo, kAtSbo128);

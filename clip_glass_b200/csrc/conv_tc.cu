@@ -75,6 +75,7 @@ constexpr EpiSpec kEpiSpecs[] = {
     {false, false, false, true, kStRegular, false, kActLrelu},    // 8: D conv1 + residual, NHWC store
     {false, false, false, false, kStRegular, false, kActNone},    // 9: D projection (1x1, linear)
     {false, false, false, false, kStRegular, false, kActLrelu},   // 10: D conv0 of the exact form, NHWC store
+    {false, false, false, false, kStS2D, true, kActLrelu},        // 11: D conv0, space-to-depth I8 (feeds MODE 6)
 };
 constexpr int kNumEpiSpecs = sizeof(kEpiSpecs) / sizeof(kEpiSpecs[0]);
 
@@ -109,13 +110,21 @@ struct Cfg {
   // trip through the producer / MMA / epilogue bookkeeping; their accumulators sit side by side in TMEM.  Halves the
   // per-element bookkeeping of the epilogue-bound small-channel layers and gives every epilogue warp two independent
   // chunks to overlap.
-  static constexpr int kPairM = (MODE == 4 && BK <= 64) ? 2 : 1;
+  // MODE 6 ("I8 + streamed taps"): the I8 haloed box of MODE 4 for layers whose nine taps do NOT fit beside it in
+  //   shared memory (Cin = 128, BN = 64: 147 KB of weights).  The input box of a tile PAIR stays put while the nine
+  //   taps stream through a small ring of 64-channel chunks (one weight pass per 256 pixels).  Against MODE 0 the
+  //   L2->SM traffic of the folded D 512^2 down-conv drops from 435 KB to 115 KB per 128 pixels (it ran at the
+  //   TMA/L2 delivery limit: 60 GB per launch, profiles/).
+  static constexpr bool kI8 = (MODE == 4 || MODE == 6);
+  static constexpr int kBStages = (MODE == 6) ? 6 : 0;            // ring of streamed weight chunks
+  static constexpr int kPairM = ((MODE == 4 && BK <= 64) || MODE == 6) ? 2 : 1;
   static constexpr int kI8TW = 8, kI8TH = 16;
   static constexpr int kI8RowBytes = (kI8TW * kPairM + 2) * 16;                 // one (row, group): 10 or 18 pixels x 16 B
   static constexpr int kI8StageBytes = (kI8TH + 2) * (BK / 8) * kI8RowBytes;
   static constexpr int kStageBytes = MODE == 0 ? kABytes + kBBytes
-                                     : (MODE == 1 ? 3 * kCopyBytes : (MODE == 4 ? kI8StageBytes : kABytes));
-  static constexpr int kWBytes = MODE == 0 ? 0 : ((MODE == 1 || MODE == 4) ? 9 : 1) * kBBytes;   // resident taps
+                                     : (MODE == 1 ? 3 * kCopyBytes : (kI8 ? kI8StageBytes : kABytes));
+  static constexpr int kWBytes = MODE == 0 ? 0   // resident taps, or MODE 6's ring of weight chunks
+                                 : (MODE == 6 ? kBStages * kBChunkBytes : ((MODE == 1 || MODE == 4) ? 9 : 1) * kBBytes);
   // Epilogue warps: two per TMEM lane quarter (each owning half of the columns).  Four per quarter (16 warps, 96
   // registers/thread) was measured at P=64: it helps the wide resident-tap instance (G up 64->32 @1024^2: 4.23 ->
   // 3.56 ms) and costs 5-25 % on the streamed large-K instances (spills), so only that instance uses it.
@@ -153,7 +162,8 @@ __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" 
 template <bool kRgb, int kActT = -1>
 __device__ __forceinline__ void epilogue_fast16(const EpiParams& e, const float* __restrict__ par, int BN, int j0,
                                                 const uint32_t (&acc)[16], float nz, const __half* res_ptr,
-                                                __half* out_ptr, size_t out_half_stride, float (&rgb)[3]) {
+                                                __half* out_ptr, size_t out_half_stride, float (&rgb)[3],
+                                                const uint4* res_pre = nullptr) {
   const float4* sc = reinterpret_cast<const float4*>(par + 0 * BN + j0);
   const float4* sh = reinterpret_cast<const float4*>(par + 1 * BN + j0);
   const float4* os = reinterpret_cast<const float4*>(par + 2 * BN + j0);
@@ -192,9 +202,10 @@ __device__ __forceinline__ void epilogue_fast16(const EpiParams& e, const float*
       rgb[2] = fmaf(t[4 * g + 2], c.z, rgb[2]); rgb[2] = fmaf(t[4 * g + 3], c.w, rgb[2]);
     }
   }
-  if (res_ptr != nullptr) {
+  if (res_ptr != nullptr || res_pre != nullptr) {
     const uint4* rp = reinterpret_cast<const uint4*>(res_ptr);
-    const uint4 q0 = __ldg(rp), q1 = __ldg(rp + 1);
+    // res_pre: the 16 residual values were fetched before the accumulator wait (their DRAM latency is hidden)
+    const uint4 q0 = res_pre != nullptr ? res_pre[0] : __ldg(rp), q1 = res_pre != nullptr ? res_pre[1] : __ldg(rp + 1);
     const __half2* h0 = reinterpret_cast<const __half2*>(&q0);
     const __half2* h1 = reinterpret_cast<const __half2*>(&q1);
 #pragma unroll
@@ -240,7 +251,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   uint64_t* tmem_full = bars + 2 * C::kStages;
   uint64_t* tmem_empty = tmem_full + 2;
   uint64_t* w_bar = tmem_empty + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_bar + 1);
+  uint64_t* b_full = w_bar + 1;                 // MODE 6: ring of streamed weight chunks (kBStages == 0 otherwise)
+  uint64_t* b_empty = b_full + C::kBStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(b_empty + C::kBStages);
+  static_assert((2 * C::kStages + 5 + 2 * C::kBStages) * 8 + 8 <= 256, "barrier block overflows its 256 bytes");
   float* nscale_slot = reinterpret_cast<float*>(tmem_slot + 1);
 
   const int warp = threadIdx.x >> 5;
@@ -263,6 +277,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       mbar_init(&tmem_empty[s], C::kEpiWarps);
     }
     mbar_init(w_bar, 1);
+    for (int s = 0; s < C::kBStages; ++s) {
+      mbar_init(&b_full[s], 1);
+      mbar_init(&b_empty[s], 1);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -277,10 +295,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 
   if (warp == 0) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
+    if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
-      if (MODE != 0) {
+      int bstage = 0;
+      uint32_t bphase = 0;
+      if (MODE != 0 && MODE != 6) {
         // resident filter taps of this CTA's n-tile (grid is a multiple of n_tiles, so n_tile is fixed)
         const int n_tile = blockIdx.x % n_tiles;
         mbar_expect_tx(w_bar, p.taps * C::kBBytes);
@@ -289,14 +309,39 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             tma_load_3d(&map_b, smem_w + (tap * C::kKChunks + ch) * C::kBChunkBytes, w_bar, ch * C::kBKc, n_tile * BN,
                         tap);
       }
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      if (MODE == 6) {
+        // The box of tile i+1 is requested BEFORE the taps of tile i are streamed: the producer blocks on the weight
+        // ring while it streams, and an input box requested only after that would arrive a full L2 round trip late
+        // at every tile boundary.
+        auto load_box = [&](int tile) {
+          const TileCoord tc = decode_tile<kPow2>(p, tile, n_tiles);
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          mbar_expect_tx(&full_bar[stage], C::kI8StageBytes);
+          tma_load_4d(&map_a, smem + stage * C::kStageBytes, &full_bar[stage], (tc.tx * p.TW - 1) * 8, 0,
+                      tc.ty * p.TH - 1, tc.tn * p.TN);
+          if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+        };
+        const int n_tile = blockIdx.x % n_tiles;
+        if ((int)blockIdx.x < total_tiles) load_box(blockIdx.x);
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+          if (tile + (int)gridDim.x < total_tiles) load_box(tile + gridDim.x);
+          for (int tap = 0; tap < 9; ++tap)
+            for (int ch = 0; ch < C::kKChunks; ++ch) {
+              mbar_wait(&b_empty[bstage], bphase ^ 1);
+              mbar_expect_tx(&b_full[bstage], C::kBChunkBytes);
+              tma_load_3d(&map_b, smem_w + bstage * C::kBChunkBytes, &b_full[bstage], ch * C::kBKc, n_tile * BN, tap);
+              if (++bstage == C::kBStages) { bstage = 0; bphase ^= 1; }
+            }
+        }
+      }
+      for (int tile = blockIdx.x; MODE != 6 && tile < total_tiles; tile += gridDim.x) {
         const TileCoord tc = decode_tile<kPow2>(p, tile, n_tiles);
         const int n_tile = tc.n_tile;
         const int x0 = tc.tx * p.TW, y0 = tc.ty * p.TH, i0 = tc.tn * p.TN;
         if (MODE != 0) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * C::kStageBytes;
-          if (MODE == 4) {
+          if (C::kI8) {
             mbar_expect_tx(&full_bar[stage], C::kI8StageBytes);
             // coordinates: ((x0-1)*8 elements, group 0, row y0-1, image); out-of-image parts are zero-filled
             tma_load_4d(&map_a, sa, &full_bar[stage], (x0 - 1) * 8, 0, y0 - 1, i0);
@@ -328,11 +373,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
+    if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
-      if (MODE != 0) {
+      int bstage = 0;
+      uint32_t bphase = 0;
+      if (MODE != 0 && MODE != 6) {
         mbar_wait(w_bar, 0);
         tc_fence_after();
       }
@@ -347,6 +394,47 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * C::kStageBytes);
           const uint32_t sw = smem_u32(smem_w);
+          if (MODE == 6) {
+            // One thread issues 144 MMAs per tile pair: everything but two 32-bit adds per MMA is folded at compile
+            // time.  The loops are fully unrolled (18 weight chunks per tile is a multiple of the ring depth, so a
+            // chunk's ring slot is a constant), and operand descriptors are a per-stage base plus a constant: the
+            // start-address field is the low 14 bits (bytes >> 4) and cannot carry out while the operand lies inside
+            // the 227 KB window.  (Built per MMA at run time, the descriptor arithmetic of this single thread was the
+            // bottleneck: ~100 cycles per MMA against a 32-cycle tensor-pipe floor.)
+            constexpr uint32_t kLbo = C::kI8RowBytes;
+            constexpr uint32_t kSbo = (BK / 8) * C::kI8RowBytes;
+            constexpr int kPerChunk = C::kBKc / 16;
+            constexpr int kRing = C::kBStages > 0 ? C::kBStages : 1;      // (this branch is dead unless MODE == 6)
+            static_assert((9 * C::kKChunks) % kRing == 0, "ring slots must be compile-time constants");
+            const uint64_t da0 = make_smem_desc_noswz(sa, kLbo, kSbo);
+            const uint64_t db0 = make_smem_desc<C::kBKc>(sw);
+#pragma unroll
+            for (int tap = 0; tap < 9; ++tap) {
+#pragma unroll
+              for (int ch = 0; ch < C::kKChunks; ++ch) {
+                const int slot = (tap * C::kKChunks + ch) % kRing;                  // constant after unrolling
+                mbar_wait(&b_full[slot], bphase);
+                tc_fence_after();
+#pragma unroll
+                for (int h = 0; h < C::kPairM; ++h) {
+#pragma unroll
+                  for (int kk = 0; kk < kPerChunk; ++kk) {
+                    const int k = ch * kPerChunk + kk;
+                    const uint32_t a_off = (tap / 3) * kSbo + ((tap % 3) + 8 * h) * 16 + k * 2 * kLbo;
+                    const uint32_t b_off = slot * C::kBChunkBytes + kk * 32;
+                    tc_mma_f16(d_tmem + h * BN, da0 + (uint64_t)(a_off >> 4), db0 + (uint64_t)(b_off >> 4), C::kIdesc,
+                               (tap | k) != 0);
+                  }
+                }
+                tc_commit(&b_empty[slot]);
+                if (slot == kRing - 1) bphase ^= 1;
+              }
+            }
+            tc_commit(&empty_bar[stage]);
+            if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+            tc_commit(&tmem_full[as]);
+            continue;
+          }
           if (MODE == 4) {
             constexpr uint32_t kLbo = C::kI8RowBytes;                 // next 8-channel group
             constexpr uint32_t kSbo = (BK / 8) * C::kI8RowBytes;      // next image row (= next 8-pixel group)
@@ -421,7 +509,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     const int ry = rr / geo_w;
     const int rx = rr - ry * geo_w;         // tile h of a pair: pixel column rx + 8h
     // every row of a tile belongs to one image (always for I8 tiles and for the specialised layers)
-    const bool fast = (MODE == 4 || !S.generic) ? true : (p.TN == 1);
+    const bool fast = (C::kI8 || !S.generic) ? true : (p.TN == 1);
     const float gain = (S.generic ? (e.act == kActLrelu) : (S.act == kActLrelu)) ? kSqrt2 : 1.f;
     constexpr int kParts = C::kParts;
     constexpr int kHalf = BN / kParts;      // columns per warp
@@ -568,6 +656,21 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         const int i8_x0 = tc.tx * p.TW + rx;
         float nscale;
         asm volatile("ld.shared.f32 %0, [%1];" : "=f"(nscale) : "r"(smem_u32(nscale_slot)));
+        // Specialised residual layers fetch the whole tile's residual values NOW, before waiting for the accumulator:
+        // loaded chunk by chunk inside the math, every chunk exposed a full DRAM round trip and the epilogue, not the
+        // tensor pipe, paced the D conv1 layers (tensor pipe 36 % active in the 512^2 down-conv).
+        constexpr bool kResPre = !S.generic && S.residual;
+        uint4 resv[kResPre ? kPairM : 1][kResPre ? kChunks : 1][2];
+        if (kResPre) {
+#pragma unroll
+          for (int h = 0; h < kPairM; ++h)
+#pragma unroll
+            for (int c = 0; c < kChunks; ++c) {
+              const uint4* rp = reinterpret_cast<const uint4*>(res_row + (size_t)(8 * h) * p.Ntot + c * 16);
+              resv[kResPre ? h : 0][kResPre ? c : 0][0] = __ldg(rp);
+              resv[kResPre ? h : 0][kResPre ? c : 0][1] = __ldg(rp + 1);
+            }
+        }
         mbar_wait(&tmem_full[as], aphase);
         tc_fence_after();
         uint32_t acc[2][16];
@@ -616,10 +719,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
               } else if (out_row != nullptr) {
                 optr = out_row + h * out_row_hstep + c * 16;
               }
-              const __half* rptr = res_row != nullptr ? res_row + (size_t)(8 * h) * p.Ntot + c * 16 : nullptr;
+              const __half* rptr = (!kResPre && res_row != nullptr) ? res_row + (size_t)(8 * h) * p.Ntot + c * 16 : nullptr;
+              const uint4* rpre = kResPre ? resv[kResPre ? h : 0][kResPre ? c : 0] : nullptr;
               constexpr int kActT = S.generic ? -1 : S.act;
-              if (has_rgb) epilogue_fast16<true, kActT>(e, par, BN, j0, acc[ci & 1], nzc, rptr, optr, half_stride, rgb[h]);
-              else epilogue_fast16<false, kActT>(e, par, BN, j0, acc[ci & 1], nzc, rptr, optr, half_stride, rgb[h]);
+              if (has_rgb) epilogue_fast16<true, kActT>(e, par, BN, j0, acc[ci & 1], nzc, rptr, optr, half_stride, rgb[h], rpre);
+              else epilogue_fast16<false, kActT>(e, par, BN, j0, acc[ci & 1], nzc, rptr, optr, half_stride, rgb[h], rpre);
             }
           }
         }
@@ -794,6 +898,9 @@ cudaError_t launch_conv_tc(const ConvParams& p, const TmaMaps& maps, int num_sms
   GLASS_SPEC(128, 64, 2, 9)
   GLASS_SPEC(256, 64, 0, 9)
   GLASS_SPEC(128, 64, 0, 10)
+  GLASS_SPEC(32, 32, 4, 11)
+  GLASS_SPEC(64, 128, 6, 7)
+  GLASS_SPEC(64, 128, 6, 8)
 #undef GLASS_SPEC
 #define GLASS_CASE(bn, bk, md) \
   if (p.BN == bn && p.BK == bk && p.mode == md) return launch_one<bn, bk, md>(p, maps, num_sms, s);
@@ -816,6 +923,7 @@ cudaError_t launch_conv_tc(const ConvParams& p, const TmaMaps& maps, int num_sms
   GLASS_CASE(32, 64, 4)
   GLASS_CASE(64, 64, 4)
   GLASS_CASE(32, 128, 4)
+  GLASS_CASE(64, 128, 6)
   GLASS_CASE(32, 32, 2)
   GLASS_CASE(64, 32, 2)
   GLASS_CASE(128, 32, 2)

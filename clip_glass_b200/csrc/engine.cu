@@ -232,15 +232,16 @@ int make_conv(glass_engine* e, ConvLaunch* out, const __half* in, int Nimg, int 
   if (in_i8) {
     // channel-group-interleaved input: 8-wide x 16-tall tiles, one un-swizzled haloed box per tile (MODE 4)
     // Cin <= 64: tile pairs (two 8x16 tiles side by side share one box; conv_tc.cu Cfg::kPairM)
-    const int tw = Cin <= 64 ? 16 : 8;
+    const int tw = 16;
     if (gemm || table != nullptr || taps != 9 || (Cin != 32 && Cin != 64 && Cin != 128) || H < 16 || W < tw || H % 16 ||
         W % tw)
       return fail(GLASS_ERR_ARG, "I8 input layout needs a 3x3 conv with 32/64/128 channels on a >=16x16 grid");
-    p.mode = 4;
+    p.mode = Cin == 128 ? 6 : 4;       // 128 channels: the nine taps do not fit beside the box -> streamed (MODE 6)
     p.BK = Cin;                        // whole K of a tap in one stage
     p.TW = tw; p.TH = 16; p.TN = 1;
     p.tiles_x = W / tw; p.tiles_y = H / 16; p.tiles_n = Nimg;
-    while (p.BN > (Cin == 128 ? 32 : (Cin == 64 ? 64 : 128))) p.BN /= 2;   // nine resident taps + >= 2 stages must fit
+    while (p.BN > (Cin == 32 ? 128 : 64)) p.BN /= 2;   // nine resident taps (or the tile pair's box) + >= 2 stages must fit
+    if (p.mode == 6 && p.BN != 64) return fail(GLASS_ERR_ARG, "I8 input with 128 channels needs Ntot %% 64 == 0");
   } else if (!gemm && table == nullptr && (Cin == 32 || Cin == 64) && p.TW == 16 && p.TH == 8 && p.TN == 1 &&
              (taps == 9 || taps == 1)) {
     if (taps == 9) {
@@ -269,7 +270,7 @@ int make_conv(glass_engine* e, ConvLaunch* out, const __half* in, int Nimg, int 
   const uint64_t ndecl = (uint64_t)p.tiles_n * p.TN;
   uint64_t dims[4] = {(uint64_t)Cin, wdecl, (uint64_t)p.in_H, ndecl};
   uint64_t strides[3] = {(uint64_t)Cin * 2, (uint64_t)Cin * 2 * wdecl, (uint64_t)Cin * 2 * wdecl * p.in_H};
-  if (p.mode == 4) {
+  if (p.mode == 4 || p.mode == 6) {
     // [N][H][G][W][8] seen as dims (W*8, G, H, N); box ((TW+2)*8, G, TH+2, 1), no swizzle
     const uint64_t G = Cin / 8;
     uint64_t d4[4] = {(uint64_t)W * 8, G, (uint64_t)H, (uint64_t)Nimg};
@@ -414,10 +415,13 @@ void derive_arch(glass_engine* e) {
   e->d_c1_i8.clear();
   for (int b = 0; b + 1 < c.num_blocks; ++b) {
     const int Ci = e->gch[c.num_blocks - 1 - b];
-    // Measured slower (D0:c1 5.35 ms vs 4.45 ms at P=64): the nine resident 128-channel taps only leave room for
-    // BN = 32, which doubles the tile count of an epilogue-bound layer.  Kept behind GLASS_DEBUG_C1_I8 for round 2.
+    // 4*Ci = 128 channels: conv_tc MODE 6 (haloed I8 box per tile pair, the nine taps streamed through a ring).
+    // (MODE 4 with nine resident 128-channel taps only leaves room for BN = 32 and measured slower than the
+    // streamed NHWC form: 5.35 vs 4.45 ms at P=64.)  GLASS_DEBUG_C1_I8=0 keeps the space-to-depth tensor NHWC.
     const char* c1i8 = getenv("GLASS_DEBUG_C1_I8");
-    e->d_c1_i8.push_back((i8_ok && c1i8 && atoi(c1i8) && !e->d_exact[b] && Ci == 32 && (e->R >> b) / 2 >= 16) ? 1 : 0);
+    const bool on = c1i8 == nullptr || atoi(c1i8) != 0;
+    e->d_c1_i8.push_back((i8_ok && on && !e->d_exact[b] && Ci == 32 && (e->R >> b) / 2 >= 16 &&
+                          e->gch[c.num_blocks - 2 - b] % 64 == 0) ? 1 : 0);
   }
   const bool pair_ok = (c.flags & GLASS_FLAG_NO_PAIR_PACK) == 0 && c.conv_impl == 0;
   e->g_pair.clear();

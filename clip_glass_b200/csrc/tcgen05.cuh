@@ -12,6 +12,18 @@ constexpr long long kWaitLimitCycles = 4000000000ll;   // ~2 s at 1.9 GHz
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
+// One lane of a CONVERGED warp, chosen by the hardware.  Unlike `lane == 0`, the compiler knows that the guarded
+// region runs on a single thread, so instructions with uniform-register operands (UTCHMMA, UTMALDG, UTCBAR) are
+// emitted directly instead of inside a per-instruction elect/broadcast loop (~80 cycles per MMA, measured).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.b32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
