@@ -159,33 +159,42 @@ __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" 
 //   t = act(acc*scale + shift + nz) ; rgb += t*rgbw ; t = (t + residual) * oscale ; store fp16
 // (the sqrt(2) gain of lrelu is folded into scale/shift/nz: lrelu(a)*g == lrelu(a*g) for g > 0)
 // kActT: -1 = activation and fp16 pre-rounding from EpiParams at run time; kActNone / kActLrelu = fixed, no rounding
-template <bool kRgb, int kActT = -1>
-__device__ __forceinline__ void epilogue_fast16(const EpiParams& e, const float* __restrict__ par, int BN, int j0,
-                                                const uint32_t (&acc)[16], float nz, const __half* res_ptr,
-                                                __half* out_ptr, size_t out_half_stride, float (&rgb)[3],
-                                                const uint4* res_pre = nullptr) {
+// NT = 2: the two tiles of a pair in one pass -- every parameter vector is read from shared memory ONCE for both
+// tiles.  (The broadcast LDS.128 of the staged parameters were 42 % of the shared-memory wavefronts of the 32-channel
+// 1024^2 layers, whose LSU data pipe ran at 89 %: profiles/.)
+template <int NT, bool kRgb, int kActT = -1>
+__device__ __forceinline__ void epilogue_fastN(const EpiParams& e, const float* __restrict__ par, int BN, int j0,
+                                               const uint32_t (*acc)[16], const float* nz, const __half* const* res_ptr,
+                                               __half* const* out_ptr, size_t out_half_stride, float (*rgb)[3],
+                                               const uint4* const* res_pre) {
   const float4* sc = reinterpret_cast<const float4*>(par + 0 * BN + j0);
   const float4* sh = reinterpret_cast<const float4*>(par + 1 * BN + j0);
   const float4* os = reinterpret_cast<const float4*>(par + 2 * BN + j0);
-  float t[16];
+  float t[NT][16];
 #pragma unroll
   for (int g = 0; g < 4; ++g) {
     const float4 a = sc[g], b = sh[g];
-    t[4 * g + 0] = fmaf(__uint_as_float(acc[4 * g + 0]), a.x, b.x + nz);
-    t[4 * g + 1] = fmaf(__uint_as_float(acc[4 * g + 1]), a.y, b.y + nz);
-    t[4 * g + 2] = fmaf(__uint_as_float(acc[4 * g + 2]), a.z, b.z + nz);
-    t[4 * g + 3] = fmaf(__uint_as_float(acc[4 * g + 3]), a.w, b.w + nz);
+#pragma unroll
+    for (int n = 0; n < NT; ++n) {
+      t[n][4 * g + 0] = fmaf(__uint_as_float(acc[n][4 * g + 0]), a.x, b.x + nz[n]);
+      t[n][4 * g + 1] = fmaf(__uint_as_float(acc[n][4 * g + 1]), a.y, b.y + nz[n]);
+      t[n][4 * g + 2] = fmaf(__uint_as_float(acc[n][4 * g + 2]), a.z, b.z + nz[n]);
+      t[n][4 * g + 3] = fmaf(__uint_as_float(acc[n][4 * g + 3]), a.w, b.w + nz[n]);
+    }
   }
-  if (kActT < 0 && e.round_fp16_before_act) {
 #pragma unroll
-    for (int j = 0; j < 16; ++j) t[j] = __half2float(__float2half_rn(t[j]));
-  }
-  if (kActT == kActLrelu || (kActT < 0 && e.act == kActLrelu)) {
+  for (int n = 0; n < NT; ++n) {
+    if (kActT < 0 && e.round_fp16_before_act) {
 #pragma unroll
-    for (int j = 0; j < 16; ++j) t[j] = fmaxf(t[j], 0.2f * t[j]);
-  } else if (kActT < 0 && e.act == kActQuickGelu) {
+      for (int j = 0; j < 16; ++j) t[n][j] = __half2float(__float2half_rn(t[n][j]));
+    }
+    if (kActT == kActLrelu || (kActT < 0 && e.act == kActLrelu)) {
 #pragma unroll
-    for (int j = 0; j < 16; ++j) t[j] = t[j] / (1.f + __expf(-1.702f * t[j]));
+      for (int j = 0; j < 16; ++j) t[n][j] = fmaxf(t[n][j], 0.2f * t[n][j]);
+    } else if (kActT < 0 && e.act == kActQuickGelu) {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) t[n][j] = t[n][j] / (1.f + __expf(-1.702f * t[n][j]));
+    }
   }
   if (kRgb) {
     const float4* r0 = reinterpret_cast<const float4*>(par + 3 * BN + j0);
@@ -194,42 +203,71 @@ __device__ __forceinline__ void epilogue_fast16(const EpiParams& e, const float*
 #pragma unroll
     for (int g = 0; g < 4; ++g) {
       const float4 a = r0[g], b = r1[g], c = r2[g];
-      rgb[0] = fmaf(t[4 * g + 0], a.x, rgb[0]); rgb[0] = fmaf(t[4 * g + 1], a.y, rgb[0]);
-      rgb[0] = fmaf(t[4 * g + 2], a.z, rgb[0]); rgb[0] = fmaf(t[4 * g + 3], a.w, rgb[0]);
-      rgb[1] = fmaf(t[4 * g + 0], b.x, rgb[1]); rgb[1] = fmaf(t[4 * g + 1], b.y, rgb[1]);
-      rgb[1] = fmaf(t[4 * g + 2], b.z, rgb[1]); rgb[1] = fmaf(t[4 * g + 3], b.w, rgb[1]);
-      rgb[2] = fmaf(t[4 * g + 0], c.x, rgb[2]); rgb[2] = fmaf(t[4 * g + 1], c.y, rgb[2]);
-      rgb[2] = fmaf(t[4 * g + 2], c.z, rgb[2]); rgb[2] = fmaf(t[4 * g + 3], c.w, rgb[2]);
-    }
-  }
-  if (res_ptr != nullptr || res_pre != nullptr) {
-    const uint4* rp = reinterpret_cast<const uint4*>(res_ptr);
-    // res_pre: the 16 residual values were fetched before the accumulator wait (their DRAM latency is hidden)
-    const uint4 q0 = res_pre != nullptr ? res_pre[0] : __ldg(rp), q1 = res_pre != nullptr ? res_pre[1] : __ldg(rp + 1);
-    const __half2* h0 = reinterpret_cast<const __half2*>(&q0);
-    const __half2* h1 = reinterpret_cast<const __half2*>(&q1);
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const float2 a = __half22float2(h0[j]), b = __half22float2(h1[j]);
-      t[2 * j] += a.x; t[2 * j + 1] += a.y; t[8 + 2 * j] += b.x; t[8 + 2 * j + 1] += b.y;
+      for (int n = 0; n < NT; ++n) {
+        rgb[n][0] = fmaf(t[n][4 * g + 0], a.x, rgb[n][0]); rgb[n][0] = fmaf(t[n][4 * g + 1], a.y, rgb[n][0]);
+        rgb[n][0] = fmaf(t[n][4 * g + 2], a.z, rgb[n][0]); rgb[n][0] = fmaf(t[n][4 * g + 3], a.w, rgb[n][0]);
+        rgb[n][1] = fmaf(t[n][4 * g + 0], b.x, rgb[n][1]); rgb[n][1] = fmaf(t[n][4 * g + 1], b.y, rgb[n][1]);
+        rgb[n][1] = fmaf(t[n][4 * g + 2], b.z, rgb[n][1]); rgb[n][1] = fmaf(t[n][4 * g + 3], b.w, rgb[n][1]);
+        rgb[n][2] = fmaf(t[n][4 * g + 0], c.x, rgb[n][2]); rgb[n][2] = fmaf(t[n][4 * g + 1], c.y, rgb[n][2]);
+        rgb[n][2] = fmaf(t[n][4 * g + 2], c.z, rgb[n][2]); rgb[n][2] = fmaf(t[n][4 * g + 3], c.w, rgb[n][2]);
+      }
     }
   }
-  if (out_ptr != nullptr) {
-    uint4 w0, w1;
-    __half2* h0 = reinterpret_cast<__half2*>(&w0);
-    __half2* h1 = reinterpret_cast<__half2*>(&w1);
 #pragma unroll
-    for (int g = 0; g < 2; ++g) {
-      const float4 a = os[g], b = os[g + 2];
-      h0[2 * g] = __floats2half2_rn(t[4 * g] * a.x, t[4 * g + 1] * a.y);
-      h0[2 * g + 1] = __floats2half2_rn(t[4 * g + 2] * a.z, t[4 * g + 3] * a.w);
-      h1[2 * g] = __floats2half2_rn(t[8 + 4 * g] * b.x, t[8 + 4 * g + 1] * b.y);
-      h1[2 * g + 1] = __floats2half2_rn(t[8 + 4 * g + 2] * b.z, t[8 + 4 * g + 3] * b.w);
+  for (int n = 0; n < NT; ++n) {
+    if (res_ptr[n] != nullptr || res_pre[n] != nullptr) {
+      const uint4* rp = reinterpret_cast<const uint4*>(res_ptr[n]);
+      // res_pre: the 16 residual values were fetched before the accumulator wait (their DRAM latency is hidden)
+      const uint4 q0 = res_pre[n] != nullptr ? res_pre[n][0] : __ldg(rp);
+      const uint4 q1 = res_pre[n] != nullptr ? res_pre[n][1] : __ldg(rp + 1);
+      const __half2* h0 = reinterpret_cast<const __half2*>(&q0);
+      const __half2* h1 = reinterpret_cast<const __half2*>(&q1);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 a = __half22float2(h0[j]), b = __half22float2(h1[j]);
+        t[n][2 * j] += a.x; t[n][2 * j + 1] += a.y; t[n][8 + 2 * j] += b.x; t[n][8 + 2 * j + 1] += b.y;
+      }
     }
-    // channels [0,8) and [8,16) of the chunk: adjacent in NHWC, one channel-group plane apart in the I8 layout
-    *reinterpret_cast<uint4*>(out_ptr) = w0;
-    *reinterpret_cast<uint4*>(out_ptr + out_half_stride) = w1;
   }
+  bool any_out = false;
+#pragma unroll
+  for (int n = 0; n < NT; ++n) any_out |= out_ptr[n] != nullptr;
+  if (any_out) {
+    float4 osv[4];
+#pragma unroll
+    for (int g = 0; g < 4; ++g) osv[g] = os[g];
+#pragma unroll
+    for (int n = 0; n < NT; ++n) {
+      if (out_ptr[n] == nullptr) continue;
+      uint4 w0, w1;
+      __half2* h0 = reinterpret_cast<__half2*>(&w0);
+      __half2* h1 = reinterpret_cast<__half2*>(&w1);
+#pragma unroll
+      for (int g = 0; g < 2; ++g) {
+        const float4 a = osv[g], b = osv[g + 2];
+        h0[2 * g] = __floats2half2_rn(t[n][4 * g] * a.x, t[n][4 * g + 1] * a.y);
+        h0[2 * g + 1] = __floats2half2_rn(t[n][4 * g + 2] * a.z, t[n][4 * g + 3] * a.w);
+        h1[2 * g] = __floats2half2_rn(t[n][8 + 4 * g] * b.x, t[n][8 + 4 * g + 1] * b.y);
+        h1[2 * g + 1] = __floats2half2_rn(t[n][8 + 4 * g + 2] * b.z, t[n][8 + 4 * g + 3] * b.w);
+      }
+      // channels [0,8) and [8,16) of the chunk: adjacent in NHWC, one channel-group plane apart in the I8 layout
+      *reinterpret_cast<uint4*>(out_ptr[n]) = w0;
+      *reinterpret_cast<uint4*>(out_ptr[n] + out_half_stride) = w1;
+    }
+  }
+}
+
+template <bool kRgb, int kActT = -1>
+__device__ __forceinline__ void epilogue_fast16(const EpiParams& e, const float* __restrict__ par, int BN, int j0,
+                                                const uint32_t (&acc)[16], float nz, const __half* res_ptr,
+                                                __half* out_ptr, size_t out_half_stride, float (&rgb)[3],
+                                                const uint4* res_pre = nullptr) {
+  const __half* rp[1] = {res_ptr};
+  __half* op[1] = {out_ptr};
+  const uint4* pre[1] = {res_pre};
+  const float nzv[1] = {nz};
+  epilogue_fastN<1, kRgb, kActT>(e, par, BN, j0, &acc, nzv, rp, op, out_half_stride, &rgb, pre);
 }
 
 template <int BN, int BK, int MODE, int EPI>
@@ -673,11 +711,74 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         }
         mbar_wait(&tmem_full[as], aphase);
         tc_fence_after();
+        // output address of chunk c of tile h of the pair (nullptr: nothing stored)
+        auto out_addr = [&](int h, int c, size_t& half_stride) -> __half* {
+          const int i8_x = i8_x0 + 8 * h;
+          const int j0 = half * kHalf + c * 16;
+          half_stride = 8;
+          if (d2s) {
+            // column n -> phase (py,px) and channel o; output pixel (2y+py, 2x+px)
+            const int n0 = n_tile * BN + j0;
+            const int ph = cout_p2 ? (n0 >> cout_sh) : (n0 / e.Cout);
+            const int o0 = n0 - ph * e.Cout;
+            if (!has_out) return nullptr;
+            if (out_i8) {
+              const int yo = 2 * (tc.ty * p.TH + ry) + (ph >> 1), xo = 2 * i8_x + (ph & 1);
+              half_stride = (size_t)(2 * W) * 8;
+              return e.out + (((size_t)(img * 2 * H + yo) * i8_groups + (o0 >> 3)) * (2 * W) + xo) * 8;
+            }
+            return e.out + (size_t)(d2s_pix + 16 * h + (ph >> 1) * (2 * W) + (ph & 1)) * e.Cout + o0;
+          }
+          if (out_i8 && s2d && has_out) {
+            // space-to-depth + I8: [n][y/2][(phase*Ntot + o)/8][x/2][8] with 4*Ntot channels per cell
+            const int yy = tc.ty * p.TH + ry;
+            const int k0 = ((yy & 1) * 2 + (i8_x & 1)) * p.Ntot + n_first + c * 16;
+            half_stride = (size_t)(W >> 1) * 8;
+            return e.out + (((size_t)(img * (H >> 1) + (yy >> 1)) * (p.Ntot >> 1) + (k0 >> 3)) * (W >> 1) + (i8_x >> 1)) * 8;
+          }
+          if (out_i8 && has_out) {
+            const int o0 = n_first + c * 16;                     // regular store: Ntot == Cout
+            half_stride = (size_t)W * 8;
+            return e.out + (((size_t)i8_row * i8_groups + (o0 >> 3)) * W + i8_x) * 8;
+          }
+          if (out_row != nullptr) return out_row + h * out_row_hstep + c * 16;
+          return nullptr;
+        };
+        constexpr int kActT = S.generic ? -1 : S.act;
+        // specialised pair layers: both tiles of the pair per chunk, parameters read once (epilogue_fastN<2>)
+        constexpr bool kPairFused = (kPairM == 2) && !S.generic;
+        if constexpr (kPairFused) {
+          uint32_t accp[2][2][16];                     // [pipeline buffer][tile of the pair]
+          tc_ld16_issue(taddr, accp[0][0]);
+          tc_ld16_issue(taddr + BN, accp[0][1]);
+#pragma unroll
+          for (int c = 0; c < kChunks; ++c) {
+            tc_ld_wait();
+            if (c + 1 < kChunks) {
+              tc_ld16_issue(taddr + (c + 1) * 16, accp[(c + 1) & 1][0]);
+              tc_ld16_issue(taddr + BN + (c + 1) * 16, accp[(c + 1) & 1][1]);
+            }
+            if (valid && !(p.debug_skip & 1)) {
+              const int j0 = half * kHalf + c * 16;
+              size_t half_stride = 8, hs1 = 8;
+              __half* optr[2] = {out_addr(0, c, half_stride), out_addr(1, c, hs1)};
+              const float nzc[2] = {nscale * nz_cur[0][d2s ? c : 0], nscale * nz_cur[1][d2s ? c : 0]};
+              const __half* rptr[2];
+              const uint4* rpre[2];
+#pragma unroll
+              for (int h = 0; h < 2; ++h) {
+                rptr[h] = (!kResPre && res_row != nullptr) ? res_row + (size_t)(8 * h) * p.Ntot + c * 16 : nullptr;
+                rpre[h] = kResPre ? resv[kResPre ? h : 0][kResPre ? c : 0] : nullptr;
+              }
+              if (has_rgb) epilogue_fastN<2, true, kActT>(e, par, BN, j0, accp[c & 1], nzc, rptr, optr, half_stride, rgb, rpre);
+              else epilogue_fastN<2, false, kActT>(e, par, BN, j0, accp[c & 1], nzc, rptr, optr, half_stride, rgb, rpre);
+            }
+          }
+        } else {
         uint32_t acc[2][16];
         tc_ld16_issue(taddr, acc[0]);
 #pragma unroll
         for (int h = 0; h < kPairM; ++h) {
-          const int i8_x = i8_x0 + 8 * h;
 #pragma unroll
           for (int c = 0; c < kChunks; ++c) {
             constexpr int kTotal = kPairM * kChunks;
@@ -690,42 +791,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             if (valid && !(p.debug_skip & 1)) {
               const int j0 = half * kHalf + c * 16;
               const float nzc = nscale * nz_cur[h][d2s ? c : 0];
-              __half* optr = nullptr;
               size_t half_stride = 8;
-              if (d2s) {
-                // column n -> phase (py,px) and channel o; output pixel (2y+py, 2x+px)
-                const int n0 = n_tile * BN + j0;
-                const int ph = cout_p2 ? (n0 >> cout_sh) : (n0 / e.Cout);
-                const int o0 = n0 - ph * e.Cout;
-                if (has_out) {
-                  if (out_i8) {
-                    const int yo = 2 * (tc.ty * p.TH + ry) + (ph >> 1), xo = 2 * i8_x + (ph & 1);
-                    half_stride = (size_t)(2 * W) * 8;
-                    optr = e.out + (((size_t)(img * 2 * H + yo) * i8_groups + (o0 >> 3)) * (2 * W) + xo) * 8;
-                  } else {
-                    optr = e.out + (size_t)(d2s_pix + 16 * h + (ph >> 1) * (2 * W) + (ph & 1)) * e.Cout + o0;
-                  }
-                }
-              } else if (out_i8 && s2d && has_out) {
-                // space-to-depth + I8: [n][y/2][(phase*Ntot + o)/8][x/2][8] with 4*Ntot channels per cell
-                const int yy = tc.ty * p.TH + ry;
-                const int k0 = ((yy & 1) * 2 + (i8_x & 1)) * p.Ntot + n_first + c * 16;
-                half_stride = (size_t)(W >> 1) * 8;
-                optr = e.out + (((size_t)(img * (H >> 1) + (yy >> 1)) * (p.Ntot >> 1) + (k0 >> 3)) * (W >> 1) + (i8_x >> 1)) * 8;
-              } else if (out_i8 && has_out) {
-                const int o0 = n_first + c * 16;                     // regular store: Ntot == Cout
-                half_stride = (size_t)W * 8;
-                optr = e.out + (((size_t)i8_row * i8_groups + (o0 >> 3)) * W + i8_x) * 8;
-              } else if (out_row != nullptr) {
-                optr = out_row + h * out_row_hstep + c * 16;
-              }
+              __half* optr = out_addr(h, c, half_stride);
               const __half* rptr = (!kResPre && res_row != nullptr) ? res_row + (size_t)(8 * h) * p.Ntot + c * 16 : nullptr;
               const uint4* rpre = kResPre ? resv[kResPre ? h : 0][kResPre ? c : 0] : nullptr;
-              constexpr int kActT = S.generic ? -1 : S.act;
               if (has_rgb) epilogue_fast16<true, kActT>(e, par, BN, j0, acc[ci & 1], nzc, rptr, optr, half_stride, rgb[h], rpre);
               else epilogue_fast16<false, kActT>(e, par, BN, j0, acc[ci & 1], nzc, rptr, optr, half_stride, rgb[h], rpre);
             }
           }
+        }
         }
       } else {
         // ---- generic path (tiles that span several images: 4x4 / 8x8 layers; never a tile pair) ----
