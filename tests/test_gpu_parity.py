@@ -149,6 +149,64 @@ def test_full_size_properties(full_engine):
     assert np.isfinite(f_all).all() and np.abs(f_all).max() <= 1.0 and (h_all >= 0).all()
 
 
+def _full_scores(flags=0, env=None, evals=1):
+    """Scores of the full-size fixture from a fresh engine built with `flags` / environment knobs."""
+    from clip_glass_b200.engine import GlassEngine
+    inp = build_inputs("full")
+    gold = load_golden("full")
+    old = {k: os.environ.get(k) for k in (env or {})}
+    os.environ.update(env or {})
+    try:
+        eng = GlassEngine(inp["gan"], inp["clip"], inp["g_sd"], inp["d_sd"], inp["c_sd"], batch_size=inp["batch"],
+                          max_population=4, flags=flags)
+    finally:
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+    eng.set_text_features(torch.from_numpy(gold["text_features"]))
+    outs = [eng.evaluate(inp["x"], noise=inp["noise"]) for _ in range(evals)]
+    eng.close()
+    return outs, gold
+
+
+def test_tcgen05_attention_against_simt_cross_check():
+    """attention_tc.cu (QK^T / PV on the tensor cores, P rounded to fp16 like the reference's fp16 softmax output)
+    against the scalar shared-memory kernel (GLASS_FLAG_SIMT_ATTENTION = 16) on the full ViT-B/32: the final cosine
+    moves by far less than the 1e-3 budget."""
+    (tc,), gold = _full_scores(flags=0)
+    (simt,), _ = _full_scores(flags=16)
+    np.testing.assert_allclose(tc[0], simt[0], rtol=3e-4)
+    np.testing.assert_array_equal(tc[1], simt[1])          # the discriminator does not depend on the CLIP tower
+    sim32 = gold["sim_oracle_fp32"]
+    assert np.abs(-simt[0] - sim32).max() / np.abs(sim32).min() <= 1e-3
+
+
+def test_graph_replay_equals_eager_launches():
+    """glass_evaluate_host: the first evaluation of a plan launches eagerly, later ones replay a CUDA graph with
+    the CLIP tower and the discriminator as parallel branches -- bit-identical scores, and identical to an engine
+    that never builds a graph (GLASS_FLAG_NO_GRAPH = 32)."""
+    outs, _ = _full_scores(flags=0, evals=4)
+    for o in outs[1:]:
+        np.testing.assert_array_equal(o[0], outs[0][0])
+        np.testing.assert_array_equal(o[1], outs[0][1])
+    (eager,), _ = _full_scores(flags=32)
+    np.testing.assert_array_equal(eager[0], outs[0][0])
+    np.testing.assert_array_equal(eager[1], outs[0][1])
+
+
+def test_streamed_tap_i8_downconv_against_nhwc_form():
+    """conv_tc MODE 6 (D 512^2 folded down-conv on the I8 space-to-depth tensor, taps streamed through a ring)
+    against the same layer on the NHWC tensor with MODE 0 (GLASS_DEBUG_C1_I8=0): same products, different
+    accumulation order only."""
+    (m6,), gold = _full_scores()
+    (m0,), _ = _full_scores(env={"GLASS_DEBUG_C1_I8": "0"})
+    np.testing.assert_array_equal(m6[0], m0[0])            # G and CLIP are untouched
+    np.testing.assert_allclose(m6[1], m0[1], atol=5e-4)
+    np.testing.assert_allclose(m6[1], gold["F"][:, 1], atol=2e-3)
+
+
 def test_population_must_be_multiple_of_batch(full_engine):
     eng, inp, gold = full_engine
     with pytest.raises(AssertionError):            # models.py:112,124
