@@ -974,6 +974,7 @@ cudaError_t launch_conv_tc(const ConvParams& p, const TmaMaps& maps, int num_sms
   GLASS_SPEC(128, 64, 0, 10)
   GLASS_SPEC(32, 32, 4, 11)
   GLASS_SPEC(64, 128, 6, 7)
+  GLASS_SPEC(32, 128, 4, 7)
   GLASS_SPEC(64, 128, 6, 8)
 #undef GLASS_SPEC
 #define GLASS_CASE(bn, bk, md) \

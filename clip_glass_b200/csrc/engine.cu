@@ -232,15 +232,18 @@ int make_conv(glass_engine* e, ConvLaunch* out, const __half* in, int Nimg, int 
   if (in_i8) {
     // channel-group-interleaved input: 8-wide x 16-tall tiles, one un-swizzled haloed box per tile (MODE 4)
     // Cin <= 64: tile pairs (two 8x16 tiles side by side share one box; conv_tc.cu Cfg::kPairM)
-    const int tw = 16;
+    // 128 channels: MODE 6 (tile pairs, streamed taps) or, behind GLASS_DEBUG_C1_MODE4, MODE 4 with nine resident
+    // taps of a 32-column n-tile and single 8-wide tiles (A/B knob)
+    static const bool c128_mode4 = getenv("GLASS_DEBUG_C1_MODE4") != nullptr;
+    const int tw = (Cin == 128 && c128_mode4) ? 8 : 16;
     if (gemm || table != nullptr || taps != 9 || (Cin != 32 && Cin != 64 && Cin != 128) || H < 16 || W < tw || H % 16 ||
         W % tw)
       return fail(GLASS_ERR_ARG, "I8 input layout needs a 3x3 conv with 32/64/128 channels on a >=16x16 grid");
-    p.mode = Cin == 128 ? 6 : 4;       // 128 channels: the nine taps do not fit beside the box -> streamed (MODE 6)
+    p.mode = (Cin == 128 && !c128_mode4) ? 6 : 4;   // 128 channels: the nine taps do not fit beside the box -> streamed
     p.BK = Cin;                        // whole K of a tap in one stage
     p.TW = tw; p.TH = 16; p.TN = 1;
     p.tiles_x = W / tw; p.tiles_y = H / 16; p.tiles_n = Nimg;
-    while (p.BN > (Cin == 32 ? 128 : 64)) p.BN /= 2;   // nine resident taps (or the tile pair's box) + >= 2 stages must fit
+    while (p.BN > (Cin == 32 ? 128 : (p.mode == 4 && Cin == 128 ? 32 : 64))) p.BN /= 2;   // resident taps / pair box + >= 2 stages must fit
     if (p.mode == 6 && p.BN != 64) return fail(GLASS_ERR_ARG, "I8 input with 128 channels needs Ntot %% 64 == 0");
   } else if (!gemm && table == nullptr && (Cin == 32 || Cin == 64) && p.TW == 16 && p.TH == 8 && p.TN == 1 &&
              (taps == 9 || taps == 1)) {
