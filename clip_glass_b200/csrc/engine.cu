@@ -97,6 +97,7 @@ struct glass_engine {
   std::vector<int> g_in_i8;   // per G layer: its INPUT activation is stored [N][H][C/8][W][8]
   std::vector<int> d_in_i8;   // per D block: its input activation likewise
   std::vector<int> d_c1_i8;   // per D block: the space-to-depth tensor between conv0 and the folded conv1 likewise
+  std::vector<int> d_proj_fused;   // per D block: projection FIR + 1x1 GEMM in one kernel (fir_proj_tc.cu)
   std::vector<int> g_pair;    // per G layer: 1 = 32-channel conv on horizontally paired pixels
   std::vector<int> d_pair;    // per D block: conv0 likewise
   float4 *slabs = nullptr, *yA = nullptr, *yB = nullptr;
@@ -127,6 +128,7 @@ struct glass_engine {
   // timing of tensor-core launches
   bool timing = false;
   std::vector<cudaEvent_t> ev;
+  std::vector<const void*> ev_conv;   // which ConvLaunch each event pair timed
   size_t ev_used = 0;
   float last_conv_ms = 0.f;
   int last_conv_launches = 0;
@@ -305,6 +307,7 @@ int run_conv(glass_engine* e, const ConvLaunch& c, cudaStream_t s) {
       cudaEventRecord(e->ev[e->ev_used], s);
       err = launch_conv_tc(c.p, c.maps, e->num_sms, s);
       cudaEventRecord(e->ev[e->ev_used + 1], s);
+      e->ev_conv[e->ev_used / 2] = &c;
       e->ev_used += 2;
     } else {
       err = launch_conv_tc(c.p, c.maps, e->num_sms, s);
@@ -425,6 +428,12 @@ void derive_arch(glass_engine* e) {
     const bool on = c1i8 == nullptr || atoi(c1i8) != 0;
     e->d_c1_i8.push_back((i8_ok && on && !e->d_exact[b] && Ci == 32 && (e->R >> b) / 2 >= 16 &&
                           e->gch[c.num_blocks - 2 - b] % 64 == 0) ? 1 : 0);
+  }
+  e->d_proj_fused.clear();
+  for (int b = 0; b + 1 < c.num_blocks; ++b) {
+    const int Ci = e->gch[c.num_blocks - 1 - b], Co = e->gch[c.num_blocks - 2 - b];
+    const bool on = (c.flags & GLASS_FLAG_PROJ_FUSION) != 0 && c.conv_impl == 0;   // opt-in: measured slower
+    e->d_proj_fused.push_back((on && k_fir_proj_supported(Ci, Co, false)) ? 1 : 0);
   }
   const bool pair_ok = (c.flags & GLASS_FLAG_NO_PAIR_PACK) == 0 && c.conv_impl == 0;
   e->g_pair.clear();
@@ -918,7 +927,12 @@ int run_discriminator(glass_engine* e, const float* images, int P, float* logits
   // fromRGB + the first block's projection FIR in one pass (GLASS_DEBUG_SPLIT_FRGB: the two-kernel route)
   static const bool split_frgb = getenv("GLASS_DEBUG_SPLIT_FRGB") != nullptr;
   const bool fused_frgb = !split_frgb && dch(0) % 32 == 0;
-  if (fused_frgb)
+  // block 0: fromRGB + FIR + projection GEMM in one kernel where the shapes allow it
+  const bool frgb_proj = fused_frgb && e->d_proj_fused[0] && k_fir_proj_supported(dch(0), dch(1), true);
+  if (frgb_proj)
+    LAUNCH(k_from_rgb_fir_proj(images, e->frgb_folded.data(), e->actA, e->d_in_i8[0], tptr<__half>(e, "d.b0.proj.w"), e->dR,
+                               P, e->R, dch(0), dch(1), s));
+  else if (fused_frgb)
     LAUNCH(k_from_rgb_fir(images, e->frgb_folded.data(), e->actA, e->dXd, P, e->R, dch(0), e->d_in_i8[0], s));
   else
     LAUNCH(k_from_rgb(images, tptr<float>(e, "d.frgb.w"), tptr<float>(e, "d.frgb.b"), e->actA, P, e->R, dch(0),
@@ -927,10 +941,21 @@ int run_discriminator(glass_engine* e, const float* images, int P, float* logits
   int res = e->R;
   size_t ci = 0;
   for (int b = 0; b < nb - 1; ++b) {
-    if (b > 0 || !fused_frgb) LAUNCH(k_fir_down(x, e->dXd, P, res, res, dch(b), e->d_in_i8[b], s));
+    // projection path: FIR (+ 1x1 GEMM -> dR when fused; block 0 may already have it from the fromRGB kernel)
+    const bool proj_done = (b == 0 && frgb_proj);
+    const bool proj_fused = proj_done || (e->d_proj_fused[b] && !(b == 0 && fused_frgb));
+    if (!proj_done) {
+      if (proj_fused) {
+        snprintf(nm, sizeof nm, "d.b%d.proj.w", b);
+        LAUNCH(k_fir_proj(x, e->d_in_i8[b], tptr<__half>(e, nm), e->dR, P, res, res, dch(b), dch(b + 1), s));
+      } else if (b > 0 || !fused_frgb) {
+        LAUNCH(k_fir_down(x, e->dXd, P, res, res, dch(b), e->d_in_i8[b], s));
+      }
+    }
     RC(run_conv(e, e->d_convs[ci++], s));   // conv0 -> actB (space-to-depth, or NHWC for the exact form)
     if (e->d_exact[b]) LAUNCH(k_blur_s2d(e->actB, e->actC, P, res, res, dch(b), s));
-    RC(run_conv(e, e->d_convs[ci++], s));   // projection -> dR
+    if (proj_fused) ci++;                   // projection already in dR
+    else RC(run_conv(e, e->d_convs[ci++], s));   // projection -> dR
     const ConvLaunch& c1 = e->d_convs[ci++];
     RC(run_conv(e, c1, s));                 // conv1 + residual
     x = c1.p.epi.out;
@@ -1079,6 +1104,7 @@ int glass_finalize(glass_engine* e) {
   e->arena.off = 0;
   layout_workspace(e, e->arena);
   e->ev.resize(512);
+  e->ev_conv.assign(256, nullptr);
   for (auto& ev : e->ev) CUDA_OK(cudaEventCreate(&ev));
   CUDA_OK(cudaStreamCreateWithFlags(&e->cap_stream, cudaStreamNonBlocking));
   CUDA_OK(cudaStreamCreateWithFlags(&e->side_stream, cudaStreamNonBlocking));
@@ -1247,12 +1273,18 @@ int glass_conv_breakdown(glass_engine* e, float* ms, double* flops, int32_t cap)
   for (auto& c : e->g_convs) all.push_back(&c);
   for (auto& c : e->c_convs) all.push_back(&c);
   for (auto& c : e->d_convs) all.push_back(&c);
+  // one entry per PLANNED conv/GEMM, in plan order; launches that the last call did not make (a projection that
+  // ran inside k_fir_proj) report 0 ms
   int n = 0;
-  for (size_t i = 0; i + 1 < e->ev_used && n < cap && (size_t)n < all.size(); i += 2, ++n) {
-    float t = 0.f;
-    cudaEventElapsedTime(&t, e->ev[i], e->ev[i + 1]);
-    ms[n] = t;
+  for (; n < cap && (size_t)n < all.size(); ++n) {
+    ms[n] = 0.f;
     flops[n] = all[n]->flops;
+    for (size_t i = 0; i + 1 < e->ev_used; i += 2)
+      if (e->ev_conv[i / 2] == all[n]) {
+        float t = 0.f;
+        cudaEventElapsedTime(&t, e->ev[i], e->ev[i + 1]);
+        ms[n] += t;
+      }
   }
   return n;
 }

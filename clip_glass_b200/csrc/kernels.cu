@@ -2,6 +2,7 @@
 // matters, warp-shuffle reductions.  Everything GEMM-shaped lives in conv_tc.cu.
 #include <type_traits>
 #include "kernels.cuh"
+#include "fir_tile.cuh"
 
 namespace glass {
 
@@ -487,182 +488,46 @@ __global__ void from_rgb_kernel(const float* __restrict__ images, const float* _
   }
 }
 
-// FIR (pad 1) sampled at stride 2.  One block = 8x16 outputs x 32 channels: the (18 x 34)-pixel input patch is
-// staged once in shared memory, so HBM/L2 see every input byte once and the 16 taps per output come from shared
-// memory.  The tile is stored in 16-byte units (one pixel, 8 channels) as planes [channel group g][column parity]
-// [row][column/2]: the stride-2 reads of the FIR then touch consecutive units (conflict-free LDS.128), and so do
-// the writes of consecutive pixels.  Plane strides are padded so that the parity planes sit 64 B apart modulo the
-// 128-byte bank row and the group planes 16 B apart.
-#ifndef GLASS_FIR_MINB
-#define GLASS_FIR_MINB 3
-#endif
-constexpr int kFdTH = 8, kFdTW = 16, kFdC = 32;
-constexpr int kFdIW = 2 * kFdTW + 2, kFdIH = 2 * kFdTH + 2;     // 34 x 18 input pixels
-constexpr int kFdPlane = kFdIH * (kFdIW / 2) + 2;               // 308 units: 16 words (mod 32) between parity planes
-constexpr int kFdGroup = 2 * kFdPlane + 1;                      // 617 units: 4 words (mod 32) between channel groups
-constexpr int kFdUnits = 4 * kFdGroup;
-constexpr int kFdPix = kFdIW * kFdIH;                           // 612 pixels per tile
-__device__ __forceinline__ int fd_unit(int g, int py, int px) {
-  return g * kFdGroup + (px & 1) * kFdPlane + py * (kFdIW / 2) + (px >> 1);
-}
-
-// Second half of fir_down_kernel / from_rgb_fir_kernel: separable [1,3,3,1]/8 FIR at stride 2 from the staged tile.
-// One thread = one output column, 8 channels, two vertically adjacent outputs: six input rows are filtered
-// horizontally once ((a+d) + 3(b+c): two adds and one FMA per channel instead of four FMAs) and shared by both.
-__device__ __forceinline__ void fir_down_from_tile(const uint4* tile, __half* __restrict__ out, int b, int ty, int tx,
-                                                   int Ho, int Wo, int C, int c0) {
-  static_assert(kFdTH == 8 && kFdTW == 16, "thread mapping below: 16 columns x 4 groups x 4 row pairs = 256 threads");
-  const int ox = threadIdx.x & 15;
-  const int g = (threadIdx.x >> 4) & 3;
-  const int oyp = threadIdx.x >> 6;                 // output rows 2*oyp, 2*oyp+1 <- input rows 4*oyp .. 4*oyp+5
-  float hrow[6][8];
-#pragma unroll
-  for (int r = 0; r < 6; ++r) {
-    float v[4][8];
-#pragma unroll
-    for (int jx = 0; jx < 4; ++jx) {
-      const uint4 q = tile[fd_unit(g, 4 * oyp + r, 2 * ox + jx)];
-      const __half2* h2 = reinterpret_cast<const __half2*>(&q);
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float2 tt = __half22float2(h2[j]);
-        v[jx][2 * j] = tt.x;
-        v[jx][2 * j + 1] = tt.y;
-      }
-    }
-#pragma unroll
-    for (int j = 0; j < 8; ++j) hrow[r][j] = fmaf(3.f, v[1][j] + v[2][j], v[0][j] + v[3][j]);
-  }
+// Stride-2 FIR passes of the discriminator (shared pieces: fir_tile.cuh).  Each thread of fir_down_compute owns one
+// output column, 8 channels and two vertically adjacent outputs.
+__device__ __forceinline__ void fir_down_store(const uint4* tile, __half* __restrict__ out, int b, int ty, int tx, int Ho,
+                                               int Wo, int C, int c0) {
+  uint4 o[2];
+  fir_down_compute(tile, o);
+  const int ox = threadIdx.x & 15, g = (threadIdx.x >> 4) & 3, oyp = threadIdx.x >> 6;
 #pragma unroll
   for (int k = 0; k < 2; ++k) {
     const int zy = ty * kFdTH + 2 * oyp + k, zx = tx * kFdTW + ox;
-    if (zy < Ho && zx < Wo) {
-      uint4 o;
-      __half2* oh = reinterpret_cast<__half2*>(&o);
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float e0 = fmaf(3.f, hrow[2 * k + 1][2 * j] + hrow[2 * k + 2][2 * j], hrow[2 * k][2 * j] + hrow[2 * k + 3][2 * j]);
-        const float e1 = fmaf(3.f, hrow[2 * k + 1][2 * j + 1] + hrow[2 * k + 2][2 * j + 1],
-                              hrow[2 * k][2 * j + 1] + hrow[2 * k + 3][2 * j + 1]);
-        oh[j] = __floats2half2_rn(e0 * (1.f / 64.f), e1 * (1.f / 64.f));
-      }
-      *reinterpret_cast<uint4*>(out + (((size_t)b * Ho + zy) * Wo + zx) * C + c0 + g * 8) = o;
-    }
+    if (zy < Ho && zx < Wo) *reinterpret_cast<uint4*>(out + (((size_t)b * Ho + zy) * Wo + zx) * C + c0 + g * 8) = o[k];
   }
 }
 
-constexpr int kFdItems = kFdPix * 4;                                  // (pixel, 8-channel group) items per tile
-constexpr int kFdPerThread = (kFdItems + 255) / 256;
-
-// kI8: x is channel-group-interleaved ([N][H][C/8][W][8]): consecutive threads take consecutive pixels of one group
-// (contiguous 16-byte pieces); NHWC: consecutive threads take the four groups of one pixel (64 contiguous bytes).
 template <bool kI8>
 __global__ void __launch_bounds__(256, GLASS_FIR_MINB) fir_down_kernel(const __half* __restrict__ x, __half* __restrict__ out, int N,
                                                        int H, int W, int C) {
   __shared__ uint4 tile[kFdUnits];
   const int Ho = H >> 1, Wo = W >> 1;
-  const int tiles_x = (Wo + kFdTW - 1) / kFdTW, tiles_y = (Ho + kFdTH - 1) / kFdTH;
-  int t = blockIdx.x;
-  const int tx = t % tiles_x; t /= tiles_x;
-  const int ty = t % tiles_y;
-  const int b = t / tiles_y;
+  int b, ty, tx;
+  fd_decode_tile(blockIdx.x, Ho, Wo, b, ty, tx);
   const int c0 = blockIdx.y * kFdC;
-  const int iy0 = 2 * ty * kFdTH - 1, ix0 = 2 * tx * kFdTW - 1;
-  // all of a thread's loads are issued before the first one is consumed (ten 16-byte loads in flight per thread)
-  uint4 v[kFdPerThread];
-#pragma unroll
-  for (int k = 0; k < kFdPerThread; ++k) {
-    const int i = threadIdx.x + k * 256;
-    const int g = kI8 ? i / kFdPix : (i & 3), pix = kI8 ? i - g * kFdPix : (i >> 2);
-    const int py = pix / kFdIW, px = pix - py * kFdIW;
-    const int yy = iy0 + py, xx = ix0 + px;
-    v[k] = make_uint4(0, 0, 0, 0);
-    if (i < kFdItems && yy >= 0 && yy < H && xx >= 0 && xx < W) {
-      const size_t off = kI8 ? ((((size_t)b * H + yy) * (C >> 3) + (c0 >> 3) + g) * W + xx) * 8
-                             : (((size_t)b * H + yy) * W + xx) * C + c0 + g * 8;
-      v[k] = __ldg(reinterpret_cast<const uint4*>(x + off));
-    }
-  }
-#pragma unroll
-  for (int k = 0; k < kFdPerThread; ++k) {
-    const int i = threadIdx.x + k * 256;
-    const int g = kI8 ? i / kFdPix : (i & 3), pix = kI8 ? i - g * kFdPix : (i >> 2);
-    const int py = pix / kFdIW, px = pix - py * kFdIW;
-    if (i < kFdItems) tile[fd_unit(g, py, px)] = v[k];
-  }
+  fd_stage_tile<kI8>(tile, x, b, H, W, C, c0, 2 * ty * kFdTH - 1, 2 * tx * kFdTW - 1);
   __syncthreads();
-  fir_down_from_tile(tile, out, b, ty, tx, Ho, Wo, C, c0);
+  fir_down_store(tile, out, b, ty, tx, Ho, Wo, C, c0);
 }
 
-// fromRGB fused with the first block's projection FIR: the tile of x = lrelu(W.rgb + b)*sqrt2 is computed once from
-// the image (halo pixels are recomputed by the neighbouring block: 19 % extra arithmetic, no extra HBM traffic),
-// written to HBM for conv0 (interior pixels only) and filtered from shared memory, so the 32-channel 1024^2
-// tensor is never read back for the FIR.  One thread computes all 32 channels of a pixel (index math and the rgb
-// loads are paid once per pixel, not once per 8-channel group); the folded constants
-//   x = lrelu(W.(2 rgb - 1) + b) * sqrt2 = lrelu((2 sqrt2 W).rgb + sqrt2 (b - sum W))
-// arrive as a kernel parameter, i.e. through the constant bank / uniform registers, not through shared memory.
-// The kernel is issue-bound: 1.95 G -> 1.60 G warp instructions per launch at P = 64, 3.0 -> 1.7 ms (profiles/).
-struct FrgbConsts { float w[4][kFdC]; };     // rows: r, g, b weights and the bias, channels c0 .. c0+31
-constexpr int kFrPerThread = (kFdPix + 255) / 256;
+// fromRGB fused with the first block's projection FIR (fir_tile.cuh: fd_stage_tile_from_rgb): the 32-channel 1024^2
+// tensor is never read back for the FIR.
 __global__ void __launch_bounds__(256, GLASS_FIR_MINB) from_rgb_fir_kernel(const float* __restrict__ images,
                                                            const __grid_constant__ FrgbConsts k,
                                                            __half* __restrict__ xout, __half* __restrict__ down, int P,
                                                            int R, int C, int c0, int out_i8) {
   __shared__ uint4 tile[kFdUnits];
   const int Ho = R >> 1, Wo = R >> 1;
-  const int tiles_x = (Wo + kFdTW - 1) / kFdTW, tiles_y = (Ho + kFdTH - 1) / kFdTH;
-  int t = blockIdx.x;
-  const int tx = t % tiles_x; t /= tiles_x;
-  const int ty = t % tiles_y;
-  const int b = t / tiles_y;
-  const int iy0 = 2 * ty * kFdTH - 1, ix0 = 2 * tx * kFdTW - 1;
-  const size_t plane = (size_t)R * R;
-  const float* img = images + (size_t)b * 3 * plane;
-  float rgb[kFrPerThread][3];
-#pragma unroll
-  for (int it = 0; it < kFrPerThread; ++it) {
-    const int pix = threadIdx.x + it * 256;
-    const int py = pix / kFdIW, px = pix - py * kFdIW;
-    const int yy = iy0 + py, xx = ix0 + px;
-    rgb[it][0] = rgb[it][1] = rgb[it][2] = 0.f;
-    if (pix < kFdPix && yy >= 0 && yy < R && xx >= 0 && xx < R) {
-      const float* ip = img + (size_t)yy * R + xx;
-      rgb[it][0] = __ldg(ip); rgb[it][1] = __ldg(ip + plane); rgb[it][2] = __ldg(ip + 2 * plane);
-    }
-  }
-#pragma unroll
-  for (int it = 0; it < kFrPerThread; ++it) {
-    const int pix = threadIdx.x + it * 256;
-    if (pix >= kFdPix) continue;
-    const int py = pix / kFdIW, px = pix - py * kFdIW;
-    const int yy = iy0 + py, xx = ix0 + px;
-    const bool inside = yy >= 0 && yy < R && xx >= 0 && xx < R;
-    const float r = rgb[it][0], gg = rgb[it][1], bl = rgb[it][2];
-    // interior pixels of the tile (rows/cols 1 .. IH-2 / IW-2) belong to this block
-    const bool mine = inside && py >= 1 && py < kFdIH - 1 && px >= 1 && px < kFdIW - 1;
-#pragma unroll
-    for (int g = 0; g < 4; ++g) {
-      uint4 pk = make_uint4(0, 0, 0, 0);                 // outside the image: the FIR's zero padding
-      if (inside) {
-        __half2* h2 = reinterpret_cast<__half2*>(&pk);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int c = g * 8 + 2 * j;
-          const float t0 = fmaf(r, k.w[0][c], fmaf(gg, k.w[1][c], fmaf(bl, k.w[2][c], k.w[3][c])));
-          const float t1 = fmaf(r, k.w[0][c + 1], fmaf(gg, k.w[1][c + 1], fmaf(bl, k.w[2][c + 1], k.w[3][c + 1])));
-          h2[j] = __floats2half2_rn(fmaxf(t0, 0.2f * t0), fmaxf(t1, 0.2f * t1));
-        }
-      }
-      if (mine) {
-        const size_t off = out_i8 ? ((((size_t)b * R + yy) * (C >> 3) + (c0 >> 3) + g) * R + xx) * 8
-                                  : (((size_t)b * R + yy) * R + xx) * C + c0 + g * 8;
-        *reinterpret_cast<uint4*>(xout + off) = pk;
-      }
-      tile[fd_unit(g, py, px)] = pk;
-    }
-  }
+  int b, ty, tx;
+  fd_decode_tile(blockIdx.x, Ho, Wo, b, ty, tx);
+  fd_stage_tile_from_rgb(tile, images, k, xout, b, R, C, c0, out_i8, 2 * ty * kFdTH - 1, 2 * tx * kFdTW - 1);
   __syncthreads();
-  fir_down_from_tile(tile, down, b, ty, tx, Ho, Wo, C, c0);
+  fir_down_store(tile, down, b, ty, tx, Ho, Wo, C, c0);
 }
 
 // ---------------------------------------------------------------------------

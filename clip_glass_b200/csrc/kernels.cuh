@@ -70,6 +70,14 @@ cudaError_t k_from_rgb_fir(const float* images, const float* folded_host, __half
 // projection path FIR (pad 1) sampled at stride 2 (modules.py:1204-1220, 1243-1246): [N,H,W,C] -> [N,H/2,W/2,C]
 // in_i8: x is channel-group-interleaved [N][H][C/8][W][8]; the output is always NHWC
 cudaError_t k_fir_down(const __half* x, __half* out, int N, int H, int W, int C, int in_i8, cudaStream_t s);
+// The same FIR fused with the block's 1x1 stride-2 projection (modules.py:1587-1601) on the tensor cores
+// (fir_proj_tc.cu): x -> dR [N][H/2][W/2][Co]; wproj is [Co][C] fp16.  Co in {64,128,256}.
+bool k_fir_proj_supported(int C, int Co, bool from_rgb);
+cudaError_t k_fir_proj(const __half* x, int in_i8, const __half* wproj, __half* out, int N, int H, int W, int C, int Co,
+                       cudaStream_t s);
+// ... and with fromRGB in front (the first block): image -> x (xout) and dR
+cudaError_t k_from_rgb_fir_proj(const float* images, const float* folded_host, __half* xout, int out_i8,
+                                const __half* wproj, __half* out, int P, int R, int C, int Co, cudaStream_t s);
 // modules.py:701-747 incl. the in-place centring; x [P,16,C] -> out [P,16,Cpad] (channel C = std feature)
 cudaError_t k_mbstd(const __half* x, __half* out, int P, int batch, int group, int C, int Cpad, cudaStream_t s);
 // models.py:1224-1225 last dense + problem.py:23 hinge

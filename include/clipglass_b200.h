@@ -74,6 +74,11 @@ typedef struct glass_config {
 /* glass_evaluate_device / glass_evaluate_host replay one CUDA graph per launch plan (built on the second evaluation;
  * CLIP and the discriminator as parallel branches).  The facade calls always launch eagerly. */
 #define GLASS_FLAG_NO_GRAPH 32         /* launch every kernel eagerly */
+/* Opt-in: the projection path of the D blocks with 64/128/256 output channels (FIR + 1x1 stride-2 conv) as one kernel
+ * (fir_proj_tc.cu: FIR in fp32 -> fp16 A operand in shared memory -> tcgen05 GEMM).  Measured SLOWER than k_fir_down
+ * + a 1x1 conv_tc launch at P=64 (2.86 vs 2.55 ms on the 1024^2 block: its serial stage/FIR/MMA/store phases leave
+ * three resident blocks per SM idle too often), so it is off by default and kept as a cross-checked variant. */
+#define GLASS_FLAG_PROJ_FUSION 64
 
 /* -- lifetime ------------------------------------------------------------- */
 /* Replaces Generator.__init__ (generator.py:12-27): allocate the engine. */

@@ -63,6 +63,12 @@ def test_tiny_layerwise_exact_resampling_variant():
     check_diag(run_diag("tiny", 0, 600, flags=2))
 
 
+def test_tiny_layerwise_fused_projection_variant():
+    """GLASS_FLAG_PROJ_FUSION on the tiny config: block 0 runs fromRGB + FIR + projection (two 32-channel chunks),
+    block 1 the I8-input variant, block 2 (32 output channels) stays on the separate launches."""
+    check_diag(run_diag("tiny", 0, 600, flags=64))
+
+
 def test_tiny_layerwise_single_pixel_variant():
     """GLASS_FLAG_NO_PAIR_PACK: the 32-channel convs on single pixels (resident-tap MODE 1 with 64-byte rows)
     instead of the default horizontally paired pixels."""
@@ -205,6 +211,17 @@ def test_streamed_tap_i8_downconv_against_nhwc_form():
     np.testing.assert_array_equal(m6[0], m0[0])            # G and CLIP are untouched
     np.testing.assert_allclose(m6[1], m0[1], atol=5e-4)
     np.testing.assert_allclose(m6[1], gold["F"][:, 1], atol=2e-3)
+
+
+def test_fused_projection_kernel_against_separate_launches():
+    """fir_proj_tc.cu (GLASS_FLAG_PROJ_FUSION = 64: stride-2 FIR + 1x1 projection GEMM of the D blocks in one kernel,
+    opt-in) against the default k_fir_down + conv_tc route: the projection accumulates in fp32 from the same fp16
+    operands either way, so the hinge agrees to fp16 rounding of the residual tensor."""
+    (fused,), gold = _full_scores(flags=64)
+    (ref,), _ = _full_scores(flags=0)
+    np.testing.assert_array_equal(fused[0], ref[0])
+    np.testing.assert_allclose(fused[1], ref[1], atol=5e-4)
+    np.testing.assert_allclose(fused[1], gold["F"][:, 1], atol=2e-3)
 
 
 def test_population_must_be_multiple_of_batch(full_engine):
