@@ -348,28 +348,40 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                         tap);
       }
       if (MODE == 6) {
-        // The box of tile i+1 is requested BEFORE the taps of tile i are streamed: the producer blocks on the weight
-        // ring while it streams, and an input box requested only after that would arrive a full L2 round trip late
-        // at every tile boundary.
-        auto load_box = [&](int tile) {
+        // The box of tile i+1 goes into the stage that tile i-1 is still using when the producer starts streaming the
+        // taps of tile i (two stages), so it cannot be requested up front without stalling the weight ring for a
+        // whole tile; requested only after tile i's taps it would arrive a full TMA round trip late.  Hence: while
+        // streaming tile i's taps, poll that stage's barrier without blocking and request the box as soon as tile
+        // i-1's MMAs have released it (a few chunks into tile i).
+        auto issue_box = [&](int tile) {
           const TileCoord tc = decode_tile<kPow2>(p, tile, n_tiles);
-          mbar_wait(&empty_bar[stage], phase ^ 1);
           mbar_expect_tx(&full_bar[stage], C::kI8StageBytes);
           tma_load_4d(&map_a, smem + stage * C::kStageBytes, &full_bar[stage], (tc.tx * p.TW - 1) * 8, 0,
                       tc.ty * p.TH - 1, tc.tn * p.TN);
           if (++stage == C::kStages) { stage = 0; phase ^= 1; }
         };
         const int n_tile = blockIdx.x % n_tiles;
-        if ((int)blockIdx.x < total_tiles) load_box(blockIdx.x);
+        if ((int)blockIdx.x < total_tiles) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          issue_box(blockIdx.x);
+        }
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-          if (tile + (int)gridDim.x < total_tiles) load_box(tile + gridDim.x);
+          bool next_pending = tile + (int)gridDim.x < total_tiles;
           for (int tap = 0; tap < 9; ++tap)
             for (int ch = 0; ch < C::kKChunks; ++ch) {
+              if (next_pending && mbar_test(&empty_bar[stage], phase ^ 1)) {
+                issue_box(tile + gridDim.x);
+                next_pending = false;
+              }
               mbar_wait(&b_empty[bstage], bphase ^ 1);
               mbar_expect_tx(&b_full[bstage], C::kBChunkBytes);
               tma_load_3d(&map_b, smem_w + bstage * C::kBChunkBytes, &b_full[bstage], ch * C::kBKc, n_tile * BN, tap);
               if (++bstage == C::kBStages) { bstage = 0; bphase ^= 1; }
             }
+          if (next_pending) {
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            issue_box(tile + gridDim.x);
+          }
         }
       }
       for (int tile = blockIdx.x; MODE != 6 && tile < total_tiles; tile += gridDim.x) {
