@@ -565,7 +565,10 @@ __device__ __forceinline__ void hfir2(const uint4 (&c)[5], float (&h0)[8], float
 // k_upfir: one thread = 8 channels x 2 output columns x kUpRows output rows.  v[Z][X] = sum f f u[Z+jy-1][X+jx-1]
 // with f = [1,3,3,1]/4; then + noise + bias, lrelu*sqrt2, * next style.
 constexpr int kUpRows = 8;
-__global__ void __launch_bounds__(256) upfir_kernel(
+#ifndef GLASS_POLY_MINB
+#define GLASS_POLY_MINB 1
+#endif
+__global__ void __launch_bounds__(256, GLASS_POLY_MINB) upfir_kernel(
     const __half* __restrict__ u, __half* __restrict__ out, const float* __restrict__ noise, size_t noise_group_stride,
     int noise_group_div, const float* __restrict__ noise_strength, const float* __restrict__ bias,
     const float* __restrict__ out_scale, int out_scale_stride, int P, int Hout, int Wout, int C) {
@@ -637,7 +640,7 @@ __global__ void __launch_bounds__(256) upfir_kernel(
 // vertically (2*kBlurCells output rows).  u[Y][X] = sum f f a[Y+jy-2][X+jx-2], f = [1,3,3,1]/8, for Y,X in [0,H];
 // cell (z,w), phase (py,px) holds u[2z+py][2w+px]; positions beyond H are written as zeros.
 constexpr int kBlurCells = 4;
-__global__ void __launch_bounds__(256) blur_s2d_kernel(const __half* __restrict__ a, __half* __restrict__ out, int P,
+__global__ void __launch_bounds__(256, GLASS_POLY_MINB) blur_s2d_kernel(const __half* __restrict__ a, __half* __restrict__ out, int P,
                                                        int H, int W, int C) {
   const int C8 = C >> 3, Hs = (H >> 1) + 1, Ws = (W >> 1) + 1, Hp = (Hs + kBlurCells - 1) / kBlurCells;
   const size_t n = (size_t)P * Hp * Ws * C8;
