@@ -1,16 +1,18 @@
 // Implicit-GEMM convolution / GEMM on the 5th-gen tensor cores (sm_100a).
 //
-//   warp 0      TMA producer: per K step one 4-D box of the NHWC activation
-//               tensor (shifted by the filter tap; out-of-image rows/cols are
-//               zero-filled by TMA) + one box of the [taps][Ntot][Cin] weights,
-//               both landing 128B/64B-swizzled in shared memory.
-//   warp 1      tcgen05.mma issuer (one elected lane), fp16 x fp16 -> fp32
-//               accumulators in TMEM, double-buffered (2 x BN columns).
-//   warps 2..5  epilogue: tcgen05.ld the 128 x BN tile, apply the fused
-//               demod / noise / bias / activation / toRGB / residual / style
-//               pre-scale (common.cuh: epilogue_row16) and store fp16 NHWC.
+//   warp 0      TMA producer (one lane, chosen with elect.sync).  MODE 0: per K step one 4-D box of the NHWC
+//               activation tensor (shifted by the filter tap; out-of-image rows/cols are zero-filled by TMA) + one
+//               box of the [taps][Ntot][Cin] weights, both landing 128B/64B-swizzled in shared memory.
+//               MODE 1/2/4: the taps of the CTA's n-tile stay resident, a stage holds the (haloed) input tile.
+//               MODE 6: the input box of a tile pair stays put, the taps stream through a ring (Cfg below).
+//   warp 1      tcgen05.mma issuer (one elected lane), fp16 x fp16 -> fp32 accumulators in TMEM, double-buffered
+//               (2 x BN columns, 2 x 2 x BN for tile pairs).
+//   warps 2..   epilogue (8 warps, 16 for one instance): tcgen05.ld the 128 x BN tile, apply the fused demod / noise /
+//               bias / activation / toRGB / residual / style pre-scale and store fp16 (NHWC, depth-to-space,
+//               space-to-depth, each also channel-group-interleaved).  Compile-time epilogue specialisations
+//               (kEpiSpecs) for the hot layers; common.cuh: epilogue_row16 for tiles that span several images.
 //
-// Persistent CTAs (one per SM), static round-robin over (m_tile, n_tile).
+// Persistent CTAs (one or two per SM), static round-robin over (m_tile, n_tile).
 // The SIMT kernel at the bottom computes the same accumulators the slow way and
 // shares the epilogue: it exists for bring-up and as the in-library cross-check
 // (glass_config.conv_impl = 1); it is never used by the product path.
