@@ -245,3 +245,24 @@ def test_sharded_evaluate_equals_single_rank_gloo(pop):
             assert groups == [bounds[rank][0] // 4]
         else:
             assert groups == []
+
+
+# ---------------------------------------------------------------------------
+# evidence consistency: the summaries DESIGN.md / bench.py cite are what profiles/summarize.py derives from the
+# committed ncu logs
+def test_profile_summaries_match_the_committed_ncu_logs(tmp_path):
+    import importlib.util
+    import json
+    prof = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "profiles")
+    spec = importlib.util.spec_from_file_location("summarize", os.path.join(prof, "summarize.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    out = tmp_path / "traffic.json"
+    mod.traffic(os.path.join(prof, "r01_conv_dram_p64_final.csv"), str(out))
+    got = json.load(open(out))
+    ref = json.load(open(os.path.join(prof, "conv_tc_traffic.json")))
+    assert got["launches"] == ref["launches"] == 92                    # one step = 92 tcgen05 conv/GEMM launches
+    assert abs(got["bytes_per_launch"] - ref["bytes_per_launch"]) < 1.0
+    shares = tmp_path / "shares.txt"
+    mod.launches(os.path.join(prof, "r01_launches_p64_final.csv"), str(shares))
+    assert open(shares).read() == open(os.path.join(prof, "r01_launch_shares_p64_final.txt")).read()
