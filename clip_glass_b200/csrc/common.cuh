@@ -41,6 +41,7 @@ struct EpiParams {
   const float* out_scale;   // next layer's style s[img*out_scale_stride + o], or null
   int out_scale_stride;
   const __half* residual;   // [pix][Ntot] (regular layout) or null
+  int res_i8;               // the residual tensor is channel-group-interleaved: [n][y][Ntot/8][x][8]
   float post_scale;         // applied after the residual add
   __half* out;              // null => nothing stored (G's last conv only feeds toRGB)
   int store_mode;
@@ -123,8 +124,10 @@ __device__ __forceinline__ void epilogue_row16(const ConvParams& p, int img, int
   }
   float res[16];
   if (e.residual != nullptr) {
-    const uint4* rp = reinterpret_cast<const uint4*>(e.residual + ((size_t)(img * p.H + y) * p.W + x) * p.Ntot + n0);
-    uint4 r0 = __ldg(rp), r1 = __ldg(rp + 1);
+    const __half* rbase = e.res_i8 ? e.residual + (((size_t)(img * p.H + y) * (p.Ntot >> 3) + (n0 >> 3)) * p.W + x) * 8
+                                   : e.residual + ((size_t)(img * p.H + y) * p.W + x) * p.Ntot + n0;
+    const uint4* rp = reinterpret_cast<const uint4*>(rbase);
+    uint4 r0 = __ldg(rp), r1 = __ldg(e.res_i8 ? rp + p.W : rp + 1);
     const __half2* h0 = reinterpret_cast<const __half2*>(&r0);
     const __half2* h1 = reinterpret_cast<const __half2*>(&r1);
 #pragma unroll

@@ -78,6 +78,7 @@ constexpr EpiSpec kEpiSpecs[] = {
     {false, false, false, false, kStRegular, false, kActNone},    // 9: D projection (1x1, linear)
     {false, false, false, false, kStRegular, false, kActLrelu},   // 10: D conv0 of the exact form, NHWC store
     {false, false, false, false, kStS2D, true, kActLrelu},        // 11: D conv0, space-to-depth I8 (feeds MODE 6)
+    {false, false, false, false, kStRegular, true, kActNone},     // 12: D projection (1x1, linear), I8 store
 };
 constexpr int kNumEpiSpecs = sizeof(kEpiSpecs) / sizeof(kEpiSpecs[0]);
 
@@ -168,7 +169,7 @@ template <int NT, bool kRgb, int kActT = -1>
 __device__ __forceinline__ void epilogue_fastN(const EpiParams& e, const float* __restrict__ par, int BN, int j0,
                                                const uint32_t (*acc)[16], const float* nz, const __half* const* res_ptr,
                                                __half* const* out_ptr, size_t out_half_stride, float (*rgb)[3],
-                                               const uint4* const* res_pre) {
+                                               const uint4* const* res_pre, size_t res_half_stride = 8) {
   const float4* sc = reinterpret_cast<const float4*>(par + 0 * BN + j0);
   const float4* sh = reinterpret_cast<const float4*>(par + 1 * BN + j0);
   const float4* os = reinterpret_cast<const float4*>(par + 2 * BN + j0);
@@ -222,7 +223,9 @@ __device__ __forceinline__ void epilogue_fastN(const EpiParams& e, const float* 
       const uint4* rp = reinterpret_cast<const uint4*>(res_ptr[n]);
       // res_pre: the 16 residual values were fetched before the accumulator wait (their DRAM latency is hidden)
       const uint4 q0 = res_pre[n] != nullptr ? res_pre[n][0] : __ldg(rp);
-      const uint4 q1 = res_pre[n] != nullptr ? res_pre[n][1] : __ldg(rp + 1);
+      // channels [8,16) of the chunk: adjacent in NHWC, one channel-group plane further in an I8 residual tensor
+      const uint4 q1 = res_pre[n] != nullptr ? res_pre[n][1]
+                                             : __ldg(reinterpret_cast<const uint4*>(res_ptr[n] + res_half_stride));
       const __half2* h0 = reinterpret_cast<const __half2*>(&q0);
       const __half2* h1 = reinterpret_cast<const __half2*>(&q1);
 #pragma unroll
@@ -264,12 +267,12 @@ template <bool kRgb, int kActT = -1>
 __device__ __forceinline__ void epilogue_fast16(const EpiParams& e, const float* __restrict__ par, int BN, int j0,
                                                 const uint32_t (&acc)[16], float nz, const __half* res_ptr,
                                                 __half* out_ptr, size_t out_half_stride, float (&rgb)[3],
-                                                const uint4* res_pre = nullptr) {
+                                                const uint4* res_pre = nullptr, size_t res_half_stride = 8) {
   const __half* rp[1] = {res_ptr};
   __half* op[1] = {out_ptr};
   const uint4* pre[1] = {res_pre};
   const float nzv[1] = {nz};
-  epilogue_fastN<1, kRgb, kActT>(e, par, BN, j0, &acc, nzv, rp, op, out_half_stride, &rgb, pre);
+  epilogue_fastN<1, kRgb, kActT>(e, par, BN, j0, &acc, nzv, rp, op, out_half_stride, &rgb, pre, res_half_stride);
 }
 
 template <int BN, int BK, int MODE, int EPI>
@@ -706,6 +709,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         const int i8_groups = e.Cout >> 3;
         const int i8_row = img * H + tc.ty * p.TH + ry;          // regular store: image row of this pixel
         const int i8_x0 = tc.tx * p.TW + rx;
+        // residual operand of chunk c of tile h: NHWC [pix][Ntot], or I8 [n][y][Ntot/8][x][8] (EpiParams.res_i8: the D
+        // projections store it that way so that both their stores and these loads are 128-byte contiguous per 8 lanes)
+        const bool res_i8 = has_res && e.res_i8 != 0;
+        const size_t res_stride = res_i8 ? (size_t)W * 8 : 8;      // halfs from channels [0,8) to [8,16) of a chunk
+        auto res_addr = [&](int h, int c) -> const __half* {
+          if (!has_res) return nullptr;
+          if (res_i8)
+            return e.residual + (((size_t)i8_row * (p.Ntot >> 3) + ((n_first + c * 16) >> 3)) * W + i8_x0 + 8 * h) * 8;
+          return res_row + (size_t)(8 * h) * p.Ntot + c * 16;
+        };
         float nscale;
         asm volatile("ld.shared.f32 %0, [%1];" : "=f"(nscale) : "r"(smem_u32(nscale_slot)));
         // Specialised residual layers fetch the whole tile's residual values NOW, before waiting for the accumulator:
@@ -718,9 +731,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           for (int h = 0; h < kPairM; ++h)
 #pragma unroll
             for (int c = 0; c < kChunks; ++c) {
-              const uint4* rp = reinterpret_cast<const uint4*>(res_row + (size_t)(8 * h) * p.Ntot + c * 16);
-              resv[kResPre ? h : 0][kResPre ? c : 0][0] = __ldg(rp);
-              resv[kResPre ? h : 0][kResPre ? c : 0][1] = __ldg(rp + 1);
+              const __half* rp = res_addr(h, c);
+              resv[kResPre ? h : 0][kResPre ? c : 0][0] = __ldg(reinterpret_cast<const uint4*>(rp));
+              resv[kResPre ? h : 0][kResPre ? c : 0][1] = __ldg(reinterpret_cast<const uint4*>(rp + res_stride));
             }
         }
         mbar_wait(&tmem_full[as], aphase);
@@ -781,11 +794,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
               const uint4* rpre[2];
 #pragma unroll
               for (int h = 0; h < 2; ++h) {
-                rptr[h] = (!kResPre && res_row != nullptr) ? res_row + (size_t)(8 * h) * p.Ntot + c * 16 : nullptr;
+                rptr[h] = !kResPre ? res_addr(h, c) : nullptr;
                 rpre[h] = kResPre ? resv[kResPre ? h : 0][kResPre ? c : 0] : nullptr;
               }
-              if (has_rgb) epilogue_fastN<2, true, kActT>(e, par, BN, j0, accp[c & 1], nzc, rptr, optr, half_stride, rgb, rpre);
-              else epilogue_fastN<2, false, kActT>(e, par, BN, j0, accp[c & 1], nzc, rptr, optr, half_stride, rgb, rpre);
+              if (has_rgb) epilogue_fastN<2, true, kActT>(e, par, BN, j0, accp[c & 1], nzc, rptr, optr, half_stride, rgb, rpre, res_stride);
+              else epilogue_fastN<2, false, kActT>(e, par, BN, j0, accp[c & 1], nzc, rptr, optr, half_stride, rgb, rpre, res_stride);
             }
           }
         } else {
@@ -807,10 +820,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
               const float nzc = nscale * nz_cur[h][d2s ? c : 0];
               size_t half_stride = 8;
               __half* optr = out_addr(h, c, half_stride);
-              const __half* rptr = (!kResPre && res_row != nullptr) ? res_row + (size_t)(8 * h) * p.Ntot + c * 16 : nullptr;
+              const __half* rptr = !kResPre ? res_addr(h, c) : nullptr;
               const uint4* rpre = kResPre ? resv[kResPre ? h : 0][kResPre ? c : 0] : nullptr;
-              if (has_rgb) epilogue_fast16<true, kActT>(e, par, BN, j0, acc[ci & 1], nzc, rptr, optr, half_stride, rgb[h], rpre);
-              else epilogue_fast16<false, kActT>(e, par, BN, j0, acc[ci & 1], nzc, rptr, optr, half_stride, rgb[h], rpre);
+              if (has_rgb) epilogue_fast16<true, kActT>(e, par, BN, j0, acc[ci & 1], nzc, rptr, optr, half_stride, rgb[h], rpre, res_stride);
+              else epilogue_fast16<false, kActT>(e, par, BN, j0, acc[ci & 1], nzc, rptr, optr, half_stride, rgb[h], rpre, res_stride);
             }
           }
         }
@@ -985,6 +998,9 @@ cudaError_t launch_conv_tc(const ConvParams& p, const TmaMaps& maps, int num_sms
   GLASS_SPEC(64, 32, 2, 9)
   GLASS_SPEC(128, 64, 2, 9)
   GLASS_SPEC(256, 64, 0, 9)
+  GLASS_SPEC(64, 32, 2, 12)
+  GLASS_SPEC(128, 64, 2, 12)
+  GLASS_SPEC(256, 64, 0, 12)
   GLASS_SPEC(128, 64, 0, 10)
   GLASS_SPEC(32, 32, 4, 11)
   GLASS_SPEC(64, 128, 6, 7)

@@ -98,6 +98,7 @@ struct glass_engine {
   std::vector<int> d_in_i8;   // per D block: its input activation likewise
   std::vector<int> d_c1_i8;   // per D block: the space-to-depth tensor between conv0 and the folded conv1 likewise
   std::vector<int> d_proj_fused;   // per D block: projection FIR + 1x1 GEMM in one kernel (fir_proj_tc.cu)
+  std::vector<int> d_res_i8;       // per D block: the projection output (conv1's residual operand) is stored I8
   std::vector<int> g_pair;    // per G layer: 1 = 32-channel conv on horizontally paired pixels
   std::vector<int> d_pair;    // per D block: conv0 likewise
   float4 *slabs = nullptr, *yA = nullptr, *yB = nullptr;
@@ -435,6 +436,17 @@ void derive_arch(glass_engine* e) {
     const bool on = (c.flags & GLASS_FLAG_PROJ_FUSION) != 0 && c.conv_impl == 0;   // opt-in: measured slower
     e->d_proj_fused.push_back((on && k_fir_proj_supported(Ci, Co, false)) ? 1 : 0);
   }
+  // The projection output dR is written by a K <= 512, 1x1 GEMM whose epilogue is bound by its own stores: NHWC
+  // stores put 16 bytes per lane at the pixel pitch (32 shared/L1 wavefronts per instruction), I8 stores are 128-byte
+  // contiguous per 8 lanes (4 wavefronts), and conv1's residual loads coalesce the same way.  (GLASS_DEBUG_RES_I8=0:
+  // NHWC, for A/B.)
+  e->d_res_i8.clear();
+  for (int b = 0; b + 1 < c.num_blocks; ++b) {
+    const int Co = e->gch[c.num_blocks - 2 - b], ro = (e->R >> b) / 2;
+    const char* env = getenv("GLASS_DEBUG_RES_I8");
+    const bool on = env == nullptr || atoi(env) != 0;
+    e->d_res_i8.push_back((i8_ok && on && !e->d_proj_fused[b] && ro >= 16 && ro % 16 == 0 && Co % 16 == 0) ? 1 : 0);
+  }
   const bool pair_ok = (c.flags & GLASS_FLAG_NO_PAIR_PACK) == 0 && c.conv_impl == 0;
   e->g_pair.clear();
   for (size_t li = 0; li < e->glayers.size(); ++li) {
@@ -753,12 +765,13 @@ int build_plan(glass_engine* e, int P) {
       }
       cl.flops = 2.0 * 9.0 * (double)P * res * res * Ci * Ci; e->d_convs.push_back(cl);
       // projection: 1x1 on the FIR-downsampled input
-      ep = epi_default(); ep.Cout = Co; ep.out = e->dR;
+      ep = epi_default(); ep.Cout = Co; ep.out = e->dR; ep.out_i8 = e->d_res_i8[b];
       RC(make_conv(e, &cl, e->dXd, P, res / 2, res / 2, Ci, tptr<__half>(e, nmf("proj.w")), 1, Co, ep, false));
       cl.flops = 2.0 * (double)P * (res / 2) * (res / 2) * Ci * Co; e->d_convs.push_back(cl);
       // conv1
       ep = epi_default();
       ep.Cout = Co; ep.bias = tptr<float>(e, nmf("c1.b")); ep.act = kActLrelu; ep.residual = e->dR;
+      ep.res_i8 = e->d_res_i8[b];
       ep.post_scale = kInvSqrt2; ep.out = outs[b & 1];
       ep.out_i8 = (b + 1 < nb - 1) ? e->d_in_i8[b + 1] : 0;
       if (e->d_exact[b]) {
