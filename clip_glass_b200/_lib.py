@@ -15,6 +15,15 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 # CLIPGLASS_LIB: load another build of the same ABI (A/B timing of kernel variants; never set in tests or bench)
 LIB_PATH = os.environ.get("CLIPGLASS_LIB") or os.path.join(_HERE, "libclipglass_b200.so")
 
+# glass_config.flags (include/clipglass_b200.h: GLASS_FLAG_*): cross-checked kernel variants
+FLAG_FOLDED_RESAMPLE = 1
+FLAG_EXACT_RESAMPLE = 2
+FLAG_NO_PAIR_PACK = 4
+FLAG_NO_I8_LAYOUT = 8
+FLAG_SIMT_ATTENTION = 16
+FLAG_NO_GRAPH = 32
+FLAG_PROJ_FUSION = 64
+
 SYMBOLS = [
     "glass_create", "glass_set_tensor", "glass_finalize", "glass_set_text_features", "glass_destroy",
     "glass_evaluate_host", "glass_evaluate_device", "glass_generate", "glass_clip_similarity",

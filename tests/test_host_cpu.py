@@ -266,3 +266,13 @@ def test_profile_summaries_match_the_committed_ncu_logs(tmp_path):
     shares = tmp_path / "shares.txt"
     mod.launches(os.path.join(prof, "r01_launches_p64_final.csv"), str(shares))
     assert open(shares).read() == open(os.path.join(prof, "r01_launch_shares_p64_final.txt")).read()
+
+
+def test_python_flag_constants_match_the_header():
+    hdr = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include",
+                            "clipglass_b200.h")).read()
+    defs = {m.group(1): int(m.group(2)) for m in re.finditer(r"#define GLASS_FLAG_(\w+)\s+(\d+)", hdr)}
+    assert defs, "no GLASS_FLAG_* in the header"
+    for name, value in defs.items():
+        assert getattr(_lib, "FLAG_" + name) == value, name
+    assert len(set(defs.values())) == len(defs) and all(v & (v - 1) == 0 for v in defs.values())   # distinct bits
