@@ -23,12 +23,15 @@ FLAG_NO_I8_LAYOUT = 8
 FLAG_SIMT_ATTENTION = 16
 FLAG_NO_GRAPH = 32
 FLAG_PROJ_FUSION = 64
+FLAG_C1_NHWC = 128
 
 SYMBOLS = [
     "glass_create", "glass_set_tensor", "glass_finalize", "glass_set_text_features", "glass_destroy",
     "glass_evaluate_host", "glass_evaluate_device", "glass_generate", "glass_clip_similarity",
     "glass_discriminate", "glass_last_error", "glass_launch_count", "glass_debug_read",
     "glass_set_debug", "glass_conv_breakdown", "glass_last_conv_time", "glass_set_batch_size",
+    "glass_debug_build", "glass_set_range_check", "glass_range_report",
+    "glass_last_images_gather", "glass_image_grid_u8", "glass_biggan_latent",
 ]
 
 
@@ -101,6 +104,12 @@ def load_library() -> ctypes.CDLL:
     lib.glass_debug_read.restype = i64
     lib.glass_set_debug.argtypes = [vp, i32, i32]
     lib.glass_set_batch_size.argtypes = [vp, i32]
+    lib.glass_debug_build.argtypes = []
+    lib.glass_last_images_gather.argtypes = [vp, vp, i32, vp, vp]
+    lib.glass_image_grid_u8.argtypes = [vp, vp, i32, i32, i32, i32, vp, vp]
+    lib.glass_biggan_latent.argtypes = [vp, i32, i32, i32, vp, vp, vp]
+    lib.glass_set_range_check.argtypes = [vp, i32]
+    lib.glass_range_report.argtypes = [vp, ctypes.POINTER(i64), ctypes.POINTER(i64), ctypes.POINTER(ctypes.c_float)]
     lib.glass_conv_breakdown.argtypes = [vp, vp, vp, i32]
     lib.glass_last_conv_time.argtypes = [vp, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(i32)]
     for name in SYMBOLS:

@@ -48,14 +48,32 @@ configs = dict(
     StyleGAN2_church_nod=_stylegan2("./stylegan2/weights/church-config-f", False),
 )
 
-_OUT_OF_SCOPE = {"GPT2": GPT2LatentSpace, "DeepMindBigGAN256": DeepMindBigGANLatentSpace,
-                 "DeepMindBigGAN512": DeepMindBigGANLatentSpace}
+def _biggan(res: int, pop: int, batch: int):                  # config.py:27-71
+    return dict(
+        task="txt2img", dim_z=128, num_classes=1000, latent=DeepMindBigGANLatentSpace, model="DeepMindBigGAN",
+        weights=f"biggan-deep-{res}", use_discriminator=False, algorithm="ga", norm=biggan_norm, denorm=biggan_denorm,
+        truncation=1.0, pop_size=pop, batch_size=batch,
+        problem_args=dict(n_var=128 + 1000, n_obj=1, n_constr=128, xl=-2, xu=2),
+    )
+
+
+configs.update(
+    # config.py:5-25 (img2txt: GPT-2 token latents scored by CLIP's text tower against the target image)
+    GPT2=dict(
+        task="img2txt", dim_z=20, max_tokens_len=30, max_text_len=50, encoder_size=50257, latent=GPT2LatentSpace,
+        model="GPT2", use_discriminator=False, init_text="the picture of",
+        weights="./gpt2/weights/gpt2-pytorch_model.bin", encoder="./gpt2/weights/encoder.json",
+        vocab="./gpt2/weights/vocab.bpe", stochastic=False, algorithm="ga", pop_size=100, batch_size=25,
+        problem_args=dict(n_var=20, n_obj=1, n_constr=20, xl=0, xu=50256),
+    ),
+    # latent arithmetic + operators are built (latent.py, operators.py); the generator is not: the reference takes it
+    # from the un-vendored pytorch_pretrained_biggan package (models.py:4,69)
+    DeepMindBigGAN256=_biggan(256, 64, 32),
+    DeepMindBigGAN512=_biggan(512, 32, 8),
+)
 
 
 def get_config(name):
-    if name in _OUT_OF_SCOPE:
-        raise NotImplementedError(
-            f"config {name!r}: the BigGAN / GPT-2 paths are 'next' rows of SURVEY.md §8(f), not built yet")
     return copy.deepcopy(configs[name])
 
 

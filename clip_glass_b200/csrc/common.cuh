@@ -4,11 +4,32 @@
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 namespace glass {
 
 constexpr float kSqrt2 = 1.4142135623730951f;
 constexpr float kInvSqrt2 = 0.7071067811865476f;
+
+// A/B and work-skipping knobs (GLASS_DEBUG_* environment variables, ConvParams::debug_skip) exist only in builds
+// made with -DGLASS_DEBUG.  The product library never reads the environment: nothing outside glass_config can
+// change what its kernels compute.
+#ifdef GLASS_DEBUG
+constexpr bool kDebugBuild = true;
+inline const char* debug_env(const char* name) { return getenv(name); }
+#else
+constexpr bool kDebugBuild = false;
+inline const char* debug_env(const char*) { return nullptr; }
+#endif
+
+// fp32 pair -> fp16x2, round-to-nearest, SATURATING to +-65504 instead of overflowing to inf (one F2FP.SATFINITE
+// instruction, the same cost as the plain conversion).  Every fp16 activation store goes through this: the
+// reference runs G/D in fp32, so an out-of-range value must degrade to a clamp, never to inf -> NaN scores.
+__device__ __forceinline__ __half2 f2h2_sat(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return *reinterpret_cast<__half2*>(&r);
+}
 
 // ---------------------------------------------------------------------------
 // Implicit-GEMM convolution / GEMM description.
@@ -162,8 +183,8 @@ __device__ __forceinline__ void epilogue_row16(const ConvParams& p, int img, int
     __half2* h1 = reinterpret_cast<__half2*>(&w1);
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      h0[j] = __floats2half2_rn(v[2 * j], v[2 * j + 1]);
-      h1[j] = __floats2half2_rn(v[8 + 2 * j], v[8 + 2 * j + 1]);
+      h0[j] = f2h2_sat(v[2 * j], v[2 * j + 1]);
+      h1[j] = f2h2_sat(v[8 + 2 * j], v[8 + 2 * j + 1]);
     }
     *reinterpret_cast<uint4*>(e.out + out_idx) = w0;
     *reinterpret_cast<uint4*>(e.out + out_idx + half_stride) = w1;

@@ -251,10 +251,10 @@ __device__ __forceinline__ void epilogue_fastN(const EpiParams& e, const float* 
 #pragma unroll
       for (int g = 0; g < 2; ++g) {
         const float4 a = osv[g], b = osv[g + 2];
-        h0[2 * g] = __floats2half2_rn(t[n][4 * g] * a.x, t[n][4 * g + 1] * a.y);
-        h0[2 * g + 1] = __floats2half2_rn(t[n][4 * g + 2] * a.z, t[n][4 * g + 3] * a.w);
-        h1[2 * g] = __floats2half2_rn(t[n][8 + 4 * g] * b.x, t[n][8 + 4 * g + 1] * b.y);
-        h1[2 * g + 1] = __floats2half2_rn(t[n][8 + 4 * g + 2] * b.z, t[n][8 + 4 * g + 3] * b.w);
+        h0[2 * g] = f2h2_sat(t[n][4 * g] * a.x, t[n][4 * g + 1] * a.y);
+        h0[2 * g + 1] = f2h2_sat(t[n][4 * g + 2] * a.z, t[n][4 * g + 3] * a.w);
+        h1[2 * g] = f2h2_sat(t[n][8 + 4 * g] * b.x, t[n][8 + 4 * g + 1] * b.y);
+        h1[2 * g + 1] = f2h2_sat(t[n][8 + 4 * g + 2] * b.z, t[n][8 + 4 * g + 3] * b.w);
       }
       // channels [0,8) and [8,16) of the chunk: adjacent in NHWC, one channel-group plane apart in the I8 layout
       *reinterpret_cast<uint4*>(out_ptr[n]) = w0;
@@ -493,8 +493,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           if (MODE == 4) {
             constexpr uint32_t kLbo = C::kI8RowBytes;                 // next 8-channel group
             constexpr uint32_t kSbo = (BK / 8) * C::kI8RowBytes;      // next image row (= next 8-pixel group)
-            const uint32_t lbo = (p.debug_skip & 2) ? kSbo : kLbo;    // (bring-up knob: swapped roles)
-            const uint32_t sbo = (p.debug_skip & 2) ? kLbo : kSbo;
+            const uint32_t lbo = (kDebugBuild && (p.debug_skip & 2)) ? kSbo : kLbo;    // (bring-up knob: swapped roles)
+            const uint32_t sbo = (kDebugBuild && (p.debug_skip & 2)) ? kLbo : kSbo;
 #pragma unroll
             for (int h = 0; h < C::kPairM; ++h) {                     // tile h of the pair: 8 pixels further right
               for (int tap = 0; tap < 9; ++tap) {
@@ -785,7 +785,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
               tc_ld16_issue(taddr + (c + 1) * 16, accp[(c + 1) & 1][0]);
               tc_ld16_issue(taddr + BN + (c + 1) * 16, accp[(c + 1) & 1][1]);
             }
-            if (valid && !(p.debug_skip & 1)) {
+            if (valid && !(kDebugBuild && (p.debug_skip & 1))) {
               const int j0 = half * kHalf + c * 16;
               size_t half_stride = 8, hs1 = 8;
               __half* optr[2] = {out_addr(0, c, half_stride), out_addr(1, c, hs1)};
@@ -815,7 +815,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
               const int h2 = (ci + 1) / kChunks, c2 = (ci + 1) - h2 * kChunks;
               tc_ld16_issue(taddr + h2 * BN + c2 * 16, acc[(ci + 1) & 1]);
             }
-            if (valid && !(p.debug_skip & 1)) {
+            if (valid && !(kDebugBuild && (p.debug_skip & 1))) {
               const int j0 = half * kHalf + c * 16;
               const float nzc = nscale * nz_cur[h][d2s ? c : 0];
               size_t half_stride = 8;
@@ -956,7 +956,7 @@ __global__ void conv_simt_kernel(const ConvParams p) {
 // The specialised epilogue whose compile-time switches equal this layer's run-time ones, or 0.
 static int pick_epi_spec(const ConvParams& p) {
   const EpiParams& e = p.epi;
-  static const bool off = getenv("GLASS_DEBUG_GENERIC_EPI") != nullptr;     // A/B knob: always the run-time spec
+  static const bool off = debug_env("GLASS_DEBUG_GENERIC_EPI") != nullptr;     // A/B knob: always the run-time spec
   if (off || p.TN != 1 || !p.pow2 || !p.all_valid || p.debug_skip != 0) return 0;
   if ((e.act != kActLrelu && e.act != kActNone) || e.round_fp16_before_act || e.x_phases == 2 || e.cout_shift < 0) return 0;
   if (e.noise != nullptr && e.noise_div_shift < 0) return 0;
@@ -978,7 +978,7 @@ static int pick_epi_spec(const ConvParams& p) {
 
 cudaError_t launch_conv_tc(const ConvParams& p, const TmaMaps& maps, int num_sms, cudaStream_t s) {
   const int spec = pick_epi_spec(p);
-  static const bool log_spec = getenv("GLASS_DEBUG_SPEC_LOG") != nullptr;
+  static const bool log_spec = debug_env("GLASS_DEBUG_SPEC_LOG") != nullptr;
   if (log_spec)
     fprintf(stderr, "conv_tc: H=%d W=%d Cin=%d taps=%d Ntot=%d BN=%d BK=%d mode=%d spec=%d\n", p.H, p.W, p.Cin, p.taps,
             p.Ntot, p.BN, p.BK, p.mode, spec);

@@ -89,6 +89,7 @@ struct glass_engine {
   // workspace (sized for cfg.max_population)
   Arena arena;
   float *z32 = nullptr, *wA = nullptr, *wB = nullptr, *styles = nullptr, *noise = nullptr;
+  float *styles_n = nullptr, *mscale = nullptr;   // power-of-two normalised conv styles + their scales (k_style_norm)
   std::vector<float*> dmod;
   std::vector<float*> rgbw;
   __half *actA = nullptr, *actB = nullptr, *actC = nullptr;   // actC: intermediate of the exact polyphase forms
@@ -109,6 +110,8 @@ struct glass_engine {
   __half *dXd = nullptr, *dR = nullptr, *dOut = nullptr, *dFin = nullptr, *dFinOut = nullptr, *dDense = nullptr;
   float *dlogits = nullptr, *hinge = nullptr;
   double* x_host_stage = nullptr;   // device staging for f64 latents
+  int* gather_rows = nullptr;       // device staging for glass_last_images_gather
+  int last_eval_pop = 0;            // candidates whose images the last fused evaluation left in `images`
   bool have_text = false;
 
   // plan (rebuilt when pop changes)
@@ -133,6 +136,9 @@ struct glass_engine {
   size_t ev_used = 0;
   float last_conv_ms = 0.f;
   int last_conv_launches = 0;
+  // debug: fp16 range scan of every G / D activation tensor (glass_set_range_check)
+  bool range_check = false;
+  unsigned long long* range_ctr = nullptr;
   // debug capture
   bool capture = false;
   std::map<std::string, std::vector<float>> captured;
@@ -224,7 +230,7 @@ int make_conv(glass_engine* e, ConvLaunch* out, const __half* in, int Nimg, int 
   p.tiles_n = (Nimg + p.TN - 1) / p.TN;
   p.BN = pick_bn(Ntot);
   if (gemm) {
-    static const char* cap = getenv("GLASS_DEBUG_GEMM_BN");      // A/B knob for the plain GEMMs' tile width
+    static const char* cap = debug_env("GLASS_DEBUG_GEMM_BN");      // A/B knob for the plain GEMMs' tile width
     if (cap != nullptr && atoi(cap) >= 32 && p.BN > atoi(cap) && Ntot % atoi(cap) == 0) p.BN = atoi(cap);
   }
   p.BK = (Cin % 64 == 0) ? 64 : 32;
@@ -237,7 +243,7 @@ int make_conv(glass_engine* e, ConvLaunch* out, const __half* in, int Nimg, int 
     // Cin <= 64: tile pairs (two 8x16 tiles side by side share one box; conv_tc.cu Cfg::kPairM)
     // 128 channels: MODE 6 (tile pairs, streamed taps) or, behind GLASS_DEBUG_C1_MODE4, MODE 4 with nine resident
     // taps of a 32-column n-tile and single 8-wide tiles (A/B knob)
-    static const bool c128_mode4 = getenv("GLASS_DEBUG_C1_MODE4") != nullptr;
+    static const bool c128_mode4 = debug_env("GLASS_DEBUG_C1_MODE4") != nullptr;
     const int tw = (Cin == 128 && c128_mode4) ? 8 : 16;
     if (gemm || table != nullptr || taps != 9 || (Cin != 32 && Cin != 64 && Cin != 128) || H < 16 || W < tw || H % 16 ||
         W % tw)
@@ -265,7 +271,7 @@ int make_conv(glass_engine* e, ConvLaunch* out, const __half* in, int Nimg, int 
     p.pow2 = (ln >= 0 && lx >= 0 && ly >= 0) ? 1 : 0;
     p.sh_n = ln; p.sh_x = lx; p.sh_y = ly;
     p.all_valid = (H % p.TH == 0 && W % p.TW == 0 && Nimg % p.TN == 0) ? 1 : 0;
-    const char* dbg = getenv("GLASS_DEBUG_SKIP");     // timing experiments only; never set in tests or bench
+    const char* dbg = debug_env("GLASS_DEBUG_SKIP");     // timing experiments only; never set in tests or bench
     p.debug_skip = dbg ? atoi(dbg) : 0;
     p.epi.cout_shift = lg(p.epi.Cout);
     p.epi.noise_div_shift = lg(p.epi.noise_group_div);
@@ -424,9 +430,8 @@ void derive_arch(glass_engine* e) {
     const int Ci = e->gch[c.num_blocks - 1 - b];
     // 4*Ci = 128 channels: conv_tc MODE 6 (haloed I8 box per tile pair, the nine taps streamed through a ring).
     // (MODE 4 with nine resident 128-channel taps only leaves room for BN = 32 and measured slower than the
-    // streamed NHWC form: 5.35 vs 4.45 ms at P=64.)  GLASS_DEBUG_C1_I8=0 keeps the space-to-depth tensor NHWC.
-    const char* c1i8 = getenv("GLASS_DEBUG_C1_I8");
-    const bool on = c1i8 == nullptr || atoi(c1i8) != 0;
+    // streamed NHWC form: 5.35 vs 4.45 ms at P=64.)  GLASS_FLAG_C1_NHWC keeps the space-to-depth tensor NHWC (cross-check).
+    const bool on = (c.flags & GLASS_FLAG_C1_NHWC) == 0;
     e->d_c1_i8.push_back((i8_ok && on && !e->d_exact[b] && Ci == 32 && (e->R >> b) / 2 >= 16 &&
                           e->gch[c.num_blocks - 2 - b] % 64 == 0) ? 1 : 0);
   }
@@ -443,7 +448,7 @@ void derive_arch(glass_engine* e) {
   e->d_res_i8.clear();
   for (int b = 0; b + 1 < c.num_blocks; ++b) {
     const int Co = e->gch[c.num_blocks - 2 - b], ro = (e->R >> b) / 2;
-    const char* env = getenv("GLASS_DEBUG_RES_I8");
+    const char* env = debug_env("GLASS_DEBUG_RES_I8");
     const bool on = env == nullptr || atoi(env) != 0;
     e->d_res_i8.push_back((i8_ok && on && !e->d_proj_fused[b] && ro >= 16 && ro % 16 == 0 && Co % 16 == 0) ? 1 : 0);
   }
@@ -539,10 +544,14 @@ void layout_workspace(glass_engine* e, Arena& a) {
   const int L = c.latent_size;
   const int nb = c.num_blocks;
   e->x_host_stage = (double*)a.take(P * L * 8);
+  e->gather_rows = (int*)a.take(P * 4);
   e->z32 = (float*)a.take(P * L * 4);
   e->wA = (float*)a.take(P * L * 4);
   e->wB = (float*)a.take(P * L * 4);
   e->styles = (float*)a.take(P * e->S * 4);
+  e->styles_n = (float*)a.take(P * e->S * 4);
+  e->mscale = (float*)a.take(P * e->glayers.size() * 4);
+  e->range_ctr = (unsigned long long*)a.take(4 * 8);
   e->max_groups = (int)(P / c.batch_size);
   e->noise = (float*)a.take((size_t)e->max_groups * e->noise_per_group * 4);
   e->dmod.clear();
@@ -654,7 +663,7 @@ int build_plan(glass_engine* e, int P) {
       ep.rgb_out = e->slabs;
     }
     if (li + 1 < nl) {
-      ep.out_scale = e->styles + e->conv_off[li + 1];
+      ep.out_scale = e->styles_n + e->conv_off[li + 1];
       ep.out_scale_stride = e->S;
       ep.out = bufs[cur ^ 1];
       ep.out_i8 = e->g_in_i8[li + 1];
@@ -825,6 +834,7 @@ int run_generator(glass_engine* e, const float* z, int P, const glass_noise* nz,
   const int L = c.latent_size;
   char nm[64];
   if (!noise_ready) RC(fill_noise(e, P, nz, s));
+  RC(capture_f32(e, "noise", e->noise, (size_t)(P / c.batch_size) * e->noise_per_group, s));
   // mapping (stylegan2/models.py:590-627)
   LAUNCH(k_pixelnorm(z, e->wA, P, L, s));
   float* cur = e->wA;
@@ -840,6 +850,13 @@ int run_generator(glass_engine* e, const float* z, int P, const glass_noise* nz,
   // all style affines in one pass (same dlatent for every layer, models.py:427-430)
   LAUNCH(k_vecmat(cur, L, tptr<float>(e, "g.style.w"), tptr<float>(e, "g.style.b"), e->styles, e->S, P, L, e->S, 0, s));
   RC(capture_f32(e, "styles", e->styles, (size_t)P * e->S, s));
+  // fp16 range safety: conv styles normalised per (sample, layer) by a power of two, folded back into dmod below
+  {
+    StyleSlices sl;
+    sl.n = (int)e->glayers.size();
+    for (int li = 0; li < sl.n; ++li) { sl.off[li] = e->conv_off[li]; sl.cin[li] = e->glayers[li].cin; }
+    LAUNCH(k_style_norm(e->styles, e->styles_n, e->mscale, e->S, P, sl, s));
+  }
   // demodulation coefficients of every layer (modules.py:945-954): independent GEMVs, kMaxVecmatJobs per launch
   for (size_t l0 = 0; l0 < e->glayers.size(); l0 += kMaxVecmatJobs) {
     VecmatBatch vb;
@@ -847,7 +864,8 @@ int run_generator(glass_engine* e, const float* z, int P, const glass_noise* nz,
     for (size_t li = l0; li < e->glayers.size() && vb.n < kMaxVecmatJobs; ++li) {
       const GLayer& l = e->glayers[li];
       snprintf(nm, sizeof nm, "g.conv%zu.wsq", li);
-      vb.job[vb.n++] = VecmatJob{e->styles + e->conv_off[li], tptr<float>(e, nm), e->dmod[li], l.cin, l.cout};
+      vb.job[vb.n++] = VecmatJob{e->styles + e->conv_off[li], tptr<float>(e, nm), e->dmod[li], l.cin, l.cout,
+                                 e->mscale + li, (int)e->glayers.size()};
     }
     LAUNCH(k_vecmat_batched(vb, e->S, P, 2, s));
   }
@@ -855,7 +873,7 @@ int run_generator(glass_engine* e, const float* z, int P, const glass_noise* nz,
     snprintf(nm, sizeof nm, "g.rgb%d.w", b);
     LAUNCH(k_rgb_weights(tptr<float>(e, nm), e->styles + e->rgb_off[b], e->S, e->rgbw[b], P, e->gch[b], s));
   }
-  LAUNCH(k_const_input(tptr<float>(e, "g.const"), e->styles + e->conv_off[0], e->S, e->actA, P, e->gch[0], s));
+  LAUNCH(k_const_input(tptr<float>(e, "g.const"), e->styles_n + e->conv_off[0], e->S, e->actA, P, e->gch[0], s));
   RC(capture_f16(e, "x0", e->actA, (size_t)P * 16 * e->gch[0], s));
   float4* ybuf[2] = {e->yA, e->yB};
   int ycur = 0;
@@ -874,9 +892,11 @@ int run_generator(glass_engine* e, const float* z, int P, const glass_noise* nz,
       const float* bias = tptr<float>(e, nm);
       snprintf(nm, sizeof nm, "g.conv%zu.nstr", li);
       LAUNCH(k_upfir(e->actC, dst, e->noise + e->noise_layer_off[li], e->noise_per_group, c.batch_size,
-                     tptr<float>(e, nm), bias, e->styles + e->conv_off[li + 1], e->S, P, l.res, l.res, l.cout, s));
+                     tptr<float>(e, nm), bias, e->styles_n + e->conv_off[li + 1], e->S, P, l.res, l.res, l.cout, s));
       layer_out = dst;
     }
+    if (layer_out != nullptr && e->range_check)
+      LAUNCH(k_range_scan(layer_out, (size_t)P * l.res * l.res * l.cout, e->range_ctr, s));
     if (layer_out != nullptr) {
       snprintf(nm, sizeof nm, "xs%zu", li);
       const bool i8 = li + 1 < nl && e->g_in_i8[li + 1];
@@ -938,7 +958,7 @@ int run_discriminator(glass_engine* e, const float* images, int P, float* logits
   auto dch = [&](int i) { return e->gch[nb - 1 - i]; };
   char nm[64];
   // fromRGB + the first block's projection FIR in one pass (GLASS_DEBUG_SPLIT_FRGB: the two-kernel route)
-  static const bool split_frgb = getenv("GLASS_DEBUG_SPLIT_FRGB") != nullptr;
+  static const bool split_frgb = debug_env("GLASS_DEBUG_SPLIT_FRGB") != nullptr;
   const bool fused_frgb = !split_frgb && dch(0) % 32 == 0;
   // block 0: fromRGB + FIR + projection GEMM in one kernel where the shapes allow it
   const bool frgb_proj = fused_frgb && e->d_proj_fused[0] && k_fir_proj_supported(dch(0), dch(1), true);
@@ -973,6 +993,7 @@ int run_discriminator(glass_engine* e, const float* images, int P, float* logits
     RC(run_conv(e, c1, s));                 // conv1 + residual
     x = c1.p.epi.out;
     res /= 2;
+    if (e->range_check) LAUNCH(k_range_scan(x, (size_t)P * res * res * dch(b + 1), e->range_ctr, s));
     snprintf(nm, sizeof nm, "d%d", b);
     const bool i8 = (b + 1 < nb - 1) && e->d_in_i8[b + 1];
     RC(capture_f16(e, nm, x, (size_t)P * res * res * dch(b + 1), s, i8 ? res : 0, i8 ? dch(b + 1) : 0));
@@ -1006,7 +1027,7 @@ int check_pop(glass_engine* e, int pop) {
 // CLIP tower and the discriminator both depend only on the images, so they are captured as parallel branches
 // (CLIP on the side stream): its small GEMMs fill the SMs that the discriminator's kernel tails leave idle.
 int evaluate_body(glass_engine* e, int pop, cudaStream_t s) {
-  static const bool no_fork = getenv("GLASS_DEBUG_NO_FORK") != nullptr;
+  static const bool no_fork = debug_env("GLASS_DEBUG_NO_FORK") != nullptr;
   RC(run_generator(e, e->z32, pop, nullptr, e->images, s, true));
   const bool fork = e->cfg.use_discriminator && !no_fork;
   cudaStream_t cs = fork ? e->side_stream : s;
@@ -1180,9 +1201,10 @@ int glass_evaluate_device(glass_engine* e, const float* z_dev, int32_t pop, cons
   RC(check_pop(e, pop));
   if (e->cfg.use_discriminator && hinge_dev == nullptr) return fail(GLASS_ERR_ARG, "hinge output is required");
   cudaStream_t s = (cudaStream_t)stream;
-  static const bool no_graph_env = getenv("GLASS_DEBUG_NO_GRAPH") != nullptr;
+  static const bool no_graph_env = debug_env("GLASS_DEBUG_NO_GRAPH") != nullptr;
   const bool use_graph = !no_graph_env && !(e->cfg.flags & GLASS_FLAG_NO_GRAPH) && e->cfg.conv_impl == 0 &&
-                         !e->timing && !e->capture;
+                         !e->timing && !e->capture && !e->range_check;
+  e->last_eval_pop = pop;
   if (!use_graph || e->graph_evals++ == 0) {
     timing_begin(e);
     RC(run_generator(e, z_dev, pop, noise, e->images, s));
@@ -1257,6 +1279,69 @@ int glass_set_debug(glass_engine* e, int32_t capture, int32_t timing) {
   e->capture = capture != 0;
   e->timing = timing != 0;
   if (!e->capture) e->captured.clear();
+  return GLASS_OK;
+}
+
+int glass_debug_build(void) { return kDebugBuild ? 1 : 0; }
+
+int glass_last_images_gather(glass_engine* e, const int32_t* rows_host, int32_t n, float* out_dev, void* stream) {
+  if (!e || !e->finalized) return fail(GLASS_ERR_STATE, "engine is not finalized");
+  if (!rows_host || !out_dev || n <= 0 || n > e->cfg.max_population) return fail(GLASS_ERR_ARG, "bad argument");
+  if (e->last_eval_pop <= 0) return fail(GLASS_ERR_STATE, "no fused evaluation has produced images yet");
+  for (int i = 0; i < n; ++i)
+    if (rows_host[i] < 0 || rows_host[i] >= e->last_eval_pop)
+      return fail(GLASS_ERR_ARG, "row %d is outside the last evaluation's population of %d", rows_host[i], e->last_eval_pop);
+  cudaStream_t s = (cudaStream_t)stream;
+  CUDA_OK(cudaMemcpyAsync(e->gather_rows, rows_host, (size_t)n * 4, cudaMemcpyHostToDevice, s));
+  LAUNCH(k_gather_images(e->images, e->gather_rows, n, (size_t)3 * e->R * e->R, out_dev, s));
+  CUDA_OK(cudaStreamSynchronize(s));      // rows_host is the caller's
+  return GLASS_OK;
+}
+
+int glass_image_grid_u8(glass_engine* e, const float* images_dev, int32_t n, int32_t resolution, int32_t nrow,
+                        int32_t padding, uint8_t* out_dev, void* stream) {
+  if (!images_dev || !out_dev || n <= 0 || resolution <= 0 || nrow <= 0 || padding < 0)
+    return fail(GLASS_ERR_ARG, "bad argument");
+  cudaError_t err = k_image_grid_u8(images_dev, n, resolution, nrow, padding, out_dev, (cudaStream_t)stream);
+  if (e) e->launches++;
+  if (err != cudaSuccess) return fail(GLASS_ERR_CUDA, "k_image_grid_u8 failed: %s", cudaGetErrorString(err));
+  return GLASS_OK;
+}
+
+int glass_biggan_latent(const double* x_host, int32_t pop, int32_t dim_z, int32_t num_classes, float* z_dev,
+                        float* cls_dev, void* stream) {
+  if (!x_host || !z_dev || !cls_dev || pop <= 0 || dim_z <= 0 || num_classes <= 0)
+    return fail(GLASS_ERR_ARG, "bad argument");
+  cudaStream_t s = (cudaStream_t)stream;
+  double* stage = nullptr;
+  const size_t bytes = (size_t)pop * (dim_z + num_classes) * 8;
+  CUDA_OK(cudaMallocAsync((void**)&stage, bytes, s));
+  CUDA_OK(cudaMemcpyAsync(stage, x_host, bytes, cudaMemcpyHostToDevice, s));
+  cudaError_t err = k_biggan_latent(stage, z_dev, cls_dev, pop, dim_z, num_classes, s);
+  cudaFreeAsync(stage, s);
+  if (err != cudaSuccess) return fail(GLASS_ERR_CUDA, "k_biggan_latent failed: %s", cudaGetErrorString(err));
+  CUDA_OK(cudaStreamSynchronize(s));      // x_host is the caller's
+  return GLASS_OK;
+}
+
+int glass_set_range_check(glass_engine* e, int32_t enable) {
+  if (!e || !e->finalized) return fail(GLASS_ERR_STATE, "engine is not finalized");
+  CUDA_OK(cudaSetDevice(e->cfg.device));
+  CUDA_OK(cudaDeviceSynchronize());
+  CUDA_OK(cudaMemset(e->range_ctr, 0, 4 * 8));
+  e->range_check = enable != 0;
+  return GLASS_OK;
+}
+
+int glass_range_report(glass_engine* e, int64_t* nonfinite, int64_t* saturated, float* max_abs) {
+  if (!e || !e->finalized) return fail(GLASS_ERR_STATE, "engine is not finalized");
+  CUDA_OK(cudaSetDevice(e->cfg.device));
+  CUDA_OK(cudaDeviceSynchronize());
+  unsigned long long h[4];
+  CUDA_OK(cudaMemcpy(h, e->range_ctr, sizeof h, cudaMemcpyDeviceToHost));
+  if (nonfinite) *nonfinite = (int64_t)h[0];
+  if (saturated) *saturated = (int64_t)h[1];
+  if (max_abs) { const uint32_t bits = (uint32_t)h[2]; memcpy(max_abs, &bits, 4); }
   return GLASS_OK;
 }
 

@@ -138,8 +138,8 @@ fir_proj_kernel(const __half* __restrict__ x, const float* __restrict__ images, 
         __half2* d = reinterpret_cast<__half2*>(&w1);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          a[j] = __floats2half2_rn(__uint_as_float(r[c & 1][2 * j]), __uint_as_float(r[c & 1][2 * j + 1]));
-          d[j] = __floats2half2_rn(__uint_as_float(r[c & 1][8 + 2 * j]), __uint_as_float(r[c & 1][8 + 2 * j + 1]));
+          a[j] = f2h2_sat(__uint_as_float(r[c & 1][2 * j]), __uint_as_float(r[c & 1][2 * j + 1]));
+          d[j] = f2h2_sat(__uint_as_float(r[c & 1][8 + 2 * j]), __uint_as_float(r[c & 1][8 + 2 * j + 1]));
         }
         *reinterpret_cast<uint4*>(orow + c * 16) = w0;
         *reinterpret_cast<uint4*>(orow + c * 16 + 8) = w1;

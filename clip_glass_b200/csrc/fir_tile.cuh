@@ -62,7 +62,7 @@ __device__ __forceinline__ void fir_down_compute(const uint4* tile, uint4 (&o)[2
       const float e0 = fmaf(3.f, hrow[2 * k + 1][2 * j] + hrow[2 * k + 2][2 * j], hrow[2 * k][2 * j] + hrow[2 * k + 3][2 * j]);
       const float e1 = fmaf(3.f, hrow[2 * k + 1][2 * j + 1] + hrow[2 * k + 2][2 * j + 1],
                             hrow[2 * k][2 * j + 1] + hrow[2 * k + 3][2 * j + 1]);
-      oh[j] = __floats2half2_rn(e0 * (1.f / 64.f), e1 * (1.f / 64.f));
+      oh[j] = f2h2_sat(e0 * (1.f / 64.f), e1 * (1.f / 64.f));
     }
   }
 }
@@ -142,7 +142,7 @@ __device__ __forceinline__ void fd_stage_tile_from_rgb(uint4* tile, const float*
           const int c = g * 8 + 2 * j;
           const float t0 = fmaf(r, k.w[0][c], fmaf(gg, k.w[1][c], fmaf(bl, k.w[2][c], k.w[3][c])));
           const float t1 = fmaf(r, k.w[0][c + 1], fmaf(gg, k.w[1][c + 1], fmaf(bl, k.w[2][c + 1], k.w[3][c + 1])));
-          h2[j] = __floats2half2_rn(fmaxf(t0, 0.2f * t0), fmaxf(t1, 0.2f * t1));
+          h2[j] = f2h2_sat(fmaxf(t0, 0.2f * t0), fmaxf(t1, 0.2f * t1));
         }
       }
       if (mine) {

@@ -126,7 +126,54 @@ __global__ void vecmat_batched_kernel(const VecmatBatch jobs, int in_stride, int
   float acc = (a0 + a1) + (a2 + a3);
   if (mode == 1) acc = (acc > 0.f ? acc : 0.2f * acc) * kSqrt2;
   if (mode == 2) acc = rsqrtf(acc + 1e-8f);
+  if (jb.post_mul != nullptr) acc *= jb.post_mul[(size_t)b * jb.post_stride];
   jb.out[(size_t)b * N + n] = acc;
+}
+
+// one block per (layer, sample): m = 2^ceil(log2 max|s|) over the layer's slice; styles_n = s / m
+__global__ void style_norm_kernel(const float* __restrict__ styles, float* __restrict__ styles_n,
+                                  float* __restrict__ mscale, int S, const StyleSlices sl) {
+  __shared__ float red[32];
+  const int layer = blockIdx.x, b = blockIdx.y;
+  const int off = sl.off[layer], cin = sl.cin[layer];
+  const float* src = styles + (size_t)b * S + off;
+  float mx = 0.f;
+  for (int i = threadIdx.x; i < cin; i += blockDim.x) {
+    const float a = fabsf(src[i]);
+    mx = (a > mx && a <= 3.0e38f) ? a : mx;          // ignores NaN / inf (they propagate through s/m anyway)
+  }
+  mx = warp_max(mx);
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31, nw = (blockDim.x + 31) >> 5;
+  if (l == 0) red[w] = mx;
+  __syncthreads();
+  mx = 0.f;
+  for (int i = 0; i < nw; ++i) mx = fmaxf(mx, red[i]);
+  int ex = 0;
+  float m = 1.f;
+  if (mx > 0.f) {
+    frexpf(mx, &ex);                                   // mx = f * 2^ex, f in [0.5, 1)  =>  |s| / 2^ex < 1
+    m = ldexpf(1.f, ex);
+  }
+  const float inv = 1.f / m;                           // exact
+  for (int i = threadIdx.x; i < cin; i += blockDim.x) styles_n[(size_t)b * S + off + i] = src[i] * inv;
+  if (threadIdx.x == 0) mscale[(size_t)b * sl.n + layer] = m;
+}
+
+__global__ void range_scan_kernel(const __half* __restrict__ x, size_t n, unsigned long long* ctr) {
+  unsigned long long bad = 0, sat = 0;
+  float mx = 0.f;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const float v = fabsf(__half2float(x[i]));
+    if (!(v <= 3.0e38f)) ++bad;                        // inf or NaN
+    else {
+      if (v >= 65504.f) ++sat;
+      mx = fmaxf(mx, v);
+    }
+  }
+  if (bad) atomicAdd(ctr + 0, bad);
+  if (sat) atomicAdd(ctr + 1, sat);
+  mx = warp_max(mx);
+  if ((threadIdx.x & 31) == 0 && mx > 0.f) atomicMax(ctr + 2, (unsigned long long)__float_as_uint(mx));
 }
 
 __global__ void const_input_kernel(const float* cst, const float* styles, int stride, __half* out, int P, int C) {
@@ -265,7 +312,7 @@ __device__ __forceinline__ void st8(__half* p, const float (&v)[8]) {
   uint4 o;
   __half2* oh = reinterpret_cast<__half2*>(&o);
 #pragma unroll
-  for (int j = 0; j < 4; ++j) oh[j] = __floats2half2_rn(v[2 * j], v[2 * j + 1]);
+  for (int j = 0; j < 4; ++j) oh[j] = f2h2_sat(v[2 * j], v[2 * j + 1]);
   *reinterpret_cast<uint4*>(p) = o;
 }
 
@@ -448,6 +495,62 @@ __global__ void final_cosine_kernel(const __half* __restrict__ tokens, const flo
 }
 
 // ---------------------------------------------------------------------------
+// image output path / BigGAN latent arithmetic
+// ---------------------------------------------------------------------------
+__global__ void image_grid_u8_kernel(const float* __restrict__ images, int n, int R, int xmaps, int padding,
+                                     int Hg, int Wg, uint8_t* __restrict__ out) {
+  const int cell = R + padding;
+  const size_t total = (size_t)Hg * Wg;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int X = (int)(i % Wg), Y = (int)(i / Wg);
+    const int gy = Y / cell, gx = X / cell;
+    const int py = Y - gy * cell - padding, px = X - gx * cell - padding;
+    const int k = gy * xmaps + gx;
+    uint8_t v[3] = {0, 0, 0};
+    if (py >= 0 && px >= 0 && gx < xmaps && k < n) {
+      const float* src = images + (size_t)k * 3 * R * R + (size_t)py * R + px;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        // save_image: mul(255).add_(0.5).clamp_(0, 255).to(uint8)  (the cast truncates)
+        const float t = fminf(fmaxf(__fadd_rn(__fmul_rn(src[(size_t)c * R * R], 255.f), 0.5f), 0.f), 255.f);
+        v[c] = (uint8_t)t;
+      }
+    }
+    out[i * 3 + 0] = v[0]; out[i * 3 + 1] = v[1]; out[i * 3 + 2] = v[2];
+  }
+}
+
+__global__ void gather_images_kernel(const float4* __restrict__ images, const int* __restrict__ rows, size_t vec_per_image,
+                                     float4* __restrict__ out) {
+  const float4* src = images + (size_t)rows[blockIdx.y] * vec_per_image;
+  float4* dst = out + (size_t)blockIdx.y * vec_per_image;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < vec_per_image; i += (size_t)gridDim.x * blockDim.x)
+    dst[i] = __ldg(src + i);
+}
+
+// one block per candidate: clip the first dz genes, softmax (fp32, like torch.softmax on a float tensor) over the rest
+__global__ void biggan_latent_kernel(const double* __restrict__ x, float* __restrict__ z, float* __restrict__ cls, int dz,
+                                     int ncls) {
+  __shared__ float red[32];
+  const double* xi = x + (size_t)blockIdx.x * (dz + ncls);
+  for (int i = threadIdx.x; i < dz; i += blockDim.x)
+    z[(size_t)blockIdx.x * dz + i] = fminf(fmaxf((float)xi[i], -2.f), 2.f);
+  float mx = -INFINITY;
+  for (int i = threadIdx.x; i < ncls; i += blockDim.x) mx = fmaxf(mx, (float)xi[dz + i]);
+  mx = warp_max(mx);
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31, nw = (blockDim.x + 31) >> 5;
+  if (l == 0) red[w] = mx;
+  __syncthreads();
+  mx = -INFINITY;
+  for (int i = 0; i < nw; ++i) mx = fmaxf(mx, red[i]);
+  float sum = 0.f;
+  for (int i = threadIdx.x; i < ncls; i += blockDim.x) sum += expf((float)xi[dz + i] - mx);
+  sum = block_sum(sum, red);
+  for (int i = threadIdx.x; i < ncls; i += blockDim.x)
+    cls[(size_t)blockIdx.x * ncls + i] = expf((float)xi[dz + i] - mx) / sum;
+}
+
+// ---------------------------------------------------------------------------
 // discriminator
 // ---------------------------------------------------------------------------
 template <int C>
@@ -477,7 +580,7 @@ __global__ void from_rgb_kernel(const float* __restrict__ images, const float* _
         const float t = fmaf(r, w[c], fmaf(gg, w[C + c], fmaf(bl, w[2 * C + c], w[3 * C + c])));
         a[u] = fmaxf(t, 0.2f * t) * kSqrt2;
       }
-      h2[j] = __floats2half2_rn(a[0], a[1]);
+      h2[j] = f2h2_sat(a[0], a[1]);
     }
     if (out_i8) {
       const size_t y = pix / R, x = pix - y * R;
@@ -806,6 +909,35 @@ cudaError_t k_vecmat_batched(const VecmatBatch& jobs, int in_stride, int P, int 
   int maxN = 0, maxK = 0;
   for (int i = 0; i < jobs.n; ++i) { maxN = jobs.job[i].N > maxN ? jobs.job[i].N : maxN; maxK = jobs.job[i].K > maxK ? jobs.job[i].K : maxK; }
   vecmat_batched_kernel<<<dim3((maxN + 127) / 128, P, jobs.n), 128, maxK * sizeof(float), s>>>(jobs, in_stride, mode);
+  GLASS_RET();
+}
+cudaError_t k_style_norm(const float* styles, float* styles_n, float* mscale, int S, int P, const StyleSlices& sl,
+                         cudaStream_t s) {
+  if (sl.n <= 0 || sl.n > kMaxStyleSlices) return cudaErrorInvalidValue;
+  style_norm_kernel<<<dim3(sl.n, P), 128, 0, s>>>(styles, styles_n, mscale, S, sl);
+  GLASS_RET();
+}
+cudaError_t k_range_scan(const __half* x, size_t n, unsigned long long* ctr, cudaStream_t s) {
+  range_scan_kernel<<<blocks_for(n), kThreads, 0, s>>>(x, n, ctr);
+  GLASS_RET();
+}
+cudaError_t k_image_grid_u8(const float* images, int n, int R, int nrow, int padding, uint8_t* out, cudaStream_t s) {
+  if (n <= 0 || nrow <= 0 || padding < 0) return cudaErrorInvalidValue;
+  const int xmaps = n < nrow ? n : nrow, ymaps = (n + xmaps - 1) / xmaps;
+  const int Hg = (R + padding) * ymaps + padding, Wg = (R + padding) * xmaps + padding;
+  image_grid_u8_kernel<<<blocks_for((size_t)Hg * Wg), kThreads, 0, s>>>(images, n, R, xmaps, padding, Hg, Wg, out);
+  GLASS_RET();
+}
+cudaError_t k_gather_images(const float* images, const int* rows, int n, size_t image_elems, float* out, cudaStream_t s) {
+  if (n <= 0 || image_elems % 4 != 0) return cudaErrorInvalidValue;
+  const size_t vec = image_elems / 4;
+  gather_images_kernel<<<dim3(blocks_for(vec, kThreads, 148 * 4), n), kThreads, 0, s>>>(
+      reinterpret_cast<const float4*>(images), rows, vec, reinterpret_cast<float4*>(out));
+  GLASS_RET();
+}
+cudaError_t k_biggan_latent(const double* x, float* z, float* cls, int P, int dz, int ncls, cudaStream_t s) {
+  if (P <= 0 || dz <= 0 || ncls <= 0) return cudaErrorInvalidValue;
+  biggan_latent_kernel<<<P, 256, 0, s>>>(x, z, cls, dz, ncls);
   GLASS_RET();
 }
 cudaError_t k_layernorm(const __half* x, const float* w, const float* b, __half* out, int M, int W, cudaStream_t s) {

@@ -14,9 +14,21 @@ cudaError_t k_vecmat(const float* in, int in_stride, const float* Wt, const floa
                      int P, int K, int N, int mode, cudaStream_t s);
 // the same for up to kMaxVecmatJobs independent (in, Wt, out) triples in one launch; out row stride = N, no bias
 constexpr int kMaxVecmatJobs = 32;
-struct VecmatJob { const float* in; const float* Wt; float* out; int K, N; };
+// post_mul (optional): per-sample scalar, out[b,n] *= post_mul[b*post_stride]
+struct VecmatJob { const float* in; const float* Wt; float* out; int K, N; const float* post_mul; int post_stride; };
 struct VecmatBatch { VecmatJob job[kMaxVecmatJobs]; int n; };
 cudaError_t k_vecmat_batched(const VecmatBatch& jobs, int in_stride, int P, int mode, cudaStream_t s);
+// fp16 range safety (stylegan2/modules.py:936-958 runs in fp32): every modulated conv's style slice
+// s[b, off : off+cin] is divided by m[b,layer] = the power of two >= max|s| before it pre-scales the fp16 activation,
+// and the layer's demodulation coefficient is multiplied by m (k_vecmat_batched post_mul).  Demodulation cancels a
+// per-sample scalar exactly, and a power of two changes no rounding, so results are bit-identical to the
+// un-normalised algebra wherever that one stayed finite.
+constexpr int kMaxStyleSlices = 32;
+struct StyleSlices { int off[kMaxStyleSlices]; int cin[kMaxStyleSlices]; int n; };
+cudaError_t k_style_norm(const float* styles, float* styles_n, float* mscale, int S, int P, const StyleSlices& sl,
+                         cudaStream_t s);
+// debug: counts non-finite and saturated (|x| >= 65504) fp16 values and tracks max|x| (as float bits) in ctr[0..2]
+cudaError_t k_range_scan(const __half* x, size_t n, unsigned long long* ctr, cudaStream_t s);
 // x0[b][pix][c] = fp16(const[pix][c] * s[b*stride + c])   (models.py:987 + pre-scale by the first style)
 cudaError_t k_const_input(const float* cst, const float* styles, int stride, __half* out, int P, int C, cudaStream_t s);
 // wr[b][c][o] = W[c][o] * styles[b*stride + off + o]   (toRGB modulated 1x1 weights, no demod; models.py:848-871)
@@ -37,6 +49,17 @@ cudaError_t k_upfir(const __half* u, __half* out, const float* noise, size_t noi
 // Exact down-conv, first half (modules.py:1243-1246 FilterLayer pad 2): a [P][H][W][C] -> blurred (H+1)x(W+1),
 // written space-to-depth as [P][H/2+1][W/2+1][4C] (phase-major channels), zeros beyond row/col H
 cudaError_t k_blur_s2d(const __half* a, __half* out, int P, int H, int W, int C, cudaStream_t s);
+
+// ---- image output path (run.py:29-51 save_callback -> generator.py:63-68 -> utils.py:5-7) ----
+// torchvision.utils.make_grid (xmaps = min(nrow, n) images per row, `padding` zero pixels around each) fused with
+// save_image's mul(255).add(0.5).clamp(0,255).to(uint8) and the CHW -> HWC permute: images [n,3,R,R] fp32 in [0,1]
+// -> out [Hg][Wg][3] uint8 with Hg = (R+padding)*ceil(n/xmaps)+padding, Wg = (R+padding)*xmaps+padding.
+cudaError_t k_image_grid_u8(const float* images, int n, int R, int nrow, int padding, uint8_t* out, cudaStream_t s);
+// out[i] = images[rows[i]] for whole [3,R,R] fp32 images (rows on the device)
+cudaError_t k_gather_images(const float* images, const int* rows, int n, size_t image_elems, float* out, cudaStream_t s);
+// ---- BigGAN latent arithmetic (latent.py:16-24): x f64 [P, dz + ncls] -> z = clip(x[:, :dz], -2, 2) fp32,
+// cls = softmax(x[:, dz:]) fp32 over the ncls "bool" genes ----
+cudaError_t k_biggan_latent(const double* x, float* z, float* cls, int P, int dz, int ncls, cudaStream_t s);
 
 // ---- CLIP tower ----
 // generator.py:45 (bilinear 1024->224, align_corners=False) fused with the im2col of

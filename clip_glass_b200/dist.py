@@ -4,8 +4,11 @@ Candidates are independent through G and CLIP, and coupled only inside one
 reference minibatch (shared noise draw, modules.py:426-452; MinibatchStd
 groups, modules.py:726).  So the population is cut into contiguous blocks that
 are whole multiples of ``batch_size``, each rank evaluates its block, and ONE
-all-gather of the [P_local, n_obj] fp32 fitnesses per generation rebuilds F
-on every rank — 4 KB at P=512.  No other collective is on the data path.
+all-gather of the [n_obj, P_local] fp32 fitnesses per generation rebuilds F
+on every rank — 4 KB at P=512.  No other collective is on the data path: the
+column count comes from the config (``n_obj``), not from a second collective,
+and with NCCL the gather runs straight from the engine's device outputs (one
+D2H copy of the gathered F at the end instead of one per rank-local array).
 """
 from __future__ import annotations
 
@@ -36,49 +39,54 @@ def _world():
     return 0, 1
 
 
-def all_gather_fitness(local: np.ndarray, bounds, device: Optional[torch.device] = None) -> np.ndarray:
-    """All-gather of per-rank [P_r, k] fp32 blocks (padded to the largest shard)."""
+def _gather_blocks(send: torch.Tensor, world: int) -> torch.Tensor:
+    """The one collective: all ranks' [k, longest] blocks -> [world, k, longest]."""
+    recv = torch.empty((world,) + tuple(send.shape), dtype=send.dtype, device=send.device)
+    if tdist.get_backend() == "gloo":
+        # (all_gather_into_tensor is not implemented by every gloo build)
+        tdist.all_gather(list(recv.unbind(0)), send)
+    else:
+        tdist.all_gather_into_tensor(recv, send)
+    return recv
+
+
+def all_gather_fitness(local, bounds, n_obj: int, device: Optional[torch.device] = None) -> np.ndarray:
+    """All-gather of per-rank fitness blocks.  ``local``: [P_r, n_obj] ndarray, or a tuple of ``n_obj`` device
+    (or host) tensors of length P_r.  Returns the full [P, n_obj] fp32 ndarray on every rank."""
     rank, world = _world()
+    cols = [torch.as_tensor(c) for c in (local if isinstance(local, (tuple, list)) else np.asarray(local).T)]
+    assert len(cols) == n_obj or (len(cols) == 0 and bounds[rank][0] == bounds[rank][1]), (len(cols), n_obj)
     if world == 1:
-        return local
-    k = local.shape[1]
+        return torch.stack([c.float().cpu() for c in cols], 1).numpy()
     longest = max(e - s for s, e in bounds)
-    backend = tdist.get_backend()
-    dev = device if device is not None else (torch.device("cuda", torch.cuda.current_device())
-                                             if backend == "nccl" else torch.device("cpu"))
-    send = torch.zeros(longest, k, dtype=torch.float32, device=dev)
-    if local.shape[0]:
-        send[:local.shape[0]] = torch.from_numpy(np.ascontiguousarray(local, dtype=np.float32)).to(dev)
-    recv = torch.empty(world * longest, k, dtype=torch.float32, device=dev)
-    tdist.all_gather_into_tensor(recv, send)
-    recv = recv.reshape(world, longest, k).cpu().numpy()
-    return np.concatenate([recv[r, : e - s] for r, (s, e) in enumerate(bounds)], axis=0)
+    if device is None:
+        device = (torch.device("cuda", torch.cuda.current_device()) if tdist.get_backend() == "nccl"
+                  else torch.device("cpu"))
+    send = torch.zeros(n_obj, longest, dtype=torch.float32, device=device)
+    for j, c in enumerate(cols):
+        if c.numel():
+            send[j, :c.numel()].copy_(c.to(device=device, dtype=torch.float32), non_blocking=True)
+    recv = _gather_blocks(send, world).cpu().numpy()                # [world, n_obj, longest]
+    return np.concatenate([recv[r, :, : e - s].T for r, (s, e) in enumerate(bounds)], axis=0)
 
 
-def sharded_evaluate(x: np.ndarray, batch_size: int,
-                     evaluate_local: Callable[[np.ndarray, int], Tuple[np.ndarray, Optional[np.ndarray]]]):
-    """Evaluate ``x`` [P, n_var] over all ranks.  ``evaluate_local(x_shard, first_group)``
-    returns (neg_sim[P_r], hinge[P_r] | None); ``first_group`` is the global index of the
-    shard's first minibatch (so that seeded noise is identical to the single-rank run)."""
+def sharded_evaluate(x: np.ndarray, batch_size: int, n_obj: int,
+                     evaluate_local: Callable[[np.ndarray, int], Tuple]):
+    """Evaluate ``x`` [P, n_var] over all ranks.  ``evaluate_local(x_shard, first_group)`` returns
+    (neg_sim[P_r], hinge[P_r] | None) as host arrays or device tensors; ``first_group`` is the global index of
+    the shard's first minibatch (so that seeded noise is identical to the single-rank run).  ``n_obj`` = 2 when
+    the hinge column exists (config.problem_args["n_obj"] == 2 and config.use_discriminator), else 1."""
     rank, world = _world()
     if world == 1:
-        return evaluate_local(x, 0)
+        neg_sim, hinge = evaluate_local(x, 0)
+        as_np = lambda t: t.float().cpu().numpy() if isinstance(t, torch.Tensor) else t
+        return as_np(neg_sim), (as_np(hinge) if hinge is not None else None)
     bounds = shard_bounds(x.shape[0], batch_size, world)
     s, e = bounds[rank]
+    cols: list = []
     if e > s:
         neg_sim, hinge = evaluate_local(x[s:e], s // batch_size)
-        cols = [neg_sim] + ([hinge] if hinge is not None else [])
-        local = np.stack(cols, axis=1).astype(np.float32)
-        have_hinge = hinge is not None
-    else:
-        local, have_hinge = None, None
-    # ranks with empty shards need the column count
-    ncol = torch.tensor([0 if local is None else local.shape[1]], dtype=torch.int64)
-    if tdist.get_backend() == "nccl":
-        ncol = ncol.cuda()
-    tdist.all_reduce(ncol, op=tdist.ReduceOp.MAX)
-    k = int(ncol.item())
-    if local is None:
-        local = np.zeros((0, k), dtype=np.float32)
-    full = all_gather_fitness(local, bounds)
-    return full[:, 0], (full[:, 1] if k == 2 else None)
+        cols = [neg_sim] + ([hinge] if n_obj == 2 else [])
+        assert n_obj == 1 or hinge is not None, "n_obj == 2 needs the discriminator's hinge column"
+    full = all_gather_fitness(tuple(cols), bounds, n_obj)
+    return full[:, 0], (full[:, 1] if n_obj == 2 else None)

@@ -165,6 +165,28 @@ class GlassEngine:
         check(self.lib.glass_discriminate(self._h, images.data_ptr(), images.shape[0], out.data_ptr(), self._stream()))
         return out.unsqueeze(1)
 
+    # -- image output path -------------------------------------------------
+    def last_images(self, rows) -> torch.Tensor:
+        """Images [n,3,R,R] (fp32, [0,1], device) of rows ``rows`` of the last fused evaluation — the images that were
+        scored (run.py:29-51 save_callback would render them again)."""
+        rows = np.ascontiguousarray(rows, dtype=np.int32)
+        R = self.gan.resolution
+        out = torch.empty(len(rows), 3, R, R, dtype=torch.float32, device=torch.device("cuda", self.device))
+        check(self.lib.glass_last_images_gather(self._h, rows.ctypes.data, len(rows), out.data_ptr(), self._stream()))
+        return out
+
+    def image_grid_u8(self, images: torch.Tensor, nrow: int = 8, padding: int = 2) -> np.ndarray:
+        """utils.py:5-7: make_grid + save_image's uint8 conversion, on the device; returns the HWC uint8 ndarray."""
+        assert images.is_cuda and images.dtype == torch.float32 and images.is_contiguous() and images.shape[1] == 3
+        n, _, R, R2 = images.shape
+        assert R == R2
+        xmaps = min(nrow, n)
+        ymaps = (n + xmaps - 1) // xmaps
+        Hg, Wg = (R + padding) * ymaps + padding, (R + padding) * xmaps + padding
+        out = torch.empty(Hg, Wg, 3, dtype=torch.uint8, device=images.device)
+        check(self.lib.glass_image_grid_u8(self._h, images.data_ptr(), n, R, nrow, padding, out.data_ptr(), self._stream()))
+        return out.cpu().numpy()
+
     # -- introspection -----------------------------------------------------
     @property
     def launch_count(self) -> int:
@@ -172,6 +194,16 @@ class GlassEngine:
 
     def set_debug(self, capture: bool = False, timing: bool = False) -> None:
         check(self.lib.glass_set_debug(self._h, int(capture), int(timing)))
+
+    def set_range_check(self, enable: bool = True) -> None:
+        """Scan every G / D fp16 activation tensor of later calls (resets the counters; eager launches)."""
+        check(self.lib.glass_set_range_check(self._h, int(enable)))
+
+    def range_report(self) -> dict:
+        """{'nonfinite', 'saturated', 'max_abs'} over the activations scanned since ``set_range_check``."""
+        bad, sat, mx = ctypes.c_int64(), ctypes.c_int64(), ctypes.c_float()
+        check(self.lib.glass_range_report(self._h, ctypes.byref(bad), ctypes.byref(sat), ctypes.byref(mx)))
+        return dict(nonfinite=int(bad.value), saturated=int(sat.value), max_abs=float(mx.value))
 
     def debug_read(self, name: str) -> np.ndarray:
         n = self.lib.glass_debug_read(self._h, name.encode(), None, 0)

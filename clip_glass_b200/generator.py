@@ -19,6 +19,7 @@ from __future__ import annotations
 import os
 from typing import Optional
 
+import numpy as np
 import torch
 
 from . import weights as W
@@ -39,12 +40,11 @@ def _load_state_dicts(config):
         raise GlassError(f"weights not found under {wdir!r} and no synthetic_seed given "
                          "(the reference would print 'Run: ./download-weights.sh' and exit, models.py:91-101)")
     if have_real and seed is None:
-        def sd_of(path):
-            blob = torch.load(path, map_location="cpu", weights_only=False)
-            sd = blob["state_dict"] if isinstance(blob, dict) and "state_dict" in blob else blob
-            return {k: v for k, v in sd.items()}
-        g_sd = sd_of(os.path.join(wdir, "G.pth"))
-        d_sd = sd_of(os.path.join(wdir, "D.pth")) if config.use_discriminator else None
+        g_sd, g_kw = W.load_reference_checkpoint(os.path.join(wdir, "G.pth"))
+        d_sd, d_kw = (W.load_reference_checkpoint(os.path.join(wdir, "D.pth"))
+                      if config.use_discriminator else (None, None))
+        if not hasattr(config, "gan_spec"):
+            gan = W.gan_spec_from_checkpoint(g_sd, g_kw, d_kw)       # church / car / ffhq: built from the pickle
         clip_path = getattr(config, "clip_weights", os.path.expanduser("~/.cache/clip/ViT-B-32.pt"))
         full = torch.jit.load(clip_path, map_location="cpu").state_dict()
         c_sd = {k[len("visual."):]: v for k, v in full.items() if k.startswith("visual.")}
@@ -80,14 +80,52 @@ class Generator:
         self.engine.set_text_features(self.text_features)
         self._calls = 0
 
+    # -- image output path -------------------------------
+    def remember_population(self, x, offset: int = 0):
+        """Called by ``GenerationProblem._evaluate`` after a fused evaluation: the engine still holds the images it
+        scored (fp32 [P,3,R,R] in its workspace).  run.py:29-51 ``save_callback`` asks for images of candidates of
+        the current population — most of them rendered by this very evaluation — through ``generate``; rows that are
+        found here are copied out of the engine instead of being rendered a second time."""
+        self._last_x32 = np.ascontiguousarray(np.asarray(x, dtype=np.float64)).astype(np.float32)
+        self._last_rows = {row.tobytes(): i for i, row in enumerate(self._last_x32)}
+        self.reuse_stats = dict(reused=0, rendered=0)
+
+    def _cached_rows(self, z_host: np.ndarray):
+        rows = getattr(self, "_last_rows", None)
+        if not rows or not getattr(self.config, "reuse_evaluated_images", True):
+            return [None] * len(z_host)
+        return [rows.get(np.ascontiguousarray(r).tobytes()) for r in z_host]
+
     # generator.py:29-34
     def generate(self, ls, minibatch=None, noise=None):
         z = ls()[0]
         z = z.to(self.config.device, torch.float32).contiguous()
-        self.engine.set_batch_size(minibatch if minibatch is not None else z.shape[0])
-        self._calls += 1
-        seed = int(getattr(self.config, "noise_seed", 0)) + self._calls
-        return self.engine.generate(z, noise=noise, seed=seed)     # already normalised to [0,1]
+        n = z.shape[0]
+        hits = self._cached_rows(z.cpu().numpy()) if noise is None else [None] * n
+        missing = [i for i, h in enumerate(hits) if h is None]
+        if len(missing) == n:
+            self.engine.set_batch_size(minibatch if minibatch is not None else n)
+            self._calls += 1
+            seed = int(getattr(self.config, "noise_seed", 0)) + self._calls
+            return self.engine.generate(z, noise=noise, seed=seed)     # already normalised to [0,1]
+        # some (usually all) of the requested candidates were rendered and scored by the last _evaluate
+        R = self.gan.resolution
+        out = torch.empty(n, 3, R, R, dtype=torch.float32, device=z.device)
+        have = [i for i, h in enumerate(hits) if h is not None]
+        got = self.engine.last_images([hits[i] for i in have])
+        out[torch.as_tensor(have, device=z.device)] = got
+        self.reuse_stats["reused"] += len(have)
+        if missing:
+            # render the rest: whole minibatches (models.py:112), padded by repeating the last missing row
+            mb = minibatch if minibatch is not None else len(missing)
+            idx = missing + [missing[-1]] * ((-len(missing)) % mb)
+            self.engine.set_batch_size(mb)
+            self._calls += 1
+            seed = int(getattr(self.config, "noise_seed", 0)) + self._calls
+            extra = self.engine.generate(z[torch.as_tensor(idx, device=z.device)].contiguous(), seed=seed)
+            out[torch.as_tensor(missing, device=z.device)] = extra[:len(missing)]
+            self.reuse_stats["rendered"] += len(missing)
+        return out
 
     # generator.py:36-38
     def discriminate(self, images, minibatch=None):
@@ -105,6 +143,16 @@ class Generator:
 
     # generator.py:63-68
     def save(self, input, path):
+        """utils.py:5-7 ``save_grid`` (torchvision make_grid + save_image) for P > 1, ``save_image(input[0])`` for one
+        image.  Device tensors go through ``glass_image_grid_u8``: grid assembly, the x255 + 0.5 clamp, the uint8 cast
+        and the CHW->HWC permute happen in one kernel and a quarter of the bytes cross PCIe; PIL encodes the file
+        exactly as torchvision's save_image would (``Image.fromarray(ndarr).save(path)``)."""
+        if isinstance(input, torch.Tensor) and input.is_cuda:
+            from PIL import Image
+            grid = self.engine.image_grid_u8(input.detach().float().contiguous(),
+                                             nrow=8, padding=2 if input.shape[0] > 1 else 0)
+            Image.fromarray(grid).save(path)
+            return
         from torchvision.utils import save_image
         from .utils import save_grid
         if input.shape[0] > 1:

@@ -57,13 +57,22 @@ class GenerationProblem(_Base):
             self.generator.engine.set_batch_size(self.config.batch_size)
             noise = kwargs.get("noise")     # explicit noise: [groups][layers] tensors (tests / parity runs)
 
+            multi = dist._world()[1] > 1
+
             def local(xs, first_group):
                 nz = None
                 if noise is not None:
                     nz = noise[first_group:first_group + xs.shape[0] // self.config.batch_size]
+                self.generator.remember_population(xs)      # the engine keeps this shard's images (save_callback)
+                if multi:
+                    # outputs stay on the device: the all-gather reads them there (one D2H of the gathered F)
+                    z = torch.from_numpy(np.ascontiguousarray(xs, dtype=np.float64)).to(
+                        self.config.device, non_blocking=True).float()           # latent.py:38
+                    return self.generator.engine.evaluate_device(z, noise=nz, seed=seed, first_group=first_group)
                 return self.generator.engine.evaluate(xs, noise=nz, seed=seed, first_group=first_group)
 
-            neg_sim, hinge = dist.sharded_evaluate(x, self.config.batch_size, local)
+            n_obj = 2 if self._two_objective() else 1
+            neg_sim, hinge = dist.sharded_evaluate(x, self.config.batch_size, n_obj, local)
             if self._two_objective():
                 out["F"] = np.column_stack((neg_sim, hinge))
             else:

@@ -94,8 +94,13 @@ def _gen(seed: int) -> torch.Generator:
     return g
 
 
-def make_generator_weights(spec: GanSpec = FFHQ, seed: int = 0) -> Dict[str, torch.Tensor]:
-    """State dict (learnable tensors only) for the reference ``Generator``."""
+def make_generator_weights(spec: GanSpec = FFHQ, seed: int = 0, stress: bool = False) -> Dict[str, torch.Tensor]:
+    """State dict (learnable tensors only) for the reference ``Generator``.
+
+    ``stress``: fp16-range stress variant (the reference runs G in fp32).  Trained ffhq styles reach magnitudes far
+    above the ``1 + N(0, 0.1^2)`` drawn here, so the style-affine biases of the modulated 3x3 convs are scaled by
+    30 on four input channels (even layers) or by 20000 on two (odd layers: activation x style then exceeds the
+    fp16 maximum of 65504 unless the style is normalised), and three output channels of every conv weight by 10."""
     g = _gen(seed)
     n = lambda *s, std=1.0: torch.randn(*s, generator=g) * std
     L = spec.latent_size
@@ -127,6 +132,17 @@ def make_generator_weights(spec: GanSpec = FFHQ, seed: int = 0) -> Dict[str, tor
         # utils.py:14-17 does not hide errors behind saturation
         sd[p + ".layer.weight"] *= 0.15
         sd[p + ".bias"] = n(3, std=0.1)
+    if stress:
+        li = 0
+        for b in range(spec.num_blocks):
+            for l in range(1 if b == 0 else 2):
+                p = f"G_synthesis.conv_blocks.{b}.conv_block.{l}.layer.layer"
+                if li % 2 == 0:
+                    sd[p + ".dense.bias"][0:4] *= 30.0
+                else:
+                    sd[p + ".dense.bias"][4:6] *= 20000.0
+                sd[p + ".weight"][0:3] *= 10.0
+                li += 1
     return sd
 
 
@@ -222,3 +238,85 @@ def make_latents(pop: int, dim: int = 512, seed: int = 4):
     import numpy as np
     x = np.random.default_rng(seed).normal(0.0, 1.0, size=(pop, dim))
     return np.clip(x, -10.0, 10.0)
+
+
+# ---------------------------------------------------------------------------
+# real checkpoints: the reference's pickle-dict format (stylegan2/models.py:111-132, 160-196, 249-262)
+# ---------------------------------------------------------------------------
+def flatten_reference_blob(blob, prefix: str = ""):
+    """``G.pth`` / ``D.pth`` as written by the reference's ``_serialize``: a dict
+    ``{'name', 'kwargs', 'state_dict', <sub-model name>: <the same, recursively>}``.  ``Generator`` overrides
+    ``_get_state_dict`` (stylegan2/models.py:249-262), so its top-level ``state_dict`` holds only the ``dlatent_avg``
+    buffer and the weights sit under ``blob['G_mapping']['state_dict']`` (keys ``main.0...``) and
+    ``blob['G_synthesis']['state_dict']`` (keys ``const``, ``conv_blocks...``).  Returns
+    ``(flat_state_dict, kwargs_by_prefix)`` with the sub-model names as key prefixes — the layout
+    ``nn.Module.state_dict()`` of the assembled model has and ``packing.pack_*`` read."""
+    if not (isinstance(blob, dict) and "state_dict" in blob):
+        return dict(blob), {prefix.rstrip("."): {}}            # a bare state_dict
+    flat = {prefix + k: v for k, v in blob["state_dict"].items()}
+    kwargs = {prefix.rstrip("."): dict(blob.get("kwargs", {}))}
+    for key, sub in blob.items():
+        if key in ("name", "kwargs", "state_dict"):
+            continue
+        if isinstance(sub, dict) and "state_dict" in sub:
+            f2, k2 = flatten_reference_blob(sub, prefix + key + ".")
+            flat.update(f2)
+            kwargs.update(k2)
+    return flat, kwargs
+
+
+def load_reference_checkpoint(path: str):
+    """torch.load + ``flatten_reference_blob``."""
+    blob = torch.load(path, map_location="cpu", weights_only=False)
+    return flatten_reference_blob(blob)
+
+
+class UnsupportedArchitecture(ValueError):
+    pass
+
+
+def gan_spec_from_checkpoint(g_sd, g_kwargs, d_kwargs=None) -> GanSpec:
+    """Architecture hyper-parameters from the checkpoint itself (the reference rebuilds the nets from the pickled
+    kwargs, stylegan2/models.py:160-180; config.py only names the weight folder), so that the church / car / ffhq
+    config-f checkpoints all load without a hand-written spec.  Shapes are read from the tensors, flags from kwargs;
+    anything the CUDA path does not implement fails here with a message instead of a KeyError in packing."""
+    syn = g_kwargs.get("G_synthesis", {})
+    mp = g_kwargs.get("G_mapping", {})
+    n_blocks = 0
+    while f"G_synthesis.to_data_layers.{n_blocks}.layer.weight" in g_sd:
+        n_blocks += 1
+    if n_blocks < 2:
+        raise UnsupportedArchitecture("no G_synthesis.to_data_layers.* tensors: not a skip-architecture StyleGAN2 generator")
+    ch_first_to_last = [int(g_sd[f"G_synthesis.to_data_layers.{b}.layer.weight"].shape[1]) for b in range(n_blocks)]
+    n_map = 0
+    while f"G_mapping.main.{n_map}.layer.weight" in g_sd:
+        n_map += 1
+    latent = int(g_sd["G_mapping.main.0.layer.weight"].shape[1])
+    problems = []
+    if syn.get("resnet", False) or not syn.get("skip", True):
+        problems.append("G_synthesis must be the skip architecture (skip=True, resnet=False)")
+    if syn.get("data_channels", 3) != 3:
+        problems.append("data_channels must be 3")
+    if mp.get("label_size", 0):
+        problems.append("conditional mapping networks (label_size > 0) are not supported")
+    if any(c % 32 or c <= 0 or c > 512 for c in ch_first_to_last):
+        problems.append(f"channels {ch_first_to_last} must be multiples of 32 in [32, 512]")
+    if tuple(g_sd["G_synthesis.const"].shape[1:]) != (4, 4):
+        problems.append("base resolution must be 4x4")
+    for key in ("conv_filter", "skip_filter", "conv_resample_filter"):
+        f = syn.get(key, [1, 3, 3, 1])
+        if list(f) != [1, 3, 3, 1]:
+            problems.append(f"{key} must be [1,3,3,1]")
+    if str(syn.get("activation", "leaky:0.2")) not in ("leaky:0.2", "lrelu:0.2"):
+        problems.append("activation must be leaky:0.2")
+    d_kwargs = (d_kwargs or {}).get("", d_kwargs or {})
+    if d_kwargs:
+        if not d_kwargs.get("resnet", True) or d_kwargs.get("skip", False):
+            problems.append("the discriminator must be the resnet architecture")
+        if d_kwargs.get("mbstd_group_size", 4) not in (0, 1, 2, 4, 8) and d_kwargs.get("mbstd_group_size") is not None:
+            problems.append("mbstd_group_size must be <= 8")
+    if problems:
+        raise UnsupportedArchitecture("checkpoint architecture not supported by the B200 path: " + "; ".join(problems))
+    mb = d_kwargs.get("mbstd_group_size", 4) if d_kwargs else 4
+    return GanSpec(channels=tuple(ch_first_to_last[::-1]), latent_size=latent, mapping_layers=n_map,
+                   mbstd_group_size=int(mb or 0))

@@ -79,6 +79,9 @@ typedef struct glass_config {
  * + a 1x1 conv_tc launch at P=64 (2.86 vs 2.55 ms on the 1024^2 block: its serial stage/FIR/MMA/store phases leave
  * three resident blocks per SM idle too often), so it is off by default and kept as a cross-checked variant. */
 #define GLASS_FLAG_PROJ_FUSION 64
+/* Cross-check variant: keep the space-to-depth tensor between conv0 and the folded conv1 of the D 1024^2 block NHWC
+ * (conv_tc MODE 0 instead of the I8 layout + MODE 6 streamed taps).  Same products, different accumulation order. */
+#define GLASS_FLAG_C1_NHWC 128
 
 /* -- lifetime ------------------------------------------------------------- */
 /* Replaces Generator.__init__ (generator.py:12-27): allocate the engine. */
@@ -143,6 +146,25 @@ int glass_clip_similarity(glass_engine* e, const float* images_dev, int32_t pop,
 int glass_discriminate(glass_engine* e, const float* images_dev, int32_t pop,
                        float* logits_dev, void* stream);
 
+/* -- image output path ----------------------------------- */
+/* run.py:29-51 save_callback calls generator.generate on candidates the last _evaluate already rendered.  Copies the
+ * images of rows `rows_host[0..n)` of the LAST glass_evaluate_host / glass_evaluate_device call (fp32 NCHW in [0,1],
+ * the images that were scored) into DEVICE memory out_dev [n,3,R,R].  GLASS_ERR_STATE before the first evaluation. */
+int glass_last_images_gather(glass_engine* e, const int32_t* rows_host, int32_t n, float* out_dev, void* stream);
+/* utils.py:5-7 save_grid = torchvision make_grid (nrow images per row, `padding` zero pixels) + save_image's
+ * mul(255).add(0.5).clamp(0,255).to(uint8): images_dev [n,3,R,R] fp32 -> out_dev uint8 HWC
+ * [(R+padding)*ceil(n/min(n,nrow))+padding][(R+padding)*min(n,nrow)+padding][3], ready for the JPEG encoder.
+ * `e` may be NULL (it only counts the launch). */
+int glass_image_grid_u8(glass_engine* e, const float* images_dev, int32_t n, int32_t resolution, int32_t nrow,
+                        int32_t padding, uint8_t* out_dev, void* stream);
+
+/* -- BigGAN latent arithmetic (latent.py:16-24) ------------ */
+/* x: HOST float64 [pop, dim_z + num_classes] as pymoo passes the mixed real/bool population.  z_dev [pop, dim_z] =
+ * clip(x[:, :dim_z], -2, 2); cls_dev [pop, num_classes] = softmax(x[:, dim_z:], dim=1) (fp32, DEVICE).  The generator
+ * itself (pytorch_pretrained_biggan 0.1.1) is not vendored by the reference and is not built here. */
+int glass_biggan_latent(const double* x_host, int32_t pop, int32_t dim_z, int32_t num_classes, float* z_dev,
+                        float* cls_dev, void* stream);
+
 /* -- introspection ---------------------------------------------------------- */
 const char* glass_last_error(void);
 /* Number of kernels launched by this engine since creation (bench.py's gpu_launches). */
@@ -154,6 +176,14 @@ int64_t glass_debug_read(glass_engine* e, const char* name, float* host_out, int
 /* capture != 0: keep host copies of intermediates for glass_debug_read (slow;
  * tests only).  timing != 0: bracket every tensor-core launch with CUDA events. */
 int glass_set_debug(glass_engine* e, int32_t capture, int32_t timing);
+/* 1 if the library was built with -DGLASS_DEBUG (GLASS_DEBUG_* environment knobs honoured: A/B and work-skipping
+ * experiments), 0 for the product build, which never reads the environment.  bench.py refuses a debug build. */
+int glass_debug_build(void);
+/* fp16 range evidence (tests only; forces eager launches): with enable != 0 every G / D activation tensor written by
+ * later calls is scanned; glass_range_report returns the totals since the last glass_set_range_check: values that
+ * are inf/NaN, values saturated at +-65504 by the epilogues' satfinite conversion, and the largest finite |x|. */
+int glass_set_range_check(glass_engine* e, int32_t enable);
+int glass_range_report(glass_engine* e, int64_t* nonfinite, int64_t* saturated, float* max_abs);
 /* Per-launch device time (ms) and algorithmic FLOPs (as the reference writes
  * the op) of the tensor-core launches of the last timed call, in launch order
  * (G convs, CLIP GEMMs, D convs).  Returns the number of entries written. */

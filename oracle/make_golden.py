@@ -130,9 +130,13 @@ def make_text_features(feats: torch.Tensor, seed: int) -> torch.Tensor:
     return (t * 10.0)[None].half()
 
 
-FIXTURES = {
+FIXTURES = {      # must match tests/fixtures.py CONFIGS
     "tiny": dict(gan=W.TINY_GAN, clip=W.TINY_CLIP, pop=8, batch=4, seed=100),
     "full": dict(gan=W.FFHQ, clip=W.VIT_B32, pop=4, batch=4, seed=200),
+    "full_b": dict(gan=W.FFHQ, clip=W.VIT_B32, pop=4, batch=4, seed=300),
+    "full_c": dict(gan=W.FFHQ, clip=W.VIT_B32, pop=8, batch=4, seed=400),
+    "tiny_stress": dict(gan=W.TINY_GAN, clip=W.TINY_CLIP, pop=8, batch=4, seed=500, stress=True),
+    "full_stress": dict(gan=W.FFHQ, clip=W.VIT_B32, pop=4, batch=4, seed=600, stress=True),
 }
 
 
@@ -140,7 +144,7 @@ def make_fixture(name: str, out_dir: str):
     cfg = FIXTURES[name]
     gan, clipspec, P, B, seed = cfg["gan"], cfg["clip"], cfg["pop"], cfg["batch"], cfg["seed"]
     t0 = time.time()
-    g_sd = W.make_generator_weights(gan, seed + 0)
+    g_sd = W.make_generator_weights(gan, seed + 0, stress=cfg.get("stress", False))
     d_sd = W.make_discriminator_weights(gan, seed + 1)
     c_sd = W.make_clip_visual_weights(clipspec, seed + 2)
     noise = W.make_noise(gan, P // B, seed + 3)

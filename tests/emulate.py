@@ -122,7 +122,14 @@ def emu_generator(pk, spec, z, noise, batch, capture=None, fp16=True, exact=True
     if capture is not None:
         capture["w"] = w
         capture["styles"] = styles
+    def pow2_scale(sl):
+        """k_style_norm: m = the power of two with max|s| / m in [0.5, 1) per sample (1 for an all-zero slice)."""
+        mx = sl.abs().amax(dim=1, keepdim=True)
+        _, ex = torch.frexp(mx)
+        return torch.where(mx > 0, torch.ldexp(torch.ones_like(mx), ex), torch.ones_like(mx))
+
     s0 = styles[:, conv_off[0]:conv_off[0] + ch[0]]
+    s0 = s0 / pow2_scale(s0)
     x = r(T(pk["g.const"]).reshape(1, 4, 4, ch[0]) * s0[:, None, None, :])   # pre-scaled input
     if capture is not None:
         capture["x0"] = x
@@ -130,7 +137,7 @@ def emu_generator(pk, spec, z, noise, batch, capture=None, fp16=True, exact=True
     for li, ly in enumerate(layers):
         cin, cout = ly["cin"], ly["cout"]
         s = styles[:, conv_off[li]:conv_off[li] + cin]
-        d = torch.rsqrt((s * s) @ T(pk[f"g.conv{li}.wsq"]) + 1e-8)            # [P,cout]
+        d = torch.rsqrt((s * s) @ T(pk[f"g.conv{li}.wsq"]) + 1e-8) * pow2_scale(s)   # [P,cout]; x carries s / m
         in_res = x.shape[1]
         if ly["up"] and exact and in_res >= 16:
             # exact polyphase transposed conv on the (H+1)x(W+1) grid -> u (fp16), then the FIR pass
@@ -162,6 +169,7 @@ def emu_generator(pk, spec, z, noise, batch, capture=None, fp16=True, exact=True
                 capture[f"rgb{b}"] = y
         if li + 1 < len(layers):
             sn = styles[:, conv_off[li + 1]:conv_off[li + 1] + cout]
+            sn = sn / pow2_scale(sn)
             x = r(v * sn[:, None, None, :])
             if capture is not None:
                 capture[f"xs{li}"] = x

@@ -13,7 +13,14 @@ REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CONFIGS = {
     "tiny": dict(gan=W.TINY_GAN, clip=W.TINY_CLIP, pop=8, batch=4, seed=100),
     "full": dict(gan=W.FFHQ, clip=W.VIT_B32, pop=4, batch=4, seed=200),
+    # round 2: more weight / latent / noise seeds at full size; "full_c" has two noise groups (P=8)
+    "full_b": dict(gan=W.FFHQ, clip=W.VIT_B32, pop=4, batch=4, seed=300),
+    "full_c": dict(gan=W.FFHQ, clip=W.VIT_B32, pop=8, batch=4, seed=400),
+    # fp16-range stress (weights.make_generator_weights(stress=True)): large style magnitudes
+    "tiny_stress": dict(gan=W.TINY_GAN, clip=W.TINY_CLIP, pop=8, batch=4, seed=500, stress=True),
+    "full_stress": dict(gan=W.FFHQ, clip=W.VIT_B32, pop=4, batch=4, seed=600, stress=True),
 }
+FULL_FIXTURES = ("full", "full_b", "full_c", "full_stress")
 
 
 def load_golden(name):
@@ -26,7 +33,7 @@ def build_inputs(name):
     gan, clip = cfg["gan"], cfg["clip"]
     return dict(
         gan=gan, clip=clip, pop=cfg["pop"], batch=cfg["batch"],
-        g_sd=W.make_generator_weights(gan, seed + 0),
+        g_sd=W.make_generator_weights(gan, seed + 0, stress=cfg.get("stress", False)),
         d_sd=W.make_discriminator_weights(gan, seed + 1),
         c_sd=W.make_clip_visual_weights(clip, seed + 2),
         noise=W.make_noise(gan, cfg["pop"] // cfg["batch"], seed + 3),

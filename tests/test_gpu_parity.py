@@ -6,7 +6,8 @@ Tolerances (north_star: scores within 1e-3 relative of the reference):
   * sim: |ours - oracle_fp32| / |oracle_fp32| <= 1e-3, compared in fp32
     "before the final cast"; against the reference's own fp16-rounded value
     1.5e-3 (its last bit alone is 8e-4 at 0.3).
-  * hinge: |ours - reference| <= 2e-3 absolute (values ~0.9).
+  * hinge: |ours - reference| <= 8e-4 absolute (values ~0.9: <= 1e-3 relative; achieved errors are recorded in
+    profiles/r02_parity_full.json).
   * layer intermediates vs the emulation (identical rounding points):
     <= 3e-3 of the tensor's max (a few fp16 ulps).
 """
@@ -43,7 +44,7 @@ def check_diag(lines, layer_tol=3e-3):
                 tol = 1e-5
             assert d["rel"] <= tol, (name, d)
     assert lines["neg_sim_vs_oracle"]["max_rel"] <= 1e-3, lines["neg_sim_vs_oracle"]
-    assert lines["hinge_vs_oracle"]["max_abs"] <= 2e-3, lines["hinge_vs_oracle"]
+    assert lines["hinge_vs_oracle"]["max_abs"] <= 8e-4, lines["hinge_vs_oracle"]
     assert lines["sim_vs_reference_fixture_fp16"]["max_rel"] <= 1.5e-3
     assert lines["launches"]["count"] > 0
 
@@ -101,7 +102,7 @@ def test_full_size_resampling_variants_agree(flags):
     eng.close()
     sim32 = gold["sim_oracle_fp32"]
     assert np.abs(-neg_sim - sim32).max() / np.abs(sim32).min() <= 1e-3, (-neg_sim, sim32)
-    np.testing.assert_allclose(hinge, gold["F"][:, 1], atol=2e-3)
+    np.testing.assert_allclose(hinge, gold["F"][:, 1], atol=8e-4)
 
 
 def test_full_size_against_reference_fixture(full_engine):
@@ -113,7 +114,7 @@ def test_full_size_against_reference_fixture(full_engine):
     assert np.abs(-neg_sim - sim32).max() / np.abs(sim32).min() <= 1e-3, (-neg_sim, sim32)
     ref16 = gold["sim_fp16"].astype(np.float32)
     assert (np.abs(-neg_sim - ref16) / np.abs(ref16)).max() <= 1.5e-3
-    np.testing.assert_allclose(hinge, gold["F"][:, 1], atol=2e-3)
+    np.testing.assert_allclose(hinge, gold["F"][:, 1], atol=8e-4)
     z = torch.from_numpy(inp["x"]).float().cuda()
     images = eng.generate(z, noise=inp["noise"])
     assert images.shape == (4, 3, 1024, 1024) and float(images.min()) >= 0 and float(images.max()) <= 1
@@ -204,13 +205,13 @@ def test_graph_replay_equals_eager_launches():
 
 def test_streamed_tap_i8_downconv_against_nhwc_form():
     """conv_tc MODE 6 (D 512^2 folded down-conv on the I8 space-to-depth tensor, taps streamed through a ring)
-    against the same layer on the NHWC tensor with MODE 0 (GLASS_DEBUG_C1_I8=0): same products, different
+    against the same layer on the NHWC tensor with MODE 0 (GLASS_FLAG_C1_NHWC = 128): same products, different
     accumulation order only."""
     (m6,), gold = _full_scores()
-    (m0,), _ = _full_scores(env={"GLASS_DEBUG_C1_I8": "0"})
+    (m0,), _ = _full_scores(flags=128)
     np.testing.assert_array_equal(m6[0], m0[0])            # G and CLIP are untouched
     np.testing.assert_allclose(m6[1], m0[1], atol=5e-4)
-    np.testing.assert_allclose(m6[1], gold["F"][:, 1], atol=2e-3)
+    np.testing.assert_allclose(m6[1], gold["F"][:, 1], atol=8e-4)
 
 
 def test_fused_projection_kernel_against_separate_launches():
@@ -221,7 +222,179 @@ def test_fused_projection_kernel_against_separate_launches():
     (ref,), _ = _full_scores(flags=0)
     np.testing.assert_array_equal(fused[0], ref[0])
     np.testing.assert_allclose(fused[1], ref[1], atol=5e-4)
-    np.testing.assert_allclose(fused[1], gold["F"][:, 1], atol=2e-3)
+    np.testing.assert_allclose(fused[1], gold["F"][:, 1], atol=8e-4)
+
+
+# ---- round 2: parity at more seeds, at the benchmarked plan, under fp16-range stress ------------------------------
+# Bounds (north_star: fitness within 1e-3 of the reference).  sim: relative, against the fp32 oracle value.  hinge =
+# relu(1 - d) with |d| <= ~0.2 on these fixtures, so a bound relative to the hinge (~0.9) and a bound relative to the
+# logit differ by 5-20x: the test bounds the ABSOLUTE error by HINGE_ATOL, i.e. <= 1e-3 relative to the hinge value,
+# and profiles/r02_parity_full.json records the achieved error next to the largest logit of each fixture.
+SIM_RTOL = 1e-3
+HINGE_ATOL = 8e-4
+
+
+@pytest.mark.parametrize("name", ["full", "full_b", "full_c"])
+def test_full_size_fixtures_multi_seed(name):
+    """Three weight / latent / noise seeds at ffhq-config-f 1024^2 + ViT-B/32; full_c has two noise groups and both
+    MinibatchStd pairings (P = 8)."""
+    from tests.parity_report import fixture_record
+    rec = fixture_record(name, with_images=True, range_check=True)
+    assert rec["finite"] and rec["range"]["nonfinite"] == 0 and rec["range"]["saturated"] == 0, rec
+    assert rec["sim_rel_vs_oracle_fp32"] <= SIM_RTOL, rec
+    assert rec["sim_rel_vs_reference_fp16"] <= 1.5e-3, rec
+    assert rec["hinge_abs"] <= HINGE_ATOL, rec
+    assert rec["image64_abs"] <= 1e-3 and rec["image_mean_abs"] <= 2e-4, rec
+
+
+def test_full_size_single_objective_config():
+    """StyleGAN2_ffhq_nod (no discriminator, F = -sim) at full size against the fixture's F_nod."""
+    from tests.parity_report import fixture_record
+    rec = fixture_record("full_b", use_d=False)
+    assert rec["finite"] and rec["sim_rel_vs_oracle_fp32"] <= SIM_RTOL and rec["sim_rel_vs_reference_fp16"] <= 1.5e-3, rec
+
+
+def test_benchmarked_plan_p64_embeds_golden_groups():
+    """max_population = P = 64, 16 noise groups: the plan bench.py times (tile decode, tiles_n and the pow2 paths
+    depend on P).  Golden groups sit at slots 0, 7 and 15 among filler candidates; their scores equal the fixture,
+    the CUDA-graph replay equals the eager first evaluation, and the same candidates in a P = 8 plan are
+    bit-identical."""
+    from tests.parity_report import embedded_p64_record
+    rec = embedded_p64_record()
+    assert rec["all_finite"] and rec["graph_equals_eager"] and rec["equals_small_plan_bitwise"], rec
+    assert rec["sim_rel_vs_oracle_fp32"] <= SIM_RTOL and rec["hinge_abs"] <= HINGE_ATOL, rec
+
+
+def test_fp16_range_stress_tiny_layerwise():
+    """Style biases x30 / x20000 and conv weights x10 on a few channels (weights.make_generator_weights(stress=True)):
+    activation x style exceeds 65504 unless the styles are normalised (k_style_norm).  Layer by layer against the
+    emulation and the oracle, on the tensor-core path."""
+    check_diag(run_diag("tiny_stress", 0, 600))
+
+
+def test_fp16_range_stress_full_size():
+    """The same stress at ffhq-config-f size: scores within the north-star bound, zero non-finite and zero saturated
+    fp16 activations over every G and D layer (glass_set_range_check)."""
+    from tests.parity_report import fixture_record
+    rec = fixture_record("full_stress", range_check=True)
+    assert rec["finite"] and rec["range"]["nonfinite"] == 0 and rec["range"]["saturated"] == 0, rec
+    assert rec["range"]["max_abs"] < 6.0e4, rec
+    assert rec["sim_rel_vs_oracle_fp32"] <= SIM_RTOL and rec["hinge_abs"] <= HINGE_ATOL, rec
+
+
+def test_device_noise_generator_is_standard_normal():
+    """noise_kernel (Philox4x32-10 + Box-Muller) replaces the reference's ``normal_()`` draw per minibatch forward
+    (stylegan2/modules.py:426-452): mean, variance, skewness, kurtosis and tails of ~700k draws, a KS test against
+    N(0,1), and independence of consecutive groups."""
+    from scipy import stats
+    from clip_glass_b200.engine import GlassEngine
+    gan, clip = W.TINY_GAN, W.TINY_CLIP
+    P, B = 256, 4
+    eng = GlassEngine(gan, clip, W.make_generator_weights(gan, 1), None, W.make_clip_visual_weights(clip, 2),
+                      batch_size=B, max_population=P)
+    eng.set_debug(capture=True)
+    z = torch.from_numpy(W.make_latents(P, gan.latent_size, 3)).float().cuda()
+    eng.generate(z, seed=12345)
+    nz = eng.debug_read("noise").astype(np.float64)
+    eng.close()
+    n = nz.size
+    assert n == (P // B) * sum(r * r for r in gan.noise_shapes())
+    assert np.isfinite(nz).all()
+    assert abs(nz.mean()) < 5.0 / np.sqrt(n)
+    assert abs(nz.var() - 1.0) < 5.0 * np.sqrt(2.0 / n)
+    assert abs(stats.skew(nz)) < 5.0 * np.sqrt(6.0 / n)
+    assert abs(stats.kurtosis(nz)) < 5.0 * np.sqrt(24.0 / n)
+    for k, p in ((2.0, 0.04550026), (3.0, 0.00269980), (4.0, 6.334e-5)):
+        frac = (np.abs(nz) > k).mean()
+        assert abs(frac - p) < 5.0 * np.sqrt(p / n) + 1e-7, (k, frac, p)
+    assert stats.kstest(nz[:200000], "norm").pvalue > 1e-4
+    g = nz.reshape(P // B, -1)
+    c = np.corrcoef(g[:-1].reshape(-1)[:500000], g[1:].reshape(-1)[:500000])[0, 1]
+    assert abs(c) < 5.0 / np.sqrt(500000)
+
+
+# ---- round 2: the callers either side of the path (SURVEY.md §8(f)) ---------------------------------------------
+def test_image_output_path_reuses_scored_images(tmp_path):
+    """§8(f)-4.  run.py:29-51 save_callback -> generator.generate -> generator.save.  After a fused _evaluate the
+    engine still holds the images it scored: generate() returns exactly those for the rows it finds (here: equal,
+    bit for bit, to a render with the same explicit noise), renders only the rest, and save() assembles the grid +
+    uint8 conversion on the device, byte-identical to torchvision's make_grid + save_image arithmetic."""
+    import torchvision
+    from PIL import Image
+    from clip_glass_b200.config import make_namespace
+    from clip_glass_b200.problem import GenerationProblem
+    gold, inp = load_golden("tiny"), build_inputs("tiny")
+    ns = make_namespace("StyleGAN2_ffhq_d", device="cuda:0", pop_size=8, batch_size=4, synthetic_seed=100,
+                        gan_spec=W.TINY_GAN, clip_spec=W.TINY_CLIP, text_features=torch.from_numpy(gold["text_features"]))
+    prob = GenerationProblem(ns)
+    gen = prob.generator
+    out = {}
+    prob._evaluate(inp["x"], out, noise=inp["noise"])
+    z = torch.from_numpy(inp["x"]).float().cuda()
+    rendered = gen.engine.generate(z, noise=inp["noise"])                 # the same candidates, same noise
+    order = [5, 2, 7, 0, 1, 3]
+    ls = ns.latent(ns)
+    ls.set_from_population(inp["x"][order])
+    got = gen.generate(ls, minibatch=2)
+    assert gen.reuse_stats == dict(reused=6, rendered=0)
+    assert torch.equal(got, rendered[order])
+    # two known rows + two new candidates: only the new ones are rendered
+    mixed = np.concatenate([inp["x"][[4, 6]], W.make_latents(2, 512, 9)])
+    ls.set_from_population(mixed)
+    got2 = gen.generate(ls, minibatch=4)
+    assert gen.reuse_stats == dict(reused=8, rendered=2) and got2.shape == (4, 3, 64, 64)
+    assert torch.equal(got2[:2], rendered[[4, 6]]) and float(got2[2:].min()) >= 0 and float(got2[2:].max()) <= 1
+    # grid + uint8 conversion: bytes equal torchvision's
+    for n, nrow in ((6, 8), (8, 3), (1, 8)):
+        imgs = rendered[:n].contiguous()
+        ours = gen.engine.image_grid_u8(imgs, nrow=nrow, padding=2 if n > 1 else 0)
+        grid = torchvision.utils.make_grid(imgs.cpu(), nrow=nrow) if n > 1 else imgs[0].cpu()
+        ref = grid.mul(255).add_(0.5).clamp_(0, 255).permute(1, 2, 0).to(torch.uint8).numpy()
+        np.testing.assert_array_equal(ours, ref)
+    path = tmp_path / "grid.jpg"
+    gen.save(rendered, str(path))
+    with Image.open(path) as im:
+        assert im.size == (8 * 66 + 2, 66 + 2)
+    with pytest.raises(Exception):
+        gen.engine.last_images([99])
+
+
+def test_biggan_latent_arithmetic_on_device():
+    """§8(f)-3, latent.py:16-24: z = clip(x[:, :128], -2, 2), class vector = softmax over the 1000 'bool' genes, from
+    the float64 mixed population as pymoo hands it over (glass_biggan_latent) against the reference's torch ops."""
+    from clip_glass_b200.config import make_namespace
+    ns = make_namespace("DeepMindBigGAN512", device="cuda:0")
+    rng = np.random.default_rng(5)
+    x = np.concatenate([rng.normal(0, 1.5, size=(32, 128)), (rng.random((32, 1000)) < 0.005).astype(float)], axis=1)
+    x[3, 128:] = 0.0                                                       # no class gene set: uniform softmax
+    ls = ns.latent(ns)
+    ls.set_from_population(x)
+    z, cl = ls()
+    zr = torch.clip(torch.tensor(x[:, :128].astype(float)).float(), -2, 2)
+    cr = torch.softmax(torch.tensor(x[:, 128:].astype(float)).float(), dim=1)
+    assert torch.equal(z.cpu(), zr)
+    np.testing.assert_allclose(cl.cpu().numpy(), cr.numpy(), rtol=2e-6, atol=0)
+    np.testing.assert_allclose(cl.sum(1).cpu().numpy(), 1.0, rtol=1e-5)
+
+
+@pytest.mark.parametrize("config,algorithm_files", [("StyleGAN2_ffhq_nod", 5), ("StyleGAN2_ffhq_d", 3)])
+def test_run_driver_end_to_end(tmp_path, config, algorithm_files):
+    """BASELINE config 1 (StyleGAN2_ffhq_nod, pop 8, 5 generations) through the driver mirror of run.py:15-125 —
+    on the GPU path, reduced network shapes — and the NSGA-II config: sampling -> _evaluate -> mating -> survival ->
+    save_callback (images reused from the last evaluation) -> result files."""
+    import pickle
+    from clip_glass_b200 import run as driver
+    gens = algorithm_files
+    res = driver.main(["--device", "cuda:0", "--config", config, "--generations", str(gens), "--save-each", "2",
+                       "--tmp-folder", str(tmp_path), "--pop-size", "8", "--batch-size", "4", "--synthetic-seed", "100",
+                       "--seed", "3"], config_overrides=dict(gan_spec=W.TINY_GAN, clip_spec=W.TINY_CLIP))
+    names = set(os.listdir(tmp_path))
+    assert {"genetic-it-2.jpg", "genetic-it-final.jpg", "output.jpg", "genetic_result", "ls_result"} <= names, names
+    with open(tmp_path / "genetic_result", "rb") as f:
+        saved = pickle.load(f)
+    F = np.atleast_2d(np.asarray(saved["F"], dtype=float))
+    assert np.isfinite(F).all() and len(res.pop) == 8
+    assert "z" in torch.load(tmp_path / "ls_result")
 
 
 def test_population_must_be_multiple_of_batch(full_engine):
@@ -256,7 +429,7 @@ def test_plugin_surface_fused_equals_facade_calls():
     assert out_f["F"].shape == (8, 2) and out_f["G"].shape == (8,) and not out_f["G"].any()
     np.testing.assert_array_equal(out_f["F"], F_u)
     np.testing.assert_allclose(out_f["F"][:, 0], gold["F"][:, 0], rtol=1.5e-3)
-    np.testing.assert_allclose(out_f["F"][:, 1], gold["F"][:, 1], atol=2e-3)
+    np.testing.assert_allclose(out_f["F"][:, 1], gold["F"][:, 1], atol=8e-4)
     assert prob.generator.has_discriminator()
     # minibatch=None == one noise draw for the whole call (generator.py:29-31 / models.py:109-110), any P
     ls.set_from_population(inp["x"][:3])
