@@ -107,23 +107,41 @@ def best_cpu_threads():
     return min(os.cpu_count() or 1, 32)
 
 
+def cpu_kind():
+    """"reference": the reference's own stylegan2 / clip modules (oracle/_ref, vendored by oracle/build_ref.py in the
+    build container) run the path; "port": the oracle restatement (when oracle/_ref is absent)."""
+    from oracle import reference_modules
+    return "reference" if reference_modules.reference_available(reference_modules.VENDORED_ROOT) else "port"
+
+
 def cpu_oracle_step(pop, batch, use_d, seed, threads):
-    """One bounded sample of the SAME workload on the host cores: the oracle port of
-    problem.py:14-29 (full ffhq-config-f G + ViT-B/32 + D, fp32 G/D, CLIP fp16 as built)."""
+    """One bounded sample of the SAME workload on the host cores (full ffhq-config-f G + ViT-B/32 + D, fp32 G/D,
+    CLIP fp16 as built): problem.py:14-29 over the reference's own modules from oracle/_ref, or over the oracle
+    port when those are absent."""
     import torch
     from clip_glass_b200 import weights as W
-    from oracle import evaluate_oracle
+    from oracle import evaluate_oracle, reference_modules
     torch.set_num_threads(threads)
     st = cpu_oracle_step.__dict__.setdefault("state", {})
     if not st:
-        st["g"] = W.make_generator_weights(W.FFHQ, 1000)
-        st["d"] = W.make_discriminator_weights(W.FFHQ, 1001)
-        st["c"] = W.clip_as_built(W.make_clip_visual_weights(W.VIT_B32, 1002))
+        st["kind"] = cpu_kind()
+        g = W.make_generator_weights(W.FFHQ, 1000)
+        d = W.make_discriminator_weights(W.FFHQ, 1001)
+        c = W.make_clip_visual_weights(W.VIT_B32, 1002)
         st["t"] = torch.randn(1, 512, generator=torch.Generator().manual_seed(5)).half()
+        if st["kind"] == "reference":
+            reference_modules.use_reference_root(reference_modules.VENDORED_ROOT)
+            st["G"], st["D"] = reference_modules.build_reference_gan(W.FFHQ, g, d)
+            st["C"] = reference_modules.build_reference_clip(W.VIT_B32, c)
+        else:
+            st["g"], st["d"], st["c"] = g, d, W.clip_as_built(c)
     x = W.make_latents(pop, 512, seed)
     noise = W.make_noise(W.FFHQ, pop // batch, seed + 1)
     t0 = time.perf_counter()
-    evaluate_oracle.evaluate(x, st["g"], st["d"], st["c"], st["t"], W.FFHQ, W.VIT_B32, batch, use_d, noise=noise)
+    if st["kind"] == "reference":
+        reference_modules.reference_evaluate(x, st["G"], st["D"], st["C"], st["t"], batch, use_d, noise)
+    else:
+        evaluate_oracle.evaluate(x, st["g"], st["d"], st["c"], st["t"], W.FFHQ, W.VIT_B32, batch, use_d, noise=noise)
     return time.perf_counter() - t0
 
 
@@ -156,8 +174,9 @@ def run_reference(args, rank, world):
         dtype="fp32 (G/D), fp16-as-built (CLIP)", data="synthetic",
         config=dict(workload=f"StyleGAN2_ffhq{args.variant} ffhq-config-f 1024^2 + CLIP ViT-B/32, batch_size {args.batch}",
                     population_per_step=sample, note="bounded sample of the same workload on host cores"),
-        cpu_baseline=dict(value=value, unit=UNIT, cores=threads, kind="port",
-                          sample=f"{sample} candidates per step x {len(times)} steps (oracle port of problem.py:14-29; "
+        cpu_baseline=dict(value=value, unit=UNIT, cores=threads, kind=cpu_kind(),
+                          sample=f"{sample} candidates per step x {len(times)} steps (problem.py:14-29 over "
+                                 f"{'the reference modules in oracle/_ref' if cpu_kind() == 'reference' else 'the oracle port'}; "
                                  f"{threads} of {os.cpu_count()} host threads, the fastest setting measured; "
                                  "steps stop early once ~4.5 min of wall time is used)"),
         e2e=dict(value=value, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0),
@@ -217,6 +236,12 @@ def main():
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device (the fitness path has no CPU fallback)")
+    from clip_glass_b200 import _lib
+    dbg_env = sorted(k for k in os.environ if k.startswith("GLASS_DEBUG_"))
+    if dbg_env or os.environ.get("CLIPGLASS_LIB") or _lib.load_library().glass_debug_build():
+        raise SystemExit(f"bench.py: refusing to time a debug configuration (GLASS_DEBUG_* set: {dbg_env}; "
+                         f"CLIPGLASS_LIB={os.environ.get('CLIPGLASS_LIB')!r}; "
+                         f"debug build: {bool(_lib.load_library().glass_debug_build())})")
     torch.cuda.set_device(local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
@@ -247,14 +272,27 @@ def main():
     # ---------------- device-resident step: inputs already in HBM -----------------
     z_all = [torch.from_numpy(W.make_latents(P, 512, 50 + i)[s0:e0]).float().cuda() for i in range(4)]
 
+    pending = []          # (work handle, gathered tensor) of the previous step's all-gather
+
     def step_device(i):
+        """One generation: evaluate the local shard, then the ONE collective of the path (all-gather of F).  The
+        gather only feeds the host GA, so it is issued asynchronously on NCCL's stream and waited for when the NEXT
+        step has been enqueued: generation k+1's kernels do not queue behind generation k's collective."""
         neg_sim, hinge = eng.evaluate_device(z_all[i % 4], seed=1 + i, first_group=s0 // args.batch)
-        local = torch.stack([neg_sim, hinge], 1) if hinge is not None else neg_sim[:, None]
+        local = torch.stack([neg_sim, hinge], 0) if hinge is not None else neg_sim[None]
         if world > 1:
-            out = torch.empty(world * local.shape[0], local.shape[1], device="cuda")
-            tdist.all_gather_into_tensor(out, local)      # the one collective on the path
+            out = torch.empty((world,) + tuple(local.shape), device="cuda")
+            work = tdist.all_gather_into_tensor(out, local.contiguous(), async_op=True)
+            while pending:
+                w, _ = pending.pop()
+                w.wait()                               # stream-level wait for the previous generation's gather
+            pending.append((work, out))
             return out
         return local
+
+    def drain():
+        while pending:
+            pending.pop()[0].wait()
 
     def timed(step_fn, n_steps, first):
         """EXACTLY n_steps, each bracketed by CUDA events on the launching stream; L2 flushed between steps
@@ -266,21 +304,47 @@ def main():
             ev[i][0].record(stream)
             step_fn(first + i)
             ev[i][1].record(stream)
+        drain()
         barrier()
         ms = torch.tensor([a.elapsed_time(b) for a, b in ev], dtype=torch.float64, device="cuda")
+        timed.per_rank = None
         if world > 1:
+            allr = torch.empty(world, n_steps, dtype=torch.float64, device="cuda")
+            tdist.all_gather_into_tensor(allr, ms)
+            timed.per_rank = allr.mean(1).cpu().numpy().tolist()      # skew between ranks vs collective latency
             tdist.all_reduce(ms, op=tdist.ReduceOp.MAX)
         return ms.cpu().numpy()
 
     for i in range(W_):
         step_device(i)
+    drain()
     barrier()
+
+    # ---------------- N > 1: the gathered F equals what one GPU computes (checked on hardware) ----------------
+    parity_check = None
+    if world > 1:
+        full = step_device(1000)
+        drain()
+        torch.cuda.synchronize()
+        peer = (rank + 1) % world                       # every rank re-evaluates its neighbour's shard
+        ps, pe = bounds[peer]
+        zp = torch.from_numpy(W.make_latents(P, 512, 50 + 1000 % 4)[ps:pe]).float().cuda()
+        n2, h2 = eng.evaluate_device(zp, seed=1 + 1000, first_group=ps // args.batch)
+        mine = torch.stack([n2, h2], 0) if h2 is not None else n2[None]
+        ok = torch.tensor([int(torch.equal(full[peer], mine))], device="cuda")
+        tdist.all_reduce(ok, op=tdist.ReduceOp.MIN)
+        parity_check = dict(what="after an NCCL all-gather of a full generation, every rank re-evaluates its "
+                                 "neighbour rank's shard locally (same seed, first_group) and compares with the gathered rows",
+                            bitwise_equal_on_all_ranks=bool(ok.item()), ranks=world, rows_checked_per_rank=pe - ps)
+        if not ok.item():
+            raise SystemExit("bench.py: gathered fitness differs from the single-GPU evaluation of the same shard")
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
         time.sleep(0.3)
     launches0 = eng.launch_count
     ms_dev = timed(step_device, args.steps, W_)
+    per_rank_ms = timed.per_rank
     launches = eng.launch_count - launches0
 
     # ---------------- e2e: host f64 population -> host F through the plugin API ----------------
@@ -362,9 +426,10 @@ def main():
         cpu_oracle_step(args.cpu_sample, args.batch, use_d, 3, threads)            # warm
         ts = [cpu_oracle_step(args.cpu_sample, args.batch, use_d, 4 + i, threads) for i in range(2)]
         v = args.cpu_sample / statistics.median(ts)
-        cpu_baseline = dict(value=v, unit=UNIT, cores=threads, kind="port",
+        cpu_baseline = dict(value=v, unit=UNIT, cores=threads, kind=cpu_kind(),
                             sample=f"{args.cpu_sample} candidates (one minibatch) x 2 timed repetitions, median; "
-                                   f"oracle port of problem.py:14-29 on torch CPU; {threads} of {os.cpu_count()} host "
+                                   f"problem.py:14-29 over {'the reference modules (oracle/_ref)' if cpu_kind() == 'reference' else 'the oracle port'} "
+                                   f"on torch CPU; {threads} of {os.cpu_count()} host "
                                    "threads (more threads are slower for a 4-candidate minibatch, see best_cpu_threads)")
 
     if rank == 0:
@@ -383,6 +448,9 @@ def main():
                      h2d_bytes_per_step=int(P_local * 512 * 8), d2h_bytes_per_step=int(P_local * (2 if use_d else 1) * 4),
                      api="GenerationProblem._evaluate(x: float64 ndarray) -> out['F'] (glass_evaluate_host)"),
             gpu_launches=int(launches),
+            flags=dict(engine_flags=args.flags, debug_build=False, glass_debug_env=[]),
+            parity_check=parity_check,
+            per_rank_ms_per_step=per_rank_ms,
             gflop_per_candidate=GFLOP_PER_CAND[args.variant],
             roofline=roofline, cpu_baseline=cpu_baseline,
         )

@@ -158,8 +158,13 @@ def test_config_values_match_reference_config_py():
     assert (n["algorithm"], n["problem_args"]["n_obj"], n["use_discriminator"]) == ("ga", 1, False)
     c["pop_size"] = 64
     assert cfgmod.get_config("StyleGAN2_ffhq_d")["pop_size"] == 16     # copies, not shared state
-    with pytest.raises(NotImplementedError):
-        cfgmod.get_config("GPT2")
+    g = cfgmod.get_config("GPT2")                   # config.py:5-25
+    assert (g["task"], g["dim_z"], g["max_tokens_len"], g["max_text_len"], g["encoder_size"], g["init_text"],
+            g["stochastic"], g["pop_size"], g["batch_size"]) == ("img2txt", 20, 30, 50, 50257, "the picture of", False, 100, 25)
+    assert g["problem_args"] == dict(n_var=20, n_obj=1, n_constr=20, xl=0, xu=50256)
+    b = cfgmod.get_config("DeepMindBigGAN512")      # config.py:52-72
+    assert (b["dim_z"], b["num_classes"], b["pop_size"], b["batch_size"], b["truncation"]) == (128, 1000, 32, 8, 1.0)
+    assert b["problem_args"] == dict(n_var=1128, n_obj=1, n_constr=128, xl=-2, xu=2)
     x = torch.rand(2, 3, 4, 4) * 4 - 2
     np.testing.assert_allclose(c["norm"](x).numpy(), ((x + 1) / 2).clamp(0, 1).numpy())
     np.testing.assert_allclose(c["denorm"](x).numpy(), (x * 2 - 1).numpy())
