@@ -24,6 +24,7 @@ FLAG_SIMT_ATTENTION = 16
 FLAG_NO_GRAPH = 32
 FLAG_PROJ_FUSION = 64
 FLAG_C1_NHWC = 128
+FLAG_NO_ZERO_SKIP = 256
 
 SYMBOLS = [
     "glass_create", "glass_set_tensor", "glass_finalize", "glass_set_text_features", "glass_destroy",
@@ -32,6 +33,9 @@ SYMBOLS = [
     "glass_set_debug", "glass_conv_breakdown", "glass_last_conv_time", "glass_set_batch_size",
     "glass_debug_build", "glass_set_range_check", "glass_range_report",
     "glass_last_images_gather", "glass_image_grid_u8", "glass_biggan_latent",
+    "glass_text_create", "glass_text_set_tensor", "glass_text_finalize", "glass_text_set_image_features",
+    "glass_text_generate", "glass_text_similarity", "glass_text_launch_count", "glass_text_last_error",
+    "glass_text_destroy",
 ]
 
 

@@ -89,6 +89,15 @@ struct ConvParams {
   int all_valid;            // H % TH == 0 && W % TW == 0 && Nimg % TN == 0: no row of any tile is out of range
   int pow2, sh_n, sh_x, sh_y;  // tile grid is a power of two in every dimension: decode with shifts
   int mode;                 // 0 = streamed taps, 1 = resident taps + halo copies (conv_tc.cu)
+  // Structural zeros of the exact polyphase forms (packing.exact_upconv / exact_downconv: 9 of the 16 (tap, phase)
+  // weight blocks are non-zero).  MODE 0 skips the zero blocks in the producer and the MMA loop alike:
+  //   1 = up-conv: the n-tile lies inside ONE output phase (BN <= skip_ch = Cout); tap (dy,dx) feeds phase (py,px)
+  //       only if (dy == 0 || py == 0) && (dx == 0 || px == 0);
+  //   2 = down-conv: a K chunk lies inside ONE input phase (BK <= skip_ch = channels per phase); tap (a,b) reads
+  //       phase (py,px) only if !(a && py) && !(b && px).
+  int skip_mode, skip_ch;
+  int rot_div;              // skip_mode 1: n_tile is rotated by m / rot_div so that a CTA's successive tiles cycle
+                            // through the phases (phase 0 has four taps, phase 3 one)
   const __half* in;         // [Nimg][H][W][Cin]   (SIMT bring-up path; the TC path reads through TMA)
   const __half* wgt;        // [taps][Ntot][Cin]
   EpiParams epi;

@@ -38,17 +38,32 @@ __device__ __forceinline__ TileCoord decode_tile(const ConvParams& p, int tile, 
   if (kPow2 || p.pow2) {
     t.n_tile = tile & (n_tiles - 1);
     int m = tile >> p.sh_n;
+    if (!kPow2 && p.skip_mode == 1) t.n_tile = (t.n_tile + m / p.rot_div) & (n_tiles - 1);
     t.tx = m & (p.tiles_x - 1); m >>= p.sh_x;
     t.ty = m & (p.tiles_y - 1);
     t.tn = m >> p.sh_y;
   } else {
     t.n_tile = tile % n_tiles;
     int m = tile / n_tiles;
+    if (p.skip_mode == 1) t.n_tile = (t.n_tile + m / p.rot_div) % n_tiles;
     t.tx = m % p.tiles_x; m /= p.tiles_x;
     t.ty = m % p.tiles_y;
     t.tn = m / p.tiles_y;
   }
   return t;
+}
+
+// true if the (tap, k-chunk) weight block of this n-tile is structurally zero (ConvParams::skip_mode)
+__device__ __forceinline__ bool skip_block(const ConvParams& p, int tap, int kc, int n_tile, int BN, int BK) {
+  if (p.skip_mode == 1) {
+    const int ph = (n_tile * BN) / p.skip_ch;
+    return (p.tap_dy[tap] != 0 && (ph >> 1)) || (p.tap_dx[tap] != 0 && (ph & 1));
+  }
+  if (p.skip_mode == 2) {
+    const int ph = (kc * BK) / p.skip_ch;
+    return ((tap >> 1) && (ph >> 1)) || ((tap & 1) && (ph & 1));
+  }
+  return false;
 }
 
 constexpr int kNumParams = 6;   // scale, shift, oscale, rgb0, rgb1, rgb2
@@ -416,6 +431,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           const int tap = kit / kchunks;
           const int kc = kit - tap * kchunks;
           const int dy = p.tap_dy[tap], dx = p.tap_dx[tap];
+          if (skip_block(p, tap, kc, n_tile, BN, BK)) continue;
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * C::kStageBytes;
           uint8_t* sb = sa + C::kABytes;
@@ -530,7 +546,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           tc_commit(&tmem_full[as]);
           continue;
         }
+        const int n_tile_mma = p.skip_mode == 1 ? decode_tile<kPow2>(p, tile, n_tiles).n_tile : 0;
+        uint32_t started = 0;
         for (int kit = 0; kit < kiters; ++kit) {
+          if (p.skip_mode != 0) {
+            const int tap = kit / kchunks;
+            if (skip_block(p, tap, kit - tap * kchunks, n_tile_mma, BN, BK)) continue;
+          }
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * C::kStageBytes);
@@ -539,8 +561,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
             // advance 16 fp16 = 32 bytes along K inside the swizzle atom
-            tc_mma_f16(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), C::kIdesc, (kit | k) != 0);
+            tc_mma_f16(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), C::kIdesc, started | (uint32_t)k);
           }
+          started = 1;
           tc_commit(&empty_bar[stage]);
           if (++stage == C::kStages) { stage = 0; phase ^= 1; }
         }
@@ -902,6 +925,12 @@ cudaError_t launch_one(const ConvParams& p, const TmaMaps& maps, int num_sms, cu
   int grid = total < ctas ? total : ctas;
   if (MODE != 0) grid = (grid / n_tiles) * n_tiles;   // keeps tile % n_tiles constant per CTA (resident taps)
   if (grid <= 0) return cudaErrorInvalidValue;
+  if (p.skip_mode == 1) {
+    ConvParams q = p;
+    q.rot_div = grid / n_tiles > 0 ? grid / n_tiles : 1;    // m advances by grid / n_tiles per persistent iteration
+    conv_tc_kernel<BN, BK, MODE, EPI><<<grid, C::kThreads, C::kSmemBytes, s>>>(maps.a, maps.b, q);
+    return cudaGetLastError();
+  }
   conv_tc_kernel<BN, BK, MODE, EPI><<<grid, C::kThreads, C::kSmemBytes, s>>>(maps.a, maps.b, p);
   return cudaGetLastError();
 }
@@ -957,7 +986,7 @@ __global__ void conv_simt_kernel(const ConvParams p) {
 static int pick_epi_spec(const ConvParams& p) {
   const EpiParams& e = p.epi;
   static const bool off = debug_env("GLASS_DEBUG_GENERIC_EPI") != nullptr;     // A/B knob: always the run-time spec
-  if (off || p.TN != 1 || !p.pow2 || !p.all_valid || p.debug_skip != 0) return 0;
+  if (off || p.TN != 1 || !p.pow2 || !p.all_valid || p.debug_skip != 0 || p.skip_mode == 1) return 0;
   if ((e.act != kActLrelu && e.act != kActNone) || e.round_fp16_before_act || e.x_phases == 2 || e.cout_shift < 0) return 0;
   if (e.noise != nullptr && e.noise_div_shift < 0) return 0;
   int store = kStNone;

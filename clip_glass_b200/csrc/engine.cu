@@ -206,7 +206,7 @@ const signed char kDownExactTaps[4][2] = {{0, 0}, {0, 1}, {1, 0}, {1, 1}};
 
 int make_conv(glass_engine* e, ConvLaunch* out, const __half* in, int Nimg, int H, int W, int Cin, const __half* wgt,
               int taps, int Ntot, const EpiParams& epi, bool gemm, const signed char (*table)[2] = nullptr,
-              int in_H = 0, int in_W = 0, bool in_i8 = false) {
+              int in_H = 0, int in_W = 0, bool in_i8 = false, int skip_mode = 0, int skip_ch = 0) {
   ConvParams& p = out->p;
   memset(&p, 0, sizeof(p));
   p.Nimg = Nimg; p.H = H; p.W = W; p.Cin = Cin; p.taps = taps; p.Ntot = Ntot;
@@ -236,6 +236,18 @@ int make_conv(glass_engine* e, ConvLaunch* out, const __half* in, int Nimg, int 
   p.BK = (Cin % 64 == 0) ? 64 : 32;
   if (p.BN == 0 || Cin % 32 != 0 || Ntot % 16 != 0)
     return fail(GLASS_ERR_ARG, "unsupported conv shape Cin=%d Ntot=%d", Cin, Ntot);
+  // structural zeros of the exact polyphase forms (common.cuh: ConvParams::skip_mode); only the tensor-core MODE 0
+  // path skips them, and only when an n-tile (up) / a K chunk (down) lies inside one phase
+  p.skip_mode = 0;
+  p.skip_ch = skip_ch;
+  p.rot_div = 1;
+  if (skip_mode == 1 && e->cfg.conv_impl == 0 && !(e->cfg.flags & GLASS_FLAG_NO_ZERO_SKIP)) {
+    while (p.BN > skip_ch) p.BN /= 2;
+    if (p.BN >= 32 && skip_ch % p.BN == 0) p.skip_mode = 1;
+  } else if (skip_mode == 2 && e->cfg.conv_impl == 0 && !(e->cfg.flags & GLASS_FLAG_NO_ZERO_SKIP) &&
+             skip_ch % p.BK == 0) {
+    p.skip_mode = 2;
+  }
   // Small-channel layers (the whole K of a tap is one chunk) on full 16x8 tiles: resident taps + halo copies.
   p.mode = 0;
   if (in_i8) {
@@ -398,16 +410,20 @@ void derive_arch(glass_engine* e) {
   // where the layer is tensor-bound (wide channels), not where it is HBM/epilogue-bound (32..256 channels).
   const bool folded = (c.flags & GLASS_FLAG_FOLDED_RESAMPLE) != 0;
   const bool exact_all = (c.flags & GLASS_FLAG_EXACT_RESAMPLE) != 0;
+  // (debug builds: GLASS_DEBUG_GEXACT="cin_min,in_res_min", GLASS_DEBUG_DEXACT="ci_min" move the thresholds for A/B)
+  int g_cin_min = 512, g_res_min = 64, d_ci_min = 128;
+  if (const char* v = debug_env("GLASS_DEBUG_GEXACT")) sscanf(v, "%d,%d", &g_cin_min, &g_res_min);
+  if (const char* v = debug_env("GLASS_DEBUG_DEXACT")) sscanf(v, "%d", &d_ci_min);
   e->g_exact.clear();
   for (const GLayer& l : e->glayers) {
     const int in_res = l.res / 2;
     const bool possible = !folded && l.up && in_res >= 16;
-    e->g_exact.push_back((possible && (exact_all || (l.cin >= 512 && in_res >= 64))) ? 1 : 0);
+    e->g_exact.push_back((possible && (exact_all || (l.cin >= g_cin_min && in_res >= g_res_min))) ? 1 : 0);
   }
   e->d_exact.clear();
   for (int b = 0; b + 1 < c.num_blocks; ++b) {
     const bool possible = !folded && (e->R >> b) >= 32;
-    e->d_exact.push_back((possible && (exact_all || e->gch[c.num_blocks - 1 - b] >= 128)) ? 1 : 0);
+    e->d_exact.push_back((possible && (exact_all || e->gch[c.num_blocks - 1 - b] >= d_ci_min)) ? 1 : 0);
   }
   // activations feeding a 32/64-channel 3x3 conv: channel-group-interleaved (MODE 4), written by the producing
   // conv's epilogue (not by k_upfir) or by k_from_rgb
@@ -681,7 +697,7 @@ int build_plan(glass_engine* e, int P) {
       eu.out = e->actC;
       snprintf(nm, sizeof nm, "g.conv%zu.wx", li);
       RC(make_conv(e, &cl, bufs[cur], P, in_res + 1, in_res + 1, l.cin, tptr<__half>(e, nm), 4, 4 * l.cout, eu, false,
-                   kUpExactTaps, in_res, in_res));
+                   kUpExactTaps, in_res, in_res, false, 1, l.cout));
     } else if (e->g_in_i8[li]) {
       snprintf(nm, sizeof nm, "g.conv%zu.w", li);
       RC(make_conv(e, &cl, bufs[cur], P, in_res, in_res, l.cin, tptr<__half>(e, nm), 9, l.up ? 4 * l.cout : l.cout, ep,
@@ -786,7 +802,7 @@ int build_plan(glass_engine* e, int P) {
       if (e->d_exact[b]) {
         // exact: blurred input (k_blur_s2d -> actC, [(res/2+1)^2][4*Ci]) then a 2x2-tap conv == 3x3 stride 2
         RC(make_conv(e, &cl, e->actC, P, res / 2, res / 2, 4 * Ci, tptr<__half>(e, nmf("c1.wx")), 4, Co, ep, false,
-                     kDownExactTaps, res / 2 + 1, res / 2 + 1));
+                     kDownExactTaps, res / 2 + 1, res / 2 + 1, false, 2, Ci));
       } else {
         // folded FIR + 3x3 stride 2 == 3x3 over the space-to-depth tensor (4*Ci channels)
         RC(make_conv(e, &cl, e->actB, P, res / 2, res / 2, 4 * Ci, tptr<__half>(e, nmf("c1.w")), 9, Co, ep, false,

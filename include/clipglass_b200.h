@@ -82,6 +82,9 @@ typedef struct glass_config {
 /* Cross-check variant: keep the space-to-depth tensor between conv0 and the folded conv1 of the D 1024^2 block NHWC
  * (conv_tc MODE 0 instead of the I8 layout + MODE 6 streamed taps).  Same products, different accumulation order. */
 #define GLASS_FLAG_C1_NHWC 128
+/* The exact polyphase weight tensors have 9 non-zero (tap, phase) blocks of 16; the tensor-core path skips the zero
+ * blocks (no TMA load, no MMA).  Cross-check variant: multiply them like any other block. */
+#define GLASS_FLAG_NO_ZERO_SKIP 256
 
 /* -- lifetime ------------------------------------------------------------- */
 /* Replaces Generator.__init__ (generator.py:12-27): allocate the engine. */
@@ -164,6 +167,41 @@ int glass_image_grid_u8(glass_engine* e, const float* images_dev, int32_t n, int
  * itself (pytorch_pretrained_biggan 0.1.1) is not vendored by the reference and is not built here. */
 int glass_biggan_latent(const double* x_host, int32_t pop, int32_t dim_z, int32_t num_classes, float* z_dev,
                         float* cls_dev, void* stream);
+
+/* -- img2txt path (BASELINE config 5) ---------------------- */
+/* GPT-2 greedy decode + CLIP text tower (clip_glass_b200/csrc/text_engine.cu).  A separate engine: it shares no
+ * weights with the StyleGAN2 path.  Either half may be left out (layers = 0). */
+typedef struct glass_text_engine glass_text_engine;
+typedef struct glass_text_config {
+  /* gpt2/config.py:6-24 */
+  int32_t gpt2_vocab, gpt2_positions, gpt2_embd, gpt2_layers, gpt2_heads;
+  float gpt2_eps;
+  /* config.py:8-9,15: latent length (dim_z = 20), number of init tokens ("the picture of" = 3), max_tokens_len = 30 */
+  int32_t dim_z, n_init, max_tokens_len;
+  /* clip/model.py:363-392, text half */
+  int32_t text_width, text_heads, text_layers, text_context, text_vocab, text_embed_dim;
+  int32_t max_population;
+  int32_t device;
+  int32_t flags;
+} glass_text_config;
+int glass_text_create(const glass_text_config* cfg, glass_text_engine** out);
+/* Packed tensors from HOST memory; names / layouts in clip_glass_b200/text_packing.py (from the reference's
+ * gpt2-pytorch_model.bin and ViT-B-32.pt state_dict layouts). */
+int glass_text_set_tensor(glass_text_engine* e, const char* name, const void* host_data, size_t nbytes);
+int glass_text_finalize(glass_text_engine* e);
+/* generator.py:26-27 caches image_features [1,E] (CLIP.encode_image of the target picture); fp32 here. */
+int glass_text_set_image_features(glass_text_engine* e, const float* host_image, int32_t n);
+/* models.py:45-60 GPT2.generate up to the token level: z HOST int64 [pop, dim_z] (latent.py:55-56) -> tokens HOST int64
+ * [pop, dim_z + n_init + max_tokens_len] = cat(z, init tokens, generated tokens), exactly what gpt2/sample.py:21-37
+ * returns with sample=False.  A latent token outside [0, vocab) is GLASS_ERR_ARG (the reference raises IndexError). */
+int glass_text_generate(glass_text_engine* e, const int64_t* z_host, int32_t pop, int64_t* tokens_host, void* stream);
+/* generator.py:53-59 after clip.tokenize: clip tokens HOST int64 [pop, context] -> sim HOST fp32 [pop] (cosine of
+ * CLIP.encode_text against the cached image features); features_host [pop, E] optional (may be NULL). */
+int glass_text_similarity(glass_text_engine* e, const int64_t* clip_tokens_host, int32_t pop, float* sim_host,
+                          float* features_host, void* stream);
+int64_t glass_text_launch_count(const glass_text_engine* e);
+const char* glass_text_last_error(void);
+int glass_text_destroy(glass_text_engine* e);
 
 /* -- introspection ---------------------------------------------------------- */
 const char* glass_last_error(void);
