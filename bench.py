@@ -184,6 +184,186 @@ def run_reference(args, rank, world):
     emit(line)
 
 
+def gpt2_reference_step(pop, seed, threads):
+    """--workload gpt2, CPU arm: models.py:45-60 + generator.py:53-59 over the reference's own gpt2 / clip modules
+    (oracle/_ref) or the oracle port, on the host cores."""
+    import torch
+    from clip_glass_b200 import text_weights as TW
+    from clip_glass_b200.models import INIT_TEXT_TOKENS, standin_clip_tokens
+    from oracle import gpt2_oracle, reference_modules
+    torch.set_num_threads(threads)
+    st = gpt2_reference_step.__dict__.setdefault("state", {})
+    init = INIT_TEXT_TOKENS["the picture of"]
+    if not st:
+        st["g"] = TW.make_gpt2_weights(TW.GPT2_SMALL, 1000)
+        st["t"] = TW.text_as_built(TW.make_clip_text_weights(TW.CLIP_TEXT_B32, 1001))
+        st["img"] = torch.randn(1, 512, generator=torch.Generator().manual_seed(6)).half()
+        st["kind"] = "port"
+        root = reference_modules.VENDORED_ROOT
+        if os.path.exists(os.path.join(root, "gpt2", "model.py")) and reference_modules.reference_available(root):
+            import importlib
+            sys.path.insert(0, root)
+            try:
+                for k in [k for k in sys.modules if k == "gpt2" or k.startswith("gpt2.")]:
+                    del sys.modules[k]
+                gm = importlib.import_module("gpt2.model")
+                gs = importlib.import_module("gpt2.sample")
+                gc = importlib.import_module("gpt2.config")
+                gu = importlib.import_module("gpt2.utils")
+            finally:
+                sys.path.remove(root)
+            reference_modules.use_reference_root(root)
+            model = gu.load_weight(gm.GPT2LMHeadModel(gc.GPT2Config()), {k: v.clone() for k, v in st["g"].items()}).eval()
+            _, clip_mod = reference_modules._import_reference()
+            sp = TW.CLIP_TEXT_B32
+            clip = clip_mod.CLIP(sp.embed_dim, 64, 1, 64, 32, sp.context, sp.vocab, sp.width, sp.heads, sp.layers)
+            clip_mod.convert_weights(clip)
+            clip.load_state_dict(st["t"], strict=False)
+            st.update(kind="reference", model=model, sample=gs.sample_sequence, clip=clip.eval())
+    z = TW.make_token_latents(pop, 20, TW.GPT2_SMALL.vocab, seed)
+    t0 = time.perf_counter()
+    with torch.no_grad():
+        if st["kind"] == "reference":
+            ctx = torch.cat((torch.tensor(z).long(), torch.tensor(init).long().repeat(pop, 1)), dim=1)
+            toks = np.asarray(st["sample"](model=st["model"], length=30, context=ctx, start_token=None, batch_size=pop,
+                                           temperature=0.7, top_k=40, device="cpu", sample=False))
+        else:
+            toks = gpt2_oracle.gpt2_generate_tokens(st["g"], TW.GPT2_SMALL, z, init, 30)
+        gen = gpt2_oracle.parse_out_tokens(toks, 20, TW.GPT2_SMALL.vocab - 1)
+        ct = torch.tensor(standin_clip_tokens(gen, TW.CLIP_TEXT_B32))
+        feats = st["clip"].encode_text(ct) if st["kind"] == "reference" else \
+            gpt2_oracle.clip_encode_text(st["t"], TW.CLIP_TEXT_B32, ct, mode="as_built")
+        torch.cosine_similarity(feats.float(), st["img"].float())
+    return time.perf_counter() - t0, st["kind"]
+
+
+GPT2_METRIC = "candidate token-latents evaluated/sec GPT2 img2txt + CLIP text tower (problem._evaluate path, config 5)"
+
+
+def run_gpt2(args, rank, world, local_rank):
+    """--workload gpt2 (BASELINE config 5: GPT2 image-to-text, pop 64 per GPU): one step = one generation's
+    _evaluate: 30-step greedy decode of P x 53 tokens + CLIP text tower + cosine."""
+    threads = best_cpu_threads()
+    P_local = args.pop_per_gpu
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        times, kind = [], "port"
+        gpt2_reference_step(args.cpu_sample_gpt2, 1, threads)
+        for i in range(max(1, min(args.steps, 5))):
+            t, kind = gpt2_reference_step(args.cpu_sample_gpt2, 10 + i, threads)
+            times.append(t)
+        ms = 1e3 * sum(times) / len(times)
+        v = args.cpu_sample_gpt2 / (ms / 1e3)
+        emit(dict(impl="reference", metric=GPT2_METRIC, value=v, unit=UNIT, n_gpus=args.gpus, steps=len(times), warmup=1,
+                  ms_per_step=ms, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="fp32 (GPT-2), fp16-as-built (CLIP)",
+                  data="synthetic", config=dict(workload="GPT2 img2txt (config 5): GPT-2 small greedy decode 23+30 tokens + CLIP text tower",
+                                                population_per_step=args.cpu_sample_gpt2),
+                  cpu_baseline=dict(value=v, unit=UNIT, cores=threads, kind=kind,
+                                    sample=f"{args.cpu_sample_gpt2} candidates per step x {len(times)} steps"),
+                  e2e=dict(value=v, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0)))
+        return
+    import torch
+    import torch.distributed as tdist
+    from clip_glass_b200 import text_weights as TW
+    from clip_glass_b200.config import make_namespace
+    from clip_glass_b200.models import standin_clip_tokens
+    from clip_glass_b200.problem import GenerationProblem
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        tdist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    P = P_local * world
+    img = torch.randn(1, 512, generator=torch.Generator().manual_seed(6))
+    config = make_namespace("GPT2", device=f"cuda:{local_rank}", target="synthetic", pop_size=P, batch_size=P_local,
+                            max_population=P_local, synthetic_seed=1000, image_features=img, clip_token_map="standin")
+    problem = GenerationProblem(config)
+    gen = problem.generator
+    eng = gen.engine
+    stream = torch.cuda.current_stream()
+    W_ = max(args.warmup, 3)
+    zs = [TW.make_token_latents(P, 20, TW.GPT2_SMALL.vocab, 50 + i) for i in range(4)]
+    lo, hi = rank * P_local, (rank + 1) * P_local
+
+    def step_local(i):
+        toks = eng.generate_tokens(zs[i % 4][lo:hi])
+        return eng.text_similarity(standin_clip_tokens(gen.model.parse_out_tokens(toks), gen.text_spec))
+
+    def barrier():
+        if world > 1:
+            tdist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(W_):
+        step_local(i)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    l0 = eng.launch_count
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    for i in range(args.steps):
+        ev[i][0].record(stream)
+        step_local(W_ + i)
+        ev[i][1].record(stream)
+    barrier()
+    launches = eng.launch_count - l0
+    ms = torch.tensor([a.elapsed_time(b) for a, b in ev], dtype=torch.float64, device="cuda")
+    if world > 1:
+        tdist.all_reduce(ms, op=tdist.ReduceOp.MAX)
+    ms_dev = float(ms.mean())
+    e2e = []
+    for i in range(args.steps):
+        barrier()
+        t0 = time.perf_counter()
+        out = {}
+        problem._evaluate(zs[i % 4].astype(np.float64), out)
+        torch.cuda.synchronize()
+        e2e.append((time.perf_counter() - t0) * 1e3)
+    e2e_ms = torch.tensor(e2e, dtype=torch.float64, device="cuda")
+    if world > 1:
+        tdist.all_reduce(e2e_ms, op=tdist.ReduceOp.MAX)
+    if rank == 0:
+        sampler.stop()
+    eng.set_timing(True)
+    step_local(0)
+    g_ms, g_n, g_bytes = eng.gemm_time()
+    eng.set_timing(False)
+    peaks = measured_peaks()
+    achieved = g_bytes / (g_ms * 1e-3) / 1e9
+    roofline = dict(bound="hbm", kernel="gemm_tc_kernel (split-fp16 tcgen05 GEMMs of the GPT-2 decode + CLIP text GEMMs)",
+                    achieved=achieved, peak=peaks["hbm_gbs"], unit="GB/s", frac=achieved / peaks["hbm_gbs"], traffic=None,
+                    peak_source=peaks["source"], launches_per_step=g_n, kernel_ms_per_step=g_ms,
+                    share_of_step=g_ms / ms_dev, algorithmic_bytes_per_step=g_bytes,
+                    note="decode steps have M = P rows: every GEMM is a pass over its (hi + lo) fp16 weights")
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        gpt2_reference_step(args.cpu_sample_gpt2, 1, threads)
+        ts = [gpt2_reference_step(args.cpu_sample_gpt2, 2 + i, threads) for i in range(2)]
+        v = args.cpu_sample_gpt2 / statistics.median(t for t, _ in ts)
+        cpu = dict(value=v, unit=UNIT, cores=threads, kind=ts[0][1],
+                   sample=f"{args.cpu_sample_gpt2} candidates x 2 timed repetitions, median (models.py:45-60 + generator.py:53-59)")
+    if rank == 0:
+        em = float(e2e_ms.mean())
+        emit(dict(metric=GPT2_METRIC, value=P / (ms_dev / 1e3), unit=UNIT, n_gpus=world, steps=args.steps, warmup=W_,
+                  ms_per_step=ms_dev, higher_is_better=True, scaling="weak", vs_baseline=None,
+                  dtype="split fp16 (22-bit) operands, fp32 accumulate for GPT-2; fp16 as built for the CLIP text tower",
+                  data="synthetic",
+                  config=dict(workload="GPT2 img2txt (config 5): GPT-2 small greedy decode 23+30 tokens + CLIP text tower",
+                              population=P, population_per_gpu=P_local, parallelism=f"population-sharded dp{world}",
+                              weights="seeded random (no checkpoints offline)",
+                              text_round_trip="token-level stand-in for BPE decode + clip.tokenize (no vocabulary files on the box)",
+                              l2="decode streams ~0.5 GB of weights per step (> 126 MB L2)"),
+                  clocks=sampler.summary(), gpu_launches=int(launches),
+                  e2e=dict(value=P / (em / 1e3), unit=UNIT, ms_per_step=em, h2d_bytes_per_step=int(P_local * (20 + 77) * 8),
+                           d2h_bytes_per_step=int(P_local * (53 * 8 + 4)),
+                           api="GenerationProblem._evaluate(x) -> out['F'] (glass_text_generate + glass_text_similarity)"),
+                  roofline=roofline, cpu_baseline=cpu, flags=dict(engine_flags=0, debug_build=False, glass_debug_env=[])))
+    if world > 1:
+        tdist.destroy_process_group()
+
+
 _JSON_FD = None
 
 
@@ -218,12 +398,23 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--flags", type=int, default=0, help="glass_config.flags (tuning experiments; 0 = product default)")
+    ap.add_argument("--workload", default="stylegan2", choices=["stylegan2", "gpt2"],
+                    help="stylegan2 = BASELINE configs 2/4 (the headline metric); gpt2 = config 5 (img2txt path)")
+    ap.add_argument("--cpu-sample-gpt2", type=int, default=16)
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
 
+    if args.workload == "gpt2":
+        if args.impl == "ours":
+            from clip_glass_b200 import _lib as _l
+            if sorted(k for k in os.environ if k.startswith("GLASS_DEBUG_")) or os.environ.get("CLIPGLASS_LIB") or \
+                    _l.load_library().glass_debug_build():
+                raise SystemExit("bench.py: refusing to time a debug configuration")
+        run_gpt2(args, rank, world, local_rank)
+        return
     if args.impl == "reference":
         run_reference(args, rank, world)
         return

@@ -35,7 +35,7 @@ SYMBOLS = [
     "glass_last_images_gather", "glass_image_grid_u8", "glass_biggan_latent",
     "glass_text_create", "glass_text_set_tensor", "glass_text_finalize", "glass_text_set_image_features",
     "glass_text_generate", "glass_text_similarity", "glass_text_launch_count", "glass_text_last_error",
-    "glass_text_destroy",
+    "glass_text_destroy", "glass_text_set_timing", "glass_text_gemm_time",
 ]
 
 

@@ -544,6 +544,11 @@ struct glass_text_engine {
   uint8_t* arena = nullptr;
   size_t arena_bytes = 0;
   int64_t launches = 0;
+  // optional CUDA-event timing of the GEMM launches (bench.py roofline)
+  bool timing = false;
+  std::vector<cudaEvent_t> ev;
+  size_t ev_used = 0;
+  double gemm_bytes = 0;      // algorithmic bytes of the timed launches: operands read once + outputs written once
   // GPT-2 workspace
   int Tctx = 0, Ttot = 0, Npad = 0;
   int* tokens = nullptr;
@@ -615,7 +620,17 @@ int launch_gemm_t(glass_text_engine* e, const __half* a_hi, const __half* a_lo, 
     TRC(get_map(e, w_lo, p.N, p.K, BN, &mwl));
   }
   dim3 grid(p.N / BN, (p.M + 127) / 128);
+  const bool timed = e->timing && e->ev_used + 2 <= e->ev.size();
+  if (timed) cudaEventRecord(e->ev[e->ev_used], s);
   gemm_tc_kernel<BN, kSplit><<<grid, 192, C::kSmemBytes, s>>>(*mah, *mal, *mwh, *mwl, p);
+  if (timed) {
+    cudaEventRecord(e->ev[e->ev_used + 1], s);
+    e->ev_used += 2;
+    const double in_b = ((double)p.M * p.K + (double)p.N * p.K) * 2.0 * (kSplit ? 2 : 1);
+    const double out_b = (double)p.M * p.N * ((p.out_f32 ? 4 : 0) + (p.out_hi ? 2 : 0) + (p.out_lo ? 2 : 0) +
+                                              (p.res_f32 ? 4 : 0) + (p.res_f16 ? 2 : 0));
+    e->gemm_bytes += in_b + out_b;
+  }
   e->launches++;
   cudaError_t err = cudaGetLastError();
   if (err != cudaSuccess) return tfail(GLASS_ERR_CUDA, "gemm_tc_kernel launch failed: %s", cudaGetErrorString(err));
@@ -936,11 +951,43 @@ int glass_text_similarity(glass_text_engine* e, const int64_t* clip_tokens_host,
 
 int64_t glass_text_launch_count(const glass_text_engine* e) { return e ? e->launches : 0; }
 
+int glass_text_set_timing(glass_text_engine* e, int32_t enable) {
+  if (!e) return tfail(GLASS_ERR_ARG, "null engine");
+  TCUDA_OK(cudaSetDevice(e->cfg.device));
+  if (enable && e->ev.empty()) {
+    e->ev.resize(8192);
+    for (auto& ev : e->ev) TCUDA_OK(cudaEventCreate(&ev));
+  }
+  e->timing = enable != 0;
+  e->ev_used = 0;
+  e->gemm_bytes = 0;
+  return GLASS_OK;
+}
+
+int glass_text_gemm_time(glass_text_engine* e, float* ms, int32_t* launches, double* bytes) {
+  if (!e) return tfail(GLASS_ERR_ARG, "null engine");
+  TCUDA_OK(cudaSetDevice(e->cfg.device));
+  TCUDA_OK(cudaDeviceSynchronize());
+  float total = 0.f;
+  for (size_t i = 0; i + 1 < e->ev_used; i += 2) {
+    float t = 0.f;
+    TCUDA_OK(cudaEventElapsedTime(&t, e->ev[i], e->ev[i + 1]));
+    total += t;
+  }
+  if (ms) *ms = total;
+  if (launches) *launches = (int32_t)(e->ev_used / 2);
+  if (bytes) *bytes = e->gemm_bytes;
+  e->ev_used = 0;
+  e->gemm_bytes = 0;
+  return GLASS_OK;
+}
+
 int glass_text_destroy(glass_text_engine* e) {
   if (!e) return GLASS_OK;
   cudaSetDevice(e->cfg.device);
   for (auto& kv : e->tensors) cudaFree(kv.second.ptr);
   if (e->arena) cudaFree(e->arena);
+  for (auto& ev : e->ev) cudaEventDestroy(ev);
   delete e;
   return GLASS_OK;
 }

@@ -59,8 +59,11 @@ class Generator:
     def __init__(self, config):
         self.config = config
         self.augmentation = None
-        if config.task != "txt2img":
-            raise NotImplementedError("img2txt (GPT-2) is a 'next' row of SURVEY.md §8(f)")
+        if not str(config.device).startswith("cuda"):
+            raise GlassError("the B200 path has no CPU fallback: config.device must be a CUDA device")
+        if config.task == "img2txt":
+            self._init_img2txt(config)
+            return
         if not str(config.device).startswith("cuda"):
             raise GlassError("the B200 path has no CPU fallback: config.device must be a CUDA device")
         dev = torch.device(config.device)
@@ -79,6 +82,47 @@ class Generator:
         self.text_features = torch.as_tensor(tf)
         self.engine.set_text_features(self.text_features)
         self._calls = 0
+
+    # -- img2txt (BASELINE config 5; generator.py:26-27, 53-59, 69-71) -------
+    def _init_img2txt(self, config):
+        from . import text_weights as TW
+        from .models import GPT2
+        from .tokenizers import ClipTokenizer
+        self.text_spec = getattr(config, "clip_text_spec", TW.CLIP_TEXT_B32)
+        seed = getattr(config, "synthetic_seed", None)
+        clip_path = getattr(config, "clip_weights", os.path.expanduser("~/.cache/clip/ViT-B-32.pt"))
+        if seed is None and os.path.exists(clip_path):
+            full = torch.jit.load(clip_path, map_location="cpu").state_dict()
+            t_sd = {k: v for k, v in full.items() if not k.startswith("visual.") and k not in
+                    ("logit_scale", "input_resolution", "context_length", "vocab_size")}
+        elif seed is not None:
+            t_sd = TW.make_clip_text_weights(self.text_spec, seed + 1)
+        else:
+            raise GlassError(f"CLIP weights not found at {clip_path!r} and no synthetic_seed given")
+        self.model = GPT2(config, text_spec=self.text_spec, text_sd=t_sd)
+        self.engine = self.model.engine
+        bpe = getattr(config, "clip_bpe", "")
+        self.clip_tokenizer = ClipTokenizer(bpe) if isinstance(bpe, str) and os.path.exists(bpe) else None
+        feats = getattr(config, "image_features", None)
+        if feats is None:
+            raise GlassError("config.image_features ([1,512], CLIP.encode_image of the target picture, "
+                             "generator.py:26-27) is required")
+        self.image_features = torch.as_tensor(feats)
+        self.engine.set_image_features(self.image_features)
+
+    def _text_similarity(self, input):
+        """generator.py:53-59.  ``input``: the list of strings ``generate`` returned, or (token-level callers: tests,
+        bench.py on a box without vocabulary files) an int64 array of clip tokens [P, context]."""
+        if isinstance(input, (np.ndarray, torch.Tensor)):
+            tokens = np.asarray(input.cpu() if isinstance(input, torch.Tensor) else input, dtype=np.int64)
+        else:
+            if self.clip_tokenizer is None:
+                raise GlassError("CLIP's BPE vocabulary (config.clip_bpe) is needed to tokenise text")
+            try:
+                tokens = self.clip_tokenizer.tokenize(list(input), self.text_spec.context)
+            except RuntimeError:
+                return torch.zeros(len(input))                       # generator.py:55-56
+        return torch.from_numpy(self.engine.text_similarity(tokens))
 
     # -- image output path (SURVEY.md §8(f)-4) -------------------------------
     def remember_population(self, x, offset: int = 0):
@@ -99,6 +143,10 @@ class Generator:
     # generator.py:29-34
     def generate(self, ls, minibatch=None, noise=None):
         z = ls()[0]
+        if self.config.task == "img2txt":
+            if getattr(self.config, "return_tokens", False):          # token-level callers (no vocabulary files)
+                return self.model.parse_out_tokens(self.model.generate_tokens(z))
+            return self.model.generate(z, minibatch=minibatch)
         z = z.to(self.config.device, torch.float32).contiguous()
         n = z.shape[0]
         hits = self._cached_rows(z.cpu().numpy()) if noise is None else [None] * n
@@ -133,10 +181,12 @@ class Generator:
         return self.engine.discriminate(images.contiguous())
 
     def has_discriminator(self):
-        return self.engine.use_discriminator
+        return False if self.config.task == "img2txt" else self.engine.use_discriminator
 
     # generator.py:43-51
     def clip_similarity(self, input):
+        if self.config.task == "img2txt":
+            return self._text_similarity(input)
         if self.augmentation is not None:
             raise NotImplementedError("augmentation hook is None in the reference (generator.py:14)")
         return self.engine.clip_similarity(input.contiguous())
@@ -147,6 +197,10 @@ class Generator:
         image.  Device tensors go through ``glass_image_grid_u8``: grid assembly, the x255 + 0.5 clamp, the uint8 cast
         and the CHW->HWC permute happen in one kernel and a quarter of the bytes cross PCIe; PIL encodes the file
         exactly as torchvision's save_image would (``Image.fromarray(ndarr).save(path)``)."""
+        if self.config.task == "img2txt":                              # generator.py:69-71
+            with open(path, "w") as f:
+                f.write("\n".join(str(t) for t in input))
+            return
         if isinstance(input, torch.Tensor) and input.is_cuda:
             from PIL import Image
             grid = self.engine.image_grid_u8(input.detach().float().contiguous(),

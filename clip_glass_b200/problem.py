@@ -51,6 +51,30 @@ class GenerationProblem(_Base):
 
     def _evaluate(self, x, out, *args, **kwargs):
         self.generation += 1
+        if self.config.task == "img2txt":
+            # problem.py:15-29 for the GPT-2 config: generate -> clip_similarity, F = -sim.  With
+            # config.clip_token_map == "standin" (no vocabulary files on the box) the text round trip is replaced by
+            # the documented token-level stand-in (models.standin_clip_tokens); the GPU work is identical.
+            from . import dist
+
+            def local_text(xs, first_group):
+                ls = self.config.latent(self.config)
+                ls.set_from_population(xs)
+                if getattr(self.config, "clip_token_map", None) == "standin":
+                    from .models import standin_clip_tokens
+                    gen = self.generator.model.parse_out_tokens(self.generator.model.generate_tokens(ls()[0]))
+                    sim = self.generator.clip_similarity(standin_clip_tokens(gen, self.generator.text_spec))
+                else:
+                    generated = self.generator.generate(ls, minibatch=self.config.batch_size)
+                    sim = self.generator.clip_similarity(generated)
+                return -sim.cpu().numpy().astype(np.float32), None
+
+            # candidates are independent on this path (the reference decodes the whole population in one batch and
+            # ignores `minibatch`, models.py:46): shards of any size, one all-gather of F
+            neg_sim, _ = dist.sharded_evaluate(x, 1, 1, local_text)
+            out["F"] = neg_sim
+            out["G"] = np.zeros((x.shape[0]))
+            return
         if getattr(self.config, "fused", True):
             from . import dist
             seed = int(getattr(self.config, "noise_seed", 0)) + self.generation

@@ -95,6 +95,9 @@ def _bind(lib):
     lib.glass_text_launch_count.restype = i64
     lib.glass_text_last_error.restype = ctypes.c_char_p
     lib.glass_text_destroy.argtypes = [vp]
+    lib.glass_text_set_timing.argtypes = [vp, i32]
+    lib.glass_text_gemm_time.argtypes = [vp, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(i32),
+                                         ctypes.POINTER(ctypes.c_double)]
     _bound = True
 
 
@@ -175,3 +178,12 @@ class TextEngine:
     @property
     def launch_count(self) -> int:
         return int(self.lib.glass_text_launch_count(self._h))
+
+    def set_timing(self, enable: bool = True) -> None:
+        _check(self.lib, self.lib.glass_text_set_timing(self._h, int(enable)))
+
+    def gemm_time(self):
+        """(ms, launches, algorithmic bytes) of the tensor-core GEMM launches since the last call (timing enabled)."""
+        ms, n, b = ctypes.c_float(), ctypes.c_int32(), ctypes.c_double()
+        _check(self.lib, self.lib.glass_text_gemm_time(self._h, ctypes.byref(ms), ctypes.byref(n), ctypes.byref(b)))
+        return float(ms.value), int(n.value), float(b.value)

@@ -200,6 +200,11 @@ int glass_text_generate(glass_text_engine* e, const int64_t* z_host, int32_t pop
 int glass_text_similarity(glass_text_engine* e, const int64_t* clip_tokens_host, int32_t pop, float* sim_host,
                           float* features_host, void* stream);
 int64_t glass_text_launch_count(const glass_text_engine* e);
+/* bench.py roofline: with timing enabled every tensor-core GEMM launch is bracketed by CUDA events;
+ * glass_text_gemm_time returns (and resets) their summed device time, their count and their algorithmic bytes
+ * (operands read once + outputs written once). */
+int glass_text_set_timing(glass_text_engine* e, int32_t enable);
+int glass_text_gemm_time(glass_text_engine* e, float* ms, int32_t* launches, double* bytes);
 const char* glass_text_last_error(void);
 int glass_text_destroy(glass_text_engine* e);
 

@@ -1,5 +1,6 @@
-"""Recipe for oracle/_ref: a git-ignored copy of the four reference files that hold 100 % of the path's arithmetic
-(stylegan2/models.py, stylegan2/modules.py, stylegan2/utils.py, clip/model.py), so that ``bench.py --impl reference``
+"""Recipe for oracle/_ref: a git-ignored copy of the reference files that hold 100 % of the path's arithmetic
+(stylegan2/models.py, stylegan2/modules.py, stylegan2/utils.py, clip/model.py; gpt2/{model,sample,config,utils}.py for
+the img2txt workload), so that ``bench.py --impl reference``
 can time the reference's OWN modules on the GPU box (which has no /root/reference).  Run in the build container by
 ``__graft_entry__.build()``:
 
@@ -16,7 +17,8 @@ import sys
 REF = "/root/reference"
 HERE = os.path.dirname(os.path.abspath(__file__))
 OUT = os.path.join(HERE, "_ref")
-FILES = ["stylegan2/models.py", "stylegan2/modules.py", "stylegan2/utils.py", "clip/model.py"]
+FILES = ["stylegan2/models.py", "stylegan2/modules.py", "stylegan2/utils.py", "clip/model.py",
+         "gpt2/model.py", "gpt2/sample.py", "gpt2/config.py", "gpt2/utils.py"]       # img2txt arm (config 5)
 
 
 def main() -> int:
@@ -27,7 +29,7 @@ def main() -> int:
         dst = os.path.join(OUT, rel)
         os.makedirs(os.path.dirname(dst), exist_ok=True)
         shutil.copyfile(os.path.join(REF, rel), dst)
-    for pkg in ("stylegan2", "clip"):
+    for pkg in ("stylegan2", "clip", "gpt2"):
         open(os.path.join(OUT, pkg, "__init__.py"), "w").close()
     print(f"build_ref: copied {len(FILES)} reference files into {OUT}")
     return 0

@@ -1,0 +1,6 @@
+cd $GRAFT_REPO_ROOT
+TAG=${1:-r02d}
+timeout 900 python -m pytest tests/test_gpu_text.py -m gpu -x -q > gpurun_out/pytest_text_$TAG.log 2>&1; tail -5 gpurun_out/pytest_text_$TAG.log
+python bench.py --workload gpt2 --steps 10 --warmup 3 > gpurun_out/bench_gpt2_$TAG.json 2> gpurun_out/bench_gpt2_$TAG.err; cut -c1-400 gpurun_out/bench_gpt2_$TAG.json; tail -3 gpurun_out/bench_gpt2_$TAG.err
+python bench.py --workload gpt2 --impl reference --steps 3 > gpurun_out/bench_gpt2_ref_$TAG.json 2>/dev/null; cut -c1-300 gpurun_out/bench_gpt2_ref_$TAG.json
+python bench.py --steps 10 --warmup 3 > gpurun_out/bench_n1_$TAG.json 2> gpurun_out/bench_n1_$TAG.err; cut -c1-300 gpurun_out/bench_n1_$TAG.json; tail -2 gpurun_out/bench_n1_$TAG.err

@@ -93,3 +93,36 @@ def test_text_engine_argument_errors():
     with pytest.raises(AssertionError):
         eng.text_similarity(ct)
     eng.close()
+
+
+def test_plugin_surface_gpt2_config():
+    """GenerationProblem._evaluate for config GPT2 (problem.py:14-29 on the img2txt task): x holds integer genes as
+    float64 (pymoo), F = -sim [P], G = zeros; the token-level route (no vocabulary files on this box) equals the two
+    engine calls made by hand; Generator.save writes the texts file (generator.py:69-71)."""
+    from clip_glass_b200.config import make_namespace
+    from clip_glass_b200.models import standin_clip_tokens
+    from clip_glass_b200.problem import GenerationProblem
+    cfg = CONFIGS["gpt2_tiny"]
+    gold = dict(np.load(os.path.join(REPO, "tests", "golden", "gpt2_tiny.npz")))
+    ns = make_namespace("GPT2", device="cuda:0", pop_size=8, batch_size=8, synthetic_seed=cfg["seed"],
+                        gpt2_spec=cfg["gpt2"], clip_text_spec=cfg["text"], clip_token_map="standin",
+                        image_features=torch.from_numpy(gold["image_features"]))
+    prob = GenerationProblem(ns)
+    assert not prob.generator.has_discriminator()
+    out = {}
+    prob._evaluate(gold["z"].astype(np.float64), out)
+    assert out["F"].shape == (8,) and out["G"].shape == (8,) and not out["G"].any()
+    toks = prob.generator.model.generate_tokens(gold["z"])
+    np.testing.assert_array_equal(toks, gold["tokens"])               # same seeds as the fixture: same weights
+    gen = prob.generator.model.parse_out_tokens(toks)
+    assert gen[1] == []                                               # EOT gene inside the latent part (models.py:35-36)
+    sim = prob.generator.clip_similarity(standin_clip_tokens(gen, cfg["text"]))
+    np.testing.assert_array_equal(out["F"], -sim.numpy())
+    ls = ns.latent(ns)
+    ls.set_from_population(gold["z"].astype(np.float64))
+    assert ls()[0].dtype == torch.int64
+    ns.return_tokens = True
+    assert prob.generator.generate(ls) == gen
+    with pytest.raises(Exception):                                    # text output needs the vocabulary files
+        ns.return_tokens = False
+        prob.generator.generate(ls)

@@ -487,3 +487,83 @@ def test_ga_loop_minimises_a_toy_problem():
         assert len(res.pop) == 16
         if n_obj == 2:
             assert len(ga.fast_non_dominated_sort(np.atleast_2d(res.F))[0]) == len(np.atleast_2d(res.F))
+
+
+# ---------------------------------------------------------------------------
+# img2txt host side: tokenizers, parse_out, oracle vs fixtures
+# ---------------------------------------------------------------------------
+_GPT2_VOCAB = ("/root/reference/gpt2/weights/encoder.json", "/root/reference/gpt2/weights/vocab.bpe")
+
+
+@pytest.mark.skipif(not all(os.path.exists(p) for p in _GPT2_VOCAB), reason="needs the GPT-2 vocabulary of the reference tree")
+def test_gpt2_tokenizer_matches_reference_encoder():
+    """clip_glass_b200.tokenizers.GPT2Tokenizer against the reference's gpt2/encoder.py on its own vocabulary:
+    encode and decode of text, and decode of arbitrary token lists (what parse_out sees)."""
+    import sys
+    from clip_glass_b200.tokenizers import GPT2Tokenizer
+    sys.path.insert(0, "/root/reference")
+    try:
+        from gpt2.encoder import get_encoder
+    finally:
+        sys.path.remove("/root/reference")
+    ref = get_encoder(cfgmod.Namespace(encoder=_GPT2_VOCAB[0], vocab=_GPT2_VOCAB[1]))
+    mine = GPT2Tokenizer(*_GPT2_VOCAB)
+    assert mine.encode("the picture of") == ref.encode("the picture of") == [1169, 4286, 286]
+    texts = ["the picture of a wolf at night with the moon in the background", "Hello, world!  It's 2021... isn't it?",
+             "naïve café — “quotes” and emoji 🙂", "   leading and trailing   ", "tabs\tand\nnewlines\n\n", "a", ""]
+    for t in texts:
+        assert mine.encode(t) == ref.encode(t), t
+        assert mine.decode(mine.encode(t)) == t
+    rng = np.random.default_rng(0)
+    for _ in range(50):
+        ids = rng.integers(0, 50257, size=int(rng.integers(1, 40))).tolist()
+        assert mine.decode(ids) == ref.decode(ids)
+    # parse_out (models.py:32-42): cut at the first EOT anywhere in the sequence, decode, truncate to 50 characters
+    seqs = rng.integers(0, 50256, size=(4, 53))
+    seqs[1, 30] = 50256          # generated EOT
+    seqs[2, 5] = 50256           # EOT gene inside the latent part -> empty text
+    got = mine.parse_out(seqs, 20, 50)
+    assert got[0] == ref.decode(seqs[0, 20:].tolist())[:50] and got[1] == ref.decode(seqs[1, 20:30].tolist())[:50]
+    assert got[2] == "" and all(len(t) <= 50 for t in got)
+
+
+def test_clip_tokenizer_shape_and_errors():
+    """CLIP's BPE vocabulary is not in the reference tree: the tokenizer is exercised on a synthetic merge table
+    (parity unpinned); tokenize() keeps the reference's contract (SOT/EOT/zero padding, RuntimeError when too long)."""
+    from clip_glass_b200.tokenizers import ClipTokenizer, byte_alphabet
+    b = byte_alphabet()
+    assert len(set(b.values())) == 256 and b[ord("a")] == "a" and b[32] == chr(256 + 32)
+    tok = ClipTokenizer(merges=[("t", "h"), ("th", "e</w>"), ("c", "a"), ("ca", "t</w>")])
+    ids = tok.encode("The  CAT the")
+    assert ids == [tok.encoder["the</w>"], tok.encoder["cat</w>"], tok.encoder["the</w>"]]
+    assert tok.decode(ids) == "the cat the "
+    t = tok.tokenize(["the cat", "cat"], context_length=8)
+    assert t.shape == (2, 8) and t[0, 0] == tok.sot and t[0, 3] == tok.eot and t[0, 4:].sum() == 0
+    assert (t.argmax(1) == [3, 2]).all()                      # the EOT id is the largest: clip/model.py:318 gathers it
+    with pytest.raises(RuntimeError):
+        tok.tokenize(["the " * 10], context_length=8)
+
+
+@pytest.mark.parametrize("name", ["gpt2_tiny", "gpt2_full"])
+def test_gpt2_oracle_reproduces_reference_fixture(name):
+    """oracle/gpt2_oracle.py against tests/golden/gpt2_*.npz (reference gpt2.model + sample_sequence, clip.model):
+    tokens bit-exact, text cosine in fp16-as-built mode within fp16 rounding of the reference's."""
+    from clip_glass_b200 import text_weights as TW
+    from oracle import gpt2_oracle
+    from tests.test_gpu_text import CONFIGS
+    cfg = CONFIGS[name]
+    gold = dict(np.load(os.path.join(REPO, "tests", "golden", f"{name}.npz")))
+    if name == "gpt2_full":
+        z, want = gold["z"][:2], gold["tokens"][:2]           # keep the CPU suite short
+    else:
+        z, want = gold["z"], gold["tokens"]
+    got = gpt2_oracle.gpt2_generate_tokens(TW.make_gpt2_weights(cfg["gpt2"], cfg["seed"]), cfg["gpt2"], z,
+                                           gold["init_tokens"].tolist(), 30)
+    np.testing.assert_array_equal(got, want)
+    assert gpt2_oracle.parse_out_tokens(gold["tokens"], 20, cfg["gpt2"].vocab - 1)[1] == []
+    built = TW.text_as_built(TW.make_clip_text_weights(cfg["text"], cfg["seed"] + 1))
+    n = 8 if name == "gpt2_tiny" else 2
+    feats = gpt2_oracle.clip_encode_text(built, cfg["text"], torch.tensor(gold["clip_tokens"][:n]), mode="fp32")
+    sim = gpt2_oracle.text_similarity(feats, torch.from_numpy(gold["image_features"])).numpy()
+    np.testing.assert_allclose(sim, gold["sim_oracle_fp32"][:n], rtol=1e-5)
+    np.testing.assert_allclose(sim, gold["sim_fp16"][:n].astype(np.float32), rtol=3e-3)
