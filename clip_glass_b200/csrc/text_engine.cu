@@ -80,6 +80,7 @@ __device__ __forceinline__ void split_store(float v, __half* hi, __half* lo) {
 enum { kTActNone = 0, kTActGeluTanh = 1, kTActQuickGelu = 2 };
 struct GemmParams {
   int M, N, K;
+  int a_rows;                 // rows of the A box (128, or 64 when M <= 64: the upper half of the tile is never read back)
   const float* bias;          // [N] or null
   int act;
   int round_fp16;             // plain mode: round acc + bias to fp16 before the activation (the reference's op boundary)
@@ -142,7 +143,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constant
       for (int kit = 0; kit < kiters; ++kit) {
         mbar_wait(&empty_bar[stage], phase ^ 1);
         uint8_t* sa = smem + stage * C::kStageBytes;
-        mbar_expect_tx(&full_bar[stage], C::kStageBytes);
+        const uint32_t a_bytes = (uint32_t)p.a_rows * 128u;
+        mbar_expect_tx(&full_bar[stage], (kSplit ? 2 : 1) * (a_bytes + C::kWBytes));
         tma_load_2d(&map_ah, sa, &full_bar[stage], kit * 64, m_tile * 128);
         tma_load_2d(&map_wh, sa + C::kABytes, &full_bar[stage], kit * 64, n_tile * BN);
         if (kSplit) {
@@ -544,6 +546,12 @@ struct glass_text_engine {
   uint8_t* arena = nullptr;
   size_t arena_bytes = 0;
   int64_t launches = 0;
+  // CUDA graphs of one whole decode (all ~2700 launches of glass_text_generate) and of one text-tower pass, per
+  // population size; built on the second call of a size (the first runs eagerly and configures the kernels)
+  cudaStream_t cap_stream = nullptr;
+  std::map<int, cudaGraphExec_t> gen_graphs, sim_graphs;
+  std::map<int, int> gen_calls, sim_calls;
+  std::map<int, int64_t> gen_graph_launches, sim_graph_launches;
   // optional CUDA-event timing of the GEMM launches (bench.py roofline)
   bool timing = false;
   std::vector<cudaEvent_t> ev;
@@ -554,6 +562,7 @@ struct glass_text_engine {
   int* tokens = nullptr;
   int* init_tokens = nullptr;
   long long* tok64 = nullptr;
+  long long* zin64 = nullptr;
   float *h = nullptr, *qkv = nullptr, *logits = nullptr, *kcache = nullptr, *vcache = nullptr;
   __half *a_hi = nullptr, *a_lo = nullptr, *g_hi = nullptr, *g_lo = nullptr, *f_hi = nullptr, *f_lo = nullptr;
   // CLIP text workspace
@@ -603,7 +612,7 @@ int get_map(glass_text_engine* e, const void* ptr, int rows, int K, int box_rows
 
 template <int BN, bool kSplit>
 int launch_gemm_t(glass_text_engine* e, const __half* a_hi, const __half* a_lo, const __half* w_hi, const __half* w_lo,
-                  const GemmParams& p, cudaStream_t s) {
+                  const GemmParams& p_in, cudaStream_t s) {
   using C = GemmCfg<BN, kSplit>;
   static bool configured = false;
   if (!configured) {
@@ -611,12 +620,14 @@ int launch_gemm_t(glass_text_engine* e, const __half* a_hi, const __half* a_lo, 
     configured = true;
   }
   const CUtensorMap *mah, *mal, *mwh, *mwl;
-  TRC(get_map(e, a_hi, p.M, p.K, 128, &mah));
+  GemmParams p = p_in;
+  p.a_rows = p.M <= 64 ? 64 : 128;
+  TRC(get_map(e, a_hi, p.M, p.K, p.a_rows, &mah));
   TRC(get_map(e, w_hi, p.N, p.K, BN, &mwh));
   mal = mah;
   mwl = mwh;
   if (kSplit) {
-    TRC(get_map(e, a_lo, p.M, p.K, 128, &mal));
+    TRC(get_map(e, a_lo, p.M, p.K, p.a_rows, &mal));
     TRC(get_map(e, w_lo, p.N, p.K, BN, &mwl));
   }
   dim3 grid(p.N / BN, (p.M + 127) / 128);
@@ -720,6 +731,7 @@ void layout_text(glass_text_engine* e, Carver& a) {
     e->tokens = a.take<int>(P * e->Ttot);
     e->init_tokens = a.take<int>(16);
     e->tok64 = a.take<long long>(P * e->Ttot);
+    e->zin64 = a.take<long long>(P * c.dim_z);
     e->h = a.take<float>(M * E);
     e->qkv = a.take<float>(M * 3 * E);
     e->logits = a.take<float>(P * e->Npad);
@@ -785,6 +797,82 @@ int gpt2_forward(glass_text_engine* e, int P, int col0, int Tn, cudaStream_t s) 
   g.M = P; g.N = e->Npad; g.K = E; g.out_f32 = e->logits;
   TRC(launch_gemm<true>(e, e->f_hi, e->f_lo, tt<__half>(e, "g2.wte.hi"), tt<__half>(e, "g2.wte.lo"), g, s));
   TLAUNCH((gpt2_argmax_kernel<<<P, 256, 0, s>>>(e->logits, e->Npad, c.gpt2_vocab, e->tokens, e->Ttot, col0 + Tn)));
+  return GLASS_OK;
+}
+
+
+// the launch sequence of glass_text_generate between the H2D of z and the D2H of the tokens
+int generate_body(glass_text_engine* e, int pop, cudaStream_t s) {
+  const glass_text_config& c = e->cfg;
+  TLAUNCH((tokens_from_i64_kernel<<<(pop * e->Tctx + 255) / 256, 256, 0, s>>>(e->zin64, c.dim_z, e->tokens, e->Ttot, pop,
+                                                                              e->init_tokens, c.n_init)));
+  TRC(gpt2_forward(e, pop, 0, e->Tctx, s));                                   // models.py:47-48: the whole context
+  for (int step = 1; step < c.max_tokens_len; ++step)                         // gpt2/sample.py:26-35
+    TRC(gpt2_forward(e, pop, e->Tctx + step - 1, 1, s));
+  TLAUNCH((tokens_to_i64_kernel<<<(pop * e->Ttot + 255) / 256, 256, 0, s>>>(e->tokens, e->tok64, pop * e->Ttot)));
+  return GLASS_OK;
+}
+
+// the launch sequence of glass_text_similarity between the H2D of the tokens and the D2H of the scores
+int similarity_body(glass_text_engine* e, int pop, cudaStream_t s) {
+  const glass_text_config& c = e->cfg;
+  const int T = c.text_context, W = c.text_width, M = pop * T;
+  char nm[64];
+  TLAUNCH((text_embed_kernel<<<M, 128, 0, s>>>(e->ctok, tt<__half>(e, "t.tok"), tt<__half>(e, "t.pos"), e->tx, e->eot, T, W)));
+  const size_t attn_smem = sizeof(float) * ((size_t)3 * T * 65 + (size_t)T * (T + 1));
+  for (int l = 0; l < c.text_layers; ++l) {
+    auto f = [&](const char* sfx) { snprintf(nm, sizeof nm, "t.l%d.%s", l, sfx); return std::string(nm); };
+    TLAUNCH((text_layernorm_kernel<<<(M + 7) / 8, 256, 0, s>>>(e->tx, tt<float>(e, f("ln1.w")), tt<float>(e, f("ln1.b")), e->th, M, W)));
+    GemmParams g{};
+    g.M = M; g.N = 3 * W; g.K = W; g.bias = tt<float>(e, f("qkv.b")); g.out_hi = e->tqkv;
+    TRC(launch_gemm<false>(e, e->th, nullptr, tt<__half>(e, f("qkv.w")), nullptr, g, s));
+    TLAUNCH((text_attention_kernel<<<pop * c.text_heads, 256, attn_smem, s>>>(e->tqkv, e->tatt, T, W)));
+    g = GemmParams{};
+    g.M = M; g.N = W; g.K = W; g.bias = tt<float>(e, f("out.b")); g.round_fp16 = 1; g.res_f16 = e->tx; g.out_hi = e->tx;
+    TRC(launch_gemm<false>(e, e->tatt, nullptr, tt<__half>(e, f("out.w")), nullptr, g, s));
+    TLAUNCH((text_layernorm_kernel<<<(M + 7) / 8, 256, 0, s>>>(e->tx, tt<float>(e, f("ln2.w")), tt<float>(e, f("ln2.b")), e->th, M, W)));
+    g = GemmParams{};
+    g.M = M; g.N = 4 * W; g.K = W; g.bias = tt<float>(e, f("fc.b")); g.round_fp16 = 1; g.act = kTActQuickGelu; g.out_hi = e->tfc;
+    TRC(launch_gemm<false>(e, e->th, nullptr, tt<__half>(e, f("fc.w")), nullptr, g, s));
+    g = GemmParams{};
+    g.M = M; g.N = W; g.K = 4 * W; g.bias = tt<float>(e, f("proj.b")); g.round_fp16 = 1; g.res_f16 = e->tx; g.out_hi = e->tx;
+    TRC(launch_gemm<false>(e, e->tfc, nullptr, tt<__half>(e, f("proj.w")), nullptr, g, s));
+  }
+  TLAUNCH((text_final_kernel<<<pop, 256, W * sizeof(float), s>>>(e->tx, e->eot, tt<float>(e, "t.lnf.w"), tt<float>(e, "t.lnf.b"),
+                                                                  tt<float>(e, "t.proj"), e->image, e->tfeat, e->tsim, T, W, c.text_embed_dim)));
+  return GLASS_OK;
+}
+
+// First call of a population size: eager launches (configures kernel attributes, fills the tensor-map cache).  Second
+// call: capture the same sequence into a CUDA graph (all pointers are engine-owned and fixed).  Later calls: replay.
+// Timing mode always launches eagerly.
+int run_or_replay(glass_text_engine* e, int pop, cudaStream_t s, std::map<int, cudaGraphExec_t>& graphs,
+                  std::map<int, int>& calls, std::map<int, int64_t>& graph_launches,
+                  int (*body)(glass_text_engine*, int, cudaStream_t)) {
+  const bool use_graph = !e->timing && !(e->cfg.flags & GLASS_FLAG_NO_GRAPH);
+  if (!use_graph || calls[pop]++ == 0) return body(e, pop, s);
+  auto it = graphs.find(pop);
+  if (it == graphs.end()) {
+    const int64_t before = e->launches;
+    cudaGraph_t graph = nullptr;
+    TCUDA_OK(cudaStreamBeginCapture(e->cap_stream, cudaStreamCaptureModeThreadLocal));
+    const int rc = body(e, pop, e->cap_stream);
+    cudaError_t err = cudaStreamEndCapture(e->cap_stream, &graph);
+    graph_launches[pop] = e->launches - before;
+    e->launches = before;
+    if (rc != GLASS_OK) {
+      if (graph) cudaGraphDestroy(graph);
+      return rc;
+    }
+    if (err != cudaSuccess) return tfail(GLASS_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(err));
+    cudaGraphExec_t exec = nullptr;
+    err = cudaGraphInstantiate(&exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (err != cudaSuccess) return tfail(GLASS_ERR_CUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(err));
+    it = graphs.emplace(pop, exec).first;
+  }
+  TCUDA_OK(cudaGraphLaunch(it->second, s));
+  e->launches += graph_launches[pop];
   return GLASS_OK;
 }
 
@@ -867,6 +955,7 @@ int glass_text_finalize(glass_text_engine* e) {
   layout_text(e, real);
   if (e->cfg.gpt2_layers > 0)
     TCUDA_OK(cudaMemcpy(e->init_tokens, tt<int>(e, "g2.init"), (size_t)e->cfg.n_init * 4, cudaMemcpyDeviceToDevice));
+  TCUDA_OK(cudaStreamCreateWithFlags(&e->cap_stream, cudaStreamNonBlocking));
   TCUDA_OK(cudaFuncSetAttribute(gpt2_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
   TCUDA_OK(cudaFuncSetAttribute(text_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 120 * 1024));
   e->finalized = true;
@@ -893,13 +982,8 @@ int glass_text_generate(glass_text_engine* e, const int64_t* z_host, int32_t pop
                    (long long)z_host[i], c.gpt2_vocab);
   TCUDA_OK(cudaSetDevice(c.device));
   cudaStream_t s = (cudaStream_t)stream;
-  TCUDA_OK(cudaMemcpyAsync(e->tok64, z_host, (size_t)pop * c.dim_z * 8, cudaMemcpyHostToDevice, s));
-  TLAUNCH((tokens_from_i64_kernel<<<(pop * e->Tctx + 255) / 256, 256, 0, s>>>(e->tok64, c.dim_z, e->tokens, e->Ttot, pop,
-                                                                              e->init_tokens, c.n_init)));
-  TRC(gpt2_forward(e, pop, 0, e->Tctx, s));                                   // models.py:47-48: the whole context
-  for (int step = 1; step < c.max_tokens_len; ++step)                         // gpt2/sample.py:26-35
-    TRC(gpt2_forward(e, pop, e->Tctx + step - 1, 1, s));
-  TLAUNCH((tokens_to_i64_kernel<<<(pop * e->Ttot + 255) / 256, 256, 0, s>>>(e->tokens, e->tok64, pop * e->Ttot)));
+  TCUDA_OK(cudaMemcpyAsync(e->zin64, z_host, (size_t)pop * c.dim_z * 8, cudaMemcpyHostToDevice, s));
+  TRC(run_or_replay(e, pop, s, e->gen_graphs, e->gen_calls, e->gen_graph_launches, generate_body));
   TCUDA_OK(cudaMemcpyAsync(tokens_host, e->tok64, (size_t)pop * e->Ttot * 8, cudaMemcpyDeviceToHost, s));
   TCUDA_OK(cudaStreamSynchronize(s));
   return GLASS_OK;
@@ -920,28 +1004,7 @@ int glass_text_similarity(glass_text_engine* e, const int64_t* clip_tokens_host,
   cudaStream_t s = (cudaStream_t)stream;
   char nm[64];
   TCUDA_OK(cudaMemcpyAsync(e->ctok, clip_tokens_host, (size_t)M * 8, cudaMemcpyHostToDevice, s));
-  TLAUNCH((text_embed_kernel<<<M, 128, 0, s>>>(e->ctok, tt<__half>(e, "t.tok"), tt<__half>(e, "t.pos"), e->tx, e->eot, T, W)));
-  const size_t attn_smem = sizeof(float) * ((size_t)3 * T * 65 + (size_t)T * (T + 1));
-  for (int l = 0; l < c.text_layers; ++l) {
-    auto f = [&](const char* sfx) { snprintf(nm, sizeof nm, "t.l%d.%s", l, sfx); return std::string(nm); };
-    TLAUNCH((text_layernorm_kernel<<<(M + 7) / 8, 256, 0, s>>>(e->tx, tt<float>(e, f("ln1.w")), tt<float>(e, f("ln1.b")), e->th, M, W)));
-    GemmParams g{};
-    g.M = M; g.N = 3 * W; g.K = W; g.bias = tt<float>(e, f("qkv.b")); g.out_hi = e->tqkv;
-    TRC(launch_gemm<false>(e, e->th, nullptr, tt<__half>(e, f("qkv.w")), nullptr, g, s));
-    TLAUNCH((text_attention_kernel<<<pop * c.text_heads, 256, attn_smem, s>>>(e->tqkv, e->tatt, T, W)));
-    g = GemmParams{};
-    g.M = M; g.N = W; g.K = W; g.bias = tt<float>(e, f("out.b")); g.round_fp16 = 1; g.res_f16 = e->tx; g.out_hi = e->tx;
-    TRC(launch_gemm<false>(e, e->tatt, nullptr, tt<__half>(e, f("out.w")), nullptr, g, s));
-    TLAUNCH((text_layernorm_kernel<<<(M + 7) / 8, 256, 0, s>>>(e->tx, tt<float>(e, f("ln2.w")), tt<float>(e, f("ln2.b")), e->th, M, W)));
-    g = GemmParams{};
-    g.M = M; g.N = 4 * W; g.K = W; g.bias = tt<float>(e, f("fc.b")); g.round_fp16 = 1; g.act = kTActQuickGelu; g.out_hi = e->tfc;
-    TRC(launch_gemm<false>(e, e->th, nullptr, tt<__half>(e, f("fc.w")), nullptr, g, s));
-    g = GemmParams{};
-    g.M = M; g.N = W; g.K = 4 * W; g.bias = tt<float>(e, f("proj.b")); g.round_fp16 = 1; g.res_f16 = e->tx; g.out_hi = e->tx;
-    TRC(launch_gemm<false>(e, e->tfc, nullptr, tt<__half>(e, f("proj.w")), nullptr, g, s));
-  }
-  TLAUNCH((text_final_kernel<<<pop, 256, W * sizeof(float), s>>>(e->tx, e->eot, tt<float>(e, "t.lnf.w"), tt<float>(e, "t.lnf.b"),
-                                                                  tt<float>(e, "t.proj"), e->image, e->tfeat, e->tsim, T, W, c.text_embed_dim)));
+  TRC(run_or_replay(e, pop, s, e->sim_graphs, e->sim_calls, e->sim_graph_launches, similarity_body));
   TCUDA_OK(cudaMemcpyAsync(sim_host, e->tsim, (size_t)pop * 4, cudaMemcpyDeviceToHost, s));
   if (features_host != nullptr)
     TCUDA_OK(cudaMemcpyAsync(features_host, e->tfeat, (size_t)pop * c.text_embed_dim * 4, cudaMemcpyDeviceToHost, s));
@@ -950,6 +1013,7 @@ int glass_text_similarity(glass_text_engine* e, const int64_t* clip_tokens_host,
 }
 
 int64_t glass_text_launch_count(const glass_text_engine* e) { return e ? e->launches : 0; }
+
 
 int glass_text_set_timing(glass_text_engine* e, int32_t enable) {
   if (!e) return tfail(GLASS_ERR_ARG, "null engine");
@@ -987,6 +1051,9 @@ int glass_text_destroy(glass_text_engine* e) {
   cudaSetDevice(e->cfg.device);
   for (auto& kv : e->tensors) cudaFree(kv.second.ptr);
   if (e->arena) cudaFree(e->arena);
+  for (auto& kv : e->gen_graphs) cudaGraphExecDestroy(kv.second);
+  for (auto& kv : e->sim_graphs) cudaGraphExecDestroy(kv.second);
+  if (e->cap_stream) cudaStreamDestroy(e->cap_stream);
   for (auto& ev : e->ev) cudaEventDestroy(ev);
   delete e;
   return GLASS_OK;
