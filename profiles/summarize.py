@@ -3,6 +3,7 @@ bench.py and DESIGN.md cite.
 
     python profiles/summarize.py launches <launches.csv> <out.txt>          # per-kernel share of the step
     python profiles/summarize.py traffic  <conv_dram.csv> <out.json>         # DRAM bytes per conv_tc launch
+    python profiles/summarize.py metrics  <metrics.csv> <out.txt>            # per-launch time / DRAM / tensor pipe
 
 The launch list comes from `ncu --metrics gpu__time_duration.sum --clock-control none --csv`; its per-launch times are
 cold-cache and serialised, so only the SHARES are meaningful.
@@ -23,6 +24,37 @@ def read(path):
 def to_ms(v, unit):
     v = float(v.replace(",", ""))
     return v / 1e6 if unit.startswith("n") else v / 1e3 if unit.startswith("u") else v if unit.startswith("m") else v * 1e3
+
+
+def metrics(src, dst):
+    """Long-format ncu CSV (one row per launch and metric) -> one line per launch: time, DRAM bytes and GB/s, tensor
+    pipe / LSU pipe / issue-slot utilisation; plus per-kernel-family totals.  Times are cold-cache and serialised."""
+    rows = read(src)
+    per = collections.OrderedDict()
+    for r in rows:
+        key = int(r[0])
+        d = per.setdefault(key, dict(name=re.sub(r"^void ", "", r[4]).split("(")[0].split("::")[-1], grid=r[8]))
+        d[r[12]] = float(r[14].replace(",", ""))
+    fam = collections.defaultdict(lambda: [0, 0.0, 0.0, 0.0])
+    with open(dst, "w") as f:
+        f.write("# one step at P=64 (tests/profile_step.py --pop 64 --evals 1) under ncu, per launch (cold, serialised)\n")
+        f.write("#  id  time_us   dram_MB  dram_GB/s  tensor%  lsu%  issue%  kernel  grid\n")
+        for k, d in per.items():
+            t = d.get("gpu__time_duration.sum", 0.0) / 1e3
+            b = d.get("dram__bytes_read.sum", 0.0) + d.get("dram__bytes_write.sum", 0.0)
+            tp = d.get("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", 0.0)
+            f.write(f"{k:5d} {t:9.1f} {b / 1e6:9.1f} {b / max(t, 1e-9) / 1e3:9.1f} {tp:7.1f} "
+                    f"{d.get('sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active', 0.0):6.1f} "
+                    f"{d.get('smsp__issue_active.avg.pct_of_peak_sustained_active', 0.0):6.1f}  {d['name'][:48]}  {d['grid']}\n")
+            name = "conv_tc_kernel<*>" if "conv_tc_kernel" in d["name"] else d["name"].split("<")[0]
+            fam[name][0] += 1
+            fam[name][1] += t
+            fam[name][2] += b
+            fam[name][3] += tp * t
+        tot = sum(v[1] for v in fam.values())
+        f.write(f"# per kernel family: launches, total time (us), share, DRAM GB, time-weighted tensor pipe %; total {tot / 1e3:.2f} ms\n")
+        for k, v in sorted(fam.items(), key=lambda kv: -kv[1][1]):
+            f.write(f"# {v[0]:4d} {v[1]:10.1f} {100 * v[1] / tot:6.1f}% {v[2] / 1e9:8.2f} GB {v[3] / max(v[1], 1e-9):6.1f}%  {k}\n")
 
 
 def launches(src, dst):
@@ -63,4 +95,4 @@ def traffic(src, dst):
 
 
 if __name__ == "__main__":
-    {"launches": launches, "traffic": traffic}[sys.argv[1]](sys.argv[2], sys.argv[3])
+    {"launches": launches, "traffic": traffic, "metrics": metrics}[sys.argv[1]](sys.argv[2], sys.argv[3])

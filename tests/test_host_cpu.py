@@ -271,14 +271,17 @@ def test_profile_summaries_match_the_committed_ncu_logs(tmp_path):
     mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)
     out = tmp_path / "traffic.json"
-    mod.traffic(os.path.join(prof, "r01_conv_dram_p64_final.csv"), str(out))
+    mod.traffic(os.path.join(prof, "r02_conv_dram_p64.csv"), str(out))
     got = json.load(open(out))
     ref = json.load(open(os.path.join(prof, "conv_tc_traffic.json")))
     assert got["launches"] == ref["launches"] == 92                    # one step = 92 tcgen05 conv/GEMM launches
     assert abs(got["bytes_per_launch"] - ref["bytes_per_launch"]) < 1.0
     shares = tmp_path / "shares.txt"
-    mod.launches(os.path.join(prof, "r01_launches_p64_final.csv"), str(shares))
-    assert open(shares).read() == open(os.path.join(prof, "r01_launch_shares_p64_final.txt")).read()
+    mod.launches(os.path.join(prof, "r02_launches_p64.csv"), str(shares))
+    assert open(shares).read() == open(os.path.join(prof, "r02_launch_shares_p64.txt")).read()
+    met = tmp_path / "metrics.txt"
+    mod.metrics(os.path.join(prof, "r02_metrics_p64.csv"), str(met))
+    assert open(met).read() == open(os.path.join(prof, "r02_metrics_p64.txt")).read()
 
 
 def test_python_flag_constants_match_the_header():
