@@ -500,10 +500,13 @@ def main():
         ms = torch.tensor([a.elapsed_time(b) for a, b in ev], dtype=torch.float64, device="cuda")
         timed.per_rank = None
         if world > 1:
+            # the contract: time K steps, take the MAX over ranks of that time (not the mean of per-step maxima,
+            # which would add every step's slowest rank together)
             allr = torch.empty(world, n_steps, dtype=torch.float64, device="cuda")
             tdist.all_gather_into_tensor(allr, ms)
             timed.per_rank = allr.mean(1).cpu().numpy().tolist()      # skew between ranks vs collective latency
-            tdist.all_reduce(ms, op=tdist.ReduceOp.MAX)
+            slowest = int(torch.argmax(allr.sum(1)).item())
+            ms = allr[slowest]
         return ms.cpu().numpy()
 
     for i in range(W_):
