@@ -94,6 +94,7 @@ constexpr EpiSpec kEpiSpecs[] = {
     {false, false, false, false, kStRegular, false, kActLrelu},   // 10: D conv0 of the exact form, NHWC store
     {false, false, false, false, kStS2D, true, kActLrelu},        // 11: D conv0, space-to-depth I8 (feeds MODE 6)
     {false, false, false, false, kStRegular, true, kActNone},     // 12: D projection (1x1, linear), I8 store
+    {false, false, false, false, kStRegular, true, kActLrelu},    // 13: D conv0 feeding the fused-FIR down-conv, I8 store
 };
 constexpr int kNumEpiSpecs = sizeof(kEpiSpecs) / sizeof(kEpiSpecs[0]);
 
@@ -1032,6 +1033,8 @@ cudaError_t launch_conv_tc(const ConvParams& p, const TmaMaps& maps, int num_sms
   GLASS_SPEC(256, 64, 0, 12)
   GLASS_SPEC(128, 64, 0, 10)
   GLASS_SPEC(32, 32, 4, 11)
+  GLASS_SPEC(32, 32, 4, 13)
+  GLASS_SPEC(64, 64, 4, 13)
   GLASS_SPEC(64, 128, 6, 7)
   GLASS_SPEC(32, 128, 4, 7)
   GLASS_SPEC(64, 128, 6, 8)

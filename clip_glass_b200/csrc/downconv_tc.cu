@@ -1,0 +1,385 @@
+// Discriminator down-conv (stylegan2/modules.py:1204-1254: FilterLayer [1,3,3,1]x[1,3,3,1]/64, pad 2 -> 3x3 conv,
+// stride 2) in its EXACT form with the FIR applied INSIDE the kernel — for the 32/64-channel blocks at 1024^2 / 512^2,
+// where the FIR-folded 3x3-over-space-to-depth form issues 4x the MACs and a separate blur pass costs more HBM time
+// than the inflation.
+//
+//   warp 0        TMA producer: the haloed raw tile of conv0's output (I8 layout [N][H][C/8][W][8]; 36 rows x 20 pixels x
+//                 32 channels per stage, zero-filled outside the image = the FIR's zero padding) and, once, the nine
+//                 3x3 taps of the n-tile (resident, [tap][BN][C], swizzled K-major).
+//   warp 1        MMA issuer: out[z] = sum_{ky,kx} W[ky,kx] . U[2z+ky, 2z+kx] as 9 x C/16 tcgen05.mma over the blurred tile,
+//                 which the blur warps leave in shared memory split by row/column parity so that a stride-2 tap is a
+//                 plain descriptor offset (un-swizzled K-major core matrices, 8 pixels x 16 B).
+//   warps 2..9    epilogue: TMEM -> bias, lrelu*sqrt2, + projection residual, * 1/sqrt2 -> fp16 store (I8 or NHWC).
+//   warps 10..17  blur: U = FIR(a) in packed-half2 arithmetic, (c0+c3)/8 + 3(c1+c2)/8 per axis (separable; ~4
+//                 thread-instructions per element against ~10 for an epilogue), written as four parity planes.
+//
+// Accumulator tile: 8 wide x 16 tall output pixels; channels are processed in 32-channel passes (C = 64: two passes
+// accumulate into the same TMEM columns).
+#include "common.cuh"
+#include "kernels.cuh"
+#include "tcgen05.cuh"
+
+namespace glass {
+namespace {
+
+constexpr int kDcTW = 8, kDcTH = 16;                    // output tile (z space)
+constexpr int kDcRawRows = 2 * kDcTH + 4, kDcRawCols = 2 * kDcTW + 4;     // 36 x 20 raw pixels
+constexpr int kDcG = 4;                                 // 8-channel groups per pass (32 channels)
+constexpr int kDcRawBytes = kDcRawRows * kDcG * kDcRawCols * 16;          // 46080
+constexpr int kDcLbo = 9 * 16;                          // plane: next 8-channel group (9 columns of 16 B)
+constexpr int kDcSbo = kDcG * kDcLbo;                   // plane: next row (= next 8-pixel group of the tile)
+constexpr int kDcPlaneBytes = (kDcTH + 1) * kDcSbo;     // 17 rows
+constexpr int kDcBlurBytes = 4 * kDcPlaneBytes;         // 39168
+constexpr int kDcThreads = 64 + 256 + 256;
+
+struct DownParams {
+  int N, Ho, Wo, Cout;
+  int sh_x, sh_y;         // log2 of the tile grid (Wo / 8, Ho / 16 are powers of two): tile decode with shifts
+  const float* bias;
+  const __half* residual;
+  int res_i8;
+  __half* out;
+  int out_i8;
+  float post_scale;
+};
+
+template <int C, int BN>
+struct DCfg {
+  static constexpr int kPasses = C / 32;
+  static constexpr int kRawStages = 2;
+  static constexpr int kBlurStages = (C == 32) ? 2 : 1;
+  static constexpr int kWBytes = 9 * BN * C * 2;
+  static constexpr int kTapBytes = BN * C * 2;
+  static constexpr int kSmemBytes = kWBytes + kRawStages * kDcRawBytes + kBlurStages * kDcBlurBytes + 1024 + 256 + BN * 4;
+  static constexpr int kTmemCols = 2 * BN < 32 ? 32 : 2 * BN;
+  static constexpr uint32_t kIdesc = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+  static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
+};
+
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// mbarrier wait for this kernel's polling warps: they share their schedulers with the blur and epilogue warps, and a
+// spinning poll loop (try_wait + clock check, ~12 instructions per iteration) took 10 % of all issued instructions.
+// Back off between polls; still bounded (a protocol bug must trap, not hang).
+__device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    __nanosleep(40);
+    if (++spins > 40000000u) {
+      printf("glass downconv_tc: mbarrier timeout (block %d thread %d)\n", blockIdx.x, threadIdx.x);
+      __trap();
+    }
+  }
+}
+
+// [1,3,3,1] on 8 channels (packed half2).  kScaled = false: (c0 + c3) + 3 (c1 + c2), 3 instructions per half2 (the
+// horizontal pass: the result is at most 8 |a|); kScaled = true: the same times 1/64 (the vertical pass applies the
+// whole normalisation of the separable filter, 1/8 per axis, so that the blurred value is back at the scale of a).
+template <bool kScaled>
+__device__ __forceinline__ uint4 fir4(const uint4& c0, const uint4& c1, const uint4& c2, const uint4& c3) {
+  const __half2 k1 = __floats2half2_rn(1.f / 64.f, 1.f / 64.f), k3 = __floats2half2_rn(3.f / 64.f, 3.f / 64.f);
+  const __half2 three = __floats2half2_rn(3.f, 3.f);
+  uint4 r;
+  const __half2* a = reinterpret_cast<const __half2*>(&c0);
+  const __half2* b = reinterpret_cast<const __half2*>(&c1);
+  const __half2* c = reinterpret_cast<const __half2*>(&c2);
+  const __half2* d = reinterpret_cast<const __half2*>(&c3);
+  __half2* o = reinterpret_cast<__half2*>(&r);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    if (kScaled) o[j] = __hfma2(__hadd2(b[j], c[j]), k3, __hmul2(__hadd2(a[j], d[j]), k1));
+    else o[j] = __hfma2(__hadd2(b[j], c[j]), three, __hadd2(a[j], d[j]));
+  }
+  return r;
+}
+
+template <int C, int BN>
+__global__ void __launch_bounds__(kDcThreads, 1)
+downconv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
+                   const DownParams p) {
+  using Cf = DCfg<C, BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem_w = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* raw = smem_w + Cf::kWBytes;
+  uint8_t* blur = raw + Cf::kRawStages * kDcRawBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(blur + Cf::kBlurStages * kDcBlurBytes);
+  uint64_t* raw_full = bars;
+  uint64_t* raw_empty = raw_full + 2;
+  uint64_t* blur_full = raw_empty + 2;
+  uint64_t* blur_empty = blur_full + 2;
+  uint64_t* tmem_full = blur_empty + 2;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint64_t* w_bar = tmem_empty + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_bar + 1);
+  float* bias_s = reinterpret_cast<float*>(bars) + 64;        // [BN] bias * sqrt2 * post_scale of this CTA's n-tile
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_tiles = p.Cout / BN;
+  const int tiles_x = p.Wo / kDcTW, tiles_y = p.Ho / kDcTH;
+  const int total_tiles = p.N * tiles_y * tiles_x * n_tiles;
+  const int n_tile = blockIdx.x % n_tiles;            // grid is a multiple of n_tiles: fixed per CTA (resident taps)
+
+  if (threadIdx.x == 0) {
+    prefetch_tmap(&map_a);
+    prefetch_tmap(&map_w);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&raw_full[s], 1);
+      mbar_init(&raw_empty[s], 8);
+      mbar_init(&blur_full[s], 8);
+      mbar_init(&blur_empty[s], 1);
+      mbar_init(&tmem_full[s], 1);
+      mbar_init(&tmem_empty[s], 8);
+    }
+    mbar_init(w_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "n"(Cf::kTmemCols));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // (n_tiles is 1 or 2; the tile grid is a power of two: an integer division costs ~20 instructions and eight warps
+  // decode every tile)
+  auto decode = [&](int tile, int& img, int& ty, int& tx) {
+    int m = n_tiles == 1 ? tile : tile >> 1;
+    tx = m & (tiles_x - 1); m >>= p.sh_x;
+    ty = m & (tiles_y - 1);
+    img = m >> p.sh_y;
+  };
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (elect_one()) {
+      mbar_expect_tx(w_bar, Cf::kWBytes);
+      for (int tap = 0; tap < 9; ++tap) tma_load_3d(&map_w, smem_w + tap * Cf::kTapBytes, w_bar, 0, n_tile * BN, tap);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        int img, ty, tx;
+        decode(tile, img, ty, tx);
+        for (int h = 0; h < Cf::kPasses; ++h) {
+          mbar_wait_backoff(&raw_empty[stage], phase ^ 1);
+          mbar_expect_tx(&raw_full[stage], kDcRawBytes);
+          // (elements, group, row, image): raw columns 2*x0-2 .. +19, groups 4h .. 4h+3, rows 2*y0-2 .. +35
+          tma_load_4d(&map_a, raw + stage * kDcRawBytes, &raw_full[stage], (2 * tx * kDcTW - 2) * 8, h * kDcG,
+                      2 * ty * kDcTH - 2, img);
+          if (++stage == Cf::kRawStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (elect_one()) {
+      mbar_wait(w_bar, 0);
+      tc_fence_after();
+      const uint32_t sw = smem_u32(smem_w);
+      int bstage = 0, it = 0;
+      uint32_t bphase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+        const int as = it & 1;
+        mbar_wait_backoff(&tmem_empty[as], ((it >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * BN;
+        for (int h = 0; h < Cf::kPasses; ++h) {
+          mbar_wait_backoff(&blur_full[bstage], bphase);
+          tc_fence_after();
+          const uint32_t sb = smem_u32(blur + bstage * kDcBlurBytes);
+#pragma unroll
+          for (int tap = 0; tap < 9; ++tap) {
+            const int ky = tap / 3, kx = tap - ky * 3;
+            const uint32_t a_addr = sb + ((ky & 1) * 2 + (kx & 1)) * kDcPlaneBytes + (ky >> 1) * kDcSbo + (kx >> 1) * 16;
+            const uint64_t db = make_smem_desc<(C > 64 ? 64 : C)>(sw + tap * Cf::kTapBytes);
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {               // 32 channels of this pass = two K=16 steps
+              const uint64_t da = make_smem_desc_noswz(a_addr + k * 2 * kDcLbo, kDcLbo, kDcSbo);
+              tc_mma_f16(d_tmem, da, db + (uint64_t)((h * 2 + k) * 2), Cf::kIdesc, (uint32_t)(h | tap | k));
+            }
+          }
+          tc_commit(&blur_empty[bstage]);
+          if (++bstage == Cf::kBlurStages) { bstage = 0; bphase ^= 1; }
+        }
+        tc_commit(&tmem_full[as]);
+      }
+    }
+  } else if (warp < 10) {
+    // ===================== epilogue (8 warps: lane quarter x column half) =====================
+    // Waiting costs issue slots that the blur warps need (an mbarrier poll is ~12 instructions per iteration): ONE
+    // warp polls the mbarrier, the other seven block on a hardware named barrier.
+    const int q = warp & 3, half = (warp - 2) >> 2;
+    const int row = q * 32 + lane;
+    const int ry = row >> 3, rx = row & 7;
+    constexpr int kCols = BN / 2, kChunks = kCols / 16;
+    static_assert(kCols % 16 == 0, "a warp's column half must be whole 16-column chunks");
+    const float s1 = kSqrt2 * p.post_scale;                  // (lrelu(a*sqrt2) + r) * ps == lrelu(a*sqrt2*ps) + r*ps
+    if (threadIdx.x - 64 < BN) bias_s[threadIdx.x - 64] = __ldg(p.bias + n_tile * BN + threadIdx.x - 64) * s1;
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    int it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      int img, ty, tx;
+      decode(tile, img, ty, tx);
+      const int as = it & 1;
+      const int y = ty * kDcTH + ry, x = tx * kDcTW + rx;
+      const int n0 = n_tile * BN + half * kCols;
+      const size_t pix = ((size_t)img * p.Ho + y) * p.Wo + x;
+      // residual operand fetched before the accumulator wait (hides its DRAM latency)
+      uint4 resv[kChunks][2];
+#pragma unroll
+      for (int c = 0; c < kChunks; ++c) {
+        const int nc = n0 + c * 16;
+        if (p.res_i8) {
+          const __half* rp = p.residual + ((((size_t)img * p.Ho + y) * (p.Cout >> 3) + (nc >> 3)) * p.Wo + x) * 8;
+          resv[c][0] = __ldg(reinterpret_cast<const uint4*>(rp));
+          resv[c][1] = __ldg(reinterpret_cast<const uint4*>(rp + (size_t)p.Wo * 8));
+        } else {
+          const uint4* rp = reinterpret_cast<const uint4*>(p.residual + pix * p.Cout + nc);
+          resv[c][0] = __ldg(rp);
+          resv[c][1] = __ldg(rp + 1);
+        }
+      }
+      if (warp == 2) mbar_wait_backoff(&tmem_full[as], (it >> 1) & 1);
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + as * BN + half * kCols;
+#pragma unroll
+      for (int c = 0; c < kChunks; ++c) {
+        float v[16];
+        tc_ld16(taddr + c * 16, v);
+        const int nc = n0 + c * 16;
+        const __half2* r0 = reinterpret_cast<const __half2*>(&resv[c][0]);
+        const __half2* r1 = reinterpret_cast<const __half2*>(&resv[c][1]);
+        const float4* bs = reinterpret_cast<const float4*>(bias_s + half * kCols + c * 16);
+        float t[16];
+#pragma unroll
+        for (int g4 = 0; g4 < 4; ++g4) {
+          const float4 b = bs[g4];
+          const float a0 = fmaf(v[4 * g4], s1, b.x), a1 = fmaf(v[4 * g4 + 1], s1, b.y);
+          const float a2 = fmaf(v[4 * g4 + 2], s1, b.z), a3 = fmaf(v[4 * g4 + 3], s1, b.w);
+          t[4 * g4] = fmaxf(a0, 0.2f * a0); t[4 * g4 + 1] = fmaxf(a1, 0.2f * a1);
+          t[4 * g4 + 2] = fmaxf(a2, 0.2f * a2); t[4 * g4 + 3] = fmaxf(a3, 0.2f * a3);
+        }
+        uint4 w0, w1;
+        __half2* h0 = reinterpret_cast<__half2*>(&w0);
+        __half2* h1 = reinterpret_cast<__half2*>(&w1);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 a = __half22float2(r0[j]), b = __half22float2(r1[j]);
+          h0[j] = f2h2_sat(fmaf(a.x, p.post_scale, t[2 * j]), fmaf(a.y, p.post_scale, t[2 * j + 1]));
+          h1[j] = f2h2_sat(fmaf(b.x, p.post_scale, t[8 + 2 * j]), fmaf(b.y, p.post_scale, t[8 + 2 * j + 1]));
+        }
+        if (p.out_i8) {
+          __half* op = p.out + ((((size_t)img * p.Ho + y) * (p.Cout >> 3) + (nc >> 3)) * p.Wo + x) * 8;
+          *reinterpret_cast<uint4*>(op) = w0;
+          *reinterpret_cast<uint4*>(op + (size_t)p.Wo * 8) = w1;
+        } else {
+          uint4* op = reinterpret_cast<uint4*>(p.out + pix * p.Cout + nc);
+          op[0] = w0;
+          op[1] = w1;
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[as]);
+    }
+  } else {
+    // ===================== blur (8 warps) =====================
+    // unit = (column j of the 17 blurred columns, channel group g, row strip s): 17 x 4 x 3 = 204 of 256 threads.
+    // Strip s produces blurred rows i in [11 s, 11 s + 11) from raw rows 11 s .. 11 s + 13.
+    // (consecutive lanes take consecutive columns of ONE channel group: the 8 lanes of an LDS.128 phase read 128
+    // contiguous bytes; with the group index in the low lane bits every phase had a 2-way bank conflict)
+    const int bt = threadIdx.x - 320;
+    const int j = bt % 17, g = (bt / 17) & 3, s = bt / 68;
+    const bool active = s < 3;
+    const int i0 = 11 * s;
+    int stage = 0, bstage = 0;
+    uint32_t phase = 0, bphase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int h = 0; h < Cf::kPasses; ++h) {
+        if (warp == 10) {                      // one polling warp; the other seven block on a named barrier
+          mbar_wait_backoff(&raw_full[stage], phase);
+          mbar_wait_backoff(&blur_empty[bstage], bphase ^ 1);
+        }
+        asm volatile("bar.sync 2, 256;" ::: "memory");
+        if (active) {
+          const uint4* rt = reinterpret_cast<const uint4*>(raw + stage * kDcRawBytes);
+          uint8_t* bt_base = blur + bstage * kDcBlurBytes + ((j & 1) * kDcPlaneBytes) + g * kDcLbo + (j >> 1) * 16;
+          uint4 hw[4];                                    // horizontal results of the last four raw rows
+#pragma unroll
+          for (int r = 0; r < 14; ++r) {
+            const uint4* rp = rt + ((i0 + r) * kDcG + g) * kDcRawCols + j;
+            const uint4 cur = fir4<false>(rp[0], rp[1], rp[2], rp[3]);
+            hw[r & 3] = cur;
+            if (r >= 3) {
+              const int i = i0 + r - 3;                   // blurred row completed by raw row i + 3
+              const uint4 u = fir4<true>(hw[(r - 3) & 3], hw[(r - 2) & 3], hw[(r - 1) & 3], cur);
+              *reinterpret_cast<uint4*>(bt_base + (i & 1) * 2 * kDcPlaneBytes + (i >> 1) * kDcSbo) = u;
+            }
+          }
+        }
+        fence_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive(&raw_empty[stage]);
+          mbar_arrive(&blur_full[bstage]);
+        }
+        if (++stage == Cf::kRawStages) { stage = 0; phase ^= 1; }
+        if (++bstage == Cf::kBlurStages) { bstage = 0; bphase ^= 1; }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(Cf::kTmemCols));
+  }
+}
+
+template <int C, int BN>
+cudaError_t launch_down(const CUtensorMap& map_a, const CUtensorMap& map_w, const DownParams& p, int num_sms,
+                        cudaStream_t s) {
+  using Cf = DCfg<C, BN>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t err = cudaFuncSetAttribute(downconv_tc_kernel<C, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           Cf::kSmemBytes);
+    if (err != cudaSuccess) return err;
+    configured = true;
+  }
+  const int n_tiles = p.Cout / BN;
+  const int total = p.N * (p.Ho / kDcTH) * (p.Wo / kDcTW) * n_tiles;
+  int grid = total < num_sms ? total : num_sms;
+  grid = (grid / n_tiles) * n_tiles;
+  if (grid <= 0) return cudaErrorInvalidValue;
+  downconv_tc_kernel<C, BN><<<grid, kDcThreads, Cf::kSmemBytes, s>>>(map_a, map_w, p);
+  return cudaGetLastError();
+}
+
+}  // namespace
+
+bool k_downconv_fused_supported(int C, int Cout, int Ho, int Wo) {
+  auto pow2 = [](int v) { return v > 0 && (v & (v - 1)) == 0; };
+  return (C == 32 || C == 64) && (Cout == 64 || Cout == 128) && Ho % kDcTH == 0 && Wo % kDcTW == 0 &&
+         pow2(Ho / kDcTH) && pow2(Wo / kDcTW);
+}
+
+cudaError_t k_downconv_fused(const CUtensorMap& map_a, const CUtensorMap& map_w, int C, int N, int Ho, int Wo, int Cout,
+                             const float* bias, const __half* residual, int res_i8, __half* out, int out_i8,
+                             float post_scale, int num_sms, cudaStream_t s) {
+  auto lg = [](int v) { int s = 0; while ((1 << s) < v) ++s; return ((1 << s) == v) ? s : -1; };
+  const int sx = lg(Wo / kDcTW), sy = lg(Ho / kDcTH);
+  if (sx < 0 || sy < 0 || Cout / 64 > 2) return cudaErrorInvalidValue;
+  DownParams p{N, Ho, Wo, Cout, sx, sy, bias, residual, res_i8, out, out_i8, post_scale};
+  if (C == 32) return launch_down<32, 64>(map_a, map_w, p, num_sms, s);
+  if (C == 64) return launch_down<64, 64>(map_a, map_w, p, num_sms, s);
+  return cudaErrorInvalidValue;
+}
+
+}  // namespace glass

@@ -55,6 +55,10 @@ struct ConvLaunch {
   ConvParams p;
   TmaMaps maps;
   double flops = 0;   // algorithmic (as written by the reference) — for reporting
+  // fused-FIR exact down-conv (downconv_tc.cu) instead of a conv_tc launch: maps.a = conv0 output (I8), maps.b = the
+  // nine 3x3 taps; p.epi carries bias / residual / out
+  bool fused_down = false;
+  int fd_C = 0, fd_N = 0, fd_Ho = 0, fd_Wo = 0, fd_Cout = 0;
 };
 
 struct Arena {
@@ -100,6 +104,7 @@ struct glass_engine {
   std::vector<int> d_c1_i8;   // per D block: the space-to-depth tensor between conv0 and the folded conv1 likewise
   std::vector<int> d_proj_fused;   // per D block: projection FIR + 1x1 GEMM in one kernel (fir_proj_tc.cu)
   std::vector<int> d_res_i8;       // per D block: the projection output (conv1's residual operand) is stored I8
+  std::vector<int> d_fused;        // per D block: conv1 runs as the fused-FIR exact down-conv (downconv_tc.cu)
   std::vector<int> g_pair;    // per G layer: 1 = 32-channel conv on horizontally paired pixels
   std::vector<int> d_pair;    // per D block: conv0 likewise
   float4 *slabs = nullptr, *yA = nullptr, *yB = nullptr;
@@ -321,6 +326,20 @@ int make_conv(glass_engine* e, ConvLaunch* out, const __half* in, int Nimg, int 
 
 int run_conv(glass_engine* e, const ConvLaunch& c, cudaStream_t s) {
   cudaError_t err;
+  if (c.fused_down) {
+    const bool timed = e->timing && e->ev_used + 2 <= e->ev.size();
+    if (timed) cudaEventRecord(e->ev[e->ev_used], s);
+    err = k_downconv_fused(c.maps.a, c.maps.b, c.fd_C, c.fd_N, c.fd_Ho, c.fd_Wo, c.fd_Cout, c.p.epi.bias, c.p.epi.residual,
+                           c.p.epi.res_i8, c.p.epi.out, c.p.epi.out_i8, c.p.epi.post_scale, e->num_sms, s);
+    if (timed) {
+      cudaEventRecord(e->ev[e->ev_used + 1], s);
+      e->ev_conv[e->ev_used / 2] = &c;
+      e->ev_used += 2;
+    }
+    e->launches++;
+    if (err != cudaSuccess) return fail(GLASS_ERR_CUDA, "fused down-conv launch failed: %s", cudaGetErrorString(err));
+    return GLASS_OK;
+  }
   if (e->cfg.conv_impl == 0) {
     if (e->timing && e->ev_used + 2 <= e->ev.size()) {
       cudaEventRecord(e->ev[e->ev_used], s);
@@ -468,6 +487,20 @@ void derive_arch(glass_engine* e) {
     const bool on = env == nullptr || atoi(env) != 0;
     e->d_res_i8.push_back((i8_ok && on && !e->d_proj_fused[b] && ro >= 16 && ro % 16 == 0 && Co % 16 == 0) ? 1 : 0);
   }
+  // 32/64-channel blocks at >= 64x64: exact down-conv with the FIR inside the kernel instead of the folded form (4x the
+  // MACs).  Needs conv0's output in the plain I8 layout and the projection residual / block output as planned above.
+  e->d_fused.clear();
+  for (int b = 0; b + 1 < c.num_blocks; ++b) {
+    const int Ci = e->gch[c.num_blocks - 1 - b], Co = e->gch[c.num_blocks - 2 - b], ro = (e->R >> b) / 2;
+    // (64-channel blocks: the kernel keeps one 64-column n-tile of taps resident, so the blur of a pixel tile is
+    // repeated per n-tile and the single blur stage serialises with the MMAs: measured 3.3 ms against 2.3 ms for
+    // the folded form on the 512^2 block; GLASS_DEBUG_FUSED64 (debug builds) switches it on for experiments)
+    static const bool fused64 = debug_env("GLASS_DEBUG_FUSED64") != nullptr;
+    const bool on = i8_ok && !folded && !(c.flags & GLASS_FLAG_NO_FUSED_DOWN) && !e->d_exact[b] &&
+                    k_downconv_fused_supported(Ci, Co, ro, ro) && ro >= 32 && (Ci == 32 || fused64);
+    e->d_fused.push_back(on ? 1 : 0);
+    if (on) e->d_c1_i8[b] = 0;
+  }
   const bool pair_ok = (c.flags & GLASS_FLAG_NO_PAIR_PACK) == 0 && c.conv_impl == 0;
   e->g_pair.clear();
   for (size_t li = 0; li < e->glayers.size(); ++li) {
@@ -536,6 +569,7 @@ int validate_weights(glass_engine* e) {
       RC(check_tensor(e, nmf("c0.b"), (size_t)dch(b) * 4));
       RC(check_tensor(e, nmf("c1.w"), (size_t)9 * dch(b + 1) * 4 * dch(b) * 2));
       if (e->d_exact[b]) RC(check_tensor(e, nmf("c1.wx"), (size_t)4 * dch(b + 1) * 4 * dch(b) * 2));
+      if (e->d_fused[b]) RC(check_tensor(e, nmf("c1.w9"), (size_t)9 * dch(b + 1) * dch(b) * 2));
       if (e->d_pair[b]) RC(check_tensor(e, nmf("c0.wp"), (size_t)9 * 2 * dch(b) * 2 * dch(b) * 2));
       RC(check_tensor(e, nmf("c1.b"), (size_t)dch(b + 1) * 4));
       RC(check_tensor(e, nmf("proj.w"), (size_t)dch(b + 1) * dch(b) * 2));
@@ -777,8 +811,8 @@ int build_plan(glass_engine* e, int P) {
       // conv0: 3x3 Ci->Ci, bias, lrelu; stored space-to-depth for the folded conv1, or plain NHWC for the blur pass
       EpiParams ep = epi_default();
       ep.Cout = Ci; ep.bias = tptr<float>(e, nmf("c0.b")); ep.act = kActLrelu; ep.out = e->actB;
-      ep.store_mode = e->d_exact[b] ? kStoreRegular : kStoreSpaceToDepth;
-      ep.out_i8 = e->d_c1_i8[b];
+      ep.store_mode = (e->d_exact[b] || e->d_fused[b]) ? kStoreRegular : kStoreSpaceToDepth;
+      ep.out_i8 = e->d_fused[b] ? 1 : e->d_c1_i8[b];
       if (e->d_in_i8[b]) {
         RC(make_conv(e, &cl, x, P, res, res, Ci, tptr<__half>(e, nmf("c0.w")), 9, Ci, ep, false, nullptr, 0, 0, true));
       } else if (e->d_pair[b]) {
@@ -799,7 +833,22 @@ int build_plan(glass_engine* e, int P) {
       ep.res_i8 = e->d_res_i8[b];
       ep.post_scale = kInvSqrt2; ep.out = outs[b & 1];
       ep.out_i8 = (b + 1 < nb - 1) ? e->d_in_i8[b + 1] : 0;
-      if (e->d_exact[b]) {
+      if (e->d_fused[b]) {
+        // exact, FIR inside the kernel (downconv_tc.cu): reads conv0's I8 output, no space-to-depth tensor, no blur pass
+        memset(&cl.p, 0, sizeof(cl.p));
+        cl.p.epi = ep;
+        cl.fused_down = true;
+        cl.fd_C = Ci; cl.fd_N = P; cl.fd_Ho = res / 2; cl.fd_Wo = res / 2; cl.fd_Cout = Co;
+        const uint64_t G = Ci / 8;
+        uint64_t d4[4] = {(uint64_t)res * 8, G, (uint64_t)res, (uint64_t)P};
+        uint64_t s4[3] = {(uint64_t)res * 16, G * res * 16, (uint64_t)res * G * res * 16};
+        uint32_t b4[4] = {160, 4, 36, 1};
+        RC(encode_map(e, &cl.maps.a, e->actB, 4, d4, s4, b4, 0));
+        uint64_t wd[3] = {(uint64_t)Ci, (uint64_t)Co, 9};
+        uint64_t ws[2] = {(uint64_t)Ci * 2, (uint64_t)Ci * 2 * Co};
+        uint32_t wb[3] = {(uint32_t)Ci, 64, 1};
+        RC(encode_map(e, &cl.maps.b, tptr<__half>(e, nmf("c1.w9")), 3, wd, ws, wb, Ci * 2));
+      } else if (e->d_exact[b]) {
         // exact: blurred input (k_blur_s2d -> actC, [(res/2+1)^2][4*Ci]) then a 2x2-tap conv == 3x3 stride 2
         RC(make_conv(e, &cl, e->actC, P, res / 2, res / 2, 4 * Ci, tptr<__half>(e, nmf("c1.wx")), 4, Co, ep, false,
                      kDownExactTaps, res / 2 + 1, res / 2 + 1, false, 2, Ci));

@@ -101,6 +101,13 @@ cudaError_t k_fir_proj(const __half* x, int in_i8, const __half* wproj, __half* 
 // ... and with fromRGB in front (the first block): image -> x (xout) and dR
 cudaError_t k_from_rgb_fir_proj(const float* images, const float* folded_host, __half* xout, int out_i8,
                                 const __half* wproj, __half* out, int P, int R, int C, int Co, cudaStream_t s);
+// D down-conv, exact form with the FIR inside the kernel (downconv_tc.cu): a = conv0 output in the I8 layout
+// [N][2Ho][C/8][2Wo][8] (map_a: dims (2Wo*8, C/8, 2Ho, N), box (160, 4, 36, 1), un-swizzled), w9 = [9][Cout][C] fp16
+// (map_w: box (C, 64, 1), swizzle C*2 bytes) -> out = (lrelu(conv3x3_s2(FIR(a)) + bias)*sqrt2 + residual) * post_scale
+bool k_downconv_fused_supported(int C, int Cout, int Ho, int Wo);
+cudaError_t k_downconv_fused(const CUtensorMap& map_a, const CUtensorMap& map_w, int C, int N, int Ho, int Wo, int Cout,
+                             const float* bias, const __half* residual, int res_i8, __half* out, int out_i8,
+                             float post_scale, int num_sms, cudaStream_t s);
 // modules.py:701-747 incl. the in-place centring; x [P,16,C] -> out [P,16,Cpad] (channel C = std feature)
 cudaError_t k_mbstd(const __half* x, __half* out, int P, int batch, int group, int C, int Cpad, cudaStream_t s);
 // models.py:1224-1225 last dense + problem.py:23 hinge

@@ -254,6 +254,8 @@ def pack_discriminator(sd: Dict[str, torch.Tensor], spec: GanSpec) -> Dict[str, 
         w1 = sd[p + ".conv_block.1.layer.weight"].float()
         out[f"d.b{b}.c1.w"] = _f16(fold_downconv(w1 * _coef(w1.shape)))
         out[f"d.b{b}.c1.wx"] = _f16(exact_downconv(w1 * _coef(w1.shape)))
+        if ch[b] in (32, 64):
+            out[f"d.b{b}.c1.w9"] = _f16(taps_plain(w1 * _coef(w1.shape)))     # fused-FIR exact down-conv (downconv_tc.cu)
         out[f"d.b{b}.c1.b"] = _f32(sd[p + ".conv_block.1.bias"])
         wp = sd[p + ".projection.weight"].float()
         out[f"d.b{b}.proj.w"] = _f16(taps_plain(wp * _coef(wp.shape)))

@@ -85,6 +85,10 @@ typedef struct glass_config {
 /* The exact polyphase weight tensors have 9 non-zero (tap, phase) blocks of 16; the tensor-core path skips the zero
  * blocks (no TMA load, no MMA).  Cross-check variant: multiply them like any other block. */
 #define GLASS_FLAG_NO_ZERO_SKIP 256
+/* The D down-convs of the 32/64-channel blocks (1024^2 -> 512^2 -> 256^2) normally run in their exact form with the
+ * FIR applied inside the kernel (downconv_tc.cu).  Cross-check variant: the FIR-folded 3x3 over the space-to-depth
+ * tensor (conv_tc MODE 6 / MODE 0), 4x the MACs. */
+#define GLASS_FLAG_NO_FUSED_DOWN 512
 
 /* -- lifetime ------------------------------------------------------------- */
 /* Replaces Generator.__init__ (generator.py:12-27): allocate the engine. */

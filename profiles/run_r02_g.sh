@@ -1,0 +1,6 @@
+cd $GRAFT_REPO_ROOT
+TAG=${1:-r02g}
+timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "fused_fir or multi_seed or benchmarked or streamed_tap or test_full_size_against" > gpurun_out/pytest_gpu_$TAG.log 2>&1; tail -15 gpurun_out/pytest_gpu_$TAG.log
+timeout 300 python tests/profile_step.py --pop 64 --evals 12 > gpurun_out/step_$TAG.log 2>&1; grep "step ms" gpurun_out/step_$TAG.log
+timeout 300 python tests/profile_step.py --pop 64 --evals 12 --flags 512 > gpurun_out/step_${TAG}_nofused.log 2>&1; grep "step ms" gpurun_out/step_${TAG}_nofused.log
+timeout 300 python tests/profile_step.py --pop 64 --evals 4 --timing > gpurun_out/breakdown_$TAG.log 2>&1; grep -E "total conv|^D[01]:" gpurun_out/breakdown_$TAG.log

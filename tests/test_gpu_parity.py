@@ -214,6 +214,19 @@ def test_streamed_tap_i8_downconv_against_nhwc_form():
     np.testing.assert_allclose(m6[1], gold["F"][:, 1], atol=8e-4)
 
 
+def test_fused_fir_downconv_against_folded_form():
+    """downconv_tc.cu (default for the 32/64-channel D blocks: exact 3x3 stride-2 conv, FIR applied inside the kernel
+    in packed-half2 arithmetic) against the FIR-folded space-to-depth form (GLASS_FLAG_NO_FUSED_DOWN = 512, 4x the
+    MACs, fp32 accumulation of the folded taps): G and CLIP are untouched, the hinge agrees to fp16 rounding of the
+    blurred operand, and both stay within the bound against the reference fixture."""
+    (fused,), gold = _full_scores(flags=0)
+    (folded,), _ = _full_scores(flags=512)
+    np.testing.assert_array_equal(fused[0], folded[0])
+    np.testing.assert_allclose(fused[1], folded[1], atol=5e-4)
+    np.testing.assert_allclose(fused[1], gold["F"][:, 1], atol=8e-4)
+    np.testing.assert_allclose(folded[1], gold["F"][:, 1], atol=8e-4)
+
+
 def test_fused_projection_kernel_against_separate_launches():
     """fir_proj_tc.cu (GLASS_FLAG_PROJ_FUSION = 64: stride-2 FIR + 1x1 projection GEMM of the D blocks in one kernel,
     opt-in) against the default k_fir_down + conv_tc route: the projection accumulates in fp32 from the same fp16
