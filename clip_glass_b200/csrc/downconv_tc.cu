@@ -94,11 +94,34 @@ __device__ __forceinline__ uint4 fir4(const uint4& c0, const uint4& c1, const ui
   return r;
 }
 
+// the same on 4 channels (two half2)
+template <bool kScaled>
+__device__ __forceinline__ uint2 fir4h(const uint2& c0, const uint2& c1, const uint2& c2, const uint2& c3) {
+  const __half2 k1 = __floats2half2_rn(1.f / 64.f, 1.f / 64.f), k3 = __floats2half2_rn(3.f / 64.f, 3.f / 64.f);
+  const __half2 three = __floats2half2_rn(3.f, 3.f);
+  uint2 r;
+  const __half2* a = reinterpret_cast<const __half2*>(&c0);
+  const __half2* b = reinterpret_cast<const __half2*>(&c1);
+  const __half2* c = reinterpret_cast<const __half2*>(&c2);
+  const __half2* d = reinterpret_cast<const __half2*>(&c3);
+  __half2* o = reinterpret_cast<__half2*>(&r);
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+    if (kScaled) o[j] = __hfma2(__hadd2(b[j], c[j]), k3, __hmul2(__hadd2(a[j], d[j]), k1));
+    else o[j] = __hfma2(__hadd2(b[j], c[j]), three, __hadd2(a[j], d[j]));
+  }
+  return r;
+}
+
 template <int C, int BN>
 __global__ void __launch_bounds__(kDcThreads, 1)
 downconv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
                    const DownParams p) {
   using Cf = DCfg<C, BN>;
+  // Worker-warp organisation, chosen by measurement at P = 64 (profiles/): dedicated blur / epilogue warps for the
+  // 32-channel block (2.20 ms against 2.6 ms merged), merged roles for the 64-channel block, whose two 32-channel
+  // passes per tile double the blur work per epilogue (2.5 ms against 3.3 ms with dedicated warps).
+  constexpr bool kSplitRoles = (C == 32);
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem_w = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* raw = smem_w + Cf::kWBytes;
@@ -125,11 +148,11 @@ downconv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
     prefetch_tmap(&map_w);
     for (int s = 0; s < 2; ++s) {
       mbar_init(&raw_full[s], 1);
-      mbar_init(&raw_empty[s], 8);
-      mbar_init(&blur_full[s], 8);
+      mbar_init(&raw_empty[s], kSplitRoles ? 8 : 16);
+      mbar_init(&blur_full[s], kSplitRoles ? 8 : 16);
       mbar_init(&blur_empty[s], 1);
       mbar_init(&tmem_full[s], 1);
-      mbar_init(&tmem_empty[s], 8);
+      mbar_init(&tmem_empty[s], kSplitRoles ? 8 : 16);
     }
     mbar_init(w_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -207,7 +230,7 @@ downconv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
         tc_commit(&tmem_full[as]);
       }
     }
-  } else if (warp < 10) {
+  } else if (kSplitRoles && warp < 10) {
     // ===================== epilogue (8 warps: lane quarter x column half) =====================
     // Waiting costs issue slots that the blur warps need (an mbarrier poll is ~12 instructions per iteration): ONE
     // warp polls the mbarrier, the other seven block on a hardware named barrier.
@@ -286,7 +309,7 @@ downconv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[as]);
     }
-  } else {
+  } else if (kSplitRoles) {
     // ===================== blur (8 warps) =====================
     // unit = (column j of the 17 blurred columns, channel group g, row strip s): 17 x 4 x 3 = 204 of 256 threads.
     // Strip s produces blurred rows i in [11 s, 11 s + 11) from raw rows 11 s .. 11 s + 13.
@@ -331,6 +354,122 @@ downconv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
         if (++bstage == Cf::kBlurStages) { bstage = 0; bphase ^= 1; }
       }
     }
+  } else {
+    // ===================== workers: 16 warps, each blurs AND runs its share of the epilogue =====================
+    // With dedicated blur / epilogue warps the blur stage paces the kernel while the epilogue warps sit blocked most
+    // of the time (issue slots 45 % busy).  Here every worker warp blurs its part of tile t, then finishes tile t-1
+    // (whose MMAs ran meanwhile): all 16 warps have work all the time.
+    //   blur unit = (column j of 17, 4-channel half-group of 8, row strip of 3): 408 of 512 threads, LDS.64 / STS.64;
+    //     lanes 2k, 2k+1 take the two halves of one pixel's 16 bytes, consecutive lane pairs consecutive columns:
+    //     the 16 lanes of an LDS.64 phase read 128 contiguous bytes (conflict-free), and so do the stores.
+    //   epilogue unit = (TMEM lane quarter = warp & 3, 16-column chunk = (warp - 2) >> 2).
+    // Waiting: ONE warp polls each mbarrier (a poll loop costs issue slots), the others block on a named barrier.
+    const int wt = threadIdx.x - 64;                       // 0 .. 511
+    const int hlow = wt & 1, j = (wt >> 1) % 17, g = ((wt >> 1) / 17) & 3, strip = (wt >> 1) / 68;
+    const bool active = strip < 3;
+    const int i0 = 11 * strip;
+    const int q = warp & 3, chunk = (warp - 2) >> 2;
+    static_assert(BN == 64, "16 worker warps = 4 lane quarters x 4 chunks of 16 columns");
+    const int row = q * 32 + lane;
+    const int ry = row >> 3, rx = row & 7;
+    const float s1 = kSqrt2 * p.post_scale;                  // (lrelu(a*sqrt2) + r) * ps == lrelu(a*sqrt2*ps) + r*ps
+    if (wt < BN) bias_s[wt] = __ldg(p.bias + n_tile * BN + wt) * s1;
+    asm volatile("bar.sync 1, 512;" ::: "memory");
+    const int nc = n_tile * BN + chunk * 16;
+
+    auto res_ptr = [&](int img, int y, int x) -> const __half* {
+      if (p.res_i8) return p.residual + ((((size_t)img * p.Ho + y) * (p.Cout >> 3) + (nc >> 3)) * p.Wo + x) * 8;
+      return p.residual + (((size_t)img * p.Ho + y) * p.Wo + x) * p.Cout + nc;
+    };
+    auto epilogue = [&](int img, int ty, int tx, int it, const uint4& q0, const uint4& q1) {
+      const int as = it & 1;
+      const int y = ty * kDcTH + ry, x = tx * kDcTW + rx;
+      if (warp == 2) mbar_wait_backoff(&tmem_full[as], (it >> 1) & 1);
+      asm volatile("bar.sync 1, 512;" ::: "memory");
+      tc_fence_after();
+      float v[16];
+      tc_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + as * BN + chunk * 16, v);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[as]);           // the accumulator is in registers: the MMAs may go on
+      const __half2* r0 = reinterpret_cast<const __half2*>(&q0);
+      const __half2* r1 = reinterpret_cast<const __half2*>(&q1);
+      const float4* bs = reinterpret_cast<const float4*>(bias_s + chunk * 16);
+      float t[16];
+#pragma unroll
+      for (int g4 = 0; g4 < 4; ++g4) {
+        const float4 b = bs[g4];
+        const float a0 = fmaf(v[4 * g4], s1, b.x), a1 = fmaf(v[4 * g4 + 1], s1, b.y);
+        const float a2 = fmaf(v[4 * g4 + 2], s1, b.z), a3 = fmaf(v[4 * g4 + 3], s1, b.w);
+        t[4 * g4] = fmaxf(a0, 0.2f * a0); t[4 * g4 + 1] = fmaxf(a1, 0.2f * a1);
+        t[4 * g4 + 2] = fmaxf(a2, 0.2f * a2); t[4 * g4 + 3] = fmaxf(a3, 0.2f * a3);
+      }
+      uint4 w0, w1;
+      __half2* h0 = reinterpret_cast<__half2*>(&w0);
+      __half2* h1 = reinterpret_cast<__half2*>(&w1);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float2 a = __half22float2(r0[k]), b = __half22float2(r1[k]);
+        h0[k] = f2h2_sat(fmaf(a.x, p.post_scale, t[2 * k]), fmaf(a.y, p.post_scale, t[2 * k + 1]));
+        h1[k] = f2h2_sat(fmaf(b.x, p.post_scale, t[8 + 2 * k]), fmaf(b.y, p.post_scale, t[8 + 2 * k + 1]));
+      }
+      if (p.out_i8) {
+        __half* op = p.out + ((((size_t)img * p.Ho + y) * (p.Cout >> 3) + (nc >> 3)) * p.Wo + x) * 8;
+        *reinterpret_cast<uint4*>(op) = w0;
+        *reinterpret_cast<uint4*>(op + (size_t)p.Wo * 8) = w1;
+      } else {
+        uint4* op = reinterpret_cast<uint4*>(p.out + (((size_t)img * p.Ho + y) * p.Wo + x) * p.Cout + nc);
+        op[0] = w0;
+        op[1] = w1;
+      }
+    };
+
+    int stage = 0, bstage = 0, it = 0;
+    uint32_t phase = 0, bphase = 0;
+    int pimg = 0, pty = 0, ptx = 0;                          // the previous tile of this CTA (epilogue pending)
+    uint4 pq0 = make_uint4(0, 0, 0, 0), pq1 = pq0;           // its residual operand, fetched one tile ahead
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      int img, ty, tx;
+      decode(tile, img, ty, tx);
+      // residual of THIS tile: in flight while the tile is blurred and its MMAs run
+      const __half* rp = res_ptr(img, ty * kDcTH + ry, tx * kDcTW + rx);
+      const uint4 q0 = __ldg(reinterpret_cast<const uint4*>(rp));
+      const uint4 q1 = __ldg(reinterpret_cast<const uint4*>(rp + (p.res_i8 ? (size_t)p.Wo * 8 : 8)));
+      for (int h = 0; h < Cf::kPasses; ++h) {
+        if (warp == 2) {
+          mbar_wait_backoff(&raw_full[stage], phase);
+          mbar_wait_backoff(&blur_empty[bstage], bphase ^ 1);
+        }
+        asm volatile("bar.sync 1, 512;" ::: "memory");
+        if (active) {
+          const uint2* rt = reinterpret_cast<const uint2*>(raw + stage * kDcRawBytes) + hlow;
+          uint8_t* bt_base = blur + bstage * kDcBlurBytes + ((j & 1) * kDcPlaneBytes) + g * kDcLbo + (j >> 1) * 16 + hlow * 8;
+          uint2 hw[4];                                     // horizontal results of the last four raw rows
+#pragma unroll
+          for (int r = 0; r < 14; ++r) {
+            const uint2* rr = rt + (((i0 + r) * kDcG + g) * kDcRawCols + j) * 2;
+            const uint2 cur = fir4h<false>(rr[0], rr[2], rr[4], rr[6]);
+            hw[r & 3] = cur;
+            if (r >= 3) {
+              const int i = i0 + r - 3;                    // blurred row completed by raw row i + 3
+              const uint2 u = fir4h<true>(hw[(r - 3) & 3], hw[(r - 2) & 3], hw[(r - 1) & 3], cur);
+              *reinterpret_cast<uint2*>(bt_base + (i & 1) * 2 * kDcPlaneBytes + (i >> 1) * kDcSbo) = u;
+            }
+          }
+        }
+        fence_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive(&raw_empty[stage]);
+          mbar_arrive(&blur_full[bstage]);
+        }
+        if (++stage == Cf::kRawStages) { stage = 0; phase ^= 1; }
+        if (++bstage == Cf::kBlurStages) { bstage = 0; bphase ^= 1; }
+      }
+      if (it > 0) epilogue(pimg, pty, ptx, it - 1, pq0, pq1);
+      pimg = img; pty = ty; ptx = tx; pq0 = q0; pq1 = q1;
+    }
+    if (it > 0) epilogue(pimg, pty, ptx, it - 1, pq0, pq1);
   }
 
   tc_fence_before();

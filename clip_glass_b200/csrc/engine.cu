@@ -492,12 +492,12 @@ void derive_arch(glass_engine* e) {
   e->d_fused.clear();
   for (int b = 0; b + 1 < c.num_blocks; ++b) {
     const int Ci = e->gch[c.num_blocks - 1 - b], Co = e->gch[c.num_blocks - 2 - b], ro = (e->R >> b) / 2;
-    // (64-channel blocks: the kernel keeps one 64-column n-tile of taps resident, so the blur of a pixel tile is
-    // repeated per n-tile and the single blur stage serialises with the MMAs: measured 3.3 ms against 2.3 ms for
-    // the folded form on the 512^2 block; GLASS_DEBUG_FUSED64 (debug builds) switches it on for experiments)
-    static const bool fused64 = debug_env("GLASS_DEBUG_FUSED64") != nullptr;
+    // (64-channel block: one 64-column n-tile of taps is resident, so the blur of a pixel tile is repeated per n-tile;
+    // its conv1 time equals the folded form's (2.5 vs 2.3 ms) but conv0 stores plain I8 instead of space-to-depth NHWC
+    // (1.1 vs 1.3 ms) and the step issues 4x fewer MMAs on that layer: 1.5 ms per step at P = 64, measured)
+    static const bool nofused64 = debug_env("GLASS_DEBUG_NOFUSED64") != nullptr;      // (debug builds: A/B)
     const bool on = i8_ok && !folded && !(c.flags & GLASS_FLAG_NO_FUSED_DOWN) && !e->d_exact[b] &&
-                    k_downconv_fused_supported(Ci, Co, ro, ro) && ro >= 32 && (Ci == 32 || fused64);
+                    k_downconv_fused_supported(Ci, Co, ro, ro) && ro >= 32 && !(Ci == 64 && nofused64);
     e->d_fused.push_back(on ? 1 : 0);
     if (on) e->d_c1_i8[b] = 0;
   }
