@@ -59,6 +59,12 @@ struct EpiParams {
   int round_fp16_before_act;  // mimic the reference's fp16 op boundaries (CLIP)
   const float* rgb_w;       // [Nimg][3][Cout] per-sample toRGB weights (W*s) or null
   float4* rgb_out;          // [n_tiles][Nimg*H*W] partial toRGB sums
+  // Last generator conv, when its n-tile holds all channels (one toRGB slab): the skip-sum / x2 upsample / bias /
+  // biggan_norm of k_rgb_combine happen right here and the image is written from the epilogue (no float4 slab round
+  // trip, one launch less).  image != null enables it; img_yprev = the previous block's skip sum [Nimg][H/2][W/2].
+  float* image;             // [Nimg][3][H][W] fp32 in [0,1], or null
+  const float4* img_yprev;
+  const float* img_bias;    // toRGB bias [3]
   const float* out_scale;   // next layer's style s[img*out_scale_stride + o], or null
   int out_scale_stride;
   const __half* residual;   // [pix][Ntot] (regular layout) or null

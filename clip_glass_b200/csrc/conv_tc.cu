@@ -888,6 +888,28 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             if (paired) {
               const size_t pix2 = ((size_t)img * H + y) * (2 * W) + 2 * x + ppx;
               e.rgb_out[pix2] = make_float4(r0, r1, r2, 0.f);
+            } else if (e.image != nullptr) {
+              // final image: y = up2(yprev) + toRGB + bias (modules.py:580-602 polyphase, models.py:1004-1013), then
+              // clip((y + 1) / 2, 0, 1) (utils.py:14-17) -- the arithmetic of rgb_combine_kernel
+              const int X = x + 8 * h, Y = y;
+              const int Hp = H >> 1, Wp = W >> 1, zy = Y >> 1, zx = X >> 1;
+              const float wy0 = (Y & 1) ? 0.25f : 0.75f, wy1 = 1.f - wy0;
+              const float wx0 = (X & 1) ? 0.25f : 0.75f, wx1 = 1.f - wx0;
+              const float4* base = e.img_yprev + (size_t)img * Hp * Wp;
+              float4 a = make_float4(0, 0, 0, 0), c = a, d = a;
+              const float4 ee = __ldg(base + (size_t)zy * Wp + zx);
+              if (zy > 0 && zx > 0) a = __ldg(base + (size_t)(zy - 1) * Wp + zx - 1);
+              if (zy > 0) c = __ldg(base + (size_t)(zy - 1) * Wp + zx);
+              if (zx > 0) d = __ldg(base + (size_t)zy * Wp + zx - 1);
+              float r = __ldg(e.img_bias) + r0, g = __ldg(e.img_bias + 1) + r1, bl = __ldg(e.img_bias + 2) + r2;
+              r += wy0 * (wx0 * a.x + wx1 * c.x) + wy1 * (wx0 * d.x + wx1 * ee.x);
+              g += wy0 * (wx0 * a.y + wx1 * c.y) + wy1 * (wx0 * d.y + wx1 * ee.y);
+              bl += wy0 * (wx0 * a.z + wx1 * c.z) + wy1 * (wx0 * d.z + wx1 * ee.z);
+              const size_t plane = (size_t)H * W;
+              float* ip = e.image + (size_t)img * 3 * plane + (size_t)Y * W + X;
+              ip[0] = fminf(fmaxf((r + 1.f) * 0.5f, 0.f), 1.f);
+              ip[plane] = fminf(fmaxf((g + 1.f) * 0.5f, 0.f), 1.f);
+              ip[2 * plane] = fminf(fmaxf((bl + 1.f) * 0.5f, 0.f), 1.f);
             } else {
               const size_t pix = ((size_t)img * H + y) * W + x + 8 * h;
               e.rgb_out[(size_t)n_tile * p.Nimg * H * W + pix] = make_float4(r0, r1, r2, 0.f);

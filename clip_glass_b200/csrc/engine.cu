@@ -946,7 +946,18 @@ int run_generator(glass_engine* e, const float* z, int P, const glass_noise* nz,
   const size_t nl = e->glayers.size();
   for (size_t li = 0; li < nl; ++li) {
     const GLayer& l = e->glayers[li];
-    const ConvLaunch& cl = e->g_convs[li];
+    ConvLaunch& cl = e->g_convs[li];
+    // Last conv with a single toRGB slab: skip sum, upsample, bias and biggan_norm run in its epilogue and the image
+    // is written from there (EpiParams::image); otherwise (debug captures, SIMT bring-up path, pixel-pair mode,
+    // several n-tiles) k_rgb_combine does it below.
+    const bool fuse_image = (li + 1 == nl) && have_y && !e->capture && e->cfg.conv_impl == 0 && cl.p.Ntot == cl.p.BN &&
+                            cl.p.epi.x_phases == 1 && cl.p.epi.rgb_w != nullptr && !(c.flags & GLASS_FLAG_NO_IMAGE_FUSION);
+    if (li + 1 == nl) {
+      snprintf(nm, sizeof nm, "g.rgb%d.bias", l.block);
+      cl.p.epi.image = fuse_image ? images_out : nullptr;
+      cl.p.epi.img_yprev = fuse_image ? ybuf[ycur] : nullptr;
+      cl.p.epi.img_bias = fuse_image ? tptr<float>(e, nm) : nullptr;
+    }
     RC(run_conv(e, cl, s));
     const __half* layer_out = cl.p.epi.out;
     if (e->g_exact[li]) {
@@ -968,7 +979,7 @@ int run_generator(glass_engine* e, const float* z, int P, const glass_noise* nz,
       RC(capture_f16(e, nm, layer_out, (size_t)P * l.res * l.res * l.cout, s, i8 ? l.res : 0, i8 ? l.cout : 0));
     }
     const bool last_in_block = (li + 1 == nl) || (e->glayers[li + 1].block != l.block);
-    if (last_in_block) {
+    if (last_in_block && !fuse_image) {
       const bool final_block = (li + 1 == nl);
       snprintf(nm, sizeof nm, "g.rgb%d.bias", l.block);
       const int n_slabs = cl.p.Ntot / cl.p.BN;

@@ -89,6 +89,10 @@ typedef struct glass_config {
  * FIR applied inside the kernel (downconv_tc.cu).  Cross-check variant: the FIR-folded 3x3 over the space-to-depth
  * tensor (conv_tc MODE 6 / MODE 0), 4x the MACs. */
 #define GLASS_FLAG_NO_FUSED_DOWN 512
+/* The last generator conv normally finishes the image in its own epilogue (skip sum + x2 upsample + toRGB bias +
+ * biggan_norm, what k_rgb_combine does for the other blocks).  Cross-check variant: write the toRGB slab and run
+ * k_rgb_combine for the last block too. */
+#define GLASS_FLAG_NO_IMAGE_FUSION 1024
 
 /* -- lifetime ------------------------------------------------------------- */
 /* Replaces Generator.__init__ (generator.py:12-27): allocate the engine. */

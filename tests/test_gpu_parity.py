@@ -227,6 +227,29 @@ def test_fused_fir_downconv_against_folded_form():
     np.testing.assert_allclose(folded[1], gold["F"][:, 1], atol=8e-4)
 
 
+def test_image_finished_in_last_conv_epilogue_against_rgb_combine():
+    """The last generator conv finishes the image in its epilogue (skip sum + x2 upsample + toRGB bias + biggan_norm)
+    instead of writing a toRGB slab for k_rgb_combine (GLASS_FLAG_NO_IMAGE_FUSION = 1024): the same fp32 arithmetic in
+    the same order, so images agree to the last bits and the scores to far below the parity bound."""
+    from clip_glass_b200.engine import GlassEngine
+    inp, gold = build_inputs("full"), load_golden("full")
+    z = torch.from_numpy(inp["x"]).float().cuda()
+    outs = []
+    for flags in (0, 1024):
+        eng = GlassEngine(inp["gan"], inp["clip"], inp["g_sd"], inp["d_sd"], inp["c_sd"], batch_size=inp["batch"],
+                          max_population=4, flags=flags)
+        eng.set_text_features(torch.from_numpy(gold["text_features"]))
+        img = eng.generate(z, noise=inp["noise"])
+        outs.append((img.clone(), eng.evaluate(inp["x"], noise=inp["noise"])))
+        eng.close()
+    (img_f, (s_f, h_f)), (img_c, (s_c, h_c)) = outs
+    assert float((img_f - img_c).abs().max()) <= 2e-6
+    np.testing.assert_allclose(s_f, s_c, rtol=2e-5)
+    np.testing.assert_allclose(h_f, h_c, atol=2e-5)
+    small = torch.nn.functional.avg_pool2d(img_f, 16).cpu().numpy()
+    np.testing.assert_allclose(small, gold["images_64"], atol=1e-3)
+
+
 def test_fused_projection_kernel_against_separate_launches():
     """fir_proj_tc.cu (GLASS_FLAG_PROJ_FUSION = 64: stride-2 FIR + 1x1 projection GEMM of the D blocks in one kernel,
     opt-in) against the default k_fir_down + conv_tc route: the projection accumulates in fp32 from the same fp16
