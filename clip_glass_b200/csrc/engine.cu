@@ -1062,7 +1062,7 @@ int run_discriminator(glass_engine* e, const float* images, int P, float* logits
       }
     }
     RC(run_conv(e, e->d_convs[ci++], s));   // conv0 -> actB (space-to-depth, or NHWC for the exact form)
-    if (e->d_exact[b]) LAUNCH(k_blur_s2d(e->actB, e->actC, P, res, res, dch(b), s));
+    if (e->d_exact[b]) LAUNCH(k_blur_s2d(e->actB, e->actC, P, res, res, dch(b), s, (c.flags & GLASS_FLAG_FP32_BLUR) != 0));
     if (proj_fused) ci++;                   // projection already in dR
     else RC(run_conv(e, e->d_convs[ci++], s));   // projection -> dR
     const ConvLaunch& c1 = e->d_convs[ci++];

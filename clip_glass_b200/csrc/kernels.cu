@@ -802,6 +802,87 @@ __global__ void __launch_bounds__(256, GLASS_POLY_MINB) blur_s2d_kernel(const __
   }
 }
 
+// k_blur_s2d, shared-memory-tiled version (the product path; blur_s2d_kernel above is kept as the fp32 cross-check,
+// GLASS_FLAG_FP32_BLUR).  The streaming version reads its 5 x 11 neighbourhood straight from global memory with a
+// serial dependence per row and runs latency-bound at 3.1 TB/s; here a block stages the 19 x 35-pixel x 32-channel
+// patch once (every 16-byte load issued up front), then each thread filters one column strip out of shared memory
+// with the packed-half2 separable FIR of downconv_tc.cu ((c0+c3) + 3(c1+c2) per axis, 1/64 applied in the vertical
+// pass).  Tile layout [row][column][4 groups]: the 8 lanes of an LDS.128 phase (4 groups x 2 columns) read 128
+// contiguous bytes, and a pixel's 4 groups are stored as 64 contiguous bytes (two full sectors).
+constexpr int kBtRows = 16, kBtCols = 32, kBtRawR = kBtRows + 3, kBtRawC = kBtCols + 3, kBtPitch = 36;
+__device__ __forceinline__ uint4 fir4_h2(const uint4& c0, const uint4& c1, const uint4& c2, const uint4& c3, bool scaled) {
+  const __half2 k1 = __floats2half2_rn(1.f / 64.f, 1.f / 64.f), k3 = __floats2half2_rn(3.f / 64.f, 3.f / 64.f);
+  const __half2 three = __floats2half2_rn(3.f, 3.f);
+  uint4 r;
+  const __half2* a = reinterpret_cast<const __half2*>(&c0);
+  const __half2* b = reinterpret_cast<const __half2*>(&c1);
+  const __half2* c = reinterpret_cast<const __half2*>(&c2);
+  const __half2* d = reinterpret_cast<const __half2*>(&c3);
+  __half2* o = reinterpret_cast<__half2*>(&r);
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+    o[j] = scaled ? __hfma2(__hadd2(b[j], c[j]), k3, __hmul2(__hadd2(a[j], d[j]), k1))
+                  : __hfma2(__hadd2(b[j], c[j]), three, __hadd2(a[j], d[j]));
+  return r;
+}
+__global__ void __launch_bounds__(256, 3) blur_s2d_tile_kernel(const __half* __restrict__ a, __half* __restrict__ out, int H,
+                                                               int W, int C, int tiles_x, int tiles_y) {
+  __shared__ uint4 tile[kBtRawR * kBtPitch * 4];
+  const int Hs = (H >> 1) + 1, Ws = (W >> 1) + 1;
+  // channel chunk fastest: the C/32 blocks of one pixel tile run together, so that whole NHWC pixel rows are consumed
+  // while they are in L2 (with the chunk in blockIdx.y every chunk pass re-read the tensor from DRAM: 2x the bytes)
+  const int nchunks = C / 32;
+  int t = blockIdx.x / nchunks;
+  const int c0 = (blockIdx.x - t * nchunks) * 32;
+  const int tx = t % tiles_x; t /= tiles_x;
+  const int ty = t % tiles_y;
+  const int b = t / tiles_y;
+  const int Y0 = ty * kBtRows, X0 = tx * kBtCols;
+  const uint4 zero4 = make_uint4(0, 0, 0, 0);
+  constexpr int kItems = kBtRawR * kBtRawC * 4;                    // (pixel, group) 16-byte pieces
+  constexpr int kPer = (kItems + 255) / 256;
+  uint4 v[kPer];
+#pragma unroll
+  for (int k = 0; k < kPer; ++k) {
+    const int i = threadIdx.x + k * 256;
+    const int g = i & 3, pixel = i >> 2;
+    const int r = pixel / kBtRawC, c = pixel - r * kBtRawC;
+    const int yy = Y0 - 2 + r, xx = X0 - 2 + c;
+    v[k] = zero4;
+    if (i < kItems && yy >= 0 && yy < H && xx >= 0 && xx < W)
+      v[k] = __ldg(reinterpret_cast<const uint4*>(a + (((size_t)b * H + yy) * W + xx) * C + c0 + g * 8));
+  }
+#pragma unroll
+  for (int k = 0; k < kPer; ++k) {
+    const int i = threadIdx.x + k * 256;
+    if (i < kItems) {
+      const int g = i & 3, pixel = i >> 2;
+      const int r = pixel / kBtRawC, c = pixel - r * kBtRawC;
+      tile[(r * kBtPitch + c) * 4 + g] = v[k];
+    }
+  }
+  __syncthreads();
+  const int g = threadIdx.x & 3, j = (threadIdx.x >> 2) & 31, strip = threadIdx.x >> 7;
+  const int i0 = 8 * strip;
+  const int X = X0 + j;
+  uint4 hw[4];
+#pragma unroll
+  for (int r = 0; r < 11; ++r) {
+    const uint4* rp = tile + ((i0 + r) * kBtPitch + j) * 4 + g;
+    const uint4 cur = fir4_h2(rp[0], rp[4], rp[8], rp[12], false);
+    hw[r & 3] = cur;
+    if (r >= 3) {
+      const int Y = Y0 + i0 + r - 3;
+      if (Y < 2 * Hs && X < 2 * Ws) {
+        uint4 u = fir4_h2(hw[(r - 3) & 3], hw[(r - 2) & 3], hw[(r - 1) & 3], cur, true);
+        if (Y > H || X > W) u = zero4;                             // beyond the blurred (H+1) x (W+1) grid
+        *reinterpret_cast<uint4*>(out + (((size_t)b * Hs + (Y >> 1)) * Ws + (X >> 1)) * (4 * C) +
+                                  ((Y & 1) * 2 + (X & 1)) * C + c0 + g * 8) = u;
+      }
+    }
+  }
+}
+
 // one block per (minibatch, member m in [0, batch/group)); samples mb*batch + gi*(batch/group) + m
 __global__ void mbstd_kernel(const __half* __restrict__ x, __half* __restrict__ out, int batch, int group, int C,
                              int Cpad) {
@@ -1004,8 +1085,13 @@ cudaError_t k_upfir(const __half* u, __half* out, const float* noise, size_t noi
                                                                      P, Hout, Wout, C);
   GLASS_RET();
 }
-cudaError_t k_blur_s2d(const __half* a, __half* out, int P, int H, int W, int C, cudaStream_t s) {
+cudaError_t k_blur_s2d(const __half* a, __half* out, int P, int H, int W, int C, cudaStream_t s, int fp32_variant) {
   if (C % 8 != 0 || (H & 1) || (W & 1)) return cudaErrorInvalidValue;
+  if (!fp32_variant && C % 32 == 0) {
+    const int tiles_x = (W + 2 + kBtCols - 1) / kBtCols, tiles_y = (H + 2 + kBtRows - 1) / kBtRows;
+    blur_s2d_tile_kernel<<<P * tiles_x * tiles_y * (C / 32), 256, 0, s>>>(a, out, H, W, C, tiles_x, tiles_y);
+    GLASS_RET();
+  }
   const size_t n = (size_t)P * ((H / 2 + 1 + kBlurCells - 1) / kBlurCells) * (W / 2 + 1) * (C / 8);
   blur_s2d_kernel<<<blocks_for(n, kThreads, 148 * 32), kThreads, 0, s>>>(a, out, P, H, W, C);
   GLASS_RET();

@@ -48,7 +48,8 @@ cudaError_t k_upfir(const __half* u, __half* out, const float* noise, size_t noi
                     int P, int Hout, int Wout, int C, cudaStream_t s);
 // Exact down-conv, first half (modules.py:1243-1246 FilterLayer pad 2): a [P][H][W][C] -> blurred (H+1)x(W+1),
 // written space-to-depth as [P][H/2+1][W/2+1][4C] (phase-major channels), zeros beyond row/col H
-cudaError_t k_blur_s2d(const __half* a, __half* out, int P, int H, int W, int C, cudaStream_t s);
+// fp32_variant != 0: the streaming fp32-cascade kernel (cross-check); default: the shared-memory-tiled half2 kernel
+cudaError_t k_blur_s2d(const __half* a, __half* out, int P, int H, int W, int C, cudaStream_t s, int fp32_variant = 0);
 
 // ---- image output path (run.py:29-51 save_callback -> generator.py:63-68 -> utils.py:5-7) ----
 // torchvision.utils.make_grid (xmaps = min(nrow, n) images per row, `padding` zero pixels around each) fused with

@@ -93,6 +93,9 @@ typedef struct glass_config {
  * biggan_norm, what k_rgb_combine does for the other blocks).  Cross-check variant: write the toRGB slab and run
  * k_rgb_combine for the last block too. */
 #define GLASS_FLAG_NO_IMAGE_FUSION 1024
+/* The blur pass of the exact down-convs (128..512-channel D blocks) normally runs shared-memory-tiled in packed-half2
+ * arithmetic.  Cross-check variant: the streaming kernel with an fp32 cascade. */
+#define GLASS_FLAG_FP32_BLUR 2048
 
 /* -- lifetime ------------------------------------------------------------- */
 /* Replaces Generator.__init__ (generator.py:12-27): allocate the engine. */

@@ -1,7 +1,7 @@
 cd $GRAFT_REPO_ROOT
 TAG=${1:-r02l}
 FLAGB=${2:-1024}
-timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "image_finished or multi_seed or tiny_layerwise_tcgen05 or plugin_surface or image_output" > gpurun_out/pytest_gpu_$TAG.log 2>&1; tail -4 gpurun_out/pytest_gpu_$TAG.log
+timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "exact or multi_seed or resampling or benchmarked" > gpurun_out/pytest_gpu_$TAG.log 2>&1; tail -4 gpurun_out/pytest_gpu_$TAG.log
 for round in 1 2 3; do
   timeout 300 python tests/profile_step.py --pop 64 --evals 21 2>&1 | grep "step ms" | sed "s/^/variant A (default) /"
   timeout 300 python tests/profile_step.py --pop 64 --evals 21 --flags $FLAGB 2>&1 | grep "step ms" | sed "s/^/variant B (flags)   /"
