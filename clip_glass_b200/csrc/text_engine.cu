@@ -91,26 +91,35 @@ struct GemmParams {
   __half* out_lo;             // [M,N] lo part of a split output, or null
 };
 
-constexpr int kGemmStages = 4;
-template <int BN, bool kSplit>
+// kARows: rows of the A tile that are actually loaded (128, or 64 for the decode steps with M <= 64: the MMA still
+// reads 128 rows, the upper half being whatever follows in shared memory; those accumulator rows are never stored).
+// A decode GEMM is a latency-bound stream of small TMA boxes: the pipeline is as deep as shared memory allows
+// (8 stages of 24 KB at kARows = 64, BN = 32 against a ~1.5 us TMA round trip).
+template <int BN, bool kSplit, int kARows>
 struct GemmCfg {
-  static constexpr int kABytes = 128 * 64 * 2, kWBytes = BN * 64 * 2;
+  static constexpr int kABytes = kARows * 64 * 2, kWBytes = BN * 64 * 2;
   static constexpr int kStageBytes = (kSplit ? 2 : 1) * (kABytes + kWBytes);
-  static constexpr int kSmemBytes = kGemmStages * kStageBytes + 1024 + 128;
+  // (full-height tiles, i.e. the prefill and the CLIP text tower with thousands of rows: four stages, so that two CTAs
+  // fit on an SM; measured 4.3 ms against 5.1 ms for the text tower with eight)
+  static constexpr int kStagesRaw = (200 * 1024) / kStageBytes;
+  static constexpr int kStagesCap = kARows == 64 ? 8 : 4;
+  static constexpr int kStages = kStagesRaw > kStagesCap ? kStagesCap : kStagesRaw;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 16 * 1024 + 1024 + 256;   // + slack the M=128 MMA may read
   static constexpr int kAccCols = (kSplit ? 2 : 1) * BN;
   static constexpr int kTmemCols = kAccCols < 32 ? 32 : kAccCols;
   static constexpr uint32_t kIdesc = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 };
 
-template <int BN, bool kSplit>
+template <int BN, bool kSplit, int kARows>
 __global__ void __launch_bounds__(192, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constant__ CUtensorMap map_al,
                const __grid_constant__ CUtensorMap map_wh, const __grid_constant__ CUtensorMap map_wl,
                const GemmParams p) {
-  using C = GemmCfg<BN, kSplit>;
+  using C = GemmCfg<BN, kSplit, kARows>;
+  constexpr int kGemmStages = C::kStages;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kGemmStages * C::kStageBytes);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kGemmStages * C::kStageBytes + 16 * 1024);
   uint64_t* empty_bar = full_bar + kGemmStages;
   uint64_t* tmem_full = empty_bar + kGemmStages;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
@@ -143,8 +152,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constant
       for (int kit = 0; kit < kiters; ++kit) {
         mbar_wait(&empty_bar[stage], phase ^ 1);
         uint8_t* sa = smem + stage * C::kStageBytes;
-        const uint32_t a_bytes = (uint32_t)p.a_rows * 128u;
-        mbar_expect_tx(&full_bar[stage], (kSplit ? 2 : 1) * (a_bytes + C::kWBytes));
+        mbar_expect_tx(&full_bar[stage], C::kStageBytes);
         tma_load_2d(&map_ah, sa, &full_bar[stage], kit * 64, m_tile * 128);
         tma_load_2d(&map_wh, sa + C::kABytes, &full_bar[stage], kit * 64, n_tile * BN);
         if (kSplit) {
@@ -265,21 +273,44 @@ __global__ void gpt2_embed_kernel(const int* __restrict__ tokens, int Ttot, int 
 }
 
 // TF-style LayerNorm (gpt2/model.py:16-29) of rows in_row(r) = r*row_mul + row_add of x -> split fp16 output row r.
-__global__ void gpt2_layernorm_split_kernel(const float* __restrict__ x, int row_mul, int row_add,
-                                            const float* __restrict__ w, const float* __restrict__ b, float eps,
-                                            __half* __restrict__ hi, __half* __restrict__ lo, int rows, int E) {
-  const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+// One 128-thread block per row (a decode step has only P rows: one warp per row left 8 blocks on 148 SMs, 7 us).
+__global__ void __launch_bounds__(128) gpt2_layernorm_split_kernel(const float* __restrict__ x, int row_mul, int row_add,
+                                                                   const float* __restrict__ w, const float* __restrict__ b,
+                                                                   float eps, __half* __restrict__ hi, __half* __restrict__ lo,
+                                                                   int rows, int E) {
+  __shared__ float red[8];
+  const int r = blockIdx.x;
   if (r >= rows) return;
-  const int lane = threadIdx.x & 31;
   const float* xr = x + (size_t)(r * row_mul + row_add) * E;
+  const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
+  float v[8];                                   // E <= 1024
   float s = 0.f;
-  for (int i = lane; i < E; i += 32) s += xr[i];
-  const float u = warp_sum_t(s) / (float)E;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int i = threadIdx.x + k * 128;
+    v[k] = i < E ? xr[i] : 0.f;
+    s += v[k];
+  }
+  s = warp_sum_t(s);
+  if (lane == 0) red[wp] = s;
+  __syncthreads();
+  const float u = (red[0] + red[1] + red[2] + red[3]) / (float)E;
   float q = 0.f;
-  for (int i = lane; i < E; i += 32) { const float d = xr[i] - u; q += d * d; }
-  const float inv = 1.f / sqrtf(warp_sum_t(q) / (float)E + eps);
-  for (int i = lane; i < E; i += 32)
-    split_store(w[i] * ((xr[i] - u) * inv) + b[i], hi + (size_t)r * E + i, lo + (size_t)r * E + i);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int i = threadIdx.x + k * 128;
+    const float d = i < E ? v[k] - u : 0.f;
+    q += d * d;
+  }
+  q = warp_sum_t(q);
+  if (lane == 0) red[4 + wp] = q;
+  __syncthreads();
+  const float inv = 1.f / sqrtf((red[4] + red[5] + red[6] + red[7]) / (float)E + eps);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int i = threadIdx.x + k * 128;
+    if (i < E) split_store(w[i] * ((v[k] - u) * inv) + b[i], hi + (size_t)r * E + i, lo + (size_t)r * E + i);
+  }
 }
 
 // Masked attention over the KV cache (gpt2/model.py:59-95).  One block per (candidate, head); head dim 64.
@@ -345,19 +376,78 @@ __global__ void gpt2_attention_kernel(const float* __restrict__ qkv, float* __re
   }
 }
 
+// Single-query form of the kernel above for the decode steps (Tn = 1): one block of 64 threads per (candidate, head).
+// The new key / value row is appended to the cache; scores: lane pairs... each of the 64 threads owns ONE key position
+// (ns <= 64 per pass) and reads its 256-byte cache row; the output dimension d is then owned by thread d.  No
+// shared-memory staging of the whole cache (that copy was most of the 16.6 us of the general kernel per step).
+__global__ void __launch_bounds__(64) gpt2_attention_decode_kernel(const float* __restrict__ qkv, float* __restrict__ kc,
+                                                                  float* __restrict__ vc, __half* __restrict__ out_hi,
+                                                                  __half* __restrict__ out_lo, int past, int Tmax, int H,
+                                                                  int E) {
+  __shared__ float qs[64];
+  __shared__ float pr[192];
+  __shared__ float red[4];
+  const int b = blockIdx.x / H, hd = blockIdx.x - b * H;
+  const int ns = past + 1;
+  const int d = threadIdx.x;
+  float* kcb = kc + ((size_t)(b * H + hd) * Tmax) * 64;
+  float* vcb = vc + ((size_t)(b * H + hd) * Tmax) * 64;
+  const float* r = qkv + (size_t)b * 3 * E + hd * 64 + d;
+  qs[d] = r[0];
+  const float knew = r[E], vnew = r[2 * E];
+  kcb[(size_t)past * 64 + d] = knew;
+  vcb[(size_t)past * 64 + d] = vnew;
+  __syncthreads();                                   // the appended row is read back below by other threads
+  float m = -INFINITY;
+  for (int c = threadIdx.x; c < ns; c += 64) {
+    const float4* kr = reinterpret_cast<const float4*>(kcb + (size_t)c * 64);
+    float acc = 0.f;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const float4 kv = kr[i];
+      acc = fmaf(qs[4 * i], kv.x, acc); acc = fmaf(qs[4 * i + 1], kv.y, acc);
+      acc = fmaf(qs[4 * i + 2], kv.z, acc); acc = fmaf(qs[4 * i + 3], kv.w, acc);
+    }
+    acc *= 0.125f;
+    pr[c] = acc;
+    m = fmaxf(m, acc);
+  }
+  m = warp_max_t(m);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+  __syncthreads();
+  m = fmaxf(red[0], red[1]);
+  float ssum = 0.f;
+  for (int c = threadIdx.x; c < ns; c += 64) {
+    const float e = expf(pr[c] - m);
+    pr[c] = e;
+    ssum += e;
+  }
+  ssum = warp_sum_t(ssum);
+  if ((threadIdx.x & 31) == 0) red[2 + (threadIdx.x >> 5)] = ssum;
+  __syncthreads();
+  const float inv = 1.f / (red[2] + red[3]);
+  float acc = 0.f;
+  for (int c = 0; c < ns; ++c) acc = fmaf(pr[c] * inv, vcb[(size_t)c * 64 + d], acc);
+  const size_t o = (size_t)b * E + hd * 64 + d;
+  split_store(acc, out_hi + o, out_lo + o);
+}
+
 // next token = arg-max of the logits over [0, vocab) (first maximum, like torch.topk k=1 on distinct values);
-// written to tokens[b][col] (gpt2/sample.py:31-35 with sample=False)
-__global__ void gpt2_argmax_kernel(const float* __restrict__ logits, int Npad, int vocab, int* __restrict__ tokens,
-                                   int Ttot, int col) {
+// written to tokens[b][col] (gpt2/sample.py:31-35 with sample=False).  1024 threads per row, 16-byte loads.
+__global__ void __launch_bounds__(1024) gpt2_argmax_kernel(const float* __restrict__ logits, int Npad, int vocab,
+                                                           int* __restrict__ tokens, int Ttot, int col) {
   __shared__ float bv[32];
   __shared__ int bi[32];
   const int b = blockIdx.x;
-  const float* l = logits + (size_t)b * Npad;
+  const float4* l4 = reinterpret_cast<const float4*>(logits + (size_t)b * Npad);
   float best = -INFINITY;
   int idx = 0x7fffffff;
-  for (int i = threadIdx.x; i < vocab; i += blockDim.x) {
-    const float v = l[i];
-    if (v > best || (v == best && i < idx)) { best = v; idx = i; }
+  auto take = [&](float v, int i) {
+    if (i < vocab && (v > best || (v == best && i < idx))) { best = v; idx = i; }
+  };
+  for (int i4 = threadIdx.x; i4 < Npad / 4; i4 += blockDim.x) {
+    const float4 v = __ldg(l4 + i4);
+    take(v.x, 4 * i4); take(v.y, 4 * i4 + 1); take(v.z, 4 * i4 + 2); take(v.w, 4 * i4 + 3);
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
@@ -368,10 +458,16 @@ __global__ void gpt2_argmax_kernel(const float* __restrict__ logits, int Npad, i
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (lane == 0) { bv[w] = best; bi[w] = idx; }
   __syncthreads();
-  if (threadIdx.x == 0) {
-    for (int k = 1; k < (int)(blockDim.x >> 5); ++k)
-      if (bv[k] > best || (bv[k] == best && bi[k] < idx)) { best = bv[k]; idx = bi[k]; }
-    tokens[(size_t)b * Ttot + col] = idx;
+  if (w == 0) {
+    best = lane < (int)(blockDim.x >> 5) ? bv[lane] : -INFINITY;
+    idx = lane < (int)(blockDim.x >> 5) ? bi[lane] : 0x7fffffff;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, idx, o);
+      if (ov > best || (ov == best && oi < idx)) { best = ov; idx = oi; }
+    }
+    if (lane == 0) tokens[(size_t)b * Ttot + col] = idx;
   }
 }
 
@@ -610,18 +706,18 @@ int get_map(glass_text_engine* e, const void* ptr, int rows, int K, int box_rows
   return GLASS_OK;
 }
 
-template <int BN, bool kSplit>
+template <int BN, bool kSplit, int kARows>
 int launch_gemm_t(glass_text_engine* e, const __half* a_hi, const __half* a_lo, const __half* w_hi, const __half* w_lo,
                   const GemmParams& p_in, cudaStream_t s) {
-  using C = GemmCfg<BN, kSplit>;
+  using C = GemmCfg<BN, kSplit, kARows>;
   static bool configured = false;
   if (!configured) {
-    TCUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<BN, kSplit>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
+    TCUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<BN, kSplit, kARows>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
     configured = true;
   }
   const CUtensorMap *mah, *mal, *mwh, *mwl;
   GemmParams p = p_in;
-  p.a_rows = p.M <= 64 ? 64 : 128;
+  p.a_rows = kARows;
   TRC(get_map(e, a_hi, p.M, p.K, p.a_rows, &mah));
   TRC(get_map(e, w_hi, p.N, p.K, BN, &mwh));
   mal = mah;
@@ -633,7 +729,7 @@ int launch_gemm_t(glass_text_engine* e, const __half* a_hi, const __half* a_lo, 
   dim3 grid(p.N / BN, (p.M + 127) / 128);
   const bool timed = e->timing && e->ev_used + 2 <= e->ev.size();
   if (timed) cudaEventRecord(e->ev[e->ev_used], s);
-  gemm_tc_kernel<BN, kSplit><<<grid, 192, C::kSmemBytes, s>>>(*mah, *mal, *mwh, *mwl, p);
+  gemm_tc_kernel<BN, kSplit, kARows><<<grid, 192, C::kSmemBytes, s>>>(*mah, *mal, *mwh, *mwl, p);
   if (timed) {
     cudaEventRecord(e->ev[e->ev_used + 1], s);
     e->ev_used += 2;
@@ -655,8 +751,12 @@ int launch_gemm(glass_text_engine* e, const __half* a_hi, const __half* a_lo, co
                 const GemmParams& p, cudaStream_t s) {
   if (p.K % 64 != 0 || p.N % 32 != 0 || p.M <= 0) return tfail(GLASS_ERR_ARG, "unsupported GEMM shape %dx%dx%d", p.M, p.N, p.K);
   const int m_tiles = (p.M + 127) / 128;
-  if (p.N % 64 == 0 && (p.N / 64) * m_tiles >= 96) return launch_gemm_t<64, kSplit>(e, a_hi, a_lo, w_hi, w_lo, p, s);
-  return launch_gemm_t<32, kSplit>(e, a_hi, a_lo, w_hi, w_lo, p, s);
+  if (p.M <= 64) {                                   // decode steps: half-height A tiles, deep pipeline
+    if (p.N % 64 == 0 && p.N / 64 >= 96) return launch_gemm_t<64, kSplit, 64>(e, a_hi, a_lo, w_hi, w_lo, p, s);
+    return launch_gemm_t<32, kSplit, 64>(e, a_hi, a_lo, w_hi, w_lo, p, s);
+  }
+  if (p.N % 64 == 0 && (p.N / 64) * m_tiles >= 96) return launch_gemm_t<64, kSplit, 128>(e, a_hi, a_lo, w_hi, w_lo, p, s);
+  return launch_gemm_t<32, kSplit, 128>(e, a_hi, a_lo, w_hi, w_lo, p, s);
 }
 
 #define TLAUNCH(expr)                                                                              \
@@ -770,18 +870,22 @@ int gpt2_forward(glass_text_engine* e, int P, int col0, int Tn, cudaStream_t s) 
   const size_t attn_smem = sizeof(float) * ((size_t)2 * e->Ttot * 65 + (size_t)Tn * 65 + (size_t)Tn * (e->Ttot + 1));
   for (int l = 0; l < c.gpt2_layers; ++l) {
     auto f = [&](const char* sfx) { snprintf(nm, sizeof nm, "g2.l%d.%s", l, sfx); return std::string(nm); };
-    TLAUNCH((gpt2_layernorm_split_kernel<<<(M + 7) / 8, 256, 0, s>>>(e->h, 1, 0, tt<float>(e, f("ln1.w")),
+    TLAUNCH((gpt2_layernorm_split_kernel<<<M, 128, 0, s>>>(e->h, 1, 0, tt<float>(e, f("ln1.w")),
                                                                       tt<float>(e, f("ln1.b")), c.gpt2_eps, e->a_hi, e->a_lo, M, E)));
     GemmParams g{};
     g.M = M; g.N = 3 * E; g.K = E; g.bias = tt<float>(e, f("attn.b")); g.out_f32 = e->qkv;
     TRC(launch_gemm<true>(e, e->a_hi, e->a_lo, tt<__half>(e, f("attn.w.hi")), tt<__half>(e, f("attn.w.lo")), g, s));
     const size_t coff = (size_t)l * P * H * e->Ttot * 64;
-    TLAUNCH((gpt2_attention_kernel<<<P * H, 128, attn_smem, s>>>(e->qkv, e->kcache + coff, e->vcache + coff, e->a_hi,
-                                                                  e->a_lo, Tn, col0, e->Ttot, H, E)));
+    if (Tn == 1 && col0 + 1 <= 192)
+      TLAUNCH((gpt2_attention_decode_kernel<<<P * H, 64, 0, s>>>(e->qkv, e->kcache + coff, e->vcache + coff, e->a_hi,
+                                                                 e->a_lo, col0, e->Ttot, H, E)));
+    else
+      TLAUNCH((gpt2_attention_kernel<<<P * H, 128, attn_smem, s>>>(e->qkv, e->kcache + coff, e->vcache + coff, e->a_hi,
+                                                                    e->a_lo, Tn, col0, e->Ttot, H, E)));
     g = GemmParams{};
     g.M = M; g.N = E; g.K = E; g.bias = tt<float>(e, f("proj.b")); g.res_f32 = e->h; g.out_f32 = e->h;
     TRC(launch_gemm<true>(e, e->a_hi, e->a_lo, tt<__half>(e, f("proj.w.hi")), tt<__half>(e, f("proj.w.lo")), g, s));
-    TLAUNCH((gpt2_layernorm_split_kernel<<<(M + 7) / 8, 256, 0, s>>>(e->h, 1, 0, tt<float>(e, f("ln2.w")),
+    TLAUNCH((gpt2_layernorm_split_kernel<<<M, 128, 0, s>>>(e->h, 1, 0, tt<float>(e, f("ln2.w")),
                                                                       tt<float>(e, f("ln2.b")), c.gpt2_eps, e->a_hi, e->a_lo, M, E)));
     g = GemmParams{};
     g.M = M; g.N = 4 * E; g.K = E; g.bias = tt<float>(e, f("fc.b")); g.act = kTActGeluTanh; g.out_hi = e->g_hi; g.out_lo = e->g_lo;
@@ -791,12 +895,12 @@ int gpt2_forward(glass_text_engine* e, int P, int col0, int Tn, cudaStream_t s) 
     TRC(launch_gemm<true>(e, e->g_hi, e->g_lo, tt<__half>(e, f("proj2.w.hi")), tt<__half>(e, f("proj2.w.lo")), g, s));
   }
   // ln_f and the LM head on the last position only (gpt2/sample.py:29: logits[:, -1, :])
-  TLAUNCH((gpt2_layernorm_split_kernel<<<(P + 7) / 8, 256, 0, s>>>(e->h, Tn, Tn - 1, tt<float>(e, "g2.lnf.w"),
+  TLAUNCH((gpt2_layernorm_split_kernel<<<P, 128, 0, s>>>(e->h, Tn, Tn - 1, tt<float>(e, "g2.lnf.w"),
                                                                     tt<float>(e, "g2.lnf.b"), c.gpt2_eps, e->f_hi, e->f_lo, P, E)));
   GemmParams g{};
   g.M = P; g.N = e->Npad; g.K = E; g.out_f32 = e->logits;
   TRC(launch_gemm<true>(e, e->f_hi, e->f_lo, tt<__half>(e, "g2.wte.hi"), tt<__half>(e, "g2.wte.lo"), g, s));
-  TLAUNCH((gpt2_argmax_kernel<<<P, 256, 0, s>>>(e->logits, e->Npad, c.gpt2_vocab, e->tokens, e->Ttot, col0 + Tn)));
+  TLAUNCH((gpt2_argmax_kernel<<<P, 1024, 0, s>>>(e->logits, e->Npad, c.gpt2_vocab, e->tokens, e->Ttot, col0 + Tn)));
   return GLASS_OK;
 }
 
