@@ -81,6 +81,8 @@ enum { kTActNone = 0, kTActGeluTanh = 1, kTActQuickGelu = 2 };
 struct GemmParams {
   int M, N, K;
   int a_rows;                 // rows of the A box (128, or 64 when M <= 64: the upper half of the tile is never read back)
+  int splits;                 // split-K: blockIdx.z handles K / splits; the raw fp32 partial sums go to
+                              // out_f32 + z*M*N (no bias / activation / residual: the consumer reduces them)
   const float* bias;          // [N] or null
   int act;
   int round_fp16;             // plain mode: round acc + bias to fp16 before the activation (the reference's op boundary)
@@ -104,7 +106,8 @@ struct GemmCfg {
   static constexpr int kStagesRaw = (200 * 1024) / kStageBytes;
   static constexpr int kStagesCap = kARows == 64 ? 8 : 4;
   static constexpr int kStages = kStagesRaw > kStagesCap ? kStagesCap : kStagesRaw;
-  static constexpr int kSmemBytes = kStages * kStageBytes + 16 * 1024 + 1024 + 256;   // + slack the M=128 MMA may read
+  static constexpr int kSlack = kARows == 64 ? 16 * 1024 : 0;       // what the M=128 MMA may read behind a half-height A tile
+  static constexpr int kSmemBytes = kStages * kStageBytes + kSlack + 1024 + 256;
   static constexpr int kAccCols = (kSplit ? 2 : 1) * BN;
   static constexpr int kTmemCols = kAccCols < 32 ? 32 : kAccCols;
   static constexpr uint32_t kIdesc = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
@@ -119,13 +122,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constant
   constexpr int kGemmStages = C::kStages;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kGemmStages * C::kStageBytes + 16 * 1024);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kGemmStages * C::kStageBytes + C::kSlack);
   uint64_t* empty_bar = full_bar + kGemmStages;
   uint64_t* tmem_full = empty_bar + kGemmStages;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_tile = blockIdx.x, m_tile = blockIdx.y;
-  const int kiters = p.K / 64;
+  const int kiters = p.K / 64 / (p.splits > 1 ? p.splits : 1);
+  const int kit0 = (p.splits > 1 ? (int)blockIdx.z : 0) * kiters;
 
   if (threadIdx.x == 0) {
     prefetch_tmap(&map_ah);
@@ -153,11 +157,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constant
         mbar_wait(&empty_bar[stage], phase ^ 1);
         uint8_t* sa = smem + stage * C::kStageBytes;
         mbar_expect_tx(&full_bar[stage], C::kStageBytes);
-        tma_load_2d(&map_ah, sa, &full_bar[stage], kit * 64, m_tile * 128);
-        tma_load_2d(&map_wh, sa + C::kABytes, &full_bar[stage], kit * 64, n_tile * BN);
+        const int kc = (kit0 + kit) * 64;
+        tma_load_2d(&map_ah, sa, &full_bar[stage], kc, m_tile * 128);
+        tma_load_2d(&map_wh, sa + C::kABytes, &full_bar[stage], kc, n_tile * BN);
         if (kSplit) {
-          tma_load_2d(&map_al, sa + C::kABytes + C::kWBytes, &full_bar[stage], kit * 64, m_tile * 128);
-          tma_load_2d(&map_wl, sa + 2 * C::kABytes + C::kWBytes, &full_bar[stage], kit * 64, n_tile * BN);
+          tma_load_2d(&map_al, sa + C::kABytes + C::kWBytes, &full_bar[stage], kc, m_tile * 128);
+          tma_load_2d(&map_wl, sa + 2 * C::kABytes + C::kWBytes, &full_bar[stage], kc, n_tile * BN);
         }
         if (++stage == kGemmStages) { stage = 0; phase ^= 1; }
       }
@@ -205,7 +210,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constant
 #pragma unroll
         for (int j = 0; j < 16; ++j) v[j] = fmaf(w[j], kLoInv, v[j]);
       }
-      if (m < p.M) {
+      if (m < p.M && p.splits > 1) {
+        float* dst = p.out_f32 + (size_t)blockIdx.z * p.M * p.N + (size_t)m * p.N + n_tile * BN + c * 16;
+#pragma unroll
+        for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+      } else if (m < p.M) {
         const int n0 = n_tile * BN + c * 16;
         const size_t o = (size_t)m * p.N + n0;
 #pragma unroll
@@ -310,6 +319,95 @@ __global__ void __launch_bounds__(128) gpt2_layernorm_split_kernel(const float* 
   for (int k = 0; k < 8; ++k) {
     const int i = threadIdx.x + k * 128;
     if (i < E) split_store(w[i] * ((v[k] - u) * inv) + b[i], hi + (size_t)r * E + i, lo + (size_t)r * E + i);
+  }
+}
+
+// Decode-step consumers of split-K partial sums.  x = sum_s part[s] + bias, reduced in the fixed order s = 0, 1, ...
+// (deterministic: the arg-max of the logits must not depend on scheduling).
+// (a) residual update + LayerNorm: h[r] += x[r]; then the TF-style LayerNorm of h[r] -> split fp16 (the LayerNorm that
+//     follows attn.c_proj / mlp.c_proj in the block structure: ln_2, the next layer's ln_1, or ln_f)
+__global__ void __launch_bounds__(128) gpt2_reduce_residual_ln_kernel(const float* __restrict__ part, int S, size_t part_stride,
+                                                                      const float* __restrict__ bias, float* __restrict__ h,
+                                                                      const float* __restrict__ w, const float* __restrict__ b,
+                                                                      float eps, __half* __restrict__ hi, __half* __restrict__ lo,
+                                                                      int E) {
+  __shared__ float red[8];
+  const int r = blockIdx.x;
+  const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
+  float v[8];
+  float s = 0.f;
+  {
+    // the S partial sums of an element are added in the fixed order z = 0, 1, ...; the loads of four splits x eight
+    // elements are issued together (a serial load-add chain per element made this kernel 22 us: 144 dependent L2 hits)
+    float acc[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+    const float* pr = part + (size_t)r * E + threadIdx.x;
+    for (int z = 0; z < S; z += 4) {
+      float t[4][8];
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          t[u][k] = (z + u < S && threadIdx.x + k * 128 < E) ? pr[(size_t)(z + u) * part_stride + k * 128] : 0.f;
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[k] += t[u][k];
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int i = threadIdx.x + k * 128;
+      v[k] = 0.f;
+      if (i < E) {
+        v[k] = h[(size_t)r * E + i] + (acc[k] + bias[i]);
+        h[(size_t)r * E + i] = v[k];
+      }
+      s += v[k];
+    }
+  }
+  s = warp_sum_t(s);
+  if (lane == 0) red[wp] = s;
+  __syncthreads();
+  const float u = (red[0] + red[1] + red[2] + red[3]) / (float)E;
+  float q = 0.f;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int i = threadIdx.x + k * 128;
+    const float d = i < E ? v[k] - u : 0.f;
+    q += d * d;
+  }
+  q = warp_sum_t(q);
+  if (lane == 0) red[4 + wp] = q;
+  __syncthreads();
+  const float inv = 1.f / sqrtf((red[4] + red[5] + red[6] + red[7]) / (float)E + eps);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int i = threadIdx.x + k * 128;
+    if (i < E) split_store(w[i] * ((v[k] - u) * inv) + b[i], hi + (size_t)r * E + i, lo + (size_t)r * E + i);
+  }
+}
+// (b) c_fc: tanh-GELU(x) -> split fp16
+__global__ void gpt2_reduce_gelu_split_kernel(const float* __restrict__ part, int S, size_t part_stride,
+                                              const float* __restrict__ bias, __half* __restrict__ hi, __half* __restrict__ lo,
+                                              int M, int N) {
+  const size_t n = (size_t)M * N;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    float acc = 0.f;
+    for (int z = 0; z < S; ++z) acc += part[(size_t)z * part_stride + i];
+    float t = acc + bias[i % N];
+    t = 0.5f * t * (1.f + tanhf(0.7978845608028654f * (t + 0.044715f * t * t * t)));
+    split_store(t, hi + i, lo + i);
+  }
+}
+// (c) c_attn: qkv[b][3E] = x (plain fp32, read by the attention kernel)
+__global__ void gpt2_reduce_bias_kernel(const float* __restrict__ part, int S, size_t part_stride, const float* __restrict__ bias,
+                                        float* __restrict__ out, int M, int N) {
+  const size_t n = (size_t)M * N;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    float acc = 0.f;
+    for (int z = 0; z < S; ++z) acc += part[(size_t)z * part_stride + i];
+    out[i] = acc + bias[i % N];
   }
 }
 
@@ -660,6 +758,7 @@ struct glass_text_engine {
   long long* tok64 = nullptr;
   long long* zin64 = nullptr;
   float *h = nullptr, *qkv = nullptr, *logits = nullptr, *kcache = nullptr, *vcache = nullptr;
+  float* partials = nullptr;   // split-K partial sums of the decode GEMMs: [splits][64][N]
   __half *a_hi = nullptr, *a_lo = nullptr, *g_hi = nullptr, *g_lo = nullptr, *f_hi = nullptr, *f_lo = nullptr;
   // CLIP text workspace
   long long* ctok = nullptr;
@@ -726,7 +825,7 @@ int launch_gemm_t(glass_text_engine* e, const __half* a_hi, const __half* a_lo, 
     TRC(get_map(e, a_lo, p.M, p.K, p.a_rows, &mal));
     TRC(get_map(e, w_lo, p.N, p.K, BN, &mwl));
   }
-  dim3 grid(p.N / BN, (p.M + 127) / 128);
+  dim3 grid(p.N / BN, (p.M + 127) / 128, p.splits > 1 ? p.splits : 1);
   const bool timed = e->timing && e->ev_used + 2 <= e->ev.size();
   if (timed) cudaEventRecord(e->ev[e->ev_used], s);
   gemm_tc_kernel<BN, kSplit, kARows><<<grid, 192, C::kSmemBytes, s>>>(*mah, *mal, *mwh, *mwl, p);
@@ -757,6 +856,21 @@ int launch_gemm(glass_text_engine* e, const __half* a_hi, const __half* a_lo, co
   }
   if (p.N % 64 == 0 && (p.N / 64) * m_tiles >= 96) return launch_gemm_t<64, kSplit, 128>(e, a_hi, a_lo, w_hi, w_lo, p, s);
   return launch_gemm_t<32, kSplit, 128>(e, a_hi, a_lo, w_hi, w_lo, p, s);
+}
+
+// Decode-step GEMM (M <= 64 rows): 128-column tiles and split-K so that n_tiles * splits CTAs fill the machine;
+// writes `splits` fp32 partial sums [splits][M][N] that the consumer kernel reduces in a fixed order.
+int launch_gemm_decode(glass_text_engine* e, const __half* a_hi, const __half* a_lo, const __half* w_hi, const __half* w_lo,
+                       int M, int N, int K, float* partials, int* splits_out, cudaStream_t s) {
+  if (K % 64 != 0 || N % 128 != 0 || M <= 0 || M > 64) return tfail(GLASS_ERR_ARG, "unsupported decode GEMM %dx%dx%d", M, N, K);
+  const int kiters = K / 64, n_tiles = N / 128;
+  int S = 1;
+  for (int d = 1; d <= kiters; ++d)
+    if (kiters % d == 0 && n_tiles * d <= e->num_sms) S = d;
+  GemmParams g{};
+  g.M = M; g.N = N; g.K = K; g.out_f32 = partials; g.splits = S;
+  *splits_out = S;
+  return launch_gemm_t<128, true, 64>(e, a_hi, a_lo, w_hi, w_lo, g, s);
 }
 
 #define TLAUNCH(expr)                                                                              \
@@ -835,6 +949,7 @@ void layout_text(glass_text_engine* e, Carver& a) {
     e->h = a.take<float>(M * E);
     e->qkv = a.take<float>(M * 3 * E);
     e->logits = a.take<float>(P * e->Npad);
+    e->partials = a.take<float>((size_t)e->num_sms * 64 * 128 + 1024);   // n_tiles * splits <= num_sms tiles of 64 x 128
     e->kcache = a.take<float>((size_t)c.gpt2_layers * P * H * e->Ttot * 64);
     e->vcache = a.take<float>((size_t)c.gpt2_layers * P * H * e->Ttot * 64);
     e->a_hi = a.take<__half>(M * E);
@@ -861,9 +976,64 @@ void layout_text(glass_text_engine* e, Carver& a) {
 
 // one GPT2LMHeadModel.forward over Tn new positions starting at column col0 (gpt2/model.py:126-175, 196-210); the
 // arg-max of the last position's logits lands in tokens[:, col0 + Tn]
+// Decode step (one new position per candidate, M = P <= 64 rows): every GEMM is a weight-streaming pass with one
+// 128-row m-tile, so it runs split-K over (N / 128) x splits ~ 148 CTAs and leaves fp32 partial sums; the reduction is
+// fused into the kernel that consumes the result (residual update + LayerNorm, bias + GELU, bias).
+int gpt2_forward_decode(glass_text_engine* e, int P, int col0, cudaStream_t s) {
+  const glass_text_config& c = e->cfg;
+  const int E = c.gpt2_embd, H = c.gpt2_heads, M = P;
+  char nm[64];
+  int S = 1;
+  const size_t ps = (size_t)M;             // partial stride factor: M * N floats per split
+  TLAUNCH((gpt2_embed_kernel<<<M, 128, 0, s>>>(e->tokens, e->Ttot, col0, 1, tt<float>(e, "g2.wte"), tt<float>(e, "g2.wpe"),
+                                               e->h, E)));
+  for (int l = 0; l < c.gpt2_layers; ++l) {
+    auto f = [&](const char* sfx) { snprintf(nm, sizeof nm, "g2.l%d.%s", l, sfx); return std::string(nm); };
+    auto fp = [&](const char* sfx) { snprintf(nm, sizeof nm, "g2.l%d.%s", l - 1, sfx); return std::string(nm); };
+    if (l == 0) {
+      TLAUNCH((gpt2_layernorm_split_kernel<<<M, 128, 0, s>>>(e->h, 1, 0, tt<float>(e, f("ln1.w")), tt<float>(e, f("ln1.b")),
+                                                             c.gpt2_eps, e->a_hi, e->a_lo, M, E)));
+    } else {      // h += mlp.c_proj of the previous layer (pending partial sums), then this layer's ln_1
+      const float* pb = tt<float>(e, fp("proj2.b"));
+      TLAUNCH((gpt2_reduce_residual_ln_kernel<<<M, 128, 0, s>>>(e->partials, S, ps * E, pb, e->h, tt<float>(e, f("ln1.w")),
+                                                                tt<float>(e, f("ln1.b")), c.gpt2_eps, e->a_hi, e->a_lo, E)));
+    }
+    TRC(launch_gemm_decode(e, e->a_hi, e->a_lo, tt<__half>(e, f("attn.w.hi")), tt<__half>(e, f("attn.w.lo")), M, 3 * E, E,
+                           e->partials, &S, s));
+    TLAUNCH((gpt2_reduce_bias_kernel<<<(M * 3 * E + 255) / 256, 256, 0, s>>>(e->partials, S, ps * 3 * E, tt<float>(e, f("attn.b")),
+                                                                             e->qkv, M, 3 * E)));
+    const size_t coff = (size_t)l * P * H * e->Ttot * 64;
+    TLAUNCH((gpt2_attention_decode_kernel<<<P * H, 64, 0, s>>>(e->qkv, e->kcache + coff, e->vcache + coff, e->a_hi, e->a_lo,
+                                                               col0, e->Ttot, H, E)));
+    TRC(launch_gemm_decode(e, e->a_hi, e->a_lo, tt<__half>(e, f("proj.w.hi")), tt<__half>(e, f("proj.w.lo")), M, E, E,
+                           e->partials, &S, s));
+    TLAUNCH((gpt2_reduce_residual_ln_kernel<<<M, 128, 0, s>>>(e->partials, S, ps * E, tt<float>(e, f("proj.b")), e->h,
+                                                              tt<float>(e, f("ln2.w")), tt<float>(e, f("ln2.b")), c.gpt2_eps,
+                                                              e->a_hi, e->a_lo, E)));
+    TRC(launch_gemm_decode(e, e->a_hi, e->a_lo, tt<__half>(e, f("fc.w.hi")), tt<__half>(e, f("fc.w.lo")), M, 4 * E, E,
+                           e->partials, &S, s));
+    TLAUNCH((gpt2_reduce_gelu_split_kernel<<<(M * 4 * E + 255) / 256, 256, 0, s>>>(e->partials, S, ps * 4 * E,
+                                                                                   tt<float>(e, f("fc.b")), e->g_hi, e->g_lo,
+                                                                                   M, 4 * E)));
+    TRC(launch_gemm_decode(e, e->g_hi, e->g_lo, tt<__half>(e, f("proj2.w.hi")), tt<__half>(e, f("proj2.w.lo")), M, E, 4 * E,
+                           e->partials, &S, s));
+  }
+  snprintf(nm, sizeof nm, "g2.l%d.proj2.b", c.gpt2_layers - 1);
+  TLAUNCH((gpt2_reduce_residual_ln_kernel<<<M, 128, 0, s>>>(e->partials, S, ps * E, tt<float>(e, nm), e->h,
+                                                            tt<float>(e, "g2.lnf.w"), tt<float>(e, "g2.lnf.b"), c.gpt2_eps,
+                                                            e->f_hi, e->f_lo, E)));
+  GemmParams g{};
+  g.M = P; g.N = e->Npad; g.K = E; g.out_f32 = e->logits;
+  TRC(launch_gemm<true>(e, e->f_hi, e->f_lo, tt<__half>(e, "g2.wte.hi"), tt<__half>(e, "g2.wte.lo"), g, s));
+  TLAUNCH((gpt2_argmax_kernel<<<P, 1024, 0, s>>>(e->logits, e->Npad, c.gpt2_vocab, e->tokens, e->Ttot, col0 + 1)));
+  return GLASS_OK;
+}
+
 int gpt2_forward(glass_text_engine* e, int P, int col0, int Tn, cudaStream_t s) {
   const glass_text_config& c = e->cfg;
   const int E = c.gpt2_embd, H = c.gpt2_heads, M = P * Tn;
+  if (Tn == 1 && P <= 64 && E % 128 == 0 && col0 + 1 <= 192 && !(c.flags & GLASS_TEXT_FLAG_NO_SPLIT_K))
+    return gpt2_forward_decode(e, P, col0, s);
   char nm[64];
   TLAUNCH((gpt2_embed_kernel<<<M, 128, 0, s>>>(e->tokens, e->Ttot, col0, Tn, tt<float>(e, "g2.wte"), tt<float>(e, "g2.wpe"),
                                                e->h, E)));

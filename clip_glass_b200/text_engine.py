@@ -16,6 +16,7 @@ from ._lib import GlassArgError, GlassError, load_library
 from .text_weights import ClipTextSpec, GPT2Spec, text_as_built
 
 LO_SCALE = 2048.0
+TEXT_FLAG_NO_SPLIT_K = 1        # include/clipglass_b200.h: GLASS_TEXT_FLAG_NO_SPLIT_K
 
 
 class GlassTextConfig(ctypes.Structure):
@@ -111,7 +112,7 @@ def _check(lib, rc: int) -> None:
 
 class TextEngine:
     def __init__(self, gpt2: Optional[GPT2Spec], gpt2_sd, text: Optional[ClipTextSpec], text_sd, init_tokens=(),
-                 dim_z: int = 20, max_tokens_len: int = 30, max_population: int = 64, device: int = 0):
+                 dim_z: int = 20, max_tokens_len: int = 30, max_population: int = 64, device: int = 0, flags: int = 0):
         self.lib = load_library()
         _bind(self.lib)
         self.gpt2, self.text = gpt2, text
@@ -125,7 +126,7 @@ class TextEngine:
         if text is not None:
             cfg.text_width, cfg.text_heads, cfg.text_layers = text.width, text.heads, text.layers
             cfg.text_context, cfg.text_vocab, cfg.text_embed_dim = text.context, text.vocab, text.embed_dim
-        cfg.max_population, cfg.device = max_population, device
+        cfg.max_population, cfg.device, cfg.flags = max_population, device, flags
         self._h = ctypes.c_void_p()
         _check(self.lib, self.lib.glass_text_create(ctypes.byref(cfg), ctypes.byref(self._h)))
         packed = {}

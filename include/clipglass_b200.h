@@ -195,6 +195,8 @@ typedef struct glass_text_config {
   int32_t device;
   int32_t flags;
 } glass_text_config;
+/* glass_text_config.flags: GLASS_FLAG_NO_GRAPH (32) = launch eagerly; cross-check variant of the decode-step GEMMs: */
+#define GLASS_TEXT_FLAG_NO_SPLIT_K 1   /* one CTA per n-tile over the whole K, epilogue-fused bias / GELU / residual */
 int glass_text_create(const glass_text_config* cfg, glass_text_engine** out);
 /* Packed tensors from HOST memory; names / layouts in clip_glass_b200/text_packing.py (from the reference's
  * gpt2-pytorch_model.bin and ViT-B-32.pt state_dict layouts). */

@@ -25,14 +25,14 @@ CONFIGS = {
 }
 
 
-def _engine(name, max_population=None):
+def _engine(name, max_population=None, flags=0):
     from clip_glass_b200.text_engine import TextEngine
     cfg = CONFIGS[name]
     gold = dict(np.load(os.path.join(REPO, "tests", "golden", f"{name}.npz")))
     g_sd = TW.make_gpt2_weights(cfg["gpt2"], cfg["seed"])
     t_sd = TW.make_clip_text_weights(cfg["text"], cfg["seed"] + 1)
     eng = TextEngine(cfg["gpt2"], g_sd, cfg["text"], t_sd, init_tokens=gold["init_tokens"].tolist(), dim_z=20,
-                     max_tokens_len=30, max_population=max_population or cfg["pop"])
+                     max_tokens_len=30, max_population=max_population or cfg["pop"], flags=flags)
     eng.set_image_features(torch.from_numpy(gold["image_features"]))
     return eng, gold, g_sd, t_sd, cfg
 
@@ -49,6 +49,16 @@ def test_gpt2_greedy_decode_tokens_are_bit_exact(name):
     # candidates are independent: a sub-population gives the same rows
     np.testing.assert_array_equal(eng.generate_tokens(gold["z"][2:5]), tokens[2:5])
     eng.close()
+
+
+def test_gpt2_decode_split_k_equals_single_pass_gemms():
+    """The decode-step GEMMs run split-K with the reduction fused into the consuming kernels; the cross-check variant
+    (GLASS_TEXT_FLAG_NO_SPLIT_K: one CTA per n-tile over the whole K, epilogue-fused bias / GELU / residual) sums the
+    same products in another order.  Both reproduce the reference's tokens."""
+    for flags in (0, 1):
+        eng, gold, g_sd, t_sd, cfg = _engine("gpt2_full", flags=flags)
+        np.testing.assert_array_equal(eng.generate_tokens(gold["z"]), gold["tokens"])
+        eng.close()
 
 
 def test_gpt2_decode_at_the_benchmarked_population():
