@@ -31,11 +31,42 @@ __device__ __forceinline__ int fd_unit(int g, int py, int px) {
 // ox = tid & 15, channel group g = (tid >> 4) & 3, output rows 2*oyp and 2*oyp+1 with oyp = tid >> 6.  Six input
 // rows are filtered horizontally once ((a+d) + 3(b+c): two adds and one FMA per channel instead of four FMAs) and
 // shared by the two outputs o[0], o[1] (8 fp16 channels each).
+// Arithmetic: packed half2 (GLASS_FIR_FP32 at compile time restores the fp32 version).  The fp32 version spent most
+// of its ~28 instructions per output element converting the 24 loaded vectors to fp32 (these passes are issue-bound
+// at 67-85 % issue-slot utilisation, profiles/r02_metrics_p64.txt); in half2 a [1,3,3,1] tap is 3 instructions per
+// channel pair ((c0 + c3) + 3 (c1 + c2), un-normalised, at most 8 |a|) and the vertical pass applies the whole 1/64.
+// Error: six fp16 roundings of the partial sums, ~1e-3 relative in the worst case, on a tensor that is rounded to
+// fp16 anyway; the D parity bounds hold unchanged (tests/test_gpu_parity.py).
+__device__ __forceinline__ uint4 fd_fir4_h2(const uint4& c0, const uint4& c1, const uint4& c2, const uint4& c3, bool scaled) {
+  const __half2 k1 = __floats2half2_rn(1.f / 64.f, 1.f / 64.f), k3 = __floats2half2_rn(3.f / 64.f, 3.f / 64.f);
+  const __half2 three = __floats2half2_rn(3.f, 3.f);
+  uint4 r;
+  const __half2* a = reinterpret_cast<const __half2*>(&c0);
+  const __half2* b = reinterpret_cast<const __half2*>(&c1);
+  const __half2* c = reinterpret_cast<const __half2*>(&c2);
+  const __half2* d = reinterpret_cast<const __half2*>(&c3);
+  __half2* o = reinterpret_cast<__half2*>(&r);
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+    o[j] = scaled ? __hfma2(__hadd2(b[j], c[j]), k3, __hmul2(__hadd2(a[j], d[j]), k1))
+                  : __hfma2(__hadd2(b[j], c[j]), three, __hadd2(a[j], d[j]));
+  return r;
+}
+
 __device__ __forceinline__ void fir_down_compute(const uint4* tile, uint4 (&o)[2]) {
   static_assert(kFdTH == 8 && kFdTW == 16, "thread mapping: 16 columns x 4 groups x 4 row pairs = 256 threads");
   const int ox = threadIdx.x & 15;
   const int g = (threadIdx.x >> 4) & 3;
   const int oyp = threadIdx.x >> 6;                 // input rows 4*oyp .. 4*oyp+5
+#ifndef GLASS_FIR_FP32
+  uint4 hrow[6];
+#pragma unroll
+  for (int r = 0; r < 6; ++r)
+    hrow[r] = fd_fir4_h2(tile[fd_unit(g, 4 * oyp + r, 2 * ox)], tile[fd_unit(g, 4 * oyp + r, 2 * ox + 1)],
+                         tile[fd_unit(g, 4 * oyp + r, 2 * ox + 2)], tile[fd_unit(g, 4 * oyp + r, 2 * ox + 3)], false);
+#pragma unroll
+  for (int k = 0; k < 2; ++k) o[k] = fd_fir4_h2(hrow[2 * k], hrow[2 * k + 1], hrow[2 * k + 2], hrow[2 * k + 3], true);
+#else
   float hrow[6][8];
 #pragma unroll
   for (int r = 0; r < 6; ++r) {
@@ -65,6 +96,7 @@ __device__ __forceinline__ void fir_down_compute(const uint4* tile, uint4 (&o)[2
       oh[j] = f2h2_sat(e0 * (1.f / 64.f), e1 * (1.f / 64.f));
     }
   }
+#endif
 }
 
 // Stage the 18 x 34 x 32-channel input patch of tile (ty, tx) of image b, channels c0..c0+31, zero outside the image.
