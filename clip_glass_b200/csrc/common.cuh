@@ -31,6 +31,53 @@ __device__ __forceinline__ __half2 f2h2_sat(float lo, float hi) {
   return *reinterpret_cast<__half2*>(&r);
 }
 
+// Packed fp32 pairs (sm_100: FFMA2 / FMUL2 / FADD2 — two IEEE fp32 operations per issued instruction, each lane
+// rounded exactly like the scalar instruction).  The epilogues of the 32/64-channel layers are bound by instruction
+// issue and per-warp latency, not by the FMA pipe: half the math instructions per element is what these buy.
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pk2(float lo, float hi) {
+  f32x2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void upk2(f32x2 v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+  f32x2 r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
+  f32x2 r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) {
+  f32x2 r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+// lrelu on a pair: max(t, 0.2 t) per lane (no packed max exists: FMUL2 + 2 FMNMX)
+__device__ __forceinline__ f32x2 lrelu2(f32x2 t) {
+  float a, b, c, d;
+  upk2(t, a, b);
+  upk2(mul2(t, pk2(0.2f, 0.2f)), c, d);
+  return pk2(fmaxf(a, c), fmaxf(b, d));
+}
+
+// Skip-path x2 upsample of one colour (stylegan2/modules.py:580-602 as polyphase weights) and the final
+// clip((y + 1) / 2, 0, 1) (utils.py:14-17).  Written with explicit roundings (the compiler may neither contract nor
+// split them), so that k_rgb_combine and the image-finishing conv epilogue produce the same bits by construction.
+__device__ __forceinline__ float skip_up2(float wy0, float wy1, float wx0, float wx1, float a, float c, float d, float e) {
+  const float top = __fmaf_rn(wx1, c, __fmul_rn(wx0, a));
+  const float bot = __fmaf_rn(wx1, e, __fmul_rn(wx0, d));
+  return __fmaf_rn(wy1, bot, __fmul_rn(wy0, top));
+}
+__device__ __forceinline__ float image_value(float y) {
+  return fminf(fmaxf(__fmul_rn(__fadd_rn(y, 1.f), 0.5f), 0.f), 1.f);
+}
+
 // ---------------------------------------------------------------------------
 // Implicit-GEMM convolution / GEMM description.
 //

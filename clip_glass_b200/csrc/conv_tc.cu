@@ -97,6 +97,15 @@ constexpr EpiSpec kEpiSpecs[] = {
     {false, false, false, false, kStRegular, true, kActLrelu},    // 13: D conv0 feeding the fused-FIR down-conv, I8 store
 };
 constexpr int kNumEpiSpecs = sizeof(kEpiSpecs) / sizeof(kEpiSpecs[0]);
+// Spec 3 (the last generator conv) may finish the image in its epilogue: the four skip-sum pixels a thread interpolates
+// are fetched with cp.async into per-thread shared-memory slots at the top of the tile (the kernel sits at its register
+// cap, and fetched at the point of use their L2/DRAM latency was exposed once per tile pair): 256 threads x 4 x 16 B.
+constexpr int kImgPrefetchBytes = 256 * 4 * 16;
+#ifdef GLASS_IMG_PREFETCH           // A/B builds only: measured slower (G16 2.44 -> 2.95 ms at P = 64)
+template <int EPI> struct EpiExtra { static constexpr int kBytes = (EPI == 3) ? kImgPrefetchBytes : 0; };
+#else
+template <int EPI> struct EpiExtra { static constexpr int kBytes = 0; };
+#endif
 
 // MODE 0 ("stream"): one pipeline stage per (filter tap, 64-channel chunk): A box + B box per stage.
 // MODE 1 ("halo"):   for layers whose whole K per tap is one chunk (Cin == BK in {32,64}): the filter taps of the
@@ -108,7 +117,8 @@ constexpr int kNumEpiSpecs = sizeof(kEpiSpecs) / sizeof(kEpiSpecs[0]);
 constexpr int kHaloTH = 8, kHaloTW = 16;
 
 
-template <int BN, int BK, int MODE>
+// kExtra: bytes of per-thread prefetch slots behind the barrier block (the last generator conv, kImgPrefetchBytes)
+template <int BN, int BK, int MODE, int kExtra = 0>
 struct Cfg {
   static constexpr int kABytes = kBlockM * BK * 2;
   static constexpr int kBBytes = BN * BK * 2;
@@ -159,14 +169,15 @@ struct Cfg {
   // the 32-channel MODE-1 layers are bookkeeping/latency-bound, not smem-bound: run two CTAs per SM there
   static constexpr int kMinBlocks = kSmallN ? GLASS_BN32_CTAS : (((MODE == 1 || MODE == 4) && BK == 32 && BN <= 32) ? 2 : 1);
   static constexpr int kBudget = (kMinBlocks == 4 ? 54 : (kMinBlocks == 3 ? 73 : (kMinBlocks == 2 ? 110 : 222))) * 1024 -
-                                 kParamBytes - kWBytes;   // of 227 KB/SM (+1 KB reserved per CTA)
+                                 kParamBytes - kWBytes - kExtra;   // of 227 KB/SM (+1 KB reserved per CTA)
   static constexpr int kStagesRaw = kBudget / kStageBytes;
   static constexpr int kStages = kStagesRaw > 12 ? 12 : kStagesRaw;
   static_assert(kStages >= 2, "not enough shared memory for a double-buffered pipeline");
   static constexpr int kAccCols = kPairM * BN;                     // TMEM columns of one accumulator stage
   static constexpr int kTmemCols = (2 * kAccCols < 32) ? 32 : 2 * kAccCols;   // power of two for BN in {32,..,256}
   static_assert(kTmemCols <= 512, "TMEM has 512 columns");
-  static constexpr int kSmemBytes = kWBytes + kStages * kStageBytes + kParamBytes + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int kSmemBytes =
+      kWBytes + kStages * kStageBytes + kParamBytes + 1024 /*align*/ + 256 /*barriers*/ + kExtra;
   // instruction descriptor: D=f32 [4,6)=1, A=B=f16 (0), K-major both, N>>3 [17,23), M>>4 [24,29)
   static constexpr uint32_t kIdesc = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(kBlockM >> 4) << 24);
 };
@@ -181,57 +192,84 @@ __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" 
 // NT = 2: the two tiles of a pair in one pass -- every parameter vector is read from shared memory ONCE for both
 // tiles.  (The broadcast LDS.128 of the staged parameters were 42 % of the shared-memory wavefronts of the 32-channel
 // 1024^2 layers, whose LSU data pipe ran at 89 %: profiles/.)
-template <int NT, bool kRgb, int kActT = -1>
+template <int NT, bool kRgb, int kActT = -1, bool kNz = true>
 __device__ __forceinline__ void epilogue_fastN(const EpiParams& e, const float* __restrict__ par, int BN, int j0,
                                                const uint32_t (*acc)[16], const float* nz, const __half* const* res_ptr,
                                                __half* const* out_ptr, size_t out_half_stride, float (*rgb)[3],
                                                const uint4* const* res_pre, size_t res_half_stride = 8) {
+  // All per-element math runs on packed fp32 pairs (common.cuh: FFMA2 / FMUL2 / FADD2): pair k of a tile holds
+  // columns 2k, 2k+1 of the chunk.  Each lane is rounded like the scalar instruction, so the values are those of the
+  // scalar form; only the toRGB dot product is summed in a different (even / odd column) order.
   const float4* sc = reinterpret_cast<const float4*>(par + 0 * BN + j0);
   const float4* sh = reinterpret_cast<const float4*>(par + 1 * BN + j0);
   const float4* os = reinterpret_cast<const float4*>(par + 2 * BN + j0);
-  float t[NT][16];
+  f32x2 t[NT][8];
+  f32x2 nz2[NT];
+#pragma unroll
+  for (int n = 0; n < NT; ++n) nz2[n] = pk2(nz[n], nz[n]);
 #pragma unroll
   for (int g = 0; g < 4; ++g) {
     const float4 a = sc[g], b = sh[g];
+    const f32x2 a01 = pk2(a.x, a.y), a23 = pk2(a.z, a.w), b01 = pk2(b.x, b.y), b23 = pk2(b.z, b.w);
 #pragma unroll
     for (int n = 0; n < NT; ++n) {
-      t[n][4 * g + 0] = fmaf(__uint_as_float(acc[n][4 * g + 0]), a.x, b.x + nz[n]);
-      t[n][4 * g + 1] = fmaf(__uint_as_float(acc[n][4 * g + 1]), a.y, b.y + nz[n]);
-      t[n][4 * g + 2] = fmaf(__uint_as_float(acc[n][4 * g + 2]), a.z, b.z + nz[n]);
-      t[n][4 * g + 3] = fmaf(__uint_as_float(acc[n][4 * g + 3]), a.w, b.w + nz[n]);
+      const f32x2 v01 = pk2(__uint_as_float(acc[n][4 * g + 0]), __uint_as_float(acc[n][4 * g + 1]));
+      const f32x2 v23 = pk2(__uint_as_float(acc[n][4 * g + 2]), __uint_as_float(acc[n][4 * g + 3]));
+      t[n][2 * g] = fma2(v01, a01, kNz ? add2(b01, nz2[n]) : b01);
+      t[n][2 * g + 1] = fma2(v23, a23, kNz ? add2(b23, nz2[n]) : b23);
     }
   }
 #pragma unroll
   for (int n = 0; n < NT; ++n) {
     if (kActT < 0 && e.round_fp16_before_act) {
 #pragma unroll
-      for (int j = 0; j < 16; ++j) t[n][j] = __half2float(__float2half_rn(t[n][j]));
+      for (int k = 0; k < 8; ++k) {
+        float lo, hi;
+        upk2(t[n][k], lo, hi);
+        t[n][k] = pk2(__half2float(__float2half_rn(lo)), __half2float(__float2half_rn(hi)));
+      }
     }
     if (kActT == kActLrelu || (kActT < 0 && e.act == kActLrelu)) {
 #pragma unroll
-      for (int j = 0; j < 16; ++j) t[n][j] = fmaxf(t[n][j], 0.2f * t[n][j]);
+      for (int k = 0; k < 8; ++k) t[n][k] = lrelu2(t[n][k]);
     } else if (kActT < 0 && e.act == kActQuickGelu) {
 #pragma unroll
-      for (int j = 0; j < 16; ++j) t[n][j] = t[n][j] / (1.f + __expf(-1.702f * t[n][j]));
+      for (int k = 0; k < 8; ++k) {
+        float lo, hi;
+        upk2(t[n][k], lo, hi);
+        t[n][k] = pk2(lo / (1.f + __expf(-1.702f * lo)), hi / (1.f + __expf(-1.702f * hi)));
+      }
     }
   }
   if (kRgb) {
     const float4* r0 = reinterpret_cast<const float4*>(par + 3 * BN + j0);
     const float4* r1 = reinterpret_cast<const float4*>(par + 4 * BN + j0);
     const float4* r2 = reinterpret_cast<const float4*>(par + 5 * BN + j0);
+    f32x2 s[NT][3];
+#pragma unroll
+    for (int n = 0; n < NT; ++n)
+#pragma unroll
+      for (int c = 0; c < 3; ++c) s[n][c] = pk2(rgb[n][c], 0.f);
 #pragma unroll
     for (int g = 0; g < 4; ++g) {
       const float4 a = r0[g], b = r1[g], c = r2[g];
+      const f32x2 a01 = pk2(a.x, a.y), a23 = pk2(a.z, a.w), b01 = pk2(b.x, b.y), b23 = pk2(b.z, b.w);
+      const f32x2 c01 = pk2(c.x, c.y), c23 = pk2(c.z, c.w);
 #pragma unroll
       for (int n = 0; n < NT; ++n) {
-        rgb[n][0] = fmaf(t[n][4 * g + 0], a.x, rgb[n][0]); rgb[n][0] = fmaf(t[n][4 * g + 1], a.y, rgb[n][0]);
-        rgb[n][0] = fmaf(t[n][4 * g + 2], a.z, rgb[n][0]); rgb[n][0] = fmaf(t[n][4 * g + 3], a.w, rgb[n][0]);
-        rgb[n][1] = fmaf(t[n][4 * g + 0], b.x, rgb[n][1]); rgb[n][1] = fmaf(t[n][4 * g + 1], b.y, rgb[n][1]);
-        rgb[n][1] = fmaf(t[n][4 * g + 2], b.z, rgb[n][1]); rgb[n][1] = fmaf(t[n][4 * g + 3], b.w, rgb[n][1]);
-        rgb[n][2] = fmaf(t[n][4 * g + 0], c.x, rgb[n][2]); rgb[n][2] = fmaf(t[n][4 * g + 1], c.y, rgb[n][2]);
-        rgb[n][2] = fmaf(t[n][4 * g + 2], c.z, rgb[n][2]); rgb[n][2] = fmaf(t[n][4 * g + 3], c.w, rgb[n][2]);
+        s[n][0] = fma2(t[n][2 * g], a01, s[n][0]); s[n][0] = fma2(t[n][2 * g + 1], a23, s[n][0]);
+        s[n][1] = fma2(t[n][2 * g], b01, s[n][1]); s[n][1] = fma2(t[n][2 * g + 1], b23, s[n][1]);
+        s[n][2] = fma2(t[n][2 * g], c01, s[n][2]); s[n][2] = fma2(t[n][2 * g + 1], c23, s[n][2]);
       }
     }
+#pragma unroll
+    for (int n = 0; n < NT; ++n)
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        float lo, hi;
+        upk2(s[n][c], lo, hi);
+        rgb[n][c] = lo + hi;
+      }
   }
 #pragma unroll
   for (int n = 0; n < NT; ++n) {
@@ -247,7 +285,8 @@ __device__ __forceinline__ void epilogue_fastN(const EpiParams& e, const float* 
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const float2 a = __half22float2(h0[j]), b = __half22float2(h1[j]);
-        t[n][2 * j] += a.x; t[n][2 * j + 1] += a.y; t[n][8 + 2 * j] += b.x; t[n][8 + 2 * j + 1] += b.y;
+        t[n][j] = add2(t[n][j], pk2(a.x, a.y));
+        t[n][4 + j] = add2(t[n][4 + j], pk2(b.x, b.y));
       }
     }
   }
@@ -255,9 +294,13 @@ __device__ __forceinline__ void epilogue_fastN(const EpiParams& e, const float* 
 #pragma unroll
   for (int n = 0; n < NT; ++n) any_out |= out_ptr[n] != nullptr;
   if (any_out) {
-    float4 osv[4];
+    f32x2 osv[8];
 #pragma unroll
-    for (int g = 0; g < 4; ++g) osv[g] = os[g];
+    for (int g = 0; g < 4; ++g) {
+      const float4 a = os[g];
+      osv[2 * g] = pk2(a.x, a.y);
+      osv[2 * g + 1] = pk2(a.z, a.w);
+    }
 #pragma unroll
     for (int n = 0; n < NT; ++n) {
       if (out_ptr[n] == nullptr) continue;
@@ -265,12 +308,12 @@ __device__ __forceinline__ void epilogue_fastN(const EpiParams& e, const float* 
       __half2* h0 = reinterpret_cast<__half2*>(&w0);
       __half2* h1 = reinterpret_cast<__half2*>(&w1);
 #pragma unroll
-      for (int g = 0; g < 2; ++g) {
-        const float4 a = osv[g], b = osv[g + 2];
-        h0[2 * g] = f2h2_sat(t[n][4 * g] * a.x, t[n][4 * g + 1] * a.y);
-        h0[2 * g + 1] = f2h2_sat(t[n][4 * g + 2] * a.z, t[n][4 * g + 3] * a.w);
-        h1[2 * g] = f2h2_sat(t[n][8 + 4 * g] * b.x, t[n][8 + 4 * g + 1] * b.y);
-        h1[2 * g + 1] = f2h2_sat(t[n][8 + 4 * g + 2] * b.z, t[n][8 + 4 * g + 3] * b.w);
+      for (int k = 0; k < 4; ++k) {
+        float lo, hi;
+        upk2(mul2(t[n][k], osv[k]), lo, hi);
+        h0[k] = f2h2_sat(lo, hi);
+        upk2(mul2(t[n][4 + k], osv[4 + k]), lo, hi);
+        h1[k] = f2h2_sat(lo, hi);
       }
       // channels [0,8) and [8,16) of the chunk: adjacent in NHWC, one channel-group plane apart in the I8 layout
       *reinterpret_cast<uint4*>(out_ptr[n]) = w0;
@@ -279,7 +322,7 @@ __device__ __forceinline__ void epilogue_fastN(const EpiParams& e, const float* 
   }
 }
 
-template <bool kRgb, int kActT = -1>
+template <bool kRgb, int kActT = -1, bool kNz = true>
 __device__ __forceinline__ void epilogue_fast16(const EpiParams& e, const float* __restrict__ par, int BN, int j0,
                                                 const uint32_t (&acc)[16], float nz, const __half* res_ptr,
                                                 __half* out_ptr, size_t out_half_stride, float (&rgb)[3],
@@ -288,14 +331,14 @@ __device__ __forceinline__ void epilogue_fast16(const EpiParams& e, const float*
   __half* op[1] = {out_ptr};
   const uint4* pre[1] = {res_pre};
   const float nzv[1] = {nz};
-  epilogue_fastN<1, kRgb, kActT>(e, par, BN, j0, &acc, nzv, rp, op, out_half_stride, &rgb, pre, res_half_stride);
+  epilogue_fastN<1, kRgb, kActT, kNz>(e, par, BN, j0, &acc, nzv, rp, op, out_half_stride, &rgb, pre, res_half_stride);
 }
 
 template <int BN, int BK, int MODE, int EPI>
-__global__ void __launch_bounds__((Cfg<BN, BK, MODE>::kThreads), (Cfg<BN, BK, MODE>::kMinBlocks))
+__global__ void __launch_bounds__((Cfg<BN, BK, MODE>::kThreads), (Cfg<BN, BK, MODE>::kMinBlocks))   // (kExtra-independent)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                const ConvParams p) {
-  using C = Cfg<BN, BK, MODE>;
+  using C = Cfg<BN, BK, MODE, EpiExtra<EPI>::kBytes>;
   constexpr EpiSpec S = kEpiSpecs[EPI];
   constexpr bool kPow2 = !S.generic;        // specialised layers have power-of-two tile grids and channel counts
   extern __shared__ uint8_t smem_raw[];
@@ -315,6 +358,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(b_empty + C::kBStages);
   static_assert((2 * C::kStages + 5 + 2 * C::kBStages) * 8 + 8 <= 256, "barrier block overflows its 256 bytes");
   float* nscale_slot = reinterpret_cast<float*>(tmem_slot + 1);
+  constexpr bool kImgPrefetch = EpiExtra<EPI>::kBytes > 0 && C::kPairM == 2 && C::kParts == 2;
+  const uint32_t img_slots = smem_u32(bars) + 256;       // [4 values][256 epilogue threads] x 16 B (kImgPrefetch)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -662,6 +707,18 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       const int n_tile = tc.n_tile, tn = tc.tn;
       const int img = tn * p.TN + ri, y = tc.ty * p.TH + ry, x = tc.tx * p.TW + rx;
       const bool valid = all_valid || (img < p.Nimg && y < H && x < W);
+      if (kImgPrefetch && e.image != nullptr) {
+        // skip-sum pixels (zy-1..zy, zx-1..zx) of the output pixel this thread finishes (tile `half` of the pair);
+        // outside the image: zero-filled (src-size 0, the pointer stays inside the tensor)
+        const int X = x + 8 * half, Wp = W >> 1, zy = y >> 1, zx = X >> 1;
+        const float4* base = e.img_yprev + ((img * (H >> 1) + zy) * Wp + zx);
+        const uint32_t dst = img_slots + et * 16;
+        cp_async16_zfill(dst, (zy > 0 && zx > 0) ? base - Wp - 1 : base, (zy > 0 && zx > 0) ? 16 : 0);
+        cp_async16_zfill(dst + 4096, zy > 0 ? base - Wp : base, zy > 0 ? 16 : 0);
+        cp_async16_zfill(dst + 8192, zx > 0 ? base - 1 : base, zx > 0 ? 16 : 0);
+        cp_async16_zfill(dst + 12288, base, 16);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+      }
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + as * C::kAccCols + half * kHalf;
@@ -796,6 +853,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           return nullptr;
         };
         constexpr int kActT = S.generic ? -1 : S.act;
+        constexpr bool kNz = S.generic || S.noise;      // specialised layers without noise: no per-element add
         // specialised pair layers: both tiles of the pair per chunk, parameters read once (epilogue_fastN<2>)
         constexpr bool kPairFused = (kPairM == 2) && !S.generic;
         if constexpr (kPairFused) {
@@ -821,8 +879,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 rptr[h] = !kResPre ? res_addr(h, c) : nullptr;
                 rpre[h] = kResPre ? resv[kResPre ? h : 0][kResPre ? c : 0] : nullptr;
               }
-              if (has_rgb) epilogue_fastN<2, true, kActT>(e, par, BN, j0, accp[c & 1], nzc, rptr, optr, half_stride, rgb, rpre, res_stride);
-              else epilogue_fastN<2, false, kActT>(e, par, BN, j0, accp[c & 1], nzc, rptr, optr, half_stride, rgb, rpre, res_stride);
+              if (has_rgb) epilogue_fastN<2, true, kActT, kNz>(e, par, BN, j0, accp[c & 1], nzc, rptr, optr, half_stride, rgb, rpre, res_stride);
+              else epilogue_fastN<2, false, kActT, kNz>(e, par, BN, j0, accp[c & 1], nzc, rptr, optr, half_stride, rgb, rpre, res_stride);
             }
           }
         } else {
@@ -846,8 +904,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
               __half* optr = out_addr(h, c, half_stride);
               const __half* rptr = !kResPre ? res_addr(h, c) : nullptr;
               const uint4* rpre = kResPre ? resv[kResPre ? h : 0][kResPre ? c : 0] : nullptr;
-              if (has_rgb) epilogue_fast16<true, kActT>(e, par, BN, j0, acc[ci & 1], nzc, rptr, optr, half_stride, rgb[h], rpre, res_stride);
-              else epilogue_fast16<false, kActT>(e, par, BN, j0, acc[ci & 1], nzc, rptr, optr, half_stride, rgb[h], rpre, res_stride);
+              if (has_rgb) epilogue_fast16<true, kActT, kNz>(e, par, BN, j0, acc[ci & 1], nzc, rptr, optr, half_stride, rgb[h], rpre, res_stride);
+              else epilogue_fast16<false, kActT, kNz>(e, par, BN, j0, acc[ci & 1], nzc, rptr, optr, half_stride, rgb[h], rpre, res_stride);
             }
           }
         }
@@ -864,55 +922,82 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         }
       }
       if (has_rgb) {
-        // The warps of a lane quarter own different column parts of the same rows: the non-leading parts stage
-        // their partial toRGB sums in shared memory and the leading part of each sum group adds them, so that one
-        // float4 per pixel goes to HBM.  (Pixel-pair rows: two sum groups, one per pixel.)
-        const int lead = (half / parts_per_sum) * parts_per_sum;
+        // The warps of a lane quarter own different column parts of the same rows: the partial toRGB sums meet in
+        // shared memory so that one float4 per pixel goes to HBM.  (Pixel-pair rows: two sum groups, one per pixel.)
         float4* stg = rgb_stage + (it & 1) * ((kParts - 1) * kPairM * 128);
-        if (parts_per_sum > 1) {
-          if (half != lead) {
-#pragma unroll
-            for (int h = 0; h < kPairM; ++h)
-              stg[((half - 1) * kPairM + h) * 128 + row] = make_float4(rgb[h][0], rgb[h][1], rgb[h][2], 0.f);
-          }
-          asm volatile("bar.sync %0, %1;" ::"r"(2 + q), "n"(32 * kParts) : "memory");
-        }
-        if (half == lead && valid) {
-#pragma unroll
-          for (int h = 0; h < kPairM; ++h) {
-            float r0 = rgb[h][0], r1 = rgb[h][1], r2 = rgb[h][2];
-            for (int o = 1; o < parts_per_sum; ++o) {
-              const float4 t = stg[((lead + o - 1) * kPairM + h) * 128 + row];
-              r0 += t.x; r1 += t.y; r2 += t.z;
-            }
-            if (paired) {
-              const size_t pix2 = ((size_t)img * H + y) * (2 * W) + 2 * x + ppx;
-              e.rgb_out[pix2] = make_float4(r0, r1, r2, 0.f);
-            } else if (e.image != nullptr) {
-              // final image: y = up2(yprev) + toRGB + bias (modules.py:580-602 polyphase, models.py:1004-1013), then
-              // clip((y + 1) / 2, 0, 1) (utils.py:14-17) -- the arithmetic of rgb_combine_kernel
-              const int X = x + 8 * h, Y = y;
-              const int Hp = H >> 1, Wp = W >> 1, zy = Y >> 1, zx = X >> 1;
-              const float wy0 = (Y & 1) ? 0.25f : 0.75f, wy1 = 1.f - wy0;
-              const float wx0 = (X & 1) ? 0.25f : 0.75f, wx1 = 1.f - wx0;
-              const float4* base = e.img_yprev + (size_t)img * Hp * Wp;
-              float4 a = make_float4(0, 0, 0, 0), c = a, d = a;
-              const float4 ee = __ldg(base + (size_t)zy * Wp + zx);
-              if (zy > 0 && zx > 0) a = __ldg(base + (size_t)(zy - 1) * Wp + zx - 1);
-              if (zy > 0) c = __ldg(base + (size_t)(zy - 1) * Wp + zx);
-              if (zx > 0) d = __ldg(base + (size_t)zy * Wp + zx - 1);
-              float r = __ldg(e.img_bias) + r0, g = __ldg(e.img_bias + 1) + r1, bl = __ldg(e.img_bias + 2) + r2;
-              r += wy0 * (wx0 * a.x + wx1 * c.x) + wy1 * (wx0 * d.x + wx1 * ee.x);
-              g += wy0 * (wx0 * a.y + wx1 * c.y) + wy1 * (wx0 * d.y + wx1 * ee.y);
-              bl += wy0 * (wx0 * a.z + wx1 * c.z) + wy1 * (wx0 * d.z + wx1 * ee.z);
-              const size_t plane = (size_t)H * W;
-              float* ip = e.image + (size_t)img * 3 * plane + (size_t)Y * W + X;
-              ip[0] = fminf(fmaxf((r + 1.f) * 0.5f, 0.f), 1.f);
-              ip[plane] = fminf(fmaxf((g + 1.f) * 0.5f, 0.f), 1.f);
-              ip[2 * plane] = fminf(fmaxf((bl + 1.f) * 0.5f, 0.f), 1.f);
+        // finish pixel (tile h of the pair) with its complete toRGB sum
+        auto finish_pixel = [&](int h, float r0, float r1, float r2) {
+          if (paired) {
+            const size_t pix2 = ((size_t)img * H + y) * (2 * W) + 2 * x + ppx;
+            e.rgb_out[pix2] = make_float4(r0, r1, r2, 0.f);
+          } else if (e.image != nullptr) {
+            // final image: y = up2(yprev) + toRGB + bias (modules.py:580-602 polyphase, models.py:1004-1013), then
+            // clip((y + 1) / 2, 0, 1) (utils.py:14-17) -- the arithmetic of rgb_combine_kernel
+            const int X = x + 8 * h, Y = y;
+            const int Wp = W >> 1, zy = Y >> 1, zx = X >> 1;
+            const float wy0 = (Y & 1) ? 0.25f : 0.75f, wy1 = 1.f - wy0;
+            const float wx0 = (X & 1) ? 0.25f : 0.75f, wx1 = 1.f - wx0;
+            float4 a = make_float4(0, 0, 0, 0), c = a, d = a, ee;
+            if (kImgPrefetch) {
+              // fetched by this thread at the top of the tile (cp.async above)
+              asm volatile("cp.async.wait_group 0;" ::: "memory");
+              const uint32_t src = img_slots + et * 16;
+              a = lds128f(src); c = lds128f(src + 4096); d = lds128f(src + 8192); ee = lds128f(src + 12288);
             } else {
-              const size_t pix = ((size_t)img * H + y) * W + x + 8 * h;
-              e.rgb_out[(size_t)n_tile * p.Nimg * H * W + pix] = make_float4(r0, r1, r2, 0.f);
+              const float4* base = e.img_yprev + ((img * (H >> 1) + zy) * Wp + zx);    // (pixel counts stay < 2^31)
+              ee = __ldg(base);
+              if (zy > 0 && zx > 0) a = __ldg(base - Wp - 1);
+              if (zy > 0) c = __ldg(base - Wp);
+              if (zx > 0) d = __ldg(base - 1);
+            }
+            const float r = __fadd_rn(__fadd_rn(__ldg(e.img_bias), r0), skip_up2(wy0, wy1, wx0, wx1, a.x, c.x, d.x, ee.x));
+            const float g = __fadd_rn(__fadd_rn(__ldg(e.img_bias + 1), r1), skip_up2(wy0, wy1, wx0, wx1, a.y, c.y, d.y, ee.y));
+            const float bl = __fadd_rn(__fadd_rn(__ldg(e.img_bias + 2), r2), skip_up2(wy0, wy1, wx0, wx1, a.z, c.z, d.z, ee.z));
+            const size_t plane = (size_t)H * W;
+            float* ip = e.image + (size_t)img * 3 * plane + (size_t)(Y * W + X);
+            ip[0] = image_value(r);
+            ip[plane] = image_value(g);
+            ip[2 * plane] = image_value(bl);
+          } else {
+            const size_t pix = ((size_t)img * H + y) * W + x + 8 * h;
+            e.rgb_out[(size_t)n_tile * p.Nimg * H * W + pix] = make_float4(r0, r1, r2, 0.f);
+          }
+        };
+        // Tile pairs with two column parts: part k finishes tile k of the pair (it hands its partial sums of the
+        // other tile over and takes the other part's sums of its own), so both warps of a lane quarter carry the
+        // same load.  With all pixels finished by the leading part, the other warp idled through the ~140
+        // instructions per pixel of the final-image arithmetic of the last generator conv.
+        constexpr bool kSplitFinish = (kPairM == 2 && kParts == 2);
+        if (kSplitFinish && !paired) {
+          const int other = half ^ 1;
+          stg[half * 128 + row] = half ? make_float4(rgb[0][0], rgb[0][1], rgb[0][2], 0.f)
+                                       : make_float4(rgb[kPairM - 1][0], rgb[kPairM - 1][1], rgb[kPairM - 1][2], 0.f);
+          asm volatile("bar.sync %0, %1;" ::"r"(2 + q), "n"(32 * kParts) : "memory");
+          if (valid) {
+            const float4 t = stg[other * 128 + row];
+            const float m0 = half ? rgb[kPairM - 1][0] : rgb[0][0], m1 = half ? rgb[kPairM - 1][1] : rgb[0][1];
+            const float m2 = half ? rgb[kPairM - 1][2] : rgb[0][2];
+            finish_pixel(half, m0 + t.x, m1 + t.y, m2 + t.z);
+          }
+        } else {
+          const int lead = (half / parts_per_sum) * parts_per_sum;
+          if (parts_per_sum > 1) {
+            if (half != lead) {
+#pragma unroll
+              for (int h = 0; h < kPairM; ++h)
+                stg[((half - 1) * kPairM + h) * 128 + row] = make_float4(rgb[h][0], rgb[h][1], rgb[h][2], 0.f);
+            }
+            asm volatile("bar.sync %0, %1;" ::"r"(2 + q), "n"(32 * kParts) : "memory");
+          }
+          if (half == lead && valid) {
+#pragma unroll
+            for (int h = 0; h < kPairM; ++h) {
+              float r0 = rgb[h][0], r1 = rgb[h][1], r2 = rgb[h][2];
+              for (int o = 1; o < parts_per_sum; ++o) {
+                const float4 t = stg[((lead + o - 1) * kPairM + h) * 128 + row];
+                r0 += t.x; r1 += t.y; r2 += t.z;
+              }
+              finish_pixel(h, r0, r1, r2);
             }
           }
         }
@@ -934,7 +1019,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 
 template <int BN, int BK, int MODE, int EPI = 0>
 cudaError_t launch_one(const ConvParams& p, const TmaMaps& maps, int num_sms, cudaStream_t s) {
-  using C = Cfg<BN, BK, MODE>;
+  using C = Cfg<BN, BK, MODE, EpiExtra<EPI>::kBytes>;
   static bool configured = false;
   if (!configured) {
     cudaError_t err = cudaFuncSetAttribute(conv_tc_kernel<BN, BK, MODE, EPI>,

@@ -24,12 +24,7 @@ namespace {
 
 constexpr int kDcTW = 8, kDcTH = 16;                    // output tile (z space)
 constexpr int kDcRawRows = 2 * kDcTH + 4, kDcRawCols = 2 * kDcTW + 4;     // 36 x 20 raw pixels
-constexpr int kDcG = 4;                                 // 8-channel groups per pass (32 channels)
-constexpr int kDcRawBytes = kDcRawRows * kDcG * kDcRawCols * 16;          // 46080
 constexpr int kDcLbo = 9 * 16;                          // plane: next 8-channel group (9 columns of 16 B)
-constexpr int kDcSbo = kDcG * kDcLbo;                   // plane: next row (= next 8-pixel group of the tile)
-constexpr int kDcPlaneBytes = (kDcTH + 1) * kDcSbo;     // 17 rows
-constexpr int kDcBlurBytes = 4 * kDcPlaneBytes;         // 39168
 constexpr int kDcThreads = 64 + 256 + 256;
 
 struct DownParams {
@@ -45,12 +40,22 @@ struct DownParams {
 
 template <int C, int BN>
 struct DCfg {
-  static constexpr int kPasses = C / 32;
+  // 8-channel groups per pass.  BN = 64: 32-channel passes.  BN = 128 (the 64 -> 128 block): all 128 output columns of a
+  // pixel tile come from ONE blur of that tile (with 64-column n-tiles every tile was loaded and blurred once per
+  // n-tile: 2.5 ms, the slowest launch of the step); the nine 128-column taps take 147 KB of shared memory, so the
+  // raw / blurred tiles shrink to 16-channel passes (one K = 16 MMA step per tap and pass).
+  static constexpr int kG = (BN == 128) ? 2 : 4;
+  static constexpr int kPasses = C / (8 * kG);
+  static constexpr int kStepsPerPass = kG / 2;             // K = 16 MMA steps per tap and pass
+  static constexpr int kRawBytes = kDcRawRows * kG * kDcRawCols * 16;      // 46080 / 23040
+  static constexpr int kSbo = kG * kDcLbo;                 // plane: next row (= next 8-pixel group of the tile)
+  static constexpr int kPlaneBytes = (kDcTH + 1) * kSbo;   // 17 rows
+  static constexpr int kBlurBytes = 4 * kPlaneBytes;       // 39168 / 19584
   static constexpr int kRawStages = 2;
   static constexpr int kBlurStages = (C == 32) ? 2 : 1;
   static constexpr int kWBytes = 9 * BN * C * 2;
   static constexpr int kTapBytes = BN * C * 2;
-  static constexpr int kSmemBytes = kWBytes + kRawStages * kDcRawBytes + kBlurStages * kDcBlurBytes + 1024 + 256 + BN * 4;
+  static constexpr int kSmemBytes = kWBytes + kRawStages * kRawBytes + kBlurStages * kBlurBytes + 1024 + 256 + BN * 4;
   static constexpr int kTmemCols = 2 * BN < 32 ? 32 : 2 * BN;
   static constexpr uint32_t kIdesc = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
   static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
@@ -125,8 +130,8 @@ downconv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem_w = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* raw = smem_w + Cf::kWBytes;
-  uint8_t* blur = raw + Cf::kRawStages * kDcRawBytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(blur + Cf::kBlurStages * kDcBlurBytes);
+  uint8_t* blur = raw + Cf::kRawStages * Cf::kRawBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(blur + Cf::kBlurStages * Cf::kBlurBytes);
   uint64_t* raw_full = bars;
   uint64_t* raw_empty = raw_full + 2;
   uint64_t* blur_full = raw_empty + 2;
@@ -188,9 +193,9 @@ downconv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
         decode(tile, img, ty, tx);
         for (int h = 0; h < Cf::kPasses; ++h) {
           mbar_wait_backoff(&raw_empty[stage], phase ^ 1);
-          mbar_expect_tx(&raw_full[stage], kDcRawBytes);
-          // (elements, group, row, image): raw columns 2*x0-2 .. +19, groups 4h .. 4h+3, rows 2*y0-2 .. +35
-          tma_load_4d(&map_a, raw + stage * kDcRawBytes, &raw_full[stage], (2 * tx * kDcTW - 2) * 8, h * kDcG,
+          mbar_expect_tx(&raw_full[stage], Cf::kRawBytes);
+          // (elements, group, row, image): raw columns 2*x0-2 .. +19, groups kG*h .. +kG-1, rows 2*y0-2 .. +35
+          tma_load_4d(&map_a, raw + stage * Cf::kRawBytes, &raw_full[stage], (2 * tx * kDcTW - 2) * 8, h * Cf::kG,
                       2 * ty * kDcTH - 2, img);
           if (++stage == Cf::kRawStages) { stage = 0; phase ^= 1; }
         }
@@ -212,16 +217,18 @@ downconv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
         for (int h = 0; h < Cf::kPasses; ++h) {
           mbar_wait_backoff(&blur_full[bstage], bphase);
           tc_fence_after();
-          const uint32_t sb = smem_u32(blur + bstage * kDcBlurBytes);
+          const uint32_t sb = smem_u32(blur + bstage * Cf::kBlurBytes);
 #pragma unroll
           for (int tap = 0; tap < 9; ++tap) {
             const int ky = tap / 3, kx = tap - ky * 3;
-            const uint32_t a_addr = sb + ((ky & 1) * 2 + (kx & 1)) * kDcPlaneBytes + (ky >> 1) * kDcSbo + (kx >> 1) * 16;
+            const uint32_t a_addr =
+                sb + ((ky & 1) * 2 + (kx & 1)) * Cf::kPlaneBytes + (ky >> 1) * Cf::kSbo + (kx >> 1) * 16;
             const uint64_t db = make_smem_desc<(C > 64 ? 64 : C)>(sw + tap * Cf::kTapBytes);
 #pragma unroll
-            for (int k = 0; k < 2; ++k) {               // 32 channels of this pass = two K=16 steps
-              const uint64_t da = make_smem_desc_noswz(a_addr + k * 2 * kDcLbo, kDcLbo, kDcSbo);
-              tc_mma_f16(d_tmem, da, db + (uint64_t)((h * 2 + k) * 2), Cf::kIdesc, (uint32_t)(h | tap | k));
+            for (int k = 0; k < Cf::kStepsPerPass; ++k) {       // the channels of this pass in K = 16 steps
+              const uint64_t da = make_smem_desc_noswz(a_addr + k * 2 * kDcLbo, kDcLbo, Cf::kSbo);
+              tc_mma_f16(d_tmem, da, db + (uint64_t)((h * Cf::kStepsPerPass + k) * 2), Cf::kIdesc,
+                         (uint32_t)(h | tap | k));
             }
           }
           tc_commit(&blur_empty[bstage]);
@@ -329,18 +336,18 @@ downconv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
         }
         asm volatile("bar.sync 2, 256;" ::: "memory");
         if (active) {
-          const uint4* rt = reinterpret_cast<const uint4*>(raw + stage * kDcRawBytes);
-          uint8_t* bt_base = blur + bstage * kDcBlurBytes + ((j & 1) * kDcPlaneBytes) + g * kDcLbo + (j >> 1) * 16;
+          const uint4* rt = reinterpret_cast<const uint4*>(raw + stage * Cf::kRawBytes);
+          uint8_t* bt_base = blur + bstage * Cf::kBlurBytes + ((j & 1) * Cf::kPlaneBytes) + g * kDcLbo + (j >> 1) * 16;
           uint4 hw[4];                                    // horizontal results of the last four raw rows
 #pragma unroll
           for (int r = 0; r < 14; ++r) {
-            const uint4* rp = rt + ((i0 + r) * kDcG + g) * kDcRawCols + j;
+            const uint4* rp = rt + ((i0 + r) * Cf::kG + g) * kDcRawCols + j;
             const uint4 cur = fir4<false>(rp[0], rp[1], rp[2], rp[3]);
             hw[r & 3] = cur;
             if (r >= 3) {
               const int i = i0 + r - 3;                   // blurred row completed by raw row i + 3
               const uint4 u = fir4<true>(hw[(r - 3) & 3], hw[(r - 2) & 3], hw[(r - 1) & 3], cur);
-              *reinterpret_cast<uint4*>(bt_base + (i & 1) * 2 * kDcPlaneBytes + (i >> 1) * kDcSbo) = u;
+              *reinterpret_cast<uint4*>(bt_base + (i & 1) * 2 * Cf::kPlaneBytes + (i >> 1) * Cf::kSbo) = u;
             }
           }
         }
@@ -357,52 +364,63 @@ downconv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
   } else {
     // ===================== workers: 16 warps, each blurs AND runs its share of the epilogue =====================
     // With dedicated blur / epilogue warps the blur stage paces the kernel while the epilogue warps sit blocked most
-    // of the time (issue slots 45 % busy).  Here every worker warp blurs its part of tile t, then finishes tile t-1
-    // (whose MMAs ran meanwhile): all 16 warps have work all the time.
-    //   blur unit = (column j of 17, 4-channel half-group of 8, row strip of 3): 408 of 512 threads, LDS.64 / STS.64;
-    //     lanes 2k, 2k+1 take the two halves of one pixel's 16 bytes, consecutive lane pairs consecutive columns:
-    //     the 16 lanes of an LDS.64 phase read 128 contiguous bytes (conflict-free), and so do the stores.
-    //   epilogue unit = (TMEM lane quarter = warp & 3, 16-column chunk = (warp - 2) >> 2).
+    // of the time (issue slots 45 % busy).  Here every worker warp blurs its part of a pass of tile t and, while the
+    // MMAs of that pass run, finishes one 16-column chunk of tile t-1: all 16 warps have work all the time.
+    //   blur unit = (column j of 17, 4-channel half-group of 2 kG, row strip): 408 (kG = 4: 3 strips of 11 rows) or 476
+    //     (kG = 2: 7 strips of 5 rows) of 512 threads, LDS.64 / STS.64; lanes 2k, 2k+1 take the two halves of one
+    //     pixel's 16 bytes, consecutive lane pairs consecutive columns: the 16 lanes of an LDS.64 phase read 128
+    //     contiguous bytes (conflict-free), and so do the stores.
+    //   epilogue unit = (TMEM lane quarter = warp & 3, BN / 4 columns = kCW chunks of 16 starting at ((warp - 2) >> 2)).
     // Waiting: ONE warp polls each mbarrier (a poll loop costs issue slots), the others block on a named barrier.
+    constexpr int kG = Cf::kG;
+    constexpr int kStrips = 512 / (34 * kG);                 // 3 / 7
+    constexpr int kStripRows = (2 * kDcTH + 1 + kStrips - 1) / kStrips;      // 11 / 5 blurred rows per strip
+    constexpr int kCW = BN / 64;                             // 16-column chunks per worker warp
+    static_assert(BN == 64 || BN == 128, "16 worker warps = 4 lane quarters x 4 column parts");
+    static_assert(Cf::kPasses >= kCW, "one epilogue chunk of the previous tile per pass of the current one");
     const int wt = threadIdx.x - 64;                       // 0 .. 511
-    const int hlow = wt & 1, j = (wt >> 1) % 17, g = ((wt >> 1) / 17) & 3, strip = (wt >> 1) / 68;
-    const bool active = strip < 3;
-    const int i0 = 11 * strip;
-    const int q = warp & 3, chunk = (warp - 2) >> 2;
-    static_assert(BN == 64, "16 worker warps = 4 lane quarters x 4 chunks of 16 columns");
+    const int hlow = wt & 1, j = (wt >> 1) % 17, g = ((wt >> 1) / 17) % kG, strip = (wt >> 1) / (17 * kG);
+    const bool active = strip < kStrips;
+    const int i0 = kStripRows * strip;
+    const int q = warp & 3, part = (warp - 2) >> 2;
     const int row = q * 32 + lane;
     const int ry = row >> 3, rx = row & 7;
     const float s1 = kSqrt2 * p.post_scale;                  // (lrelu(a*sqrt2) + r) * ps == lrelu(a*sqrt2*ps) + r*ps
     if (wt < BN) bias_s[wt] = __ldg(p.bias + n_tile * BN + wt) * s1;
     asm volatile("bar.sync 1, 512;" ::: "memory");
-    const int nc = n_tile * BN + chunk * 16;
+    const int nc0 = n_tile * BN + part * 16 * kCW;           // first output column of this warp
 
-    auto res_ptr = [&](int img, int y, int x) -> const __half* {
+    auto res_ptr = [&](int img, int y, int x, int nc) -> const __half* {
       if (p.res_i8) return p.residual + ((((size_t)img * p.Ho + y) * (p.Cout >> 3) + (nc >> 3)) * p.Wo + x) * 8;
       return p.residual + (((size_t)img * p.Ho + y) * p.Wo + x) * p.Cout + nc;
     };
-    auto epilogue = [&](int img, int ty, int tx, int it, const uint4& q0, const uint4& q1) {
+    // chunk c of the previous tile of this CTA (it = its iteration index): TMEM -> bias, lrelu, + residual -> store
+    auto epilogue = [&](int img, int ty, int tx, int it, int c, const uint4& q0, const uint4& q1) {
       const int as = it & 1;
       const int y = ty * kDcTH + ry, x = tx * kDcTW + rx;
-      if (warp == 2) mbar_wait_backoff(&tmem_full[as], (it >> 1) & 1);
-      asm volatile("bar.sync 1, 512;" ::: "memory");
-      tc_fence_after();
+      const int nc = nc0 + c * 16;
+      if (c == 0) {
+        if (warp == 2) mbar_wait_backoff(&tmem_full[as], (it >> 1) & 1);
+        asm volatile("bar.sync 1, 512;" ::: "memory");
+        tc_fence_after();
+      }
       float v[16];
-      tc_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + as * BN + chunk * 16, v);
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty[as]);           // the accumulator is in registers: the MMAs may go on
+      tc_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + as * BN + part * 16 * kCW + c * 16, v);
+      if (c == kCW - 1) {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tmem_empty[as]);         // the accumulator is in registers: the MMAs may go on
+      }
       const __half2* r0 = reinterpret_cast<const __half2*>(&q0);
       const __half2* r1 = reinterpret_cast<const __half2*>(&q1);
-      const float4* bs = reinterpret_cast<const float4*>(bias_s + chunk * 16);
-      float t[16];
+      const float4* bs = reinterpret_cast<const float4*>(bias_s + part * 16 * kCW + c * 16);
+      const f32x2 s2 = pk2(s1, s1), ps2 = pk2(p.post_scale, p.post_scale);
+      f32x2 t[8];
 #pragma unroll
       for (int g4 = 0; g4 < 4; ++g4) {
         const float4 b = bs[g4];
-        const float a0 = fmaf(v[4 * g4], s1, b.x), a1 = fmaf(v[4 * g4 + 1], s1, b.y);
-        const float a2 = fmaf(v[4 * g4 + 2], s1, b.z), a3 = fmaf(v[4 * g4 + 3], s1, b.w);
-        t[4 * g4] = fmaxf(a0, 0.2f * a0); t[4 * g4 + 1] = fmaxf(a1, 0.2f * a1);
-        t[4 * g4 + 2] = fmaxf(a2, 0.2f * a2); t[4 * g4 + 3] = fmaxf(a3, 0.2f * a3);
+        t[2 * g4] = lrelu2(fma2(pk2(v[4 * g4], v[4 * g4 + 1]), s2, pk2(b.x, b.y)));
+        t[2 * g4 + 1] = lrelu2(fma2(pk2(v[4 * g4 + 2], v[4 * g4 + 3]), s2, pk2(b.z, b.w)));
       }
       uint4 w0, w1;
       __half2* h0 = reinterpret_cast<__half2*>(&w0);
@@ -410,8 +428,11 @@ downconv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         const float2 a = __half22float2(r0[k]), b = __half22float2(r1[k]);
-        h0[k] = f2h2_sat(fmaf(a.x, p.post_scale, t[2 * k]), fmaf(a.y, p.post_scale, t[2 * k + 1]));
-        h1[k] = f2h2_sat(fmaf(b.x, p.post_scale, t[8 + 2 * k]), fmaf(b.y, p.post_scale, t[8 + 2 * k + 1]));
+        float lo, hi;
+        upk2(fma2(pk2(a.x, a.y), ps2, t[k]), lo, hi);
+        h0[k] = f2h2_sat(lo, hi);
+        upk2(fma2(pk2(b.x, b.y), ps2, t[4 + k]), lo, hi);
+        h1[k] = f2h2_sat(lo, hi);
       }
       if (p.out_i8) {
         __half* op = p.out + ((((size_t)img * p.Ho + y) * (p.Cout >> 3) + (nc >> 3)) * p.Wo + x) * 8;
@@ -427,14 +448,13 @@ downconv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
     int stage = 0, bstage = 0, it = 0;
     uint32_t phase = 0, bphase = 0;
     int pimg = 0, pty = 0, ptx = 0;                          // the previous tile of this CTA (epilogue pending)
-    uint4 pq0 = make_uint4(0, 0, 0, 0), pq1 = pq0;           // its residual operand, fetched one tile ahead
+    uint4 pq[kCW][2];                                        // its residual operand, fetched during the tile before
+#pragma unroll
+    for (int c = 0; c < kCW; ++c) pq[c][0] = pq[c][1] = make_uint4(0, 0, 0, 0);
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
       int img, ty, tx;
       decode(tile, img, ty, tx);
-      // residual of THIS tile: in flight while the tile is blurred and its MMAs run
-      const __half* rp = res_ptr(img, ty * kDcTH + ry, tx * kDcTW + rx);
-      const uint4 q0 = __ldg(reinterpret_cast<const uint4*>(rp));
-      const uint4 q1 = __ldg(reinterpret_cast<const uint4*>(rp + (p.res_i8 ? (size_t)p.Wo * 8 : 8)));
+#pragma unroll
       for (int h = 0; h < Cf::kPasses; ++h) {
         if (warp == 2) {
           mbar_wait_backoff(&raw_full[stage], phase);
@@ -442,18 +462,20 @@ downconv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
         }
         asm volatile("bar.sync 1, 512;" ::: "memory");
         if (active) {
-          const uint2* rt = reinterpret_cast<const uint2*>(raw + stage * kDcRawBytes) + hlow;
-          uint8_t* bt_base = blur + bstage * kDcBlurBytes + ((j & 1) * kDcPlaneBytes) + g * kDcLbo + (j >> 1) * 16 + hlow * 8;
+          const uint2* rt = reinterpret_cast<const uint2*>(raw + stage * Cf::kRawBytes) + hlow;
+          uint8_t* bt_base =
+              blur + bstage * Cf::kBlurBytes + ((j & 1) * Cf::kPlaneBytes) + g * kDcLbo + (j >> 1) * 16 + hlow * 8;
           uint2 hw[4];                                     // horizontal results of the last four raw rows
 #pragma unroll
-          for (int r = 0; r < 14; ++r) {
-            const uint2* rr = rt + (((i0 + r) * kDcG + g) * kDcRawCols + j) * 2;
+          for (int r = 0; r < kStripRows + 3; ++r) {
+            const int i = i0 + r - 3;                      // blurred row completed by raw row i + 3
+            if (r >= 3 && i > 2 * kDcTH) break;            // (the last strip is shorter: 33 blurred rows)
+            const uint2* rr = rt + (((i0 + r) * kG + g) * kDcRawCols + j) * 2;
             const uint2 cur = fir4h<false>(rr[0], rr[2], rr[4], rr[6]);
             hw[r & 3] = cur;
             if (r >= 3) {
-              const int i = i0 + r - 3;                    // blurred row completed by raw row i + 3
               const uint2 u = fir4h<true>(hw[(r - 3) & 3], hw[(r - 2) & 3], hw[(r - 1) & 3], cur);
-              *reinterpret_cast<uint2*>(bt_base + (i & 1) * 2 * kDcPlaneBytes + (i >> 1) * kDcSbo) = u;
+              *reinterpret_cast<uint2*>(bt_base + (i & 1) * 2 * Cf::kPlaneBytes + (i >> 1) * Cf::kSbo) = u;
             }
           }
         }
@@ -465,11 +487,24 @@ downconv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
         }
         if (++stage == Cf::kRawStages) { stage = 0; phase ^= 1; }
         if (++bstage == Cf::kBlurStages) { bstage = 0; bphase ^= 1; }
+        // while the MMAs of this pass run: one chunk of the previous tile
+        if (h < kCW && it > 0) epilogue(pimg, pty, ptx, it - 1, h, pq[h < kCW ? h : 0][0], pq[h < kCW ? h : 0][1]);
+        if (h == kCW - 1) {
+          // residual of THIS tile (consumed one tile later): in flight while the remaining passes and MMAs run
+#pragma unroll
+          for (int c = 0; c < kCW; ++c) {
+            const __half* rp = res_ptr(img, ty * kDcTH + ry, tx * kDcTW + rx, nc0 + c * 16);
+            pq[c][0] = __ldg(reinterpret_cast<const uint4*>(rp));
+            pq[c][1] = __ldg(reinterpret_cast<const uint4*>(rp + (p.res_i8 ? (size_t)p.Wo * 8 : 8)));
+          }
+        }
       }
-      if (it > 0) epilogue(pimg, pty, ptx, it - 1, pq0, pq1);
-      pimg = img; pty = ty; ptx = tx; pq0 = q0; pq1 = q1;
+      pimg = img; pty = ty; ptx = tx;
     }
-    if (it > 0) epilogue(pimg, pty, ptx, it - 1, pq0, pq1);
+    if (it > 0) {
+#pragma unroll
+      for (int c = 0; c < kCW; ++c) epilogue(pimg, pty, ptx, it - 1, c, pq[c][0], pq[c][1]);
+    }
   }
 
   tc_fence_before();
@@ -517,8 +552,22 @@ cudaError_t k_downconv_fused(const CUtensorMap& map_a, const CUtensorMap& map_w,
   if (sx < 0 || sy < 0 || Cout / 64 > 2) return cudaErrorInvalidValue;
   DownParams p{N, Ho, Wo, Cout, sx, sy, bias, residual, res_i8, out, out_i8, post_scale};
   if (C == 32) return launch_down<32, 64>(map_a, map_w, p, num_sms, s);
+#ifndef GLASS_NO_WIDE_DOWN          // (A/B builds only)
+  if (C == 64 && Cout == 128) return launch_down<64, 128>(map_a, map_w, p, num_sms, s);
+#endif
   if (C == 64) return launch_down<64, 64>(map_a, map_w, p, num_sms, s);
   return cudaErrorInvalidValue;
+}
+
+// TMA box geometry the kernel instance for (C, Cout) expects: 8-channel groups per raw box, output columns per tap box
+void k_downconv_fused_geometry(int C, int Cout, int* box_groups, int* box_cols) {
+#ifndef GLASS_NO_WIDE_DOWN
+  const bool wide = (C == 64 && Cout == 128);
+#else
+  const bool wide = false;
+#endif
+  *box_groups = wide ? DCfg<64, 128>::kG : DCfg<32, 64>::kG;
+  *box_cols = wide ? 128 : 64;
 }
 
 }  // namespace glass

@@ -842,11 +842,13 @@ int build_plan(glass_engine* e, int P) {
         const uint64_t G = Ci / 8;
         uint64_t d4[4] = {(uint64_t)res * 8, G, (uint64_t)res, (uint64_t)P};
         uint64_t s4[3] = {(uint64_t)res * 16, G * res * 16, (uint64_t)res * G * res * 16};
-        uint32_t b4[4] = {160, 4, 36, 1};
+        int box_groups = 4, box_cols = 64;        // TMA boxes of the kernel instance for this block
+        k_downconv_fused_geometry(Ci, Co, &box_groups, &box_cols);
+        uint32_t b4[4] = {160, (uint32_t)box_groups, 36, 1};
         RC(encode_map(e, &cl.maps.a, e->actB, 4, d4, s4, b4, 0));
         uint64_t wd[3] = {(uint64_t)Ci, (uint64_t)Co, 9};
         uint64_t ws[2] = {(uint64_t)Ci * 2, (uint64_t)Ci * 2 * Co};
-        uint32_t wb[3] = {(uint32_t)Ci, 64, 1};
+        uint32_t wb[3] = {(uint32_t)Ci, (uint32_t)box_cols, 1};
         RC(encode_map(e, &cl.maps.b, tptr<__half>(e, nmf("c1.w9")), 3, wd, ws, wb, Ci * 2));
       } else if (e->d_exact[b]) {
         // exact: blurred input (k_blur_s2d -> actC, [(res/2+1)^2][4*Ci]) then a 2x2-tap conv == 3x3 stride 2

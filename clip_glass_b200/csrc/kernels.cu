@@ -208,7 +208,7 @@ __global__ void rgb_combine_kernel(const float4* __restrict__ yprev, const float
     float r = b0, g = b1, bl = b2;
     for (int s = 0; s < n_slabs; ++s) {
       const float4 t = __ldg(slabs + (size_t)s * n + i);
-      r += t.x; g += t.y; bl += t.z;
+      r = __fadd_rn(r, t.x); g = __fadd_rn(g, t.y); bl = __fadd_rn(bl, t.z);
     }
     if (yprev != nullptr) {
       // v[2z] = .75 x[z-1] + .25 x[z];  v[2z+1] = .25 x[z-1] + .75 x[z];  x[-1] = 0  (per axis)
@@ -222,17 +222,17 @@ __global__ void rgb_combine_kernel(const float4* __restrict__ yprev, const float
       if (zy > 0 && zx > 0) a = __ldg(base + (size_t)(zy - 1) * Wp + zx - 1);
       if (zy > 0) c = __ldg(base + (size_t)(zy - 1) * Wp + zx);
       if (zx > 0) d = __ldg(base + (size_t)zy * Wp + zx - 1);
-      r += wy0 * (wx0 * a.x + wx1 * c.x) + wy1 * (wx0 * d.x + wx1 * e.x);
-      g += wy0 * (wx0 * a.y + wx1 * c.y) + wy1 * (wx0 * d.y + wx1 * e.y);
-      bl += wy0 * (wx0 * a.z + wx1 * c.z) + wy1 * (wx0 * d.z + wx1 * e.z);
+      r = __fadd_rn(r, skip_up2(wy0, wy1, wx0, wx1, a.x, c.x, d.x, e.x));
+      g = __fadd_rn(g, skip_up2(wy0, wy1, wx0, wx1, a.y, c.y, d.y, e.y));
+      bl = __fadd_rn(bl, skip_up2(wy0, wy1, wx0, wx1, a.z, c.z, d.z, e.z));
     }
     if (yout != nullptr) yout[i] = make_float4(r, g, bl, 0.f);
     if (image != nullptr) {
       const size_t plane = (size_t)H * W;
       float* ip = image + (size_t)b * 3 * plane + (size_t)Y * W + X;
-      ip[0] = fminf(fmaxf((r + 1.f) * 0.5f, 0.f), 1.f);
-      ip[plane] = fminf(fmaxf((g + 1.f) * 0.5f, 0.f), 1.f);
-      ip[2 * plane] = fminf(fmaxf((bl + 1.f) * 0.5f, 0.f), 1.f);
+      ip[0] = image_value(r);
+      ip[plane] = image_value(g);
+      ip[2 * plane] = image_value(bl);
     }
   }
 }

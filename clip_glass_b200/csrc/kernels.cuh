@@ -106,6 +106,7 @@ cudaError_t k_from_rgb_fir_proj(const float* images, const float* folded_host, _
 // [N][2Ho][C/8][2Wo][8] (map_a: dims (2Wo*8, C/8, 2Ho, N), box (160, 4, 36, 1), un-swizzled), w9 = [9][Cout][C] fp16
 // (map_w: box (C, 64, 1), swizzle C*2 bytes) -> out = (lrelu(conv3x3_s2(FIR(a)) + bias)*sqrt2 + residual) * post_scale
 bool k_downconv_fused_supported(int C, int Cout, int Ho, int Wo);
+void k_downconv_fused_geometry(int C, int Cout, int* box_groups, int* box_cols);
 cudaError_t k_downconv_fused(const CUtensorMap& map_a, const CUtensorMap& map_w, int C, int N, int Ho, int Wo, int Cout,
                              const float* bias, const __half* residual, int res_i8, __half* out, int out_i8,
                              float post_scale, int num_sms, cudaStream_t s);
