@@ -160,7 +160,7 @@ __device__ __forceinline__ float act_apply(float v, int act) {
   if (act == kActLrelu) {
     v = (v > 0.f ? v : 0.2f * v) * kSqrt2;
   } else if (act == kActQuickGelu) {
-    v = v / (1.f + __expf(-1.702f * v));
+    v = __fdividef(v, 1.f + __expf(-1.702f * v));    // (as epilogue_fastN: approximate reciprocal)
   }
   return v;
 }

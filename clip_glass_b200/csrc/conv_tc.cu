@@ -78,7 +78,9 @@ struct EpiSpec {
   bool generic, noise, rgb, residual;
   int store;
   bool i8;
-  int act;      // kActNone / kActLrelu (specialised specs never round to fp16 before the activation)
+  int act;      // kActNone / kActLrelu / kActQuickGelu
+  bool round = false;   // round to fp16 before the activation / residual add (CLIP's fp16 op boundaries)
+  bool pow2 = true;     // tile grid and channel count are powers of two (decode with shifts); false: plain GEMMs
 };
 constexpr EpiSpec kEpiSpecs[] = {
     {true, false, false, false, kStNone, false, 0},               // 0: run-time switches
@@ -95,6 +97,12 @@ constexpr EpiSpec kEpiSpecs[] = {
     {false, false, false, false, kStS2D, true, kActLrelu},        // 11: D conv0, space-to-depth I8 (feeds MODE 6)
     {false, false, false, false, kStRegular, true, kActNone},     // 12: D projection (1x1, linear), I8 store
     {false, false, false, false, kStRegular, true, kActLrelu},    // 13: D conv0 feeding the fused-FIR down-conv, I8 store
+    // ViT GEMMs (M = 3200 rows: 25 row tiles, N = 768 / 2304 / 3072).  Under the run-time spec these launches were
+    // bound by instruction fetch (no_instruction was their top warp stall: ~2600 unrolled SASS instructions per chunk
+    // body for a 35-85 us kernel) and by the residual loads issued chunk by chunk (profiles/r02_ncu_vit_gemms.txt).
+    {false, false, false, false, kStRegular, false, kActNone, false, false},        // 14: qkv / patch embedding: (+ bias)
+    {false, false, false, true, kStRegular, false, kActNone, true, false},          // 15: out / proj: round, + residual
+    {false, false, false, false, kStRegular, false, kActQuickGelu, true, false},    // 16: fc: round, QuickGELU
 };
 constexpr int kNumEpiSpecs = sizeof(kEpiSpecs) / sizeof(kEpiSpecs[0]);
 // Spec 3 (the last generator conv) may finish the image in its epilogue: the four skip-sum pixels a thread interpolates
@@ -192,7 +200,8 @@ __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" 
 // NT = 2: the two tiles of a pair in one pass -- every parameter vector is read from shared memory ONCE for both
 // tiles.  (The broadcast LDS.128 of the staged parameters were 42 % of the shared-memory wavefronts of the 32-channel
 // 1024^2 layers, whose LSU data pipe ran at 89 %: profiles/.)
-template <int NT, bool kRgb, int kActT = -1, bool kNz = true>
+// kRoundT: -1 = fp16 pre-rounding from EpiParams at run time, 0 / 1 = fixed
+template <int NT, bool kRgb, int kActT = -1, bool kNz = true, int kRoundT = -1>
 __device__ __forceinline__ void epilogue_fastN(const EpiParams& e, const float* __restrict__ par, int BN, int j0,
                                                const uint32_t (*acc)[16], const float* nz, const __half* const* res_ptr,
                                                __half* const* out_ptr, size_t out_half_stride, float (*rgb)[3],
@@ -221,23 +230,26 @@ __device__ __forceinline__ void epilogue_fastN(const EpiParams& e, const float* 
   }
 #pragma unroll
   for (int n = 0; n < NT; ++n) {
-    if (kActT < 0 && e.round_fp16_before_act) {
+    if (kRoundT > 0 || (kRoundT < 0 && kActT < 0 && e.round_fp16_before_act)) {
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
         float lo, hi;
         upk2(t[n][k], lo, hi);
-        t[n][k] = pk2(__half2float(__float2half_rn(lo)), __half2float(__float2half_rn(hi)));
+        const float2 r = __half22float2(__floats2half2_rn(lo, hi));
+        t[n][k] = pk2(r.x, r.y);
       }
     }
     if (kActT == kActLrelu || (kActT < 0 && e.act == kActLrelu)) {
 #pragma unroll
       for (int k = 0; k < 8; ++k) t[n][k] = lrelu2(t[n][k]);
-    } else if (kActT < 0 && e.act == kActQuickGelu) {
+    } else if (kActT == kActQuickGelu || (kActT < 0 && e.act == kActQuickGelu)) {
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
         float lo, hi;
         upk2(t[n][k], lo, hi);
-        t[n][k] = pk2(lo / (1.f + __expf(-1.702f * lo)), hi / (1.f + __expf(-1.702f * hi)));
+        // x * sigmoid(1.702 x) with the approximate reciprocal (MUFU.RCP, <= 2 ulp: the value is rounded to fp16 right
+        // after); the IEEE division was 8 of the ~14 instructions per element of the fc GEMM's epilogue
+        t[n][k] = pk2(__fdividef(lo, 1.f + __expf(-1.702f * lo)), __fdividef(hi, 1.f + __expf(-1.702f * hi)));
       }
     }
   }
@@ -322,7 +334,7 @@ __device__ __forceinline__ void epilogue_fastN(const EpiParams& e, const float* 
   }
 }
 
-template <bool kRgb, int kActT = -1, bool kNz = true>
+template <bool kRgb, int kActT = -1, bool kNz = true, int kRoundT = -1>
 __device__ __forceinline__ void epilogue_fast16(const EpiParams& e, const float* __restrict__ par, int BN, int j0,
                                                 const uint32_t (&acc)[16], float nz, const __half* res_ptr,
                                                 __half* out_ptr, size_t out_half_stride, float (&rgb)[3],
@@ -331,7 +343,7 @@ __device__ __forceinline__ void epilogue_fast16(const EpiParams& e, const float*
   __half* op[1] = {out_ptr};
   const uint4* pre[1] = {res_pre};
   const float nzv[1] = {nz};
-  epilogue_fastN<1, kRgb, kActT, kNz>(e, par, BN, j0, &acc, nzv, rp, op, out_half_stride, &rgb, pre, res_half_stride);
+  epilogue_fastN<1, kRgb, kActT, kNz, kRoundT>(e, par, BN, j0, &acc, nzv, rp, op, out_half_stride, &rgb, pre, res_half_stride);
 }
 
 template <int BN, int BK, int MODE, int EPI>
@@ -340,7 +352,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                const ConvParams p) {
   using C = Cfg<BN, BK, MODE, EpiExtra<EPI>::kBytes>;
   constexpr EpiSpec S = kEpiSpecs[EPI];
-  constexpr bool kPow2 = !S.generic;        // specialised layers have power-of-two tile grids and channel counts
+  constexpr bool kPow2 = !S.generic && S.pow2;   // power-of-two tile grids and channel counts: decode with shifts
   extern __shared__ uint8_t smem_raw[];
   // (offset arithmetic on the extern array keeps the pointers in the shared address space: LDS/STS, not generic LD/ST)
   uint8_t* smem_w = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -664,8 +676,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     const int row_s2d = (((ry >> 1) * (W >> 1) + (rx >> 1)) << 2) + ((ry & 1) * 2 + (rx & 1));
     const int cout_sh = e.cout_shift;       // log2(Cout) or -1
     const int ngrp_sh = e.noise_div_shift;  // log2(noise_group_div) or -1
-    const bool cout_p2 = S.generic ? (cout_sh >= 0) : true;
-    const bool ngrp_p2 = S.generic ? (ngrp_sh >= 0) : true;
+    const bool cout_p2 = kPow2 ? true : (cout_sh >= 0);
+    const bool ngrp_p2 = kPow2 ? true : (ngrp_sh >= 0);
 
     // Noise of the NEXT tile is fetched while the current one is processed: the (L2/DRAM) latency of this
     // scattered 4-byte load would otherwise sit on the critical path of every tile.
@@ -718,6 +730,23 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         cp_async16_zfill(dst + 8192, zx > 0 ? base - 1 : base, zx > 0 ? 16 : 0);
         cp_async16_zfill(dst + 12288, base, 16);
         asm volatile("cp.async.commit_group;" ::: "memory");
+      }
+#ifdef GLASS_IMG_REG_PREFETCH
+      constexpr bool kImgRegs = (EPI == 3) && C::kPairM == 2 && C::kParts == 2 && !kImgPrefetch;
+#else
+      constexpr bool kImgRegs = false;
+#endif
+      float4 yv[4];                       // kImgRegs: the four skip-sum pixels, requested before the accumulator wait
+      if (kImgRegs) {
+        yv[0] = yv[1] = yv[2] = yv[3] = make_float4(0, 0, 0, 0);
+        if (e.image != nullptr) {
+          const int X = x + 8 * half, Wp = W >> 1, zy = y >> 1, zx = X >> 1;
+          const float4* base = e.img_yprev + ((img * (H >> 1) + zy) * Wp + zx);
+          yv[3] = __ldg(base);
+          if (zy > 0 && zx > 0) yv[0] = __ldg(base - Wp - 1);
+          if (zy > 0) yv[1] = __ldg(base - Wp);
+          if (zx > 0) yv[2] = __ldg(base - 1);
+        }
       }
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
@@ -854,6 +883,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         };
         constexpr int kActT = S.generic ? -1 : S.act;
         constexpr bool kNz = S.generic || S.noise;      // specialised layers without noise: no per-element add
+        constexpr int kRoundT = S.generic ? -1 : (S.round ? 1 : 0);
         // specialised pair layers: both tiles of the pair per chunk, parameters read once (epilogue_fastN<2>)
         constexpr bool kPairFused = (kPairM == 2) && !S.generic;
         if constexpr (kPairFused) {
@@ -879,8 +909,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 rptr[h] = !kResPre ? res_addr(h, c) : nullptr;
                 rpre[h] = kResPre ? resv[kResPre ? h : 0][kResPre ? c : 0] : nullptr;
               }
-              if (has_rgb) epilogue_fastN<2, true, kActT, kNz>(e, par, BN, j0, accp[c & 1], nzc, rptr, optr, half_stride, rgb, rpre, res_stride);
-              else epilogue_fastN<2, false, kActT, kNz>(e, par, BN, j0, accp[c & 1], nzc, rptr, optr, half_stride, rgb, rpre, res_stride);
+              if (has_rgb) epilogue_fastN<2, true, kActT, kNz, kRoundT>(e, par, BN, j0, accp[c & 1], nzc, rptr, optr, half_stride, rgb, rpre, res_stride);
+              else epilogue_fastN<2, false, kActT, kNz, kRoundT>(e, par, BN, j0, accp[c & 1], nzc, rptr, optr, half_stride, rgb, rpre, res_stride);
             }
           }
         } else {
@@ -904,8 +934,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
               __half* optr = out_addr(h, c, half_stride);
               const __half* rptr = !kResPre ? res_addr(h, c) : nullptr;
               const uint4* rpre = kResPre ? resv[kResPre ? h : 0][kResPre ? c : 0] : nullptr;
-              if (has_rgb) epilogue_fast16<true, kActT, kNz>(e, par, BN, j0, acc[ci & 1], nzc, rptr, optr, half_stride, rgb[h], rpre, res_stride);
-              else epilogue_fast16<false, kActT, kNz>(e, par, BN, j0, acc[ci & 1], nzc, rptr, optr, half_stride, rgb[h], rpre, res_stride);
+              if (has_rgb) epilogue_fast16<true, kActT, kNz, kRoundT>(e, par, BN, j0, acc[ci & 1], nzc, rptr, optr, half_stride, rgb[h], rpre, res_stride);
+              else epilogue_fast16<false, kActT, kNz, kRoundT>(e, par, BN, j0, acc[ci & 1], nzc, rptr, optr, half_stride, rgb[h], rpre, res_stride);
             }
           }
         }
@@ -943,6 +973,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
               asm volatile("cp.async.wait_group 0;" ::: "memory");
               const uint32_t src = img_slots + et * 16;
               a = lds128f(src); c = lds128f(src + 4096); d = lds128f(src + 8192); ee = lds128f(src + 12288);
+            } else if (kImgRegs) {
+              a = yv[0]; c = yv[1]; d = yv[2]; ee = yv[3];
             } else {
               const float4* base = e.img_yprev + ((img * (H >> 1) + zy) * Wp + zx);    // (pixel counts stay < 2^31)
               ee = __ldg(base);
@@ -1094,9 +1126,9 @@ __global__ void conv_simt_kernel(const ConvParams p) {
 static int pick_epi_spec(const ConvParams& p) {
   const EpiParams& e = p.epi;
   static const bool off = debug_env("GLASS_DEBUG_GENERIC_EPI") != nullptr;     // A/B knob: always the run-time spec
-  if (off || p.TN != 1 || !p.pow2 || !p.all_valid || p.debug_skip != 0 || p.skip_mode == 1) return 0;
-  if ((e.act != kActLrelu && e.act != kActNone) || e.round_fp16_before_act || e.x_phases == 2 || e.cout_shift < 0) return 0;
-  if (e.noise != nullptr && e.noise_div_shift < 0) return 0;
+  if (off || p.TN != 1 || !p.all_valid || p.debug_skip != 0 || p.skip_mode == 1 || e.x_phases == 2) return 0;
+  // power-of-two geometry (tile grid, channel count, noise group): required by the specs that decode with shifts
+  const bool pow2 = p.pow2 && e.cout_shift >= 0 && (e.noise == nullptr || e.noise_div_shift >= 0);
   int store = kStNone;
   if (e.out != nullptr) {
     if (e.store_mode == kStoreRegular) store = kStRegular;
@@ -1107,7 +1139,8 @@ static int pick_epi_spec(const ConvParams& p) {
   for (int i = 1; i < kNumEpiSpecs; ++i) {
     const EpiSpec& sp = kEpiSpecs[i];
     if (sp.noise == (e.noise != nullptr) && sp.rgb == (e.rgb_w != nullptr) && sp.residual == (e.residual != nullptr) &&
-        sp.store == store && (store == kStNone || sp.i8 == (e.out_i8 != 0)) && sp.act == e.act)
+        sp.store == store && (store == kStNone || sp.i8 == (e.out_i8 != 0)) && sp.act == e.act &&
+        sp.round == (e.round_fp16_before_act != 0) && (!sp.pow2 || pow2) && (sp.pow2 || !e.res_i8))
       return i;
   }
   return 0;
@@ -1145,6 +1178,9 @@ cudaError_t launch_conv_tc(const ConvParams& p, const TmaMaps& maps, int num_sms
   GLASS_SPEC(64, 128, 6, 7)
   GLASS_SPEC(32, 128, 4, 7)
   GLASS_SPEC(64, 128, 6, 8)
+  GLASS_SPEC(128, 64, 0, 14)
+  GLASS_SPEC(128, 64, 0, 15)
+  GLASS_SPEC(128, 64, 0, 16)
 #undef GLASS_SPEC
 #define GLASS_CASE(bn, bk, md) \
   if (p.BN == bn && p.BK == bk && p.mode == md) return launch_one<bn, bk, md>(p, maps, num_sms, s);

@@ -48,11 +48,23 @@ struct DCfg {
   static constexpr int kPasses = C / (8 * kG);
   static constexpr int kStepsPerPass = kG / 2;             // K = 16 MMA steps per tap and pass
   static constexpr int kRawBytes = kDcRawRows * kG * kDcRawCols * 16;      // 46080 / 23040
-  static constexpr int kSbo = kG * kDcLbo;                 // plane: next row (= next 8-pixel group of the tile)
-  static constexpr int kPlaneBytes = (kDcTH + 1) * kSbo;   // 17 rows
-  static constexpr int kBlurBytes = 4 * kPlaneBytes;       // 39168 / 19584
+  // Blurred tile: four parity planes (row parity py, column parity px), each [row][8-channel group][column] x 16 B.
+  // kTrim (BN = 128): the odd planes drop the row / column they never hold (33 x 17 blurred positions: 17 even and
+  // 16 odd rows, 9 even and 8 odd columns), which is what lets TWO blurred stages fit beside 147 KB of taps, so that
+  // the blur of pass h+1 overlaps the MMAs of pass h (with one stage the 16 worker warps spent most of their stall
+  // samples on the pass barrier: profiles/).
+  static constexpr bool kTrim = (BN == 128);
+  __host__ __device__ static constexpr int plane_cols(int px) { return (kTrim && px) ? 8 : 9; }
+  __host__ __device__ static constexpr int plane_rows(int py) { return (kTrim && py) ? kDcTH : kDcTH + 1; }
+  __host__ __device__ static constexpr int plane_lbo(int px) { return plane_cols(px) * 16; }       // next channel group
+  __host__ __device__ static constexpr int plane_sbo(int px) { return kG * plane_lbo(px); }        // next row
+  __host__ __device__ static constexpr int plane_bytes(int py, int px) { return plane_rows(py) * plane_sbo(px); }
+  __host__ __device__ static constexpr int plane_off(int py, int px) {
+    return (py ? plane_bytes(0, 0) + plane_bytes(0, 1) : 0) + (px ? plane_bytes(py, 0) : 0);
+  }
+  static constexpr int kBlurBytes = plane_off(1, 1) + plane_bytes(1, 1);       // 39168 / 17952
   static constexpr int kRawStages = 2;
-  static constexpr int kBlurStages = (C == 32) ? 2 : 1;
+  static constexpr int kBlurStages = (C == 32 || BN == 128) ? 2 : 1;
   static constexpr int kWBytes = 9 * BN * C * 2;
   static constexpr int kTapBytes = BN * C * 2;
   static constexpr int kSmemBytes = kWBytes + kRawStages * kRawBytes + kBlurStages * kBlurBytes + 1024 + 256 + BN * 4;
@@ -222,11 +234,12 @@ downconv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
           for (int tap = 0; tap < 9; ++tap) {
             const int ky = tap / 3, kx = tap - ky * 3;
             const uint32_t a_addr =
-                sb + ((ky & 1) * 2 + (kx & 1)) * Cf::kPlaneBytes + (ky >> 1) * Cf::kSbo + (kx >> 1) * 16;
+                sb + Cf::plane_off(ky & 1, kx & 1) + (ky >> 1) * Cf::plane_sbo(kx & 1) + (kx >> 1) * 16;
             const uint64_t db = make_smem_desc<(C > 64 ? 64 : C)>(sw + tap * Cf::kTapBytes);
 #pragma unroll
             for (int k = 0; k < Cf::kStepsPerPass; ++k) {       // the channels of this pass in K = 16 steps
-              const uint64_t da = make_smem_desc_noswz(a_addr + k * 2 * kDcLbo, kDcLbo, Cf::kSbo);
+              const uint64_t da =
+                  make_smem_desc_noswz(a_addr + k * 2 * Cf::plane_lbo(kx & 1), Cf::plane_lbo(kx & 1), Cf::plane_sbo(kx & 1));
               tc_mma_f16(d_tmem, da, db + (uint64_t)((h * Cf::kStepsPerPass + k) * 2), Cf::kIdesc,
                          (uint32_t)(h | tap | k));
             }
@@ -337,7 +350,8 @@ downconv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
         asm volatile("bar.sync 2, 256;" ::: "memory");
         if (active) {
           const uint4* rt = reinterpret_cast<const uint4*>(raw + stage * Cf::kRawBytes);
-          uint8_t* bt_base = blur + bstage * Cf::kBlurBytes + ((j & 1) * Cf::kPlaneBytes) + g * kDcLbo + (j >> 1) * 16;
+          // (dedicated blur warps exist only for C == 32: untrimmed planes of equal size)
+          uint8_t* bt_base = blur + bstage * Cf::kBlurBytes + ((j & 1) * Cf::plane_bytes(0, 0)) + g * kDcLbo + (j >> 1) * 16;
           uint4 hw[4];                                    // horizontal results of the last four raw rows
 #pragma unroll
           for (int r = 0; r < 14; ++r) {
@@ -347,7 +361,7 @@ downconv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
             if (r >= 3) {
               const int i = i0 + r - 3;                   // blurred row completed by raw row i + 3
               const uint4 u = fir4<true>(hw[(r - 3) & 3], hw[(r - 2) & 3], hw[(r - 1) & 3], cur);
-              *reinterpret_cast<uint4*>(bt_base + (i & 1) * 2 * Cf::kPlaneBytes + (i >> 1) * Cf::kSbo) = u;
+              *reinterpret_cast<uint4*>(bt_base + (i & 1) * 2 * Cf::plane_bytes(0, 0) + (i >> 1) * Cf::plane_sbo(0)) = u;
             }
           }
         }
@@ -463,8 +477,12 @@ downconv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
         asm volatile("bar.sync 1, 512;" ::: "memory");
         if (active) {
           const uint2* rt = reinterpret_cast<const uint2*>(raw + stage * Cf::kRawBytes) + hlow;
-          uint8_t* bt_base =
-              blur + bstage * Cf::kBlurBytes + ((j & 1) * Cf::kPlaneBytes) + g * kDcLbo + (j >> 1) * 16 + hlow * 8;
+          // this thread's column in the even-row / odd-row plane of its column parity
+          const int px = j & 1;
+          const int lbo = px ? Cf::plane_lbo(1) : Cf::plane_lbo(0), sbo = kG * lbo;
+          uint8_t* bt_col = blur + bstage * Cf::kBlurBytes + g * lbo + (j >> 1) * 16 + hlow * 8;
+          uint8_t* bt_even = bt_col + (px ? Cf::plane_off(0, 1) : Cf::plane_off(0, 0));
+          uint8_t* bt_odd = bt_col + (px ? Cf::plane_off(1, 1) : Cf::plane_off(1, 0));
           uint2 hw[4];                                     // horizontal results of the last four raw rows
 #pragma unroll
           for (int r = 0; r < kStripRows + 3; ++r) {
@@ -475,7 +493,7 @@ downconv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
             hw[r & 3] = cur;
             if (r >= 3) {
               const uint2 u = fir4h<true>(hw[(r - 3) & 3], hw[(r - 2) & 3], hw[(r - 1) & 3], cur);
-              *reinterpret_cast<uint2*>(bt_base + (i & 1) * 2 * Cf::kPlaneBytes + (i >> 1) * Cf::kSbo) = u;
+              *reinterpret_cast<uint2*>(((i & 1) ? bt_odd : bt_even) + (i >> 1) * sbo) = u;
             }
           }
         }

@@ -235,8 +235,34 @@ int make_conv(glass_engine* e, ConvLaunch* out, const __half* in, int Nimg, int 
   p.tiles_n = (Nimg + p.TN - 1) / p.TN;
   p.BN = pick_bn(Ntot);
   if (gemm) {
+    // plain GEMMs: 128-column tiles (ViT: 25 row tiles x 6 / 18 / 24 column tiles fill the 148 SMs; the specialised
+    // GEMM epilogues of conv_tc.cu are instantiated for this width)
+    if (p.BN > 128 && Ntot % 128 == 0) p.BN = 128;
     static const char* cap = debug_env("GLASS_DEBUG_GEMM_BN");      // A/B knob for the plain GEMMs' tile width
-    if (cap != nullptr && atoi(cap) >= 32 && p.BN > atoi(cap) && Ntot % atoi(cap) == 0) p.BN = atoi(cap);
+    if (cap != nullptr && atoi(cap) >= 32 && Ntot % atoi(cap) == 0) p.BN = atoi(cap);
+  }
+  // Layers with fewer tiles than SMs (the 4x4 .. 16x16 blocks, the dense layer): narrower column tiles.  A K-streaming
+  // CTA is bound by TMA rows per K step (128 activation rows + BN weight rows, ~0.41 rows per cycle): at BN = 256
+  // sixteen CTAs each stream 2.4x the rows that 128 CTAs stream at BN = 32.  Cost model: waves x rows per K step.
+  // Not for the I8 / pixel-pair layers (tile width tied to their layout), the ViT GEMMs (specialised epilogues at 128
+  // columns) and the toRGB layers: their partial toRGB sums are formed per column tile and added up in tile order, so a
+  // population-dependent tile width would make a candidate's scores depend on what else is in the launch
+  // (tests/test_gpu_parity.py::test_full_size_properties).  GEMM accumulators do not depend on the tile width.
+  {
+    static const bool keep_wide = debug_env("GLASS_DEBUG_WIDE_SMALL") != nullptr;      // (debug builds: A/B)
+    const int m_tiles = p.tiles_x * p.tiles_y * p.tiles_n;
+    const bool vit_gemm = gemm && p.BN == 128 && m_tiles >= 8;
+    if (!keep_wide && !in_i8 && !vit_gemm && epi.x_phases != 2 && epi.rgb_w == nullptr &&
+        m_tiles * (Ntot / p.BN) < e->num_sms) {
+      int best = p.BN;
+      long best_cost = -1;
+      for (int bn = p.BN; bn >= 32 && Ntot % bn == 0; bn /= 2) {
+        const long waves = ((long)m_tiles * (Ntot / bn) + e->num_sms - 1) / e->num_sms;
+        const long cost = waves * (128 + bn);
+        if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = bn; }
+      }
+      p.BN = best;
+    }
   }
   p.BK = (Cin % 64 == 0) ? 64 : 32;
   if (p.BN == 0 || Cin % 32 != 0 || Ntot % 16 != 0)

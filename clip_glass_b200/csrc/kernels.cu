@@ -93,6 +93,85 @@ __global__ void vecmat_kernel(const float* __restrict__ in, int in_stride, const
   out[(size_t)b * out_stride + n] = acc;
 }
 
+// The same product for a whole population tile per block: out[b][n] for 64 candidates x 16 output columns, with the
+// candidates' input rows (64 x K fp32) and the 16-column weight slice (K x 16) staged in shared memory ONCE.
+// vecmat_kernel reads every weight through L2 once per candidate in 32 dependent batches (34 us per 512x512 mapping
+// layer at P = 64, pure latency); here a weight is read once per 64 candidates.  Thread = (column n, 4 candidates); the
+// four partial sums per output run over k = 0,4,8,.. / 1,5,9,.. / .. in ascending order and are combined as
+// (a0 + a1) + (a2 + a3): exactly vecmat_kernel's summation order, so the results are bit-identical (K % 16 == 0).
+constexpr int kVtCand = 64, kVtCols = 16;
+__global__ void __launch_bounds__(256) vecmat_tile_kernel(const float* __restrict__ in, int in_stride,
+                                                          const float* __restrict__ Wt, const float* __restrict__ bias,
+                                                          float* __restrict__ out, int out_stride, int P, int K, int N,
+                                                          int mode) {
+  extern __shared__ float4 vt_smem[];
+  float* xs = reinterpret_cast<float*>(vt_smem);            // [kVtCand][K]
+  float* ws = xs + (size_t)kVtCand * K;                     // [K][kVtCols]
+  const int n0 = blockIdx.x * kVtCols, b0 = blockIdx.y * kVtCand;
+  const int nb = min(kVtCand, P - b0);
+  // staging: eight loads in flight per thread before the first store (issued one by one, every load exposed a full L2
+  // round trip: 32 dependent round trips per thread made the first version slower than vecmat_kernel)
+  for (int i0 = threadIdx.x; i0 < K * kVtCols; i0 += 8 * blockDim.x) {
+    float v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int i = i0 + u * blockDim.x, k = i / kVtCols, c = i - k * kVtCols;
+      v[u] = (i < K * kVtCols && n0 + c < N) ? __ldg(Wt + (size_t)k * N + n0 + c) : 0.f;
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int i = i0 + u * blockDim.x;
+      if (i < K * kVtCols) ws[i] = v[u];
+    }
+  }
+  const int K4 = K >> 2;
+  for (int i0 = threadIdx.x; i0 < kVtCand * K4; i0 += 8 * blockDim.x) {
+    float4 v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int i = i0 + u * blockDim.x, r = i / K4, k4 = i - r * K4;
+      v[u] = (i < kVtCand * K4 && r < nb) ? __ldg(reinterpret_cast<const float4*>(in + (size_t)(b0 + r) * in_stride) + k4)
+                                          : make_float4(0, 0, 0, 0);
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int i = i0 + u * blockDim.x;
+      if (i < kVtCand * K4) reinterpret_cast<float4*>(xs)[i] = v[u];
+    }
+  }
+  __syncthreads();
+  const int c = threadIdx.x & (kVtCols - 1), cg = threadIdx.x / kVtCols;     // candidates 4 cg .. 4 cg + 3
+  float acc[4][4];
+#pragma unroll
+  for (int u = 0; u < 4; ++u) acc[u][0] = acc[u][1] = acc[u][2] = acc[u][3] = 0.f;
+  const float4* x4 = reinterpret_cast<const float4*>(xs) + (size_t)(4 * cg) * K4;
+#pragma unroll 2
+  for (int k4 = 0; k4 < K4; ++k4) {
+    const float w0 = ws[(4 * k4 + 0) * kVtCols + c], w1 = ws[(4 * k4 + 1) * kVtCols + c];
+    const float w2 = ws[(4 * k4 + 2) * kVtCols + c], w3 = ws[(4 * k4 + 3) * kVtCols + c];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const float4 x = x4[(size_t)u * K4 + k4];
+      acc[u][0] = fmaf(x.x, w0, acc[u][0]);
+      acc[u][1] = fmaf(x.y, w1, acc[u][1]);
+      acc[u][2] = fmaf(x.z, w2, acc[u][2]);
+      acc[u][3] = fmaf(x.w, w3, acc[u][3]);
+    }
+  }
+  const int n = n0 + c;
+  if (n >= N) return;
+  const float bv = bias != nullptr ? bias[n] : 0.f;
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const int b = b0 + 4 * cg + u;
+    if (b >= P) break;
+    float a = (acc[u][0] + acc[u][1]) + (acc[u][2] + acc[u][3]);
+    if (bias != nullptr) a += bv;
+    if (mode == 1) a = (a > 0.f ? a : 0.2f * a) * kSqrt2;
+    out[(size_t)b * out_stride + n] = a;
+  }
+}
+
 // Several independent vecmat jobs (the 17 demodulation GEMVs of one generator pass) in ONE launch: blockIdx.z = job.
 __global__ void vecmat_batched_kernel(const VecmatBatch jobs, int in_stride, int mode) {
   extern __shared__ float row[];
@@ -949,6 +1028,19 @@ cudaError_t k_pixelnorm(const float* z, float* out, int P, int L, cudaStream_t s
 }
 cudaError_t k_vecmat(const float* in, int in_stride, const float* Wt, const float* bias, float* out, int out_stride,
                      int P, int K, int N, int mode, cudaStream_t s) {
+  // population tiles (bit-identical to vecmat_kernel, see vecmat_tile_kernel) whenever the staged rows fit
+  const size_t tile_smem = ((size_t)kVtCand * K + (size_t)K * kVtCols) * sizeof(float);
+  if (mode != 2 && K % 16 == 0 && in_stride % 4 == 0 && tile_smem <= 200 * 1024 && P >= 8) {
+    static bool configured = false;
+    if (!configured) {
+      cudaError_t err = cudaFuncSetAttribute(vecmat_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+      if (err != cudaSuccess) return err;
+      configured = true;
+    }
+    dim3 grid((N + kVtCols - 1) / kVtCols, (P + kVtCand - 1) / kVtCand);
+    vecmat_tile_kernel<<<grid, 256, tile_smem, s>>>(in, in_stride, Wt, bias, out, out_stride, P, K, N, mode);
+    GLASS_RET();
+  }
   dim3 grid((N + 127) / 128, P);
   vecmat_kernel<<<grid, 128, K * sizeof(float), s>>>(in, in_stride, Wt, bias, out, out_stride, K, N, mode);
   GLASS_RET();
