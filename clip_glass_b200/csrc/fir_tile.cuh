@@ -136,53 +136,79 @@ __device__ __forceinline__ void fd_stage_tile(uint4* tile, const __half* __restr
 // constants arrive as a kernel parameter, i.e. through the constant bank / uniform registers, not through shared
 // memory.  The pass is issue-bound: 1.95 G -> 1.60 G warp instructions per launch at P = 64, 3.0 -> 1.7 ms (profiles/).
 struct FrgbConsts { float w[4][kFdC]; };     // rows: r, g, b weights and the bias, channels c0 .. c0+31
-constexpr int kFrPerThread = (kFdPix + 255) / 256;
+// Two horizontally adjacent pixels per thread and step, packed fp32 pairs (FFMA2 with the folded constant broadcast to
+// both lanes: 3 FFMA2 + 1 FMUL2 + 2 FMNMX per channel and pixel PAIR instead of 3 FFMA + 1 FMUL + 1 FMNMX per
+// pixel); each lane is the scalar arithmetic, so the values are unchanged.  The 34-pixel tile rows hold whole pairs.
+constexpr int kFrPairs = kFdPix / 2;
+constexpr int kFrPerThread = (kFrPairs + 255) / 256;
+static_assert(kFdIW % 2 == 0, "pixel pairs must not straddle tile rows");
 __device__ __forceinline__ void fd_stage_tile_from_rgb(uint4* tile, const float* __restrict__ images,
                                                        const FrgbConsts& k, __half* __restrict__ xout, int b, int R,
                                                        int C, int c0, int out_i8, int iy0, int ix0) {
   const size_t plane = (size_t)R * R;
   const float* img = images + (size_t)b * 3 * plane;
-  float rgb[kFrPerThread][3];
+  float rgb[kFrPerThread][2][3];
 #pragma unroll
   for (int it = 0; it < kFrPerThread; ++it) {
-    const int pix = threadIdx.x + it * 256;
+    const int pix = 2 * (threadIdx.x + it * 256);
     const int py = pix / kFdIW, px = pix - py * kFdIW;
-    const int yy = iy0 + py, xx = ix0 + px;
-    rgb[it][0] = rgb[it][1] = rgb[it][2] = 0.f;
-    if (pix < kFdPix && yy >= 0 && yy < R && xx >= 0 && xx < R) {
-      const float* ip = img + (size_t)yy * R + xx;
-      rgb[it][0] = __ldg(ip); rgb[it][1] = __ldg(ip + plane); rgb[it][2] = __ldg(ip + 2 * plane);
+    const int yy = iy0 + py;
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int xx = ix0 + px + u;
+      rgb[it][u][0] = rgb[it][u][1] = rgb[it][u][2] = 0.f;
+      if (pix < kFdPix && yy >= 0 && yy < R && xx >= 0 && xx < R) {
+        const float* ip = img + (size_t)yy * R + xx;
+        rgb[it][u][0] = __ldg(ip); rgb[it][u][1] = __ldg(ip + plane); rgb[it][u][2] = __ldg(ip + 2 * plane);
+      }
     }
   }
 #pragma unroll
   for (int it = 0; it < kFrPerThread; ++it) {
-    const int pix = threadIdx.x + it * 256;
+    const int pix = 2 * (threadIdx.x + it * 256);
     if (pix >= kFdPix) continue;
     const int py = pix / kFdIW, px = pix - py * kFdIW;
-    const int yy = iy0 + py, xx = ix0 + px;
-    const bool inside = yy >= 0 && yy < R && xx >= 0 && xx < R;
-    const float r = rgb[it][0], gg = rgb[it][1], bl = rgb[it][2];
-    // interior pixels of the tile (rows/cols 1 .. IH-2 / IW-2) belong to this block
-    const bool mine = inside && py >= 1 && py < kFdIH - 1 && px >= 1 && px < kFdIW - 1;
+    const int yy = iy0 + py;
+    const bool row_in = yy >= 0 && yy < R;
+    bool inside[2], mine[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int xx = ix0 + px + u;
+      inside[u] = row_in && xx >= 0 && xx < R;
+      // interior pixels of the tile (rows/cols 1 .. IH-2 / IW-2) belong to this block
+      mine[u] = inside[u] && py >= 1 && py < kFdIH - 1 && px + u >= 1 && px + u < kFdIW - 1;
+    }
+    const f32x2 r2 = pk2(rgb[it][0][0], rgb[it][1][0]), g2 = pk2(rgb[it][0][1], rgb[it][1][1]);
+    const f32x2 b2 = pk2(rgb[it][0][2], rgb[it][1][2]);
 #pragma unroll
     for (int g = 0; g < 4; ++g) {
-      uint4 pk = make_uint4(0, 0, 0, 0);                 // outside the image: the FIR's zero padding
-      if (inside) {
-        __half2* h2 = reinterpret_cast<__half2*>(&pk);
+      uint4 pk[2];
+      __half2* h2a = reinterpret_cast<__half2*>(&pk[0]);
+      __half2* h2b = reinterpret_cast<__half2*>(&pk[1]);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int c = g * 8 + 2 * j;
-          const float t0 = fmaf(r, k.w[0][c], fmaf(gg, k.w[1][c], fmaf(bl, k.w[2][c], k.w[3][c])));
-          const float t1 = fmaf(r, k.w[0][c + 1], fmaf(gg, k.w[1][c + 1], fmaf(bl, k.w[2][c + 1], k.w[3][c + 1])));
-          h2[j] = f2h2_sat(fmaxf(t0, 0.2f * t0), fmaxf(t1, 0.2f * t1));
+      for (int j = 0; j < 4; ++j) {
+        float lo[2], hi[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          const int c = g * 8 + 2 * j + u;
+          const f32x2 t = fma2(r2, pk2(k.w[0][c], k.w[0][c]),
+                               fma2(g2, pk2(k.w[1][c], k.w[1][c]), fma2(b2, pk2(k.w[2][c], k.w[2][c]), pk2(k.w[3][c], k.w[3][c]))));
+          upk2(lrelu2(t), lo[u], hi[u]);
         }
+        h2a[j] = f2h2_sat(lo[0], lo[1]);       // pixel px:     channels c, c+1
+        h2b[j] = f2h2_sat(hi[0], hi[1]);       // pixel px + 1
       }
-      if (mine) {
-        const size_t off = out_i8 ? ((((size_t)b * R + yy) * (C >> 3) + (c0 >> 3) + g) * R + xx) * 8
-                                  : (((size_t)b * R + yy) * R + xx) * C + c0 + g * 8;
-        *reinterpret_cast<uint4*>(xout + off) = pk;
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        if (!inside[u]) pk[u] = make_uint4(0, 0, 0, 0);           // outside the image: the FIR's zero padding
+        if (mine[u]) {
+          const int xx = ix0 + px + u;
+          const size_t off = out_i8 ? ((((size_t)b * R + yy) * (C >> 3) + (c0 >> 3) + g) * R + xx) * 8
+                                    : (((size_t)b * R + yy) * R + xx) * C + c0 + g * 8;
+          *reinterpret_cast<uint4*>(xout + off) = pk[u];
+        }
+        tile[fd_unit(g, py, px + u)] = pk[u];
       }
-      tile[fd_unit(g, py, px)] = pk;
     }
   }
 }
