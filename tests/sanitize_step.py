@@ -19,7 +19,24 @@ from clip_glass_b200.engine import GlassEngine                    # noqa: E402
 from clip_glass_b200.text_engine import TextEngine                # noqa: E402
 
 
+def full_size():
+    """--full: ONE eager full-size evaluation (ffhq-f 1024^2 + ViT-B/32, P = 4): the kernels the tiny configuration never
+    reaches -- the fused-FIR down-convs (32 -> 64 and the 128-column 64 -> 128 instance), the I8 / tile-pair conv modes,
+    the image-finishing epilogue, the specialised GEMM epilogues need M % 128 == 0 and stay on the run-time spec here."""
+    gan, clip = W.FFHQ, W.VIT_B32
+    eng = GlassEngine(gan, clip, W.make_generator_weights(gan, 1000), W.make_discriminator_weights(gan, 1001),
+                      W.make_clip_visual_weights(clip, 1002), batch_size=4, max_population=4, flags=32)
+    eng.set_text_features(torch.randn(1, 512, generator=torch.Generator().manual_seed(5)))
+    f, h = eng.evaluate(W.make_latents(4, 512, 50), seed=3)
+    print("full size neg_sim", f, "hinge", h)
+    eng.close()
+    torch.cuda.synchronize()
+    print("sanitize_step: full-size evaluation done")
+
+
 def main():
+    if "--full" in sys.argv:
+        return full_size()
     gan, clip = W.TINY_GAN, W.TINY_CLIP
     P, B = 8, 4
     text = torch.randn(1, 512, generator=torch.Generator().manual_seed(5))
