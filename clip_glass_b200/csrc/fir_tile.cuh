@@ -13,7 +13,7 @@ namespace {
 // the writes of consecutive pixels.  Plane strides are padded so that the parity planes sit 64 B apart modulo the
 // 128-byte bank row and the group planes 16 B apart.
 #ifndef GLASS_FIR_MINB
-#define GLASS_FIR_MINB 3
+#define GLASS_FIR_MINB 4       // 64 registers, no spills; 3 -> 4 resident blocks: from_rgb_fir 1.49 -> 1.43 ms, fir_down<I8> 653 -> 624 us
 #endif
 constexpr int kFdTH = 8, kFdTW = 16, kFdC = 32;
 constexpr int kFdIW = 2 * kFdTW + 2, kFdIH = 2 * kFdTH + 2;     // 34 x 18 input pixels

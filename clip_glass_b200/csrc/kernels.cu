@@ -747,8 +747,11 @@ __device__ __forceinline__ void hfir2(const uint4 (&c)[5], float (&h0)[8], float
 // k_upfir: one thread = 8 channels x 2 output columns x kUpRows output rows.  v[Z][X] = sum f f u[Z+jy-1][X+jx-1]
 // with f = [1,3,3,1]/4; then + noise + bias, lrelu*sqrt2, * next style.
 constexpr int kUpRows = 8;
+// Resident blocks per SM.  At one block (the compiler takes 254 registers to hoist the loads of all 11 rows) k_upfir ran
+// latency-bound at 12 % occupancy: 545 us; at two blocks (128 registers, 8 B spilled) 364 us at P = 64.  Three or four
+// blocks spill heavily (80 / 64 registers) and are slower again (profiles/r02_ab_streaming_occupancy.log).
 #ifndef GLASS_POLY_MINB
-#define GLASS_POLY_MINB 1
+#define GLASS_POLY_MINB 2
 #endif
 __global__ void __launch_bounds__(256, GLASS_POLY_MINB) upfir_kernel(
     const __half* __restrict__ u, __half* __restrict__ out, const float* __restrict__ noise, size_t noise_group_stride,
@@ -904,7 +907,10 @@ __device__ __forceinline__ uint4 fir4_h2(const uint4& c0, const uint4& c1, const
                   : __hfma2(__hadd2(b[j], c[j]), three, __hadd2(a[j], d[j]));
   return r;
 }
-__global__ void __launch_bounds__(256, 3) blur_s2d_tile_kernel(const __half* __restrict__ a, __half* __restrict__ out, int H,
+#ifndef GLASS_BLUR_MINB
+#define GLASS_BLUR_MINB 4      // 64 registers, no spills; 3 -> 4 resident blocks: 1.016 -> 0.997 ms over the four launches
+#endif
+__global__ void __launch_bounds__(256, GLASS_BLUR_MINB) blur_s2d_tile_kernel(const __half* __restrict__ a, __half* __restrict__ out, int H,
                                                                int W, int C, int tiles_x, int tiles_y) {
   __shared__ uint4 tile[kBtRawR * kBtPitch * 4];
   const int Hs = (H >> 1) + 1, Ws = (W >> 1) + 1;
