@@ -105,16 +105,6 @@ constexpr EpiSpec kEpiSpecs[] = {
     {false, false, false, false, kStRegular, false, kActQuickGelu, true, false},    // 16: fc: round, QuickGELU
 };
 constexpr int kNumEpiSpecs = sizeof(kEpiSpecs) / sizeof(kEpiSpecs[0]);
-// Spec 3 (the last generator conv) may finish the image in its epilogue: the four skip-sum pixels a thread interpolates
-// are fetched with cp.async into per-thread shared-memory slots at the top of the tile (the kernel sits at its register
-// cap, and fetched at the point of use their L2/DRAM latency was exposed once per tile pair): 256 threads x 4 x 16 B.
-constexpr int kImgPrefetchBytes = 256 * 4 * 16;
-#ifdef GLASS_IMG_PREFETCH           // A/B builds only: measured slower (G16 2.44 -> 2.95 ms at P = 64)
-template <int EPI> struct EpiExtra { static constexpr int kBytes = (EPI == 3) ? kImgPrefetchBytes : 0; };
-#else
-template <int EPI> struct EpiExtra { static constexpr int kBytes = 0; };
-#endif
-
 // MODE 0 ("stream"): one pipeline stage per (filter tap, 64-channel chunk): A box + B box per stage.
 // MODE 1 ("halo"):   for layers whose whole K per tap is one chunk (Cin == BK in {32,64}): the filter taps of the
 //                    n-tile stay resident in shared memory for the whole kernel, and a stage holds the input
@@ -125,8 +115,7 @@ template <int EPI> struct EpiExtra { static constexpr int kBytes = 0; };
 constexpr int kHaloTH = 8, kHaloTW = 16;
 
 
-// kExtra: bytes of per-thread prefetch slots behind the barrier block (the last generator conv, kImgPrefetchBytes)
-template <int BN, int BK, int MODE, int kExtra = 0>
+template <int BN, int BK, int MODE>
 struct Cfg {
   static constexpr int kABytes = kBlockM * BK * 2;
   static constexpr int kBBytes = BN * BK * 2;
@@ -169,6 +158,8 @@ struct Cfg {
   // warp per lane quarter owns all 32 columns (half the bookkeeping per element, no cross-warp toRGB combine)
   // and GLASS_BN32_CTAS small CTAs per SM supply the warps that hide latency.
   static constexpr bool kSmallN = (MODE == 4 && BK == 32 && BN == 32 && GLASS_BN32_CTAS > 2);   // measured slower
+  // (16 warps for the 64-column 64-channel MODE 4 layers, measured at the end of round 2: G15 2.40 -> 2.57 ms, D1:c0
+  // 1.25 -> 1.40 ms: 96 registers at 576 threads spill and the four column parts quadruple the toRGB exchange)
   static constexpr int kEpiWarps = (MODE == 4 && BN == 128) ? 16 : (kSmallN ? 4 : 8);
   static constexpr int kParts = kEpiWarps / 4;                      // column parts per lane quarter
   static constexpr int kThreads = 64 + 32 * kEpiWarps;
@@ -177,15 +168,14 @@ struct Cfg {
   // the 32-channel MODE-1 layers are bookkeeping/latency-bound, not smem-bound: run two CTAs per SM there
   static constexpr int kMinBlocks = kSmallN ? GLASS_BN32_CTAS : (((MODE == 1 || MODE == 4) && BK == 32 && BN <= 32) ? 2 : 1);
   static constexpr int kBudget = (kMinBlocks == 4 ? 54 : (kMinBlocks == 3 ? 73 : (kMinBlocks == 2 ? 110 : 222))) * 1024 -
-                                 kParamBytes - kWBytes - kExtra;   // of 227 KB/SM (+1 KB reserved per CTA)
+                                 kParamBytes - kWBytes;   // of 227 KB/SM (+1 KB reserved per CTA)
   static constexpr int kStagesRaw = kBudget / kStageBytes;
   static constexpr int kStages = kStagesRaw > 12 ? 12 : kStagesRaw;
   static_assert(kStages >= 2, "not enough shared memory for a double-buffered pipeline");
   static constexpr int kAccCols = kPairM * BN;                     // TMEM columns of one accumulator stage
   static constexpr int kTmemCols = (2 * kAccCols < 32) ? 32 : 2 * kAccCols;   // power of two for BN in {32,..,256}
   static_assert(kTmemCols <= 512, "TMEM has 512 columns");
-  static constexpr int kSmemBytes =
-      kWBytes + kStages * kStageBytes + kParamBytes + 1024 /*align*/ + 256 /*barriers*/ + kExtra;
+  static constexpr int kSmemBytes = kWBytes + kStages * kStageBytes + kParamBytes + 1024 /*align*/ + 256 /*barriers*/;
   // instruction descriptor: D=f32 [4,6)=1, A=B=f16 (0), K-major both, N>>3 [17,23), M>>4 [24,29)
   static constexpr uint32_t kIdesc = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(kBlockM >> 4) << 24);
 };
@@ -347,10 +337,10 @@ __device__ __forceinline__ void epilogue_fast16(const EpiParams& e, const float*
 }
 
 template <int BN, int BK, int MODE, int EPI>
-__global__ void __launch_bounds__((Cfg<BN, BK, MODE>::kThreads), (Cfg<BN, BK, MODE>::kMinBlocks))   // (kExtra-independent)
+__global__ void __launch_bounds__((Cfg<BN, BK, MODE>::kThreads), (Cfg<BN, BK, MODE>::kMinBlocks))
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                const ConvParams p) {
-  using C = Cfg<BN, BK, MODE, EpiExtra<EPI>::kBytes>;
+  using C = Cfg<BN, BK, MODE>;
   constexpr EpiSpec S = kEpiSpecs[EPI];
   constexpr bool kPow2 = !S.generic && S.pow2;   // power-of-two tile grids and channel counts: decode with shifts
   extern __shared__ uint8_t smem_raw[];
@@ -370,8 +360,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(b_empty + C::kBStages);
   static_assert((2 * C::kStages + 5 + 2 * C::kBStages) * 8 + 8 <= 256, "barrier block overflows its 256 bytes");
   float* nscale_slot = reinterpret_cast<float*>(tmem_slot + 1);
-  constexpr bool kImgPrefetch = EpiExtra<EPI>::kBytes > 0 && C::kPairM == 2 && C::kParts == 2;
-  const uint32_t img_slots = smem_u32(bars) + 256;       // [4 values][256 epilogue threads] x 16 B (kImgPrefetch)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -719,35 +707,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       const int n_tile = tc.n_tile, tn = tc.tn;
       const int img = tn * p.TN + ri, y = tc.ty * p.TH + ry, x = tc.tx * p.TW + rx;
       const bool valid = all_valid || (img < p.Nimg && y < H && x < W);
-      if (kImgPrefetch && e.image != nullptr) {
-        // skip-sum pixels (zy-1..zy, zx-1..zx) of the output pixel this thread finishes (tile `half` of the pair);
-        // outside the image: zero-filled (src-size 0, the pointer stays inside the tensor)
-        const int X = x + 8 * half, Wp = W >> 1, zy = y >> 1, zx = X >> 1;
-        const float4* base = e.img_yprev + ((img * (H >> 1) + zy) * Wp + zx);
-        const uint32_t dst = img_slots + et * 16;
-        cp_async16_zfill(dst, (zy > 0 && zx > 0) ? base - Wp - 1 : base, (zy > 0 && zx > 0) ? 16 : 0);
-        cp_async16_zfill(dst + 4096, zy > 0 ? base - Wp : base, zy > 0 ? 16 : 0);
-        cp_async16_zfill(dst + 8192, zx > 0 ? base - 1 : base, zx > 0 ? 16 : 0);
-        cp_async16_zfill(dst + 12288, base, 16);
-        asm volatile("cp.async.commit_group;" ::: "memory");
-      }
-#ifdef GLASS_IMG_REG_PREFETCH
-      constexpr bool kImgRegs = (EPI == 3) && C::kPairM == 2 && C::kParts == 2 && !kImgPrefetch;
-#else
-      constexpr bool kImgRegs = false;
-#endif
-      float4 yv[4];                       // kImgRegs: the four skip-sum pixels, requested before the accumulator wait
-      if (kImgRegs) {
-        yv[0] = yv[1] = yv[2] = yv[3] = make_float4(0, 0, 0, 0);
-        if (e.image != nullptr) {
-          const int X = x + 8 * half, Wp = W >> 1, zy = y >> 1, zx = X >> 1;
-          const float4* base = e.img_yprev + ((img * (H >> 1) + zy) * Wp + zx);
-          yv[3] = __ldg(base);
-          if (zy > 0 && zx > 0) yv[0] = __ldg(base - Wp - 1);
-          if (zy > 0) yv[1] = __ldg(base - Wp);
-          if (zx > 0) yv[2] = __ldg(base - 1);
-        }
-      }
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + as * C::kAccCols + half * kHalf;
@@ -967,21 +926,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             const int Wp = W >> 1, zy = Y >> 1, zx = X >> 1;
             const float wy0 = (Y & 1) ? 0.25f : 0.75f, wy1 = 1.f - wy0;
             const float wx0 = (X & 1) ? 0.25f : 0.75f, wx1 = 1.f - wx0;
-            float4 a = make_float4(0, 0, 0, 0), c = a, d = a, ee;
-            if (kImgPrefetch) {
-              // fetched by this thread at the top of the tile (cp.async above)
-              asm volatile("cp.async.wait_group 0;" ::: "memory");
-              const uint32_t src = img_slots + et * 16;
-              a = lds128f(src); c = lds128f(src + 4096); d = lds128f(src + 8192); ee = lds128f(src + 12288);
-            } else if (kImgRegs) {
-              a = yv[0]; c = yv[1]; d = yv[2]; ee = yv[3];
-            } else {
-              const float4* base = e.img_yprev + ((img * (H >> 1) + zy) * Wp + zx);    // (pixel counts stay < 2^31)
-              ee = __ldg(base);
-              if (zy > 0 && zx > 0) a = __ldg(base - Wp - 1);
-              if (zy > 0) c = __ldg(base - Wp);
-              if (zx > 0) d = __ldg(base - 1);
-            }
+            // (Fetching these four pixels ahead of the accumulator wait -- into registers, or with cp.async into
+            // per-thread shared-memory slots -- was measured neutral / slower: DESIGN.md 7.0.)
+            const float4* base = e.img_yprev + ((img * (H >> 1) + zy) * Wp + zx);      // (pixel counts stay < 2^31)
+            float4 a = make_float4(0, 0, 0, 0), c = a, d = a;
+            const float4 ee = __ldg(base);
+            if (zy > 0 && zx > 0) a = __ldg(base - Wp - 1);
+            if (zy > 0) c = __ldg(base - Wp);
+            if (zx > 0) d = __ldg(base - 1);
             const float r = __fadd_rn(__fadd_rn(__ldg(e.img_bias), r0), skip_up2(wy0, wy1, wx0, wx1, a.x, c.x, d.x, ee.x));
             const float g = __fadd_rn(__fadd_rn(__ldg(e.img_bias + 1), r1), skip_up2(wy0, wy1, wx0, wx1, a.y, c.y, d.y, ee.y));
             const float bl = __fadd_rn(__fadd_rn(__ldg(e.img_bias + 2), r2), skip_up2(wy0, wy1, wx0, wx1, a.z, c.z, d.z, ee.z));
@@ -1051,7 +1003,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 
 template <int BN, int BK, int MODE, int EPI = 0>
 cudaError_t launch_one(const ConvParams& p, const TmaMaps& maps, int num_sms, cudaStream_t s) {
-  using C = Cfg<BN, BK, MODE, EpiExtra<EPI>::kBytes>;
+  using C = Cfg<BN, BK, MODE>;
   static bool configured = false;
   if (!configured) {
     cudaError_t err = cudaFuncSetAttribute(conv_tc_kernel<BN, BK, MODE, EPI>,

@@ -145,15 +145,5 @@ __device__ __forceinline__ void tc_ld16_issue(uint32_t taddr, uint32_t (&r)[16])
 }
 __device__ __forceinline__ void tc_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
-// 16-byte global -> shared copy that bypasses the register file (LDGSTS); src_bytes in {0, 16}: 0 zero-fills
-__device__ __forceinline__ void cp_async16_zfill(uint32_t dst_smem, const void* src, int src_bytes) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst_smem), "l"(src), "r"(src_bytes) : "memory");
-}
-__device__ __forceinline__ float4 lds128f(uint32_t saddr) {
-  float4 v;
-  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr));
-  return v;
-}
-
 }  // namespace
 }  // namespace glass

@@ -135,6 +135,12 @@ def test_full_size_properties(full_engine):
     f_sub, h_sub = eng.evaluate(x[4:12], noise=noise[1:3])
     np.testing.assert_array_equal(f_all[4:12], f_sub)
     np.testing.assert_array_equal(h_all[4:12], h_sub)
+    # one minibatch alone: populations below 8 run the per-candidate GEMV kernel instead of the population-tiled one
+    # (kernels.cu: vecmat_tile_kernel keeps vecmat_kernel's summation order) and the small-grid tile-width rule picks
+    # other column tiles for the 4x4 .. 16x16 layers -- the scores must not notice either
+    f_one, h_one = eng.evaluate(x[4:8], noise=noise[1:2])
+    np.testing.assert_array_equal(f_all[4:8], f_one)
+    np.testing.assert_array_equal(h_all[4:8], h_one)
     perm = np.concatenate([np.arange(8, 12), np.arange(0, 4), np.arange(12, 16), np.arange(4, 8)])
     f_p, h_p = eng.evaluate(x[perm], noise=[noise[2], noise[0], noise[3], noise[1]])
     np.testing.assert_array_equal(f_p, f_all[perm])
