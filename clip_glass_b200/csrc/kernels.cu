@@ -93,13 +93,13 @@ __global__ void vecmat_kernel(const float* __restrict__ in, int in_stride, const
   out[(size_t)b * out_stride + n] = acc;
 }
 
-// The same product for a whole population tile per block: out[b][n] for 64 candidates x 16 output columns, with the
-// candidates' input rows (64 x K fp32) and the 16-column weight slice (K x 16) staged in shared memory ONCE.
+// The same product for a whole population tile per block: out[b][n] for 32 candidates x 16 output columns, with the
+// candidates' input rows (32 x K fp32) and the 16-column weight slice (K x 16) staged in shared memory ONCE.
 // vecmat_kernel reads every weight through L2 once per candidate in 32 dependent batches (34 us per 512x512 mapping
-// layer at P = 64, pure latency); here a weight is read once per 64 candidates.  Thread = (column n, 4 candidates); the
+// layer at P = 64, pure latency); here a weight is read once per 32 candidates.  Thread = (column n, 2 candidates); the
 // four partial sums per output run over k = 0,4,8,.. / 1,5,9,.. / .. in ascending order and are combined as
 // (a0 + a1) + (a2 + a3): exactly vecmat_kernel's summation order, so the results are bit-identical (K % 16 == 0).
-constexpr int kVtCand = 64, kVtCols = 16;
+constexpr int kVtCand = 32, kVtCols = 16, kVtPer = 2;       // 256 threads = 16 columns x 16 candidate pairs
 __global__ void __launch_bounds__(256) vecmat_tile_kernel(const float* __restrict__ in, int in_stride,
                                                           const float* __restrict__ Wt, const float* __restrict__ bias,
                                                           float* __restrict__ out, int out_stride, int P, int K, int N,
@@ -109,22 +109,34 @@ __global__ void __launch_bounds__(256) vecmat_tile_kernel(const float* __restric
   float* ws = xs + (size_t)kVtCand * K;                     // [K][kVtCols]
   const int n0 = blockIdx.x * kVtCols, b0 = blockIdx.y * kVtCand;
   const int nb = min(kVtCand, P - b0);
-  // staging: eight loads in flight per thread before the first store (issued one by one, every load exposed a full L2
-  // round trip: 32 dependent round trips per thread made the first version slower than vecmat_kernel)
-  for (int i0 = threadIdx.x; i0 < K * kVtCols; i0 += 8 * blockDim.x) {
-    float v[8];
+  // staging: eight 16-byte loads in flight per thread before the first store (issued one by one, every load exposed a
+  // full L2 round trip: 32 dependent round trips per thread made the first version slower than vecmat_kernel)
+  const int K4 = K >> 2;
+  const bool wvec = (N & 3) == 0 && n0 + kVtCols <= N;      // whole 16-column rows, 16-byte aligned
+  for (int i0 = threadIdx.x; i0 < K * (kVtCols / 4); i0 += 8 * blockDim.x) {
+    float4 v[8];
 #pragma unroll
     for (int u = 0; u < 8; ++u) {
-      const int i = i0 + u * blockDim.x, k = i / kVtCols, c = i - k * kVtCols;
-      v[u] = (i < K * kVtCols && n0 + c < N) ? __ldg(Wt + (size_t)k * N + n0 + c) : 0.f;
+      const int i = i0 + u * blockDim.x, k = i / (kVtCols / 4), c4 = i - k * (kVtCols / 4);
+      v[u] = make_float4(0, 0, 0, 0);
+      if (i < K * (kVtCols / 4)) {
+        const float* wp = Wt + (size_t)k * N + n0 + 4 * c4;
+        if (wvec) {
+          v[u] = __ldg(reinterpret_cast<const float4*>(wp));
+        } else {
+          if (n0 + 4 * c4 + 0 < N) v[u].x = __ldg(wp + 0);
+          if (n0 + 4 * c4 + 1 < N) v[u].y = __ldg(wp + 1);
+          if (n0 + 4 * c4 + 2 < N) v[u].z = __ldg(wp + 2);
+          if (n0 + 4 * c4 + 3 < N) v[u].w = __ldg(wp + 3);
+        }
+      }
     }
 #pragma unroll
     for (int u = 0; u < 8; ++u) {
       const int i = i0 + u * blockDim.x;
-      if (i < K * kVtCols) ws[i] = v[u];
+      if (i < K * (kVtCols / 4)) reinterpret_cast<float4*>(ws)[i] = v[u];
     }
   }
-  const int K4 = K >> 2;
   for (int i0 = threadIdx.x; i0 < kVtCand * K4; i0 += 8 * blockDim.x) {
     float4 v[8];
 #pragma unroll
@@ -140,17 +152,17 @@ __global__ void __launch_bounds__(256) vecmat_tile_kernel(const float* __restric
     }
   }
   __syncthreads();
-  const int c = threadIdx.x & (kVtCols - 1), cg = threadIdx.x / kVtCols;     // candidates 4 cg .. 4 cg + 3
-  float acc[4][4];
+  const int c = threadIdx.x & (kVtCols - 1), cg = threadIdx.x / kVtCols;     // candidates kVtPer cg .. + kVtPer - 1
+  float acc[kVtPer][4];
 #pragma unroll
-  for (int u = 0; u < 4; ++u) acc[u][0] = acc[u][1] = acc[u][2] = acc[u][3] = 0.f;
-  const float4* x4 = reinterpret_cast<const float4*>(xs) + (size_t)(4 * cg) * K4;
-#pragma unroll 2
+  for (int u = 0; u < kVtPer; ++u) acc[u][0] = acc[u][1] = acc[u][2] = acc[u][3] = 0.f;
+  const float4* x4 = reinterpret_cast<const float4*>(xs) + (size_t)(kVtPer * cg) * K4;
+#pragma unroll 4
   for (int k4 = 0; k4 < K4; ++k4) {
     const float w0 = ws[(4 * k4 + 0) * kVtCols + c], w1 = ws[(4 * k4 + 1) * kVtCols + c];
     const float w2 = ws[(4 * k4 + 2) * kVtCols + c], w3 = ws[(4 * k4 + 3) * kVtCols + c];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
+    for (int u = 0; u < kVtPer; ++u) {
       const float4 x = x4[(size_t)u * K4 + k4];
       acc[u][0] = fmaf(x.x, w0, acc[u][0]);
       acc[u][1] = fmaf(x.y, w1, acc[u][1]);
@@ -162,8 +174,8 @@ __global__ void __launch_bounds__(256) vecmat_tile_kernel(const float* __restric
   if (n >= N) return;
   const float bv = bias != nullptr ? bias[n] : 0.f;
 #pragma unroll
-  for (int u = 0; u < 4; ++u) {
-    const int b = b0 + 4 * cg + u;
+  for (int u = 0; u < kVtPer; ++u) {
+    const int b = b0 + kVtPer * cg + u;
     if (b >= P) break;
     float a = (acc[u][0] + acc[u][1]) + (acc[u][2] + acc[u][3]);
     if (bias != nullptr) a += bv;
@@ -552,15 +564,6 @@ __global__ void final_cosine_kernel(const __half* __restrict__ tokens, const flo
     // four independent partial sums (the serial 768-long dependent chain was 0.3 ms of pure latency)
     float a4[4] = {0.f, 0.f, 0.f, 0.f};
     int i = 0;
-    // sixteen projection weights in flight per thread (issued four at a time the loop was 192 dependent L2 round trips:
-    // 188 us for a 0.8 MFLOP kernel); same partial sums in the same order
-    for (; i + 16 <= W; i += 16) {
-      float w16[16];
-#pragma unroll
-      for (int u = 0; u < 16; ++u) w16[u] = __ldg(proj + (size_t)(i + u) * E + e);
-#pragma unroll
-      for (int u = 0; u < 16; ++u) a4[u & 3] = fmaf(c[i + u], w16[u], a4[u & 3]);
-    }
     for (; i + 4 <= W; i += 4) {
 #pragma unroll
       for (int u = 0; u < 4; ++u) a4[u] = fmaf(c[i + u], __ldg(proj + (size_t)(i + u) * E + e), a4[u]);
@@ -1045,10 +1048,10 @@ cudaError_t k_vecmat(const float* in, int in_stride, const float* Wt, const floa
                      int P, int K, int N, int mode, cudaStream_t s) {
   // population tiles (bit-identical to vecmat_kernel, see vecmat_tile_kernel) whenever the staged rows fit
   const size_t tile_smem = ((size_t)kVtCand * K + (size_t)K * kVtCols) * sizeof(float);
-  if (mode != 2 && K % 16 == 0 && in_stride % 4 == 0 && tile_smem <= 200 * 1024 && P >= 8) {
+  if (mode != 2 && K % 16 == 0 && in_stride % 4 == 0 && tile_smem <= 110 * 1024 && P >= 8) {
     static bool configured = false;
     if (!configured) {
-      cudaError_t err = cudaFuncSetAttribute(vecmat_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+      cudaError_t err = cudaFuncSetAttribute(vecmat_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024);
       if (err != cudaSuccess) return err;
       configured = true;
     }
