@@ -28,6 +28,7 @@ FLAG_NO_ZERO_SKIP = 256
 FLAG_NO_FUSED_DOWN = 512
 FLAG_NO_IMAGE_FUSION = 1024
 FLAG_FP32_BLUR = 2048
+FLAG_NO_PROJ_ACC = 4096
 
 SYMBOLS = [
     "glass_create", "glass_set_tensor", "glass_finalize", "glass_set_text_features", "glass_destroy",

@@ -15,6 +15,12 @@
 //
 // Accumulator tile: 8 wide x 16 tall output pixels; channels are processed in 32-channel passes (C = 64: two passes
 // accumulate into the same TMEM columns).
+//
+// kProj (the 32 -> 64 block): the block's projection path (1x1 conv of the FIR-downsampled block input,
+// stylegan2/modules.py:1352-1372, the residual operand of this conv) is a SECOND accumulator of the same tile: TMA
+// brings the 128 x 32 tile of the downsampled input next to the raw tile, two more MMAs (K = 32) run against the
+// resident projection weights, and the epilogue adds the fp32 result -- the projection GEMM launch and the round trip
+// of its fp16 output tensor through HBM (2.1 GB written and read back at P = 64) disappear.
 #include "common.cuh"
 #include "kernels.cuh"
 #include "tcgen05.cuh"
@@ -38,8 +44,12 @@ struct DownParams {
   float post_scale;
 };
 
-template <int C, int BN>
+constexpr int kDcXdBytes = 128 * 32 * 2;                 // kProj: the tile of the downsampled block input (128 pixels x 32 ch)
+template <int C, int BN, bool kProj = false>
 struct DCfg {
+  static_assert(!kProj || (C == 32 && BN == 64), "the projection accumulator exists for the 32 -> 64 block");
+  static constexpr int kProjBytes = kProj ? 2 * kDcXdBytes + BN * C * 2 : 0;      // two tile stages + the 1x1 weights
+  static constexpr int kProjPad = kProj ? 1024 : 0;                               // (alignment of those operands)
   // 8-channel groups per pass.  BN = 64: 32-channel passes.  BN = 128 (the 64 -> 128 block): all 128 output columns of a
   // pixel tile come from ONE blur of that tile (with 64-column n-tiles every tile was loaded and blurred once per
   // n-tile: 2.5 ms, the slowest launch of the step); the nine 128-column taps take 147 KB of shared memory, so the
@@ -67,8 +77,9 @@ struct DCfg {
   static constexpr int kBlurStages = (C == 32 || BN == 128) ? 2 : 1;
   static constexpr int kWBytes = 9 * BN * C * 2;
   static constexpr int kTapBytes = BN * C * 2;
-  static constexpr int kSmemBytes = kWBytes + kRawStages * kRawBytes + kBlurStages * kBlurBytes + 1024 + 256 + BN * 4;
-  static constexpr int kTmemCols = 2 * BN < 32 ? 32 : 2 * BN;
+  static constexpr int kSmemBytes =
+      kWBytes + kRawStages * kRawBytes + kBlurStages * kBlurBytes + kProjBytes + kProjPad + 1024 + 256 + BN * 4;
+  static constexpr int kTmemCols = (kProj ? 4 : 2) * BN < 32 ? 32 : (kProj ? 4 : 2) * BN;
   static constexpr uint32_t kIdesc = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
   static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
 };
@@ -130,11 +141,12 @@ __device__ __forceinline__ uint2 fir4h(const uint2& c0, const uint2& c1, const u
   return r;
 }
 
-template <int C, int BN>
+template <int C, int BN, bool kProj>
 __global__ void __launch_bounds__(kDcThreads, 1)
 downconv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
+                   const __grid_constant__ CUtensorMap map_xd, const __grid_constant__ CUtensorMap map_wp,
                    const DownParams p) {
-  using Cf = DCfg<C, BN>;
+  using Cf = DCfg<C, BN, kProj>;
   // Worker-warp organisation, chosen by measurement at P = 64 (profiles/): dedicated blur / epilogue warps for the
   // 32-channel block (2.20 ms against 2.6 ms merged), merged roles for the 64-channel block, whose two 32-channel
   // passes per tile double the blur work per epilogue (2.5 ms against 3.3 ms with dedicated warps).
@@ -143,7 +155,10 @@ downconv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
   uint8_t* smem_w = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* raw = smem_w + Cf::kWBytes;
   uint8_t* blur = raw + Cf::kRawStages * Cf::kRawBytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(blur + Cf::kBlurStages * Cf::kBlurBytes);
+  // kProj: [2 stages][128 pixels][32 ch], 64B-swizzled rows, on a 1024-byte boundary like every swizzled operand
+  uint8_t* xd = smem_w + ((Cf::kWBytes + Cf::kRawStages * Cf::kRawBytes + Cf::kBlurStages * Cf::kBlurBytes + 1023) & ~1023);
+  uint8_t* wproj = xd + 2 * kDcXdBytes;                      // kProj: [BN][C] K-major, 64B-swizzled
+  uint64_t* bars = reinterpret_cast<uint64_t*>(kProj ? xd + Cf::kProjBytes : blur + Cf::kBlurStages * Cf::kBlurBytes);
   uint64_t* raw_full = bars;
   uint64_t* raw_empty = raw_full + 2;
   uint64_t* blur_full = raw_empty + 2;
@@ -151,7 +166,8 @@ downconv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
   uint64_t* tmem_full = blur_empty + 2;
   uint64_t* tmem_empty = tmem_full + 2;
   uint64_t* w_bar = tmem_empty + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_bar + 1);
+  uint64_t* xd_empty = w_bar + 1;                            // kProj: the tile stage has been read by its MMAs
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(xd_empty + 2);
   float* bias_s = reinterpret_cast<float*>(bars) + 64;        // [BN] bias * sqrt2 * post_scale of this CTA's n-tile
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -163,6 +179,10 @@ downconv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
   if (threadIdx.x == 0) {
     prefetch_tmap(&map_a);
     prefetch_tmap(&map_w);
+    if (kProj) {
+      prefetch_tmap(&map_xd);
+      prefetch_tmap(&map_wp);
+    }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&raw_full[s], 1);
       mbar_init(&raw_empty[s], kSplitRoles ? 8 : 16);
@@ -170,6 +190,7 @@ downconv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
       mbar_init(&blur_empty[s], 1);
       mbar_init(&tmem_full[s], 1);
       mbar_init(&tmem_empty[s], kSplitRoles ? 8 : 16);
+      mbar_init(&xd_empty[s], 1);
     }
     mbar_init(w_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -196,8 +217,9 @@ downconv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (elect_one()) {
-      mbar_expect_tx(w_bar, Cf::kWBytes);
+      mbar_expect_tx(w_bar, Cf::kWBytes + (kProj ? BN * C * 2 : 0));
       for (int tap = 0; tap < 9; ++tap) tma_load_3d(&map_w, smem_w + tap * Cf::kTapBytes, w_bar, 0, n_tile * BN, tap);
+      if (kProj) tma_load_2d(&map_wp, wproj, w_bar, 0, n_tile * BN);
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -205,7 +227,10 @@ downconv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
         decode(tile, img, ty, tx);
         for (int h = 0; h < Cf::kPasses; ++h) {
           mbar_wait_backoff(&raw_empty[stage], phase ^ 1);
-          mbar_expect_tx(&raw_full[stage], Cf::kRawBytes);
+          if (kProj) mbar_wait_backoff(&xd_empty[stage], phase ^ 1);
+          mbar_expect_tx(&raw_full[stage], Cf::kRawBytes + (kProj ? kDcXdBytes : 0));
+          // kProj (one pass per tile): the 8 x 16 tile of the downsampled block input rides on the raw tile's barrier
+          if (kProj) tma_load_4d(&map_xd, xd + stage * kDcXdBytes, &raw_full[stage], 0, tx * kDcTW, ty * kDcTH, img);
           // (elements, group, row, image): raw columns 2*x0-2 .. +19, groups kG*h .. +kG-1, rows 2*y0-2 .. +35
           tma_load_4d(&map_a, raw + stage * Cf::kRawBytes, &raw_full[stage], (2 * tx * kDcTW - 2) * 8, h * Cf::kG,
                       2 * ty * kDcTH - 2, img);
@@ -219,13 +244,25 @@ downconv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
       mbar_wait(w_bar, 0);
       tc_fence_after();
       const uint32_t sw = smem_u32(smem_w);
-      int bstage = 0, it = 0;
-      uint32_t bphase = 0;
+      int bstage = 0, it = 0, rstage = 0;
+      uint32_t bphase = 0, rphase = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
         const int as = it & 1;
         mbar_wait_backoff(&tmem_empty[as], ((it >> 1) & 1) ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + as * BN;
+        if (kProj) {
+          // projection accumulator (columns 2 BN ..): W_proj . xd over the same 128 pixels, K = C = 32
+          mbar_wait_backoff(&raw_full[rstage], rphase);          // (the tile stage shares the raw tile's barrier)
+          tc_fence_after();
+          const uint64_t dxa = make_smem_desc<32>(smem_u32(xd + rstage * kDcXdBytes));
+          const uint64_t dxb = make_smem_desc<32>(smem_u32(wproj));
+#pragma unroll
+          for (int k = 0; k < 2; ++k)
+            tc_mma_f16(tmem_base + 2 * BN + as * BN, dxa + (uint64_t)(k * 2), dxb + (uint64_t)(k * 2), Cf::kIdesc, (uint32_t)k);
+          tc_commit(&xd_empty[rstage]);
+          if (++rstage == Cf::kRawStages) { rstage = 0; rphase ^= 1; }
+        }
         for (int h = 0; h < Cf::kPasses; ++h) {
           mbar_wait_backoff(&blur_full[bstage], bphase);
           tc_fence_after();
@@ -270,12 +307,15 @@ downconv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
       const int y = ty * kDcTH + ry, x = tx * kDcTW + rx;
       const int n0 = n_tile * BN + half * kCols;
       const size_t pix = ((size_t)img * p.Ho + y) * p.Wo + x;
-      // residual operand fetched before the accumulator wait (hides its DRAM latency)
+      // residual operand fetched before the accumulator wait (hides its DRAM latency); kProj: it is the second
+      // accumulator of this tile instead
       uint4 resv[kChunks][2];
 #pragma unroll
       for (int c = 0; c < kChunks; ++c) {
         const int nc = n0 + c * 16;
-        if (p.res_i8) {
+        if (kProj) {
+          resv[c][0] = resv[c][1] = make_uint4(0, 0, 0, 0);
+        } else if (p.res_i8) {
           const __half* rp = p.residual + ((((size_t)img * p.Ho + y) * (p.Cout >> 3) + (nc >> 3)) * p.Wo + x) * 8;
           resv[c][0] = __ldg(reinterpret_cast<const uint4*>(rp));
           resv[c][1] = __ldg(reinterpret_cast<const uint4*>(rp + (size_t)p.Wo * 8));
@@ -309,11 +349,21 @@ downconv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
         uint4 w0, w1;
         __half2* h0 = reinterpret_cast<__half2*>(&w0);
         __half2* h1 = reinterpret_cast<__half2*>(&w1);
+        if (kProj) {
+          float r[16];                           // projection of this pixel, fp32 (never rounded to fp16)
+          tc_ld16(taddr + 2 * BN + c * 16, r);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float2 a = __half22float2(r0[j]), b = __half22float2(r1[j]);
-          h0[j] = f2h2_sat(fmaf(a.x, p.post_scale, t[2 * j]), fmaf(a.y, p.post_scale, t[2 * j + 1]));
-          h1[j] = f2h2_sat(fmaf(b.x, p.post_scale, t[8 + 2 * j]), fmaf(b.y, p.post_scale, t[8 + 2 * j + 1]));
+          for (int j = 0; j < 4; ++j) {
+            h0[j] = f2h2_sat(fmaf(r[2 * j], p.post_scale, t[2 * j]), fmaf(r[2 * j + 1], p.post_scale, t[2 * j + 1]));
+            h1[j] = f2h2_sat(fmaf(r[8 + 2 * j], p.post_scale, t[8 + 2 * j]), fmaf(r[8 + 2 * j + 1], p.post_scale, t[8 + 2 * j + 1]));
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float2 a = __half22float2(r0[j]), b = __half22float2(r1[j]);
+            h0[j] = f2h2_sat(fmaf(a.x, p.post_scale, t[2 * j]), fmaf(a.y, p.post_scale, t[2 * j + 1]));
+            h1[j] = f2h2_sat(fmaf(b.x, p.post_scale, t[8 + 2 * j]), fmaf(b.y, p.post_scale, t[8 + 2 * j + 1]));
+          }
         }
         if (p.out_i8) {
           __half* op = p.out + ((((size_t)img * p.Ho + y) * (p.Cout >> 3) + (nc >> 3)) * p.Wo + x) * 8;
@@ -534,13 +584,13 @@ downconv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
   }
 }
 
-template <int C, int BN>
-cudaError_t launch_down(const CUtensorMap& map_a, const CUtensorMap& map_w, const DownParams& p, int num_sms,
-                        cudaStream_t s) {
-  using Cf = DCfg<C, BN>;
+template <int C, int BN, bool kProj = false>
+cudaError_t launch_down(const CUtensorMap& map_a, const CUtensorMap& map_w, const CUtensorMap& map_xd,
+                        const CUtensorMap& map_wp, const DownParams& p, int num_sms, cudaStream_t s) {
+  using Cf = DCfg<C, BN, kProj>;
   static bool configured = false;
   if (!configured) {
-    cudaError_t err = cudaFuncSetAttribute(downconv_tc_kernel<C, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t err = cudaFuncSetAttribute(downconv_tc_kernel<C, BN, kProj>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            Cf::kSmemBytes);
     if (err != cudaSuccess) return err;
     configured = true;
@@ -550,7 +600,7 @@ cudaError_t launch_down(const CUtensorMap& map_a, const CUtensorMap& map_w, cons
   int grid = total < num_sms ? total : num_sms;
   grid = (grid / n_tiles) * n_tiles;
   if (grid <= 0) return cudaErrorInvalidValue;
-  downconv_tc_kernel<C, BN><<<grid, kDcThreads, Cf::kSmemBytes, s>>>(map_a, map_w, p);
+  downconv_tc_kernel<C, BN, kProj><<<grid, kDcThreads, Cf::kSmemBytes, s>>>(map_a, map_w, map_xd, map_wp, p);
   return cudaGetLastError();
 }
 
@@ -562,28 +612,33 @@ bool k_downconv_fused_supported(int C, int Cout, int Ho, int Wo) {
          pow2(Ho / kDcTH) && pow2(Wo / kDcTW);
 }
 
-cudaError_t k_downconv_fused(const CUtensorMap& map_a, const CUtensorMap& map_w, int C, int N, int Ho, int Wo, int Cout,
-                             const float* bias, const __half* residual, int res_i8, __half* out, int out_i8,
-                             float post_scale, int num_sms, cudaStream_t s) {
+bool k_downconv_proj_supported(int C, int Cout) { return C == 32 && Cout == 64; }
+
+// map_xd / map_wp (non-null only where k_downconv_proj_supported): the projection path as a second accumulator -- the
+// FIR-downsampled block input [C, Wo, Ho, N] (box C x 8 x 16 x 1, 64B swizzle) and the 1x1 weights [C, Cout] (box
+// C x 64); `residual` is ignored then.
+cudaError_t k_downconv_fused(const CUtensorMap& map_a, const CUtensorMap& map_w, const CUtensorMap* map_xd,
+                             const CUtensorMap* map_wp, int C, int N, int Ho, int Wo, int Cout, const float* bias,
+                             const __half* residual, int res_i8, __half* out, int out_i8, float post_scale, int num_sms,
+                             cudaStream_t s) {
   auto lg = [](int v) { int s = 0; while ((1 << s) < v) ++s; return ((1 << s) == v) ? s : -1; };
   const int sx = lg(Wo / kDcTW), sy = lg(Ho / kDcTH);
   if (sx < 0 || sy < 0 || Cout / 64 > 2) return cudaErrorInvalidValue;
   DownParams p{N, Ho, Wo, Cout, sx, sy, bias, residual, res_i8, out, out_i8, post_scale};
-  if (C == 32) return launch_down<32, 64>(map_a, map_w, p, num_sms, s);
-#ifndef GLASS_NO_WIDE_DOWN          // (A/B builds only)
-  if (C == 64 && Cout == 128) return launch_down<64, 128>(map_a, map_w, p, num_sms, s);
-#endif
-  if (C == 64) return launch_down<64, 64>(map_a, map_w, p, num_sms, s);
+  if (map_xd != nullptr && map_wp != nullptr) {
+    if (!k_downconv_proj_supported(C, Cout)) return cudaErrorInvalidValue;
+    return launch_down<32, 64, true>(map_a, map_w, *map_xd, *map_wp, p, num_sms, s);
+  }
+  // (the two extra tensor maps are kernel parameters of every instance; unused ones just repeat map_a / map_w)
+  if (C == 32) return launch_down<32, 64>(map_a, map_w, map_a, map_w, p, num_sms, s);
+  if (C == 64 && Cout == 128) return launch_down<64, 128>(map_a, map_w, map_a, map_w, p, num_sms, s);
+  if (C == 64) return launch_down<64, 64>(map_a, map_w, map_a, map_w, p, num_sms, s);
   return cudaErrorInvalidValue;
 }
 
 // TMA box geometry the kernel instance for (C, Cout) expects: 8-channel groups per raw box, output columns per tap box
 void k_downconv_fused_geometry(int C, int Cout, int* box_groups, int* box_cols) {
-#ifndef GLASS_NO_WIDE_DOWN
   const bool wide = (C == 64 && Cout == 128);
-#else
-  const bool wide = false;
-#endif
   *box_groups = wide ? DCfg<64, 128>::kG : DCfg<32, 64>::kG;
   *box_cols = wide ? 128 : 64;
 }

@@ -59,6 +59,9 @@ struct ConvLaunch {
   // nine 3x3 taps; p.epi carries bias / residual / out
   bool fused_down = false;
   int fd_C = 0, fd_N = 0, fd_Ho = 0, fd_Wo = 0, fd_Cout = 0;
+  // ... with the block's projection as a second accumulator: maps2.a = FIR-downsampled block input, maps2.b = 1x1 weights
+  bool fd_proj = false;
+  TmaMaps maps2;
 };
 
 struct Arena {
@@ -104,6 +107,7 @@ struct glass_engine {
   std::vector<int> d_c1_i8;   // per D block: the space-to-depth tensor between conv0 and the folded conv1 likewise
   std::vector<int> d_proj_fused;   // per D block: projection FIR + 1x1 GEMM in one kernel (fir_proj_tc.cu)
   std::vector<int> d_res_i8;       // per D block: the projection output (conv1's residual operand) is stored I8
+  std::vector<int> d_c1_proj;      // per D block: the projection is a second accumulator of the fused down-conv
   std::vector<int> d_fused;        // per D block: conv1 runs as the fused-FIR exact down-conv (downconv_tc.cu)
   std::vector<int> g_pair;    // per G layer: 1 = 32-channel conv on horizontally paired pixels
   std::vector<int> d_pair;    // per D block: conv0 likewise
@@ -355,8 +359,9 @@ int run_conv(glass_engine* e, const ConvLaunch& c, cudaStream_t s) {
   if (c.fused_down) {
     const bool timed = e->timing && e->ev_used + 2 <= e->ev.size();
     if (timed) cudaEventRecord(e->ev[e->ev_used], s);
-    err = k_downconv_fused(c.maps.a, c.maps.b, c.fd_C, c.fd_N, c.fd_Ho, c.fd_Wo, c.fd_Cout, c.p.epi.bias, c.p.epi.residual,
-                           c.p.epi.res_i8, c.p.epi.out, c.p.epi.out_i8, c.p.epi.post_scale, e->num_sms, s);
+    err = k_downconv_fused(c.maps.a, c.maps.b, c.fd_proj ? &c.maps2.a : nullptr, c.fd_proj ? &c.maps2.b : nullptr, c.fd_C,
+                           c.fd_N, c.fd_Ho, c.fd_Wo, c.fd_Cout, c.p.epi.bias, c.p.epi.residual, c.p.epi.res_i8,
+                           c.p.epi.out, c.p.epi.out_i8, c.p.epi.post_scale, e->num_sms, s);
     if (timed) {
       cudaEventRecord(e->ev[e->ev_used + 1], s);
       e->ev_conv[e->ev_used / 2] = &c;
@@ -526,6 +531,13 @@ void derive_arch(glass_engine* e) {
                     k_downconv_fused_supported(Ci, Co, ro, ro) && ro >= 32 && !(Ci == 64 && nofused64);
     e->d_fused.push_back(on ? 1 : 0);
     if (on) e->d_c1_i8[b] = 0;
+  }
+  // ... and where that kernel can also carry the block's projection (the 32 -> 64 block): no projection launch, no dR
+  e->d_c1_proj.clear();
+  for (int b = 0; b + 1 < c.num_blocks; ++b) {
+    const int Ci = e->gch[c.num_blocks - 1 - b], Co = e->gch[c.num_blocks - 2 - b];
+    e->d_c1_proj.push_back((e->d_fused[b] && !e->d_proj_fused[b] && !(c.flags & GLASS_FLAG_NO_PROJ_ACC) &&
+                            k_downconv_proj_supported(Ci, Co)) ? 1 : 0);
   }
   const bool pair_ok = (c.flags & GLASS_FLAG_NO_PAIR_PACK) == 0 && c.conv_impl == 0;
   e->g_pair.clear();
@@ -876,6 +888,19 @@ int build_plan(glass_engine* e, int P) {
         uint64_t ws[2] = {(uint64_t)Ci * 2, (uint64_t)Ci * 2 * Co};
         uint32_t wb[3] = {(uint32_t)Ci, (uint32_t)box_cols, 1};
         RC(encode_map(e, &cl.maps.b, tptr<__half>(e, nmf("c1.w9")), 3, wd, ws, wb, Ci * 2));
+        if (e->d_c1_proj[b]) {
+          // projection as a second accumulator: tile of the FIR-downsampled block input (NHWC) + the 1x1 weights
+          cl.fd_proj = true;
+          const int ro = res / 2;
+          uint64_t xd4[4] = {(uint64_t)Ci, (uint64_t)ro, (uint64_t)ro, (uint64_t)P};
+          uint64_t xs4[3] = {(uint64_t)Ci * 2, (uint64_t)Ci * 2 * ro, (uint64_t)Ci * 2 * ro * ro};
+          uint32_t xb4[4] = {(uint32_t)Ci, 8, 16, 1};
+          RC(encode_map(e, &cl.maps2.a, e->dXd, 4, xd4, xs4, xb4, Ci * 2));
+          uint64_t pd[2] = {(uint64_t)Ci, (uint64_t)Co};
+          uint64_t ps[1] = {(uint64_t)Ci * 2};
+          uint32_t pb[2] = {(uint32_t)Ci, 64};
+          RC(encode_map(e, &cl.maps2.b, tptr<__half>(e, nmf("proj.w")), 2, pd, ps, pb, Ci * 2));
+        }
       } else if (e->d_exact[b]) {
         // exact: blurred input (k_blur_s2d -> actC, [(res/2+1)^2][4*Ci]) then a 2x2-tap conv == 3x3 stride 2
         RC(make_conv(e, &cl, e->actC, P, res / 2, res / 2, 4 * Ci, tptr<__half>(e, nmf("c1.wx")), 4, Co, ep, false,
@@ -1091,8 +1116,21 @@ int run_discriminator(glass_engine* e, const float* images, int P, float* logits
     }
     RC(run_conv(e, e->d_convs[ci++], s));   // conv0 -> actB (space-to-depth, or NHWC for the exact form)
     if (e->d_exact[b]) LAUNCH(k_blur_s2d(e->actB, e->actC, P, res, res, dch(b), s, (c.flags & GLASS_FLAG_FP32_BLUR) != 0));
-    if (proj_fused) ci++;                   // projection already in dR
-    else RC(run_conv(e, e->d_convs[ci++], s));   // projection -> dR
+    if (proj_fused) {
+      ci++;                                 // projection already in dR
+    } else if (e->d_c1_proj[b]) {
+      // projection = second accumulator of the fused down-conv below: no launch (a zero-length timing entry keeps the
+      // per-layer breakdown aligned)
+      if (e->timing && e->ev_used + 2 <= e->ev.size()) {
+        cudaEventRecord(e->ev[e->ev_used], s);
+        cudaEventRecord(e->ev[e->ev_used + 1], s);
+        e->ev_conv[e->ev_used / 2] = &e->d_convs[ci];
+        e->ev_used += 2;
+      }
+      ci++;
+    } else {
+      RC(run_conv(e, e->d_convs[ci++], s));   // projection -> dR
+    }
     const ConvLaunch& c1 = e->d_convs[ci++];
     RC(run_conv(e, c1, s));                 // conv1 + residual
     x = c1.p.epi.out;

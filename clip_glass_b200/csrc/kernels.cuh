@@ -107,9 +107,11 @@ cudaError_t k_from_rgb_fir_proj(const float* images, const float* folded_host, _
 // (map_w: box (C, 64, 1), swizzle C*2 bytes) -> out = (lrelu(conv3x3_s2(FIR(a)) + bias)*sqrt2 + residual) * post_scale
 bool k_downconv_fused_supported(int C, int Cout, int Ho, int Wo);
 void k_downconv_fused_geometry(int C, int Cout, int* box_groups, int* box_cols);
-cudaError_t k_downconv_fused(const CUtensorMap& map_a, const CUtensorMap& map_w, int C, int N, int Ho, int Wo, int Cout,
-                             const float* bias, const __half* residual, int res_i8, __half* out, int out_i8,
-                             float post_scale, int num_sms, cudaStream_t s);
+bool k_downconv_proj_supported(int C, int Cout);
+cudaError_t k_downconv_fused(const CUtensorMap& map_a, const CUtensorMap& map_w, const CUtensorMap* map_xd,
+                             const CUtensorMap* map_wp, int C, int N, int Ho, int Wo, int Cout, const float* bias,
+                             const __half* residual, int res_i8, __half* out, int out_i8, float post_scale, int num_sms,
+                             cudaStream_t s);
 // modules.py:701-747 incl. the in-place centring; x [P,16,C] -> out [P,16,Cpad] (channel C = std feature)
 cudaError_t k_mbstd(const __half* x, __half* out, int P, int batch, int group, int C, int Cpad, cudaStream_t s);
 // models.py:1224-1225 last dense + problem.py:23 hinge

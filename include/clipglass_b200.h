@@ -96,6 +96,9 @@ typedef struct glass_config {
 /* The blur pass of the exact down-convs (128..512-channel D blocks) normally runs shared-memory-tiled in packed-half2
  * arithmetic.  Cross-check variant: the streaming kernel with an fp32 cascade. */
 #define GLASS_FLAG_FP32_BLUR 2048
+/* Keep the projection path of the 32 -> 64 discriminator block as its own 1x1 GEMM launch (default: a second
+ * accumulator of that block's fused-FIR down-conv kernel; cross-check / A-B variant). */
+#define GLASS_FLAG_NO_PROJ_ACC 4096
 
 /* -- lifetime ------------------------------------------------------------- */
 /* Replaces Generator.__init__ (generator.py:12-27): allocate the engine. */

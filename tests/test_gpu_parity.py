@@ -233,6 +233,19 @@ def test_fused_fir_downconv_against_folded_form():
     np.testing.assert_allclose(folded[1], gold["F"][:, 1], atol=8e-4)
 
 
+def test_projection_accumulator_against_separate_gemm():
+    """The 32 -> 64 discriminator block computes its projection path (1x1 conv of the FIR-downsampled block input,
+    stylegan2/modules.py:1352-1372) as a second TMEM accumulator of the fused-FIR down-conv kernel, in fp32, instead of
+    a separate GEMM whose fp16 output is read back as the residual (GLASS_FLAG_NO_PROJ_ACC = 4096): G and CLIP are
+    untouched, the hinge agrees to the fp16 rounding of that residual tensor, both within the bound of the fixture."""
+    (acc,), gold = _full_scores(flags=0)
+    (sep,), _ = _full_scores(flags=4096)
+    np.testing.assert_array_equal(acc[0], sep[0])
+    np.testing.assert_allclose(acc[1], sep[1], atol=5e-4)
+    np.testing.assert_allclose(acc[1], gold["F"][:, 1], atol=8e-4)
+    np.testing.assert_allclose(sep[1], gold["F"][:, 1], atol=8e-4)
+
+
 def test_image_finished_in_last_conv_epilogue_against_rgb_combine():
     """The last generator conv finishes the image in its epilogue (skip sum + x2 upsample + toRGB bias + biggan_norm)
     instead of writing a toRGB slab for k_rgb_combine (GLASS_FLAG_NO_IMAGE_FUSION = 1024): the same fp32 arithmetic in
