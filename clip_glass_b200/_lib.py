@@ -40,6 +40,9 @@ SYMBOLS = [
     "glass_text_create", "glass_text_set_tensor", "glass_text_finalize", "glass_text_set_image_features",
     "glass_text_generate", "glass_text_similarity", "glass_text_launch_count", "glass_text_last_error",
     "glass_text_destroy", "glass_text_set_timing", "glass_text_gemm_time",
+    "glass_ga_uniform", "glass_ga_permutations", "glass_ga_tournament", "glass_ga_rand_count", "glass_ga_offspring",
+    "glass_ga_dedup_workspace", "glass_ga_dedup_append", "glass_ga_pad", "glass_ga_cast_f32",
+    "glass_ga_survive_workspace", "glass_ga_survive", "glass_ga_gather", "glass_ga_last_error",
 ]
 
 
@@ -70,6 +73,18 @@ class GlassNoise(ctypes.Structure):
         ("noise_on_device", ctypes.c_int32),
         ("seed", ctypes.c_uint64),
         ("first_group", ctypes.c_uint64),
+    ]
+
+
+class GlassGaParams(ctypes.Structure):
+    _fields_ = [
+        ("sbx_eta", ctypes.c_double),
+        ("sbx_prob", ctypes.c_double),
+        ("sbx_prob_var", ctypes.c_double),
+        ("pm_eta", ctypes.c_double),
+        ("pm_prob", ctypes.c_double),
+        ("n_var", ctypes.c_int32),
+        ("integer", ctypes.c_int32),
     ]
 
 
@@ -120,12 +135,37 @@ def load_library() -> ctypes.CDLL:
     lib.glass_range_report.argtypes = [vp, ctypes.POINTER(i64), ctypes.POINTER(i64), ctypes.POINTER(ctypes.c_float)]
     lib.glass_conv_breakdown.argtypes = [vp, vp, vp, i32]
     lib.glass_last_conv_time.argtypes = [vp, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(i32)]
+    u64, f64 = ctypes.c_uint64, ctypes.c_double
+    lib.glass_ga_uniform.argtypes = [u64, u64, vp, i64, vp]
+    lib.glass_ga_permutations.argtypes = [vp, i32, i32, vp, vp]
+    lib.glass_ga_tournament.argtypes = [vp, vp, vp, i32, vp, vp]
+    lib.glass_ga_rand_count.argtypes = [i32, i32]
+    lib.glass_ga_rand_count.restype = i64
+    lib.glass_ga_offspring.argtypes = [ctypes.POINTER(GlassGaParams), vp, vp, vp, vp, i32, vp, vp]
+    lib.glass_ga_dedup_workspace.argtypes = [i32]
+    lib.glass_ga_dedup_workspace.restype = i64
+    lib.glass_ga_dedup_append.argtypes = [vp, i32, vp, i32, vp, i32, vp, i32, f64, i32, vp, vp, vp]
+    lib.glass_ga_pad.argtypes = [vp, i32, vp, i32, vp, vp]
+    lib.glass_ga_cast_f32.argtypes = [vp, vp, i64, vp]
+    lib.glass_ga_survive_workspace.argtypes = [i32]
+    lib.glass_ga_survive_workspace.restype = i64
+    lib.glass_ga_survive.argtypes = [vp, i32, i32, i32, i32, i32, vp, vp, vp, vp, vp]
+    lib.glass_ga_gather.argtypes = [vp, vp, i32, vp, i32, i32, i32, vp, vp, i32, vp]
+    lib.glass_ga_last_error.restype = ctypes.c_char_p
     for name in SYMBOLS:
         fn = getattr(lib, name)
         if fn.restype is ctypes.c_int:
             fn.restype = ctypes.c_int
     _lib = lib
     return lib
+
+
+def check_ga(rc: int) -> None:
+    if rc < 0:
+        msg = load_library().glass_ga_last_error().decode("utf-8", "replace")
+        if rc == -1:
+            raise GlassArgError(msg)
+        raise GlassError(f"clipglass_b200 error {rc}: {msg}")
 
 
 def check(rc: int) -> None:

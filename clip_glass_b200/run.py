@@ -8,8 +8,9 @@ minimize(("n_gen", G)) with ``save_callback`` every ``--save-each`` generations 
 it is importable (the reference's own engine); otherwise ``clip_glass_b200.ga`` stands in (parity unpinned, see its
 header).  Extra flags of this build: ``--pop-size`` / ``--batch-size`` (the reference has no CLI flag for them;
 BASELINE.json's populations need them), ``--synthetic-seed`` (seeded random weights: there are no checkpoints
-offline), ``--seed``.  Under ``torchrun`` every rank runs the same seeded search and the population is sharded
-inside ``_evaluate`` (clip_glass_b200/dist.py).
+offline), ``--seed``, ``--device-ga`` (the GA / NSGA-II operators run on the GPU and the population stays in
+device memory between generations, clip_glass_b200/device_ga.py; StyleGAN2 configs).  Under ``torchrun`` every rank
+runs the same seeded search and the population is sharded inside ``_evaluate`` (clip_glass_b200/dist.py).
 """
 from __future__ import annotations
 
@@ -58,6 +59,7 @@ def main(argv=None, config_overrides=None):
     parser.add_argument("--batch-size", type=int, default=None)
     parser.add_argument("--synthetic-seed", type=int, default=None)
     parser.add_argument("--seed", type=int, default=None)
+    parser.add_argument("--device-ga", action="store_true")
     config = parser.parse_args(argv)
     vars(config).update(get_config(config.config))                         # run.py:25
     if config.pop_size is None or config.batch_size is None:
@@ -96,11 +98,22 @@ def main(argv=None, config_overrides=None):
     problem = GenerationProblem(config)                                    # run.py:54
     operators = get_operators(config)                                      # run.py:55
     os.makedirs(config.tmp_folder, exist_ok=True)
-    algorithm = get_algorithm(config.algorithm, pop_size=config.pop_size, sampling=operators["sampling"],
-                              crossover=operators["crossover"], mutation=operators["mutation"],
-                              eliminate_duplicates=True, callback=save_callback)
-    res = minimize(problem, algorithm, ("n_gen", config.generations), save_history=False, verbose=True,
-                   **({"seed": config.seed} if config.seed is not None else {}))
+    if config.device_ga:
+        # same operators and parameters (operators.py:66-71), run by the glass_ga_* kernels on the resident population
+        if config.config.split("_")[0] != "StyleGAN2":
+            raise SystemExit("--device-ga drives the StyleGAN2 configs (real-valued latents)")
+        from .device_ga import DeviceAlgorithm
+        algorithm = DeviceAlgorithm(config.algorithm, pop_size=config.pop_size, sampling=operators["sampling"],
+                                    callback=save_callback, callback_each=config.save_each,
+                                    seed=config.seed or 0, eliminate_duplicates=True,
+                                    sbx_eta=3.0, sbx_prob=1.0, pm_eta=3.0, pm_prob=0.5)
+        res = algorithm.solve(problem, config.generations, verbose=True)
+    else:
+        algorithm = get_algorithm(config.algorithm, pop_size=config.pop_size, sampling=operators["sampling"],
+                                  crossover=operators["crossover"], mutation=operators["mutation"],
+                                  eliminate_duplicates=True, callback=save_callback)
+        res = minimize(problem, algorithm, ("n_gen", config.generations), save_history=False, verbose=True,
+                       **({"seed": config.seed} if config.seed is not None else {}))
     with open(os.path.join(config.tmp_folder, "genetic_result"), "wb") as f:          # run.py:79-84
         pickle.dump(dict(X=res.X, F=res.F, G=getattr(res, "G", None), CV=getattr(res, "CV", None)), f)
     if config.problem_args["n_obj"] == 1:                                  # run.py:92-96

@@ -224,6 +224,65 @@ int glass_text_gemm_time(glass_text_engine* e, float* ms, int32_t* launches, dou
 const char* glass_text_last_error(void);
 int glass_text_destroy(glass_text_engine* e);
 
+/* -- GPU-resident genetic operators ------------------------- */
+/* The reference's search loop (run.py:59-76: pymoo get_algorithm("ga" | "nsga2") + minimize) runs its operators
+ * (operators.py:66-78: real_sbx / real_pm, int_sbx / int_pm) on the host and ships the whole population through
+ * _evaluate every generation (latent.py:38 H2D, problem.py:20,24 D2H).  These entry points are the same operators on
+ * DEVICE buffers, all asynchronous on `stream`, so that a generation is
+ *     glass_ga_uniform -> glass_ga_permutations -> glass_ga_tournament -> glass_ga_offspring -> glass_ga_dedup_append
+ *     -> glass_evaluate_device -> glass_ga_survive -> glass_ga_gather
+ * without a host round trip (clip_glass_b200/device_ga.py drives it).  pymoo 0.4.2.1 is not vendored by the reference:
+ * the arithmetic follows clip_glass_b200/ga.py (parity with pymoo itself unpinned, see that file's header); given the
+ * same uniform draws the device operators reproduce ga.py's children to the last bit of pow(), and its survivors,
+ * ranks and crowding distances exactly.  Errors: glass_ga_last_error(). */
+typedef struct glass_ga_params {
+  double sbx_eta, sbx_prob, sbx_prob_var;   /* operators.py:69: eta 3, prob 1; pymoo's per-variable probability 0.5 */
+  double pm_eta, pm_prob;                   /* operators.py:70: eta 3, prob 0.5; pm_prob < 0 => 1 / n_var           */
+  int32_t n_var;
+  int32_t integer;                          /* operators.py:75-77 int_sbx / int_pm: rint + clip after each operator */
+} glass_ga_params;
+/* out_dev[0..n): uniforms in [0,1) with 53 random bits, Philox4x32-10 keyed by `seed`; element i depends on
+ * (seed, offset + i/2) only (offset counts PAIRS), so any split of a request reproduces the same stream. */
+int glass_ga_uniform(uint64_t seed, uint64_t offset, double* out_dev, int64_t n, void* stream);
+/* n_perm random permutations of 0..n-1 from n_perm*n uniform keys: out[p] = stable argsort(keys[p]).  n <= 4096. */
+int glass_ga_permutations(const double* keys_dev, int32_t n, int32_t n_perm, int32_t* out_dev, void* stream);
+/* Binary tournament: pair t = (pairs[2t], pairs[2t+1]); lower rank wins, then larger crowding distance, then the first. */
+int glass_ga_tournament(const int32_t* pairs_dev, const int32_t* rank_dev, const double* crowd_dev, int32_t n_select,
+                        int32_t* selected_dev, void* stream);
+/* Number of uniforms one glass_ga_offspring call consumes: SBX do / u / swap [M][V], SBX keep [M], PM do / u [2M][V]. */
+int64_t glass_ga_rand_count(int32_t n_matings, int32_t n_var);
+/* x_dev f64 [n][V] population, parents_dev int32 [M][2] row indices, bounds_dev f64 [4][V] (operator lower / upper
+ * bound, then the variable's own lower / upper bound for the integer rounding), rand_dev the uniforms in the layout
+ * above.  out_dev f64 [2M][V]: the first children of all matings, then the second children (pymoo's reshape). */
+int glass_ga_offspring(const glass_ga_params* params, const double* x_dev, const int32_t* parents_dev,
+                       const double* bounds_dev, const double* rand_dev, int32_t n_matings, double* out_dev,
+                       void* stream);
+/* eliminate_duplicates=True (run.py:66): candidates equal (max |diff| <= eps) to a population row, an accepted
+ * offspring or an earlier candidate are dropped; the others are appended to off_dev [n_off][V] at *n_have_dev (device
+ * counter, advanced) until n_off rows exist; z32_dev (optional) receives the same rows as fp32 (latent.py:38).
+ * workspace_dev: glass_ga_dedup_workspace(n_cand) bytes. */
+int64_t glass_ga_dedup_workspace(int32_t n_cand);
+int glass_ga_dedup_append(const double* cand_dev, int32_t n_cand, const double* x_dev, int32_t n_x, double* off_dev,
+                          int32_t n_off, int32_t* n_have_dev, int32_t n_var, double eps, int32_t eliminate,
+                          float* z32_dev, void* workspace_dev, void* stream);
+/* Rows [*n_have, n_off) repeat the last accepted row (no-op when the offspring buffer is full). */
+int glass_ga_pad(double* off_dev, int32_t n_off, const int32_t* n_have_dev, int32_t n_var, float* z32_dev,
+                 void* stream);
+int glass_ga_cast_f32(const double* x_dev, float* z_dev, int64_t n, void* stream);
+/* Survival of the merged population.  f_dev fp32 column-major: objective k of candidate j at f_dev[k*ld + j] (the
+ * layout glass_evaluate_device writes: one array per objective).  nsga2 != 0: fast non-dominated sort + crowding
+ * distance, the last front truncated by crowding; nsga2 == 0: the n_survive smallest f_dev[j] (stable).  Outputs
+ * (n_survive entries): candidate index, rank, crowding distance (GA: -F), in survivor order.  n <= 4096; one CTA.
+ * workspace_dev: glass_ga_survive_workspace(n) bytes. */
+int64_t glass_ga_survive_workspace(int32_t n);
+int glass_ga_survive(const float* f_dev, int32_t ld, int32_t n, int32_t n_obj, int32_t n_survive, int32_t nsga2,
+                     int32_t* idx_dev, int32_t* rank_dev, double* crowd_dev, void* workspace_dev, void* stream);
+/* x_out[r] = x_all[idx[r]], f_out[k*ld_out + r] = f_all[k*ld_in + idx[r]] for r < n_out. */
+int glass_ga_gather(const double* x_all_dev, const float* f_all_dev, int32_t ld_in, const int32_t* idx_dev,
+                    int32_t n_out, int32_t n_var, int32_t n_obj, double* x_out_dev, float* f_out_dev, int32_t ld_out,
+                    void* stream);
+const char* glass_ga_last_error(void);
+
 /* -- introspection ---------------------------------------------------------- */
 const char* glass_last_error(void);
 /* Number of kernels launched by this engine since creation (bench.py's gpu_launches). */
