@@ -353,8 +353,17 @@ class Algorithm:
 
     def _mate(self, X, n_off, multiple=1):
         """Offspring that are not duplicates of the population (or of each other); the count is kept a multiple of
-        ``multiple`` (the reference asserts pop % minibatch == 0, models.py:112)."""
+        ``multiple`` (the reference asserts pop % minibatch == 0, models.py:112).  A candidate is a duplicate when
+        max |row - candidate| <= 1e-16 for a population row or an offspring accepted earlier; rows are screened on
+        their first variable (a necessary condition) before the full comparison."""
         off = []
+        Xf = np.asarray(X, dtype=float)
+        acc = np.empty((n_off, X.shape[1]), dtype=float)          # float view of the accepted offspring
+
+        def duplicate(cf, pool):
+            near = np.flatnonzero(np.abs(pool[:, 0] - cf[0]) <= 1e-16)
+            return near.size > 0 and bool((np.abs(pool[near] - cf).max(axis=1) <= 1e-16).any())
+
         for _ in range(100):
             need = n_off - len(off)
             if need <= 0:
@@ -365,14 +374,13 @@ class Algorithm:
             C = self.crossover.do(self.problem, Xp)
             C = C.reshape(-1, X.shape[1])
             C = self.mutation.do(self.problem, C)
-            for c in C:
+            Cf = np.asarray(C, dtype=float)
+            for c, cf in zip(C, Cf):
                 if len(off) >= n_off:
                     break
-                if self.eliminate_duplicates:
-                    cf = np.asarray(c, dtype=float)
-                    if any(np.abs(np.asarray(o, dtype=float) - cf).max() <= 1e-16 for o in off) or \
-                            (np.abs(np.asarray(X, dtype=float) - cf).max(axis=1) <= 1e-16).any():
-                        continue
+                if self.eliminate_duplicates and (duplicate(cf, acc[:len(off)]) or duplicate(cf, Xf)):
+                    continue
+                acc[len(off)] = cf
                 off.append(c)
         while len(off) % multiple:
             off.append(off[-1])

@@ -332,3 +332,83 @@ def test_resident_loop_sharded_over_two_ranks_gloo(host, tmp_path):
         for _ in range(5):
             g.step()
         assert np.array_equal(g.population()[0], X0)
+
+
+def _mate_reference(alg, X, n_off, multiple=1):
+    """The plain loop ga.Algorithm._mate replaces (every accepted offspring and every population row compared in
+    full): the screened version must accept exactly the same candidates from the same random draws."""
+    import math
+    off = []
+    for _ in range(100):
+        need = n_off - len(off)
+        if need <= 0:
+            break
+        n_matings = math.ceil(need / 2)
+        parents = alg._tournament(2 * n_matings).reshape(n_matings, 2)
+        Xp = np.stack([X[parents[:, 0]], X[parents[:, 1]]])
+        C = alg.mutation.do(alg.problem, alg.crossover.do(alg.problem, Xp).reshape(-1, X.shape[1]))
+        for c in C:
+            if len(off) >= n_off:
+                break
+            cf = np.asarray(c, dtype=float)
+            if alg.eliminate_duplicates and (
+                    any(np.abs(np.asarray(o, dtype=float) - cf).max() <= 1e-16 for o in off)
+                    or (np.abs(np.asarray(X, dtype=float) - cf).max(axis=1) <= 1e-16).any()):
+                continue
+            off.append(c)
+    while len(off) % multiple:
+        off.append(off[-1])
+    return np.stack(off)
+
+
+@pytest.mark.parametrize("kind", ["real", "real_dups", "int", "mixed"])
+def test_host_mating_duplicate_screen_equals_plain_loop(kind):
+    from types import SimpleNamespace
+    from clip_glass_b200 import ga
+
+    def build(seed):
+        rs = np.random.RandomState(seed)
+        if kind == "int":             # GPT-2 operators on a tiny vocabulary: equal first genes and duplicates are common
+            V, xl, xu = 3, 0.0, 2.0
+            cross = ga._IntegerFromFloat(ga.SimulatedBinaryCrossover(3.0, 1.0, rng=rs))
+            mut = ga._IntegerFromFloat(ga.PolynomialMutation(3.0, 0.5, rng=rs))
+            X = rs.randint(0, 3, size=(12, V))
+        elif kind == "mixed":         # BigGAN's mixed real / bool population (object rows)
+            V = 10
+            mask = ["real"] * 4 + ["bool"] * 6
+            cross = ga.MixedVariableCrossover(mask, {"real": ga.SimulatedBinaryCrossover(3.0, 0.3, rng=rs),
+                                                     "bool": ga.HalfUniformCrossover(0.2, rng=rs)})
+            mut = ga.MixedVariableMutation(mask, {"real": ga.PolynomialMutation(3.0, 0.05, rng=rs),
+                                                  "bool": ga.BitflipMutation(0.01, rng=rs)})
+            X = np.empty((12, V), dtype=object)
+            X[:, :4] = rs.normal(size=(12, 4))
+            X[:, 4:] = rs.random_sample((12, 6)) < 0.3
+            xl, xu = -2.0, 2.0
+        else:                         # StyleGAN2 operators; "real_dups": matings mostly kept, mutation rare => duplicates
+            V, xl, xu = 16, -10.0, 10.0
+            cross = ga.SimulatedBinaryCrossover(3.0, 1.0 if kind == "real" else 0.2, rng=rs)
+            mut = ga.PolynomialMutation(3.0, 0.5 if kind == "real" else 0.01, rng=rs)
+            X = rs.normal(size=(12, V))
+        alg = ga.Algorithm("nsga2", pop_size=12, sampling=None, crossover=cross, mutation=mut)
+        alg.rng = rs
+        alg.problem = SimpleNamespace(n_var=V, xl=np.full(V, xl), xu=np.full(V, xu))
+        alg.pop = [None] * 12
+        alg._rank, alg._crowd = rs.randint(0, 3, size=12), rs.random_sample(12)
+        return alg, X
+
+    rejected = 0
+    for seed in range(6):
+        a, X = build(seed)
+        b, Xb = build(seed)
+        got = a._mate(X, 12, 4)
+        want = _mate_reference(b, Xb, 12, 4)
+        assert got.shape == want.shape and np.array_equal(np.asarray(got, dtype=float), np.asarray(want, dtype=float))
+        # both consumed the same number of draws
+        assert a.rng.random_sample() == b.rng.random_sample()
+        Xf, gf = np.asarray(X, dtype=float), np.asarray(got, dtype=float)
+        if kind != "real":
+            c, _ = build(seed)
+            c.eliminate_duplicates = False
+            rejected += int(not np.array_equal(np.asarray(c._mate(X, 12, 4), dtype=float), gf))
+        assert not (np.abs(gf[:, None, :] - Xf[None]).max(-1) <= 1e-16).any()      # no offspring repeats a parent row
+    assert kind == "real" or rejected > 0, "the scenario never produced a duplicate"
