@@ -48,6 +48,11 @@ class DeviceGA:
         assert algorithm == "nsga2" or n_obj == 1, "the single-objective GA ranks by F[:, 0]"
         if not torch.cuda.is_available():
             raise RuntimeError("DeviceGA needs a CUDA device (there is no host fallback; use clip_glass_b200.ga)")
+        if not 0 < 2 * int(pop_size) <= 4096:
+            raise ValueError("DeviceGA handles populations of 1..2048 (the merged 2 * pop_size candidates are ranked "
+                             "by one thread block, glass_ga_survive)")
+        if not 0 < int(n_obj) <= min(8, int(n_var)):
+            raise ValueError("n_obj must be in 1..min(8, n_var)")
         self.lib = load_library()
         self.device = torch.device(device)
         self.algorithm, self.P, self.V, self.n_obj = algorithm, int(pop_size), int(n_var), int(n_obj)

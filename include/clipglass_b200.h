@@ -277,7 +277,7 @@ int glass_ga_cast_f32(const double* x_dev, float* z_dev, int64_t n, void* stream
 int64_t glass_ga_survive_workspace(int32_t n);
 int glass_ga_survive(const float* f_dev, int32_t ld, int32_t n, int32_t n_obj, int32_t n_survive, int32_t nsga2,
                      int32_t* idx_dev, int32_t* rank_dev, double* crowd_dev, void* workspace_dev, void* stream);
-/* x_out[r] = x_all[idx[r]], f_out[k*ld_out + r] = f_all[k*ld_in + idx[r]] for r < n_out. */
+/* x_out[r] = x_all[idx[r]], f_out[k*ld_out + r] = f_all[k*ld_in + idx[r]] for r < n_out (n_obj <= n_var). */
 int glass_ga_gather(const double* x_all_dev, const float* f_all_dev, int32_t ld_in, const int32_t* idx_dev,
                     int32_t n_out, int32_t n_var, int32_t n_obj, double* x_out_dev, float* f_out_dev, int32_t ld_out,
                     void* stream);
