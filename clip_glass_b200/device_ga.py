@@ -254,7 +254,7 @@ class DeviceAlgorithm:
         self.state.initialize(np.asarray(self.sampling._do(problem, self.pop_size), dtype=np.float64))
         self.n_gen = 1
         # the engine's cached images are those of the offspring it scored last, not of rows the host has seen
-        problem.generator._last_rows = None
+        problem.generator.forget_population()
         while True:
             if self.callback:
                 # run.py's save_callback counts its calls and reads .pop only on saving generations

@@ -134,6 +134,11 @@ class Generator:
         self._last_rows = {row.tobytes(): i for i, row in enumerate(self._last_x32)}
         self.reuse_stats = dict(reused=0, rendered=0)
 
+    def forget_population(self):
+        """The engine's cached images no longer belong to rows the host has seen (the GPU-resident GA evaluates
+        offspring that never reach the host, device_ga.py): ``generate`` renders instead of reusing."""
+        self._last_rows = None
+
     def _cached_rows(self, z_host: np.ndarray):
         rows = getattr(self, "_last_rows", None)
         if not rows or not getattr(self.config, "reuse_evaluated_images", True):

@@ -255,6 +255,7 @@ def test_device_algorithm_follows_run_py_callback_contract(host, monkeypatch):
         cfg = SimpleNamespace(problem_args=dict(n_obj=n_obj), use_discriminator=n_obj == 2, batch_size=4, noise_seed=0)
         problem = SimpleNamespace(config=cfg, n_var=V, xl=np.full(V, -10.0), xu=np.full(V, 10.0),
                                   generator=SimpleNamespace(engine=SimpleNamespace(device=0), _last_rows={1: 2}))
+        problem.generator.forget_population = lambda g=problem.generator: setattr(g, "_last_rows", None)
         sampling = SimpleNamespace(_do=lambda prob, n: np.random.default_rng(1).normal(0, 1, (n, prob.n_var)))
         seen = []
 
