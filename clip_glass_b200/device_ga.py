@@ -31,6 +31,7 @@ import numpy as np
 import torch
 
 from ._lib import GlassGaParams, GlassNoise, check, check_ga, load_library
+from .utils import nvtx_range
 
 
 class DeviceGA:
@@ -153,10 +154,13 @@ class DeviceGA:
     def step(self) -> None:
         """One generation; everything is enqueued on the current stream, nothing is read back."""
         assert self.generation >= 1, "call initialize() first"
-        self.mate()
+        with nvtx_range("glass.ga.mate"):
+            self.mate()
         self.generation += 1
-        self.evaluate(self.z32, self._f_cols(self.P), self.generation)
-        self._survive(2 * self.P)
+        with nvtx_range("glass.ga.fitness"):
+            self.evaluate(self.z32, self._f_cols(self.P), self.generation)
+        with nvtx_range("glass.ga.survive"):
+            self._survive(2 * self.P)
 
     # -- read-back (synchronises) ---------------------------------------------
     def population(self):

@@ -33,6 +33,30 @@ def shard_bounds(pop: int, batch_size: int, world: int) -> List[Tuple[int, int]]
     return bounds
 
 
+def init_from_env(device: str = "cuda", timeout_s: float = 600.0) -> Tuple[int, int, int]:
+    """``torchrun`` launch of the driver (SURVEY.md §5 failure detection): when WORLD_SIZE > 1 and no process group
+    exists yet, create one — NCCL for a CUDA device (bound to LOCAL_RANK's GPU), gloo otherwise — with a collective
+    timeout, so that a rank that died or hung makes the per-generation all-gather of F raise on the others instead of
+    blocking the search forever (NCCL's asynchronous error handling tears the communicator down).  Returns
+    (rank, world, local_rank); (0, 1, 0) for a plain single-process launch, in which nothing is initialised."""
+    import datetime
+    import os
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world <= 1:
+        return 0, 1, 0
+    rank, local_rank = int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0"))
+    if not tdist.is_initialized():
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("TORCH_NCCL_ASYNC_ERROR_HANDLING", "1")
+        timeout = datetime.timedelta(seconds=float(timeout_s))
+        if str(device).startswith("cuda"):
+            torch.cuda.set_device(local_rank)
+            tdist.init_process_group("nccl", timeout=timeout, device_id=torch.device("cuda", local_rank))
+        else:
+            tdist.init_process_group("gloo", timeout=timeout)
+    return rank, world, local_rank
+
+
 def _world():
     if tdist.is_available() and tdist.is_initialized():
         return tdist.get_rank(), tdist.get_world_size()

@@ -24,7 +24,7 @@ import torch
 
 from . import weights as W
 from .engine import GlassEngine
-from ._lib import GlassError
+from ._lib import GlassArgError, GlassError
 
 
 def _load_state_dicts(config):
@@ -145,6 +145,25 @@ class Generator:
             return [None] * len(z_host)
         return [rows.get(np.ascontiguousarray(r).tobytes()) for r in z_host]
 
+    def _render(self, z, mb: int, noise=None):
+        """``engine.generate`` with minibatch size ``mb`` and a fresh noise seed per call.  More candidates than the
+        engine's workspace holds (a population-sharded run sizes it for one shard, but the saving rank renders the
+        whole population, run.py:45) go through in chunks of whole minibatches."""
+        n, cap = z.shape[0], self.engine.max_population
+        step = n if n <= cap else cap // mb * mb
+        if step <= 0:
+            raise GlassArgError(f"minibatch {mb} exceeds the engine's max_population {cap}")
+        if step < n and noise is not None:
+            raise GlassArgError("explicit noise tensors are not supported for chunked rendering")
+        self.engine.set_batch_size(mb)
+        outs = []
+        for s0 in range(0, n, step):
+            self._calls += 1
+            seed = int(getattr(self.config, "noise_seed", 0)) + self._calls
+            chunk = z if step >= n else z[s0:s0 + step].contiguous()
+            outs.append(self.engine.generate(chunk, noise=noise, seed=seed))
+        return outs[0] if len(outs) == 1 else torch.cat(outs)
+
     # generator.py:29-34
     def generate(self, ls, minibatch=None, noise=None):
         z = ls()[0]
@@ -157,10 +176,7 @@ class Generator:
         hits = self._cached_rows(z.cpu().numpy()) if noise is None else [None] * n
         missing = [i for i, h in enumerate(hits) if h is None]
         if len(missing) == n:
-            self.engine.set_batch_size(minibatch if minibatch is not None else n)
-            self._calls += 1
-            seed = int(getattr(self.config, "noise_seed", 0)) + self._calls
-            return self.engine.generate(z, noise=noise, seed=seed)     # already normalised to [0,1]
+            return self._render(z, minibatch if minibatch is not None else n, noise)   # already normalised to [0,1]
         # some (usually all) of the requested candidates were rendered and scored by the last _evaluate
         R = self.gan.resolution
         out = torch.empty(n, 3, R, R, dtype=torch.float32, device=z.device)
@@ -172,10 +188,7 @@ class Generator:
             # render the rest: whole minibatches (models.py:112), padded by repeating the last missing row
             mb = minibatch if minibatch is not None else len(missing)
             idx = missing + [missing[-1]] * ((-len(missing)) % mb)
-            self.engine.set_batch_size(mb)
-            self._calls += 1
-            seed = int(getattr(self.config, "noise_seed", 0)) + self._calls
-            extra = self.engine.generate(z[torch.as_tensor(idx, device=z.device)].contiguous(), seed=seed)
+            extra = self._render(z[torch.as_tensor(idx, device=z.device)].contiguous(), mb)
             out[torch.as_tensor(missing, device=z.device)] = extra[:len(missing)]
             self.reuse_stats["rendered"] += len(missing)
         return out

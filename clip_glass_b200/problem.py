@@ -20,6 +20,7 @@ import numpy as np
 import torch
 
 from .generator import Generator
+from .utils import nvtx_range
 
 try:                                    # pymoo==0.4.2.1 is not installable offline
     from pymoo.model.problem import Problem as _Base
@@ -50,6 +51,10 @@ class GenerationProblem(_Base):
         return self.config.problem_args["n_obj"] == 2 and self.config.use_discriminator
 
     def _evaluate(self, x, out, *args, **kwargs):
+        with nvtx_range("glass._evaluate"):
+            return self._evaluate_generation(x, out, *args, **kwargs)
+
+    def _evaluate_generation(self, x, out, *args, **kwargs):
         self.generation += 1
         if self.config.task == "img2txt":
             # problem.py:15-29 for the GPT-2 config: generate -> clip_similarity, F = -sim.  With

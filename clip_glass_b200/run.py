@@ -9,8 +9,9 @@ it is importable (the reference's own engine); otherwise ``clip_glass_b200.ga`` 
 header).  Extra flags of this build: ``--pop-size`` / ``--batch-size`` (the reference has no CLI flag for them;
 BASELINE.json's populations need them), ``--synthetic-seed`` (seeded random weights: there are no checkpoints
 offline), ``--seed``, ``--device-ga`` (the GA / NSGA-II operators run on the GPU and the population stays in
-device memory between generations, clip_glass_b200/device_ga.py; StyleGAN2 configs).  Under ``torchrun`` every rank
-runs the same seeded search and the population is sharded inside ``_evaluate`` (clip_glass_b200/dist.py).
+device memory between generations, clip_glass_b200/device_ga.py; StyleGAN2 configs).  Under ``torchrun`` the driver
+creates the process group itself (NCCL, collective timeout: ``dist.init_from_env``), every rank runs the same seeded
+search, the population is sharded inside ``_evaluate`` (clip_glass_b200/dist.py) and rank 0 writes the files.
 """
 from __future__ import annotations
 
@@ -73,6 +74,17 @@ def main(argv=None, config_overrides=None):
             and config.task == "txt2img":
         # no checkpoints offline: the cached CLIP.encode_text(target) (generator.py:23-24) is a seeded stand-in
         config.text_features = torch.randn(1, 512, generator=torch.Generator().manual_seed(config.synthetic_seed + 5))
+    # torchrun: one rank per GPU, every rank runs the same seeded search, the population is sharded inside _evaluate
+    from . import dist
+    rank, world, local_rank = dist.init_from_env(config.device, timeout_s=getattr(config, "collective_timeout", 600.0))
+    if world > 1:
+        if str(config.device).startswith("cuda"):
+            config.device = "cuda:%d" % local_rank
+        if config.seed is None:
+            config.seed = 0                       # the ranks must draw the same populations
+        if getattr(config, "max_population", None) is None:
+            # each rank's workspace holds its own shard (Generator renders a whole population in chunks when saving)
+            config.max_population = max(b - a for a, b in dist.shard_bounds(config.pop_size, config.batch_size, world))
     if config.seed is not None:
         np.random.seed(config.seed)
         torch.manual_seed(config.seed)
@@ -82,7 +94,7 @@ def main(argv=None, config_overrides=None):
     def save_callback(algorithm):                                          # run.py:29-51
         state["iteration"] += 1
         it = state["iteration"]
-        if it % config.save_each == 0 or it == config.generations:
+        if (it % config.save_each == 0 or it == config.generations) and rank == 0:      # one rank writes the files
             if config.problem_args["n_obj"] == 1:
                 X = np.stack([p.X for p in sorted(algorithm.pop, key=lambda p: p.F)])
             else:
@@ -114,6 +126,8 @@ def main(argv=None, config_overrides=None):
                                   eliminate_duplicates=True, callback=save_callback)
         res = minimize(problem, algorithm, ("n_gen", config.generations), save_history=False, verbose=True,
                        **({"seed": config.seed} if config.seed is not None else {}))
+    if rank != 0:
+        return res
     with open(os.path.join(config.tmp_folder, "genetic_result"), "wb") as f:          # run.py:79-84
         pickle.dump(dict(X=res.X, F=res.F, G=getattr(res, "G", None), CV=getattr(res, "CV", None)), f)
     if config.problem_args["n_obj"] == 1:                                  # run.py:92-96

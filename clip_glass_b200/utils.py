@@ -4,7 +4,31 @@
 kernels (k_rgb_combine writes clip((y+1)/2); k_from_rgb applies x*2-1); the
 torch versions here exist for callers that hold images as tensors.
 """
+import contextlib
+
 import torch
+
+
+try:                                    # NVTX is optional instrumentation: never let it break the path
+    from torch.cuda import nvtx as _nvtx
+    _nvtx.range_push("glass.import")
+    _nvtx.range_pop()
+except Exception:                       # pragma: no cover - depends on the torch build
+    _nvtx = None
+
+
+@contextlib.contextmanager
+def nvtx_range(name: str):
+    """NVTX range around a host-side phase (SURVEY.md §5 tracing): shows up in nsys / ncu timelines as
+    ``glass.<phase>``; a no-op stub call when no profiler is attached."""
+    if _nvtx is None:
+        yield
+        return
+    _nvtx.range_push(name)
+    try:
+        yield
+    finally:
+        _nvtx.range_pop()
 
 
 def biggan_norm(images):

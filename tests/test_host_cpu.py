@@ -570,3 +570,71 @@ def test_gpt2_oracle_reproduces_reference_fixture(name):
     sim = gpt2_oracle.text_similarity(feats, torch.from_numpy(gold["image_features"])).numpy()
     np.testing.assert_allclose(sim, gold["sim_oracle_fp32"][:n], rtol=1e-5)
     np.testing.assert_allclose(sim, gold["sim_fp16"][:n].astype(np.float32), rtol=3e-3)
+
+
+# ---------------------------------------------------------------------------
+# driver plumbing for population-sharded runs
+# ---------------------------------------------------------------------------
+def test_generator_renders_more_candidates_than_the_workspace_in_chunks():
+    """A population-sharded run sizes each engine for its shard; the saving rank still renders the whole population
+    (run.py:45): whole minibatches per engine call, a fresh noise seed per call, rows in order."""
+    from types import SimpleNamespace
+    from clip_glass_b200.generator import Generator
+
+    calls = []
+
+    class Eng:
+        max_population = 8
+
+        def set_batch_size(self, b):
+            self.b = b
+
+        def generate(self, z, noise=None, seed=0):
+            assert z.shape[0] <= self.max_population and z.shape[0] % self.b == 0 and z.is_contiguous()
+            calls.append((z.shape[0], seed, self.b))
+            return z[:, :3, None, None].expand(-1, 3, 2, 2).clone()
+
+    g = Generator.__new__(Generator)
+    g.engine, g.config, g._calls = Eng(), SimpleNamespace(noise_seed=10), 0
+    z = torch.arange(20 * 4, dtype=torch.float32).reshape(20, 4)
+    out = g._render(z, 4)
+    assert calls == [(8, 11, 4), (8, 12, 4), (4, 13, 4)] and out.shape == (20, 3, 2, 2)
+    assert torch.equal(out[:, :, 0, 0], z[:, :3])
+    calls.clear()
+    out = g._render(z[:8], 8)                              # fits: one call, exactly as before
+    assert calls == [(8, 14, 8)] and torch.equal(out[:, :, 0, 0], z[:8, :3])
+    with pytest.raises(_lib.GlassArgError):
+        g._render(z, 16)                                   # a minibatch larger than the workspace
+    with pytest.raises(_lib.GlassArgError):
+        g._render(z, 4, noise=[object()])
+
+
+def _init_env_worker(rank, world, port, q):
+    os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank), MASTER_ADDR="127.0.0.1",
+                      MASTER_PORT=str(port))
+    import torch.distributed as tdist
+    got = dist.init_from_env("cpu", timeout_s=45.0)
+    again = dist.init_from_env("cpu")                       # idempotent
+    x = np.random.default_rng(3).normal(size=(12, 32))
+    neg_sim, hinge = dist.sharded_evaluate(x, 4, 2, _fake_eval)
+    q.put((rank, got, again, tdist.get_backend(), neg_sim, hinge))
+    tdist.destroy_process_group()
+
+
+def test_driver_creates_the_process_group_from_the_torchrun_environment():
+    import torch.multiprocessing as mp
+    assert dist.init_from_env("cpu") == (0, 1, 0) and not dist.tdist.is_initialized()      # plain launch: nothing
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_init_env_worker, args=(r, 2, 29871, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=120) for _ in procs], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+    x = np.random.default_rng(3).normal(size=(12, 32))
+    exp_sim, exp_hinge = _fake_eval(x, 0)
+    for r, (rank, got, again, backend, neg_sim, hinge) in enumerate(res):
+        assert got == (r, 2, r) and again == got and backend == "gloo"
+        np.testing.assert_array_equal(neg_sim, exp_sim)
+        np.testing.assert_array_equal(hinge, exp_hinge)
