@@ -638,3 +638,27 @@ def test_driver_creates_the_process_group_from_the_torchrun_environment():
         assert got == (r, 2, r) and again == got and backend == "gloo"
         np.testing.assert_array_equal(neg_sim, exp_sim)
         np.testing.assert_array_equal(hinge, exp_hinge)
+
+
+def test_ga_entry_points_validate_arguments_without_a_gpu():
+    """glass_ga_* check their arguments before touching CUDA (GLASS_ERR_ARG = -1 with a message); the size helpers
+    are pure host arithmetic."""
+    lib = _lib.load_library()
+    assert lib.glass_ga_rand_count(32, 512) == 7 * 32 * 512 + 32
+    assert lib.glass_ga_dedup_workspace(64) == 64 * 8
+    n = 128
+    assert lib.glass_ga_survive_workspace(n) >= 4 * n * 4 + 2 * n * 8
+    one = ctypes.c_void_p(16)                 # never dereferenced: every call below is refused first
+    assert lib.glass_ga_permutations(one, 5000, 1, one, None) == -1
+    assert b"4096" in lib.glass_ga_last_error()
+    assert lib.glass_ga_survive(one, 4, 8, 2, 4, 1, one, one, one, one, None) == -1       # ld < n
+    assert lib.glass_ga_survive(one, 8, 8, 2, 9, 1, one, one, one, one, None) == -1       # n_survive > n
+    assert lib.glass_ga_survive(one, 8, 8, 9, 4, 1, one, one, one, one, None) == -1       # n_obj > 8
+    assert lib.glass_ga_uniform(0, 0, None, 4, None) == -1
+    assert lib.glass_ga_tournament(one, one, one, 0, one, None) == -1
+    p = _lib.GlassGaParams(3.0, 1.0, 0.5, 3.0, 0.5, 0, 0)
+    assert lib.glass_ga_offspring(ctypes.byref(p), one, one, one, one, 4, one, None) == -1  # n_var = 0
+    assert lib.glass_ga_gather(one, one, 8, one, 4, 2, 3, one, one, 8, None) == -1          # n_obj > n_var
+    with pytest.raises(_lib.GlassArgError):
+        _lib.check_ga(lib.glass_ga_pad(None, 4, one, 4, None, None))
+    assert ctypes.sizeof(_lib.GlassGaParams) == 5 * 8 + 2 * 4
