@@ -662,3 +662,52 @@ def test_ga_entry_points_validate_arguments_without_a_gpu():
     with pytest.raises(_lib.GlassArgError):
         _lib.check_ga(lib.glass_ga_pad(None, 4, one, 4, None, None))
     assert ctypes.sizeof(_lib.GlassGaParams) == 5 * 8 + 2 * 4
+
+
+def test_generator_generate_branches_with_a_stub_engine():
+    """Generator.generate (generator.py:29-34 + the image reuse of SURVEY §8(f)-4) over a stub engine: nothing cached
+    -> one engine.generate call; everything cached -> images gathered from the last evaluation, no rendering; partly
+    cached -> the missing rows rendered as whole minibatches (padded by repeating the last missing row)."""
+    from types import SimpleNamespace
+    from clip_glass_b200.generator import Generator
+    log = []
+
+    class Eng:
+        max_population = 8
+
+        def set_batch_size(self, b):
+            log.append(("batch", b))
+
+        def generate(self, z, noise=None, seed=0):
+            log.append(("generate", z.shape[0], seed))
+            return z[:, :3, None, None].expand(-1, 3, 2, 2).clone()
+
+        def last_images(self, rows):
+            log.append(("last_images", list(rows)))
+            return torch.full((len(rows), 3, 2, 2), -1.0)
+
+    g = Generator.__new__(Generator)
+    g.engine, g._calls = Eng(), 0
+    g.config = SimpleNamespace(task="txt2img", device="cpu", noise_seed=100)
+    g.gan = SimpleNamespace(resolution=2)
+    x = np.random.default_rng(0).normal(size=(8, 4))
+    ls = lambda rows: (lambda: (torch.from_numpy(x[rows]).float(),))
+    out = g.generate(ls(slice(0, 8)), minibatch=4)                         # nothing remembered yet
+    assert log == [("batch", 4), ("generate", 8, 101)] and out.shape == (8, 3, 2, 2)
+    log.clear()
+    g.remember_population(x)
+    out = g.generate(ls([5, 2]), minibatch=4)                              # both rows were scored by the last evaluation
+    assert log == [("last_images", [5, 2])] and float(out.max()) == -1.0 and g.reuse_stats == dict(reused=2, rendered=0)
+    log.clear()
+    g.remember_population(x[:4])
+    out = g.generate(ls([1, 6, 3, 7, 5]), minibatch=2)                     # rows 6, 7, 5 are new: 3 -> padded to 4
+    assert log == [("last_images", [1, 3]), ("batch", 2), ("generate", 4, 102)]
+    assert torch.equal(out[[0, 2]], torch.full((2, 3, 2, 2), -1.0))
+    assert torch.equal(out[[1, 3, 4], :, 0, 0], torch.from_numpy(x[[6, 7, 5], :3]).float())
+    assert g.reuse_stats == dict(reused=2, rendered=3)
+    log.clear()
+    g.forget_population()
+    g.generate(ls([0]))                                                     # run.py:117-118: one candidate, minibatch=None
+    assert log == [("batch", 1), ("generate", 1, 103)]
+    out = g.generate(ls(slice(0, 8)), minibatch=4, noise=[["explicit"]])   # explicit noise never reuses cached images
+    assert log[-1] == ("generate", 8, 104)
