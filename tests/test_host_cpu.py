@@ -711,3 +711,41 @@ def test_generator_generate_branches_with_a_stub_engine():
     assert log == [("batch", 1), ("generate", 1, 103)]
     out = g.generate(ls(slice(0, 8)), minibatch=4, noise=[["explicit"]])   # explicit noise never reuses cached images
     assert log[-1] == ("generate", 8, 104)
+
+
+def test_generation_problem_evaluate_contract_with_a_stub_engine():
+    """problem.py:14-29 through the host mirror with the GPU engine stubbed out: F = (-sim, hinge) columns for the
+    NSGA-II config, F = -sim for the GA config, G zeros, the noise seed advancing per generation, the population
+    remembered for the image output path; pop % batch_size is the engine's assertion."""
+    from types import SimpleNamespace
+    from clip_glass_b200.problem import GenerationProblem
+    seen = []
+
+    class Eng:
+        def set_batch_size(self, b):
+            self.b = b
+
+        def evaluate(self, xs, noise=None, seed=0, first_group=0):
+            seen.append((xs.shape, seed, first_group, self.b))
+            return (-xs[:, 0]).astype(np.float32), np.abs(xs[:, 1]).astype(np.float32)
+
+    for n_obj, use_d in ((2, True), (1, False)):
+        remembered = []
+        gen = SimpleNamespace(engine=Eng(), remember_population=lambda xs: remembered.append(xs.shape))
+        cfg = SimpleNamespace(task="txt2img", batch_size=4, noise_seed=7, use_discriminator=use_d, device="cuda:0",
+                              problem_args=dict(n_var=6, n_obj=n_obj, n_constr=0, xl=-10.0, xu=10.0))
+        p = GenerationProblem(cfg, generator=gen)
+        x = np.random.default_rng(n_obj).normal(size=(8, 6))
+        seen.clear()
+        for g in (1, 2):
+            out = {}
+            p._evaluate(x, out)
+            assert seen[-1] == ((8, 6), 7 + g, 0, 4) and remembered[-1] == (8, 6)
+            if n_obj == 2:
+                assert out["F"].shape == (8, 2)
+                np.testing.assert_array_equal(out["F"][:, 0], (-x[:, 0]).astype(np.float32))
+                np.testing.assert_array_equal(out["F"][:, 1], np.abs(x[:, 1]).astype(np.float32))
+            else:
+                np.testing.assert_array_equal(out["F"], (-x[:, 0]).astype(np.float32))
+            assert out["G"].shape == (8,) and not out["G"].any()
+        assert p.n_var == 6 and p.n_obj == n_obj and p.xl.shape == (6,)
