@@ -749,3 +749,85 @@ def test_generation_problem_evaluate_contract_with_a_stub_engine():
                 np.testing.assert_array_equal(out["F"], (-x[:, 0]).astype(np.float32))
             assert out["G"].shape == (8,) and not out["G"].any()
         assert p.n_var == 6 and p.n_obj == n_obj and p.xl.shape == (6,)
+
+
+class _StubGenerator:
+    def __init__(self):
+        self.saved, self.generated = [], []
+
+    def generate(self, ls, minibatch=None):
+        z = ls()[0]
+        self.generated.append((tuple(z.shape), minibatch))
+        return torch.zeros(z.shape[0], 3, 2, 2)
+
+    def save(self, images, path):
+        self.saved.append(os.path.basename(path))
+        open(path, "wb").write(b"x")
+
+
+class _StubProblem:
+    """GenerationProblem's surface (problem.py:8-29) with an analytic fitness instead of the GPU engine."""
+
+    def __init__(self, config):
+        self.config, self.generator = config, _StubGenerator()
+        a = config.problem_args
+        self.n_var, self.n_obj = a["n_var"], a["n_obj"]
+        self.xl, self.xu = np.full(self.n_var, float(a["xl"])), np.full(self.n_var, float(a["xu"]))
+
+    def _evaluate(self, x, out, *args, **kwargs):
+        f = (np.asarray(x, dtype=float) ** 2).sum(1)
+        out["F"] = np.column_stack((f, np.abs(np.asarray(x, dtype=float)[:, 0] - 1))) if self.n_obj == 2 else f
+        out["G"] = np.zeros(len(x))
+
+
+_DRIVER_ARGS = ["--device", "cpu", "--generations", "5", "--save-each", "2", "--pop-size", "8", "--batch-size", "4",
+                "--synthetic-seed", "1"]
+
+
+@pytest.mark.parametrize("config_name", ["StyleGAN2_ffhq_nod", "StyleGAN2_ffhq_d"])
+def test_run_driver_flow_with_a_stub_problem(tmp_path, monkeypatch, config_name):
+    """The driver mirror (run.py:15-125) end to end on the CPU with the fitness engine stubbed out: sampling -> host
+    GA / NSGA-II -> save_callback files -> result pickles -> final output; single process (no process group)."""
+    import pickle
+    from clip_glass_b200 import run as driver
+    monkeypatch.setattr(driver, "GenerationProblem", _StubProblem)
+    monkeypatch.delenv("WORLD_SIZE", raising=False)
+    res = driver.main(_DRIVER_ARGS + ["--config", config_name, "--tmp-folder", str(tmp_path), "--seed", "3"])
+    names = set(os.listdir(tmp_path))
+    assert {"genetic-it-2.jpg", "genetic-it-4.jpg", "genetic-it-final.jpg", "output.jpg", "genetic_result",
+            "ls_result"} <= names, names
+    assert len(res.pop) == 8 and not dist.tdist.is_initialized()
+    with open(tmp_path / "genetic_result", "rb") as f:
+        saved = pickle.load(f)
+    assert np.isfinite(np.asarray(saved["F"], dtype=float)).all()
+    assert "z" in torch.load(tmp_path / "ls_result")
+
+
+def _driver_worker(rank, world, port, folder, q):
+    os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank), MASTER_ADDR="127.0.0.1",
+                      MASTER_PORT=str(port))
+    from clip_glass_b200 import run as driver
+    driver.GenerationProblem = _StubProblem
+    res = driver.main(_DRIVER_ARGS + ["--config", "StyleGAN2_ffhq_d", "--tmp-folder", folder])      # no --seed given
+    q.put((rank, np.stack([p.X for p in res.pop]), dist.tdist.is_initialized(), dist.tdist.get_backend()))
+    dist.tdist.destroy_process_group()
+
+
+def test_run_driver_under_a_two_rank_launch_writes_files_once(tmp_path):
+    """torchrun-style launch (gloo, world size 2): the driver creates the process group, every rank runs the same
+    seeded search (the missing --seed becomes 0 on all ranks), and only rank 0 writes the files."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    folders = [str(tmp_path / f"rank{r}") for r in range(2)]       # separate folders show who wrote what
+    procs = [ctx.Process(target=_driver_worker, args=(r, 2, 29877, folders[r], q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=180) for _ in procs], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+    (_, X0, init0, backend0), (_, X1, init1, _) = res
+    assert init0 and init1 and backend0 == "gloo"
+    assert np.array_equal(X0, X1)                                  # same search on both ranks
+    assert {"genetic-it-final.jpg", "output.jpg", "genetic_result", "ls_result"} <= set(os.listdir(folders[0]))
+    assert os.listdir(folders[1]) == []                            # the folder is created, nothing is written
