@@ -413,3 +413,45 @@ def test_host_mating_duplicate_screen_equals_plain_loop(kind):
             rejected += int(not np.array_equal(np.asarray(c._mate(X, 12, 4), dtype=float), gf))
         assert not (np.abs(gf[:, None, :] - Xf[None]).max(-1) <= 1e-16).any()      # no offspring repeats a parent row
     assert kind == "real" or rejected > 0, "the scenario never produced a duplicate"
+
+
+def test_run_driver_device_ga_branch_on_host_shim(host, monkeypatch, tmp_path):
+    """run.py's --device-ga branch (DeviceAlgorithm in place of pymoo's minimize) end to end on the CPU: the kernels
+    are served by their host compilation, the fitness engine by an analytic function."""
+    import pickle
+    import torch
+    from types import SimpleNamespace
+    from clip_glass_b200 import device_ga as D, run as driver
+    from tests.test_host_cpu import _StubProblem, _DRIVER_ARGS
+
+    class Problem(_StubProblem):
+        def __init__(self, config):
+            super().__init__(config)
+            self.generator.engine = SimpleNamespace(device=0)
+            self.generator.forgot = 0
+            self.generator.forget_population = lambda: setattr(self.generator, "forgot", self.generator.forgot + 1)
+
+    def fitness(z, outs, gen, first_group):
+        outs[0].copy_((z ** 2).sum(1))
+        if len(outs) > 1:
+            outs[1].copy_((z[:, 0] - 1).abs())
+
+    monkeypatch.setattr(driver, "GenerationProblem", Problem)
+    monkeypatch.setattr(D, "load_library", lambda: _HostLibShim(host))
+    monkeypatch.setattr(D.torch.cuda, "is_available", lambda: True)
+    monkeypatch.setattr(D.DeviceGA, "_stream", lambda self: None)
+    monkeypatch.setattr(D.torch, "device", lambda *a: "cpu")
+    monkeypatch.setattr(D, "engine_evaluator", lambda e, b, s=0: D.sharded_evaluator(fitness, b))
+    monkeypatch.delenv("WORLD_SIZE", raising=False)
+    for config_name in ("StyleGAN2_ffhq_d", "StyleGAN2_ffhq_nod"):
+        folder = tmp_path / config_name
+        res = driver.main(_DRIVER_ARGS + ["--config", config_name, "--tmp-folder", str(folder), "--seed", "3",
+                                          "--device-ga"])
+        names = set(os.listdir(folder))
+        assert {"genetic-it-2.jpg", "genetic-it-4.jpg", "genetic-it-final.jpg", "output.jpg", "genetic_result",
+                "ls_result"} <= names, names
+        with open(folder / "genetic_result", "rb") as f:
+            saved = pickle.load(f)
+        assert np.isfinite(np.asarray(saved["F"], dtype=float)).all() and len(res.pop) == 8
+        X = res.pop.get("X")
+        assert X.shape == (8, 512) and np.abs(X).max() <= 10.0
